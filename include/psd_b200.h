@@ -1,0 +1,127 @@
+/*
+ * psd_b200.h — C ABI of the B200 (sm_100a) dense periodic Schur library.
+ *
+ * This is the drop-in boundary for the dense pschur! hot path of
+ * RalphAS/PeriodicSchurDecompositions.jl (v0.1.6).  The reference has no FFI of its own
+ * (pure Julia, multiple dispatch); the Julia glue in
+ * periodicschurdecompositions.jl_b200/julia/PeriodicSchurB200.jl overloads the reference's
+ * methods for Float64/ComplexF64 matrices and forwards to these entry points via ccall
+ * (see INTEGRATION.md).  Each entry point cites the reference method it replaces
+ * (file:line relative to the reference repository).
+ *
+ * Conventions
+ *  - Matrices are column-major, order n, leading dimension n, one factor after another:
+ *    A[batch][p][n*n].  Complex data are interleaved (re,im) double pairs (Julia ComplexF64).
+ *  - Factors are always in the USER's order A_1..A_p.  orientation 0 = :R (product
+ *    A_1 A_2 ... A_p, Schur factor is A_1 / schurindex 1), 1 = :L (product A_p ... A_1,
+ *    Schur factor is A_p / schurindex p)   [PeriodicSchurDecompositions.jl:40-48,127-131,
+ *    1078-1093].
+ *  - On return (wantT != 0) A holds the T factors in place, with exact zeros below the
+ *    (quasi-)triangle; Z (wantZ != 0) holds the orthogonal/unitary factors indexed as in the
+ *    reference result structs (:R  Z_j' A_j Z_{j+1} = T_j ;  :L  Z_{j+1}' A_j Z_j = T_j).
+ *  - info[b] = 0 on success, k > 0 = "convergence failed at level k"
+ *    (PeriodicSchurDecompositions.jl:891-893, generalized.jl:856-858,
+ *    rgeneralized.jl:1057-1059).  One failing problem never aborts the batch.
+ *  - All functions return 0 on success and a negative code on error; the message is
+ *    available from psd_last_error_string().  No C++ exception crosses this boundary and
+ *    nothing calls exit()/abort().
+ *  - There is no CPU fallback: without a usable CUDA device every compute entry point
+ *    returns PSD_ERR_NO_DEVICE.
+ *  - Host entry points are synchronous and thread-safe (per-handle mutex); buffers belong to
+ *    the caller and are only touched during the call.
+ */
+#ifndef PSD_B200_H
+#define PSD_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PSD_VERSION 100 /* 0.1.0 */
+
+#define PSD_OK 0
+#define PSD_ERR_BAD_ARG (-1)      /* invalid n/p/batch/flags/pointer                       */
+#define PSD_ERR_NO_DEVICE (-2)    /* no CUDA device / extension unusable                    */
+#define PSD_ERR_CUDA (-3)         /* CUDA runtime error (see psd_last_error_string)        */
+#define PSD_ERR_SIGNATURE (-4)    /* "The leftmost entry in S must be true"                */
+                                  /*   (generalized.jl:140, rgeneralized.jl:37)            */
+#define PSD_ERR_UNSUPPORTED (-5)  /* shape outside what this build implements              */
+
+typedef struct psd_handle_s* psd_handle_t;
+
+int psd_version(void);
+/* Number of visible CUDA devices (0 if none / driver missing). */
+int psd_device_count(void);
+/* Thread-local description of the last error returned on this thread. */
+const char* psd_last_error_string(void);
+
+/* Create a handle owning streams, device workspaces and pinned staging on `ndev` devices
+ * (devices[i] = CUDA ordinal); ndev == 0 selects every visible device.  Batched host entry
+ * points shard the batch into ndev contiguous ranges, one host thread + stream per device,
+ * with no inter-device communication. */
+int psd_create(psd_handle_t* handle, int ndev, const int* devices);
+int psd_destroy(psd_handle_t handle);
+int psd_handle_device_count(psd_handle_t handle);
+
+/* ---------------------------------------------------------------------------------------
+ * Real standard periodic Schur decomposition, batched.
+ * Replaces pschur!(A::Vector{Matrix{Float64}}, lr; wantZ, wantT, maxitfac)
+ *   driver                      PeriodicSchurDecompositions.jl:120-152
+ *   periodic Hessenberg         PeriodicSchurDecompositions.jl:213-259  (+ householder.jl)
+ *   explicit Q                  PeriodicSchurDecompositions.jl:136-140,180 (orghr/orgqr)
+ *   periodic QR iteration       PeriodicSchurDecompositions.jl:322-1096 (+ rschur2x2.jl)
+ * for `batch` independent problems of identical shape.
+ *   A    in/out  [batch][p][n][n]   (wantT == 0: contents unspecified on return, as the
+ *                                    reference leaves "mangled" matrices, runtests.jl:118)
+ *   Z    out     [batch][p][n][n]   or NULL when wantZ == 0
+ *   eig  out     [batch][n] complex128 (re,im); complex pairs adjacent, positive imaginary
+ *                                    part first (rschur2x2.jl:89-91)
+ *   info out     [batch]
+ * maxitfac <= 0 selects the reference default 30.
+ * ------------------------------------------------------------------------------------- */
+int psd_rpschur_batched(psd_handle_t handle, int n, int p, int64_t batch, int orientation,
+                        int wantT, int wantZ, int maxitfac, double* A, double* Z, double* eig,
+                        int32_t* info);
+
+/* Same computation on buffers already resident on device `dev_index` (index into the
+ * handle's device list), enqueued on `stream` (a cudaStream_t passed as void*; NULL = the
+ * handle's own stream for that device).  Asynchronous: the caller synchronises the stream.
+ * Used by bench.py for the HBM-resident throughput figure and by host code that keeps
+ * matrices on the GPU. */
+int psd_rpschur_batched_dev(psd_handle_t handle, int dev_index, void* stream, int n, int p,
+                            int64_t batch, int orientation, int wantT, int wantZ,
+                            int maxitfac, double* dA, double* dZ, double* deig,
+                            int32_t* dinfo);
+
+/* Periodic QR iteration on input that is already in Hessenberg-triangular form (rightwards
+ * order: A_1 upper Hessenberg, A_2..A_p upper triangular; anything below is ignored and
+ * zeroed), Z initialised to the identity.
+ * Replaces the inner method pschur!(H1, Hs; wantT, wantZ, maxitfac) with Q === nothing
+ * (PeriodicSchurDecompositions.jl:322-1096), which the reference's tests use to keep exact
+ * zeros in the input (test/runtests.jl:53-66). */
+int psd_rpschur_hessut_batched(psd_handle_t handle, int n, int p, int64_t batch, int wantT,
+                               int wantZ, int maxitfac, double* A, double* Z, double* eig,
+                               int32_t* info);
+
+/* Periodic Hessenberg-triangular reduction only, batched (device or host buffers).
+ * Replaces phessenberg!(A) (PeriodicSchurDecompositions.jl:213-259) followed by the explicit
+ * Q materialisation of the driver (:136-140): on return A holds H_1 (upper Hessenberg) and
+ * H_2..H_p (upper triangular) with exact zeros below, Q (or NULL) the explicit Q_j with
+ * Q_j' A_j Q_{j+1} = H_j.  Rightwards order only (the :L driver reverses before calling). */
+int psd_rphess_batched(psd_handle_t handle, int n, int p, int64_t batch, int wantQ, double* A,
+                       double* Q);
+
+/* Counters of the most recent batched call on this handle (diagnostics; mirrors the
+ * reference's niter/maxits reporting, PeriodicSchurDecompositions.jl:458-459,1077):
+ * stats[0] = kernel launches, stats[1] = problems solved in shared memory,
+ * stats[2] = problems solved in global-memory workspaces, stats[3] = H2D bytes,
+ * stats[4] = D2H bytes, stats[5] = kernel time in microseconds summed over devices. */
+int psd_last_stats(psd_handle_t handle, int64_t stats[8]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PSD_B200_H */

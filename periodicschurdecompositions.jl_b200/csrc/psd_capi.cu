@@ -1,0 +1,435 @@
+// C ABI of the B200 periodic Schur library (see include/psd_b200.h for the contract).
+//
+// Host side: a handle owns, per device, a small pool of "slots" (stream + device buffers +
+// pinned staging).  A batched host call shards the batch into one contiguous range per
+// device (one host thread each, no inter-device traffic), cuts each range into chunks and
+// round-robins the chunks over the slots so that H2D of chunk c+1, the kernel of chunk c and
+// D2H of chunk c-1 overlap on different streams.
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/psd_b200.h"
+#include "psd_real_kernel.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+
+#define PSD_CUDA(call)                                                                     \
+  do {                                                                                     \
+    cudaError_t e__ = (call);                                                              \
+    if (e__ != cudaSuccess)                                                                \
+      return fail(PSD_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));      \
+  } while (0)
+
+constexpr int kSlotsPerDevice = 2;
+
+struct Slot {
+  cudaStream_t stream = nullptr;
+  double* dA = nullptr;
+  double* dZ = nullptr;
+  double* dEig = nullptr;
+  int32_t* dInfo = nullptr;
+  size_t capA = 0, capZ = 0, capEig = 0, capInfo = 0;
+  // pinned staging (only used when the caller's buffers are pageable)
+  double* hA = nullptr;
+  double* hZ = nullptr;
+  double* hEig = nullptr;
+  int32_t* hInfo = nullptr;
+  size_t hcapA = 0, hcapZ = 0, hcapEig = 0, hcapInfo = 0;
+  unsigned long long* dCounter = nullptr;
+  double* dScratch = nullptr;
+  size_t capScratch = 0;
+};
+
+struct Device {
+  int ordinal = 0;
+  int sm_count = 0;
+  Slot slots[kSlotsPerDevice];
+  Slot user;  // counter/scratch for *_dev entry points running on caller streams
+};
+
+}  // namespace
+
+struct psd_handle_s {
+  std::vector<Device> devs;
+  std::mutex mu;
+  int64_t stats[8] = {0};
+};
+
+namespace {
+
+template <class T>
+int ensure_dev(T*& ptr, size_t& cap, size_t bytes) {
+  if (bytes <= cap) return PSD_OK;
+  if (ptr) cudaFree(ptr);
+  ptr = nullptr;
+  cap = 0;
+  PSD_CUDA(cudaMalloc((void**)&ptr, bytes));
+  cap = bytes;
+  return PSD_OK;
+}
+template <class T>
+int ensure_pinned(T*& ptr, size_t& cap, size_t bytes) {
+  if (bytes <= cap) return PSD_OK;
+  if (ptr) cudaFreeHost(ptr);
+  ptr = nullptr;
+  cap = 0;
+  PSD_CUDA(cudaHostAlloc((void**)&ptr, bytes, cudaHostAllocDefault));
+  cap = bytes;
+  return PSD_OK;
+}
+
+bool is_pinned(const void* p) {
+  if (!p) return true;
+  cudaPointerAttributes at;
+  cudaError_t e = cudaPointerGetAttributes(&at, p);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged;
+}
+
+struct RealLaunchPlan {
+  int use_smem = 0;
+  int ldh = 0;
+  int threads = 64;
+  size_t smem_bytes = 0;
+  int grid = 1;
+  bool scratch = false;
+};
+
+// Choose staging mode, CTA size and persistent grid for the real kernel.
+int plan_real(const Device& dev, int n, int p, long long batch, bool wantZ, RealLaunchPlan& pl) {
+  const long long small = psd::rp_small_doubles(n, p);
+  const int ldh = (n % 2 == 0) ? n + 1 : n;
+  const long long mats = (long long)p * ldh * n * (wantZ ? 2 : 1);
+  const size_t need_smem = (size_t)(small + mats) * sizeof(double);
+  cudaFuncAttributes fa;
+  PSD_CUDA(cudaFuncGetAttributes(&fa, psd::rpschur_kernel));
+  int optin = 0;
+  PSD_CUDA(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev.ordinal));
+  const size_t max_dyn = (size_t)optin - fa.sharedSizeBytes;
+  if (need_smem <= max_dyn) {
+    pl.use_smem = 1;
+    pl.ldh = ldh;
+    pl.smem_bytes = need_smem;
+    pl.scratch = false;
+  } else {
+    pl.use_smem = 0;
+    pl.ldh = n;
+    if ((size_t)small * sizeof(double) <= 96 * 1024) {
+      pl.smem_bytes = (size_t)small * sizeof(double);
+      pl.scratch = false;
+    } else {
+      pl.smem_bytes = 0;
+      pl.scratch = true;
+    }
+  }
+  // one row or column per thread for the left, right and Z updates
+  int want = n * (wantZ ? 3 : 2);
+  int threads = ((want + 31) / 32) * 32;
+  threads = std::max(32, std::min(threads, pl.use_smem ? 256 : 512));
+  pl.threads = threads;
+  PSD_CUDA(cudaFuncSetAttribute(psd::rpschur_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)max_dyn));
+  int occ = 0;
+  PSD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, psd::rpschur_kernel, threads,
+                                                         pl.smem_bytes));
+  if (occ < 1) return fail(PSD_ERR_UNSUPPORTED, "kernel does not fit on an SM");
+  long long g = (long long)occ * dev.sm_count;
+  pl.grid = (int)std::max(1LL, std::min(g, batch));
+  return PSD_OK;
+}
+
+struct RealCall {
+  int n, p, left, wantT, wantZ, maxitfac, reduce_only, skip_reduce;
+};
+
+// Enqueue the real kernel for `batch` device-resident problems on `stream`.
+int launch_real(psd_handle_s* h, Device& dev, Slot& aux, cudaStream_t stream, const RealCall& rc,
+                long long batch, double* dA, double* dZ, double* dEig, int32_t* dInfo) {
+  if (batch == 0) return PSD_OK;
+  RealLaunchPlan pl;
+  const bool wantZ = rc.wantZ && dZ;
+  int e = plan_real(dev, rc.n, rc.p, batch, wantZ, pl);
+  if (e) return e;
+  if (!aux.dCounter) PSD_CUDA(cudaMalloc((void**)&aux.dCounter, sizeof(unsigned long long)));
+  PSD_CUDA(cudaMemsetAsync(aux.dCounter, 0, sizeof(unsigned long long), stream));
+  psd::RpschurParams P;
+  P.n = rc.n; P.p = rc.p; P.batch = batch;
+  P.left = rc.left; P.wantT = rc.wantT; P.wantZ = wantZ ? 1 : 0;
+  P.maxitfac = rc.maxitfac > 0 ? rc.maxitfac : 30;
+  P.A = dA; P.Z = wantZ ? dZ : nullptr; P.eig = dEig; P.info = dInfo; P.iters = nullptr;
+  P.use_smem = pl.use_smem; P.ldh = pl.ldh;
+  P.reduce_only = rc.reduce_only; P.skip_reduce = rc.skip_reduce;
+  P.counter = aux.dCounter;
+  P.scratch = nullptr; P.scratch_stride = 0;
+  if (pl.scratch) {
+    size_t stride = (size_t)psd::rp_small_doubles(rc.n, rc.p);
+    e = ensure_dev(aux.dScratch, aux.capScratch, stride * sizeof(double) * pl.grid);
+    if (e) return e;
+    P.scratch = aux.dScratch;
+    P.scratch_stride = (long long)stride;
+  }
+  psd::rpschur_kernel<<<pl.grid, pl.threads, pl.smem_bytes, stream>>>(P);
+  PSD_CUDA(cudaGetLastError());
+  __atomic_fetch_add(&h->stats[0], (int64_t)1, __ATOMIC_RELAXED);
+  __atomic_fetch_add(&h->stats[pl.use_smem ? 1 : 2], (int64_t)batch, __ATOMIC_RELAXED);
+  return PSD_OK;
+}
+
+// One device's share of a host-buffer batched call.
+int run_real_shard(psd_handle_s* h, Device& dev, const RealCall& rc, long long first, long long count,
+                   double* A, double* Z, double* eig, int32_t* info, bool pinned,
+                   int64_t* bytes_h2d, int64_t* bytes_d2h) {
+  if (count <= 0) return PSD_OK;
+  PSD_CUDA(cudaSetDevice(dev.ordinal));
+  const size_t nn = (size_t)rc.n * rc.n;
+  const size_t per = nn * rc.p;  // doubles per problem
+  const bool wantZ = rc.wantZ && Z;
+  const bool outT = rc.wantT || rc.reduce_only;
+  // chunk: at most ~512 MiB of factors per slot, at least one wave of CTAs
+  long long chunk = std::max<long long>(1, (512LL << 20) / (long long)(per * sizeof(double)));
+  chunk = std::min(chunk, count);
+  if (count > chunk) {
+    // balance chunk sizes
+    long long nchunks = (count + chunk - 1) / chunk;
+    chunk = (count + nchunks - 1) / nchunks;
+  }
+  int si = 0;
+  int rcode = PSD_OK;
+  for (long long off = 0; off < count && rcode == PSD_OK; off += chunk, si = (si + 1) % kSlotsPerDevice) {
+    const long long nb = std::min(chunk, count - off);
+    Slot& s = dev.slots[si];
+    if (!s.stream) PSD_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+    // the slot's previous chunk must have fully drained before its buffers are reused
+    PSD_CUDA(cudaStreamSynchronize(s.stream));
+    int e;
+    if ((e = ensure_dev(s.dA, s.capA, nb * per * sizeof(double)))) return e;
+    if (wantZ && (e = ensure_dev(s.dZ, s.capZ, nb * per * sizeof(double)))) return e;
+    if ((e = ensure_dev(s.dEig, s.capEig, nb * 2 * rc.n * sizeof(double)))) return e;
+    if ((e = ensure_dev(s.dInfo, s.capInfo, nb * sizeof(int32_t)))) return e;
+    double* srcA = A + (size_t)(first + off) * per;
+    const size_t bytesA = nb * per * sizeof(double);
+    if (pinned) {
+      PSD_CUDA(cudaMemcpyAsync(s.dA, srcA, bytesA, cudaMemcpyHostToDevice, s.stream));
+    } else {
+      if ((e = ensure_pinned(s.hA, s.hcapA, bytesA))) return e;
+      std::memcpy(s.hA, srcA, bytesA);
+      PSD_CUDA(cudaMemcpyAsync(s.dA, s.hA, bytesA, cudaMemcpyHostToDevice, s.stream));
+    }
+    *bytes_h2d += (int64_t)bytesA;
+    e = launch_real(h, dev, s, s.stream, rc, nb, s.dA, wantZ ? s.dZ : nullptr, s.dEig, s.dInfo);
+    if (e) return e;
+    // results
+    double* dstEig = eig ? eig + (size_t)(first + off) * 2 * rc.n : nullptr;
+    int32_t* dstInfo = info ? info + (first + off) : nullptr;
+    double* dstZ = wantZ ? Z + (size_t)(first + off) * per : nullptr;
+    const size_t bytesEig = nb * 2 * rc.n * sizeof(double);
+    const size_t bytesInfo = nb * sizeof(int32_t);
+    if (pinned) {
+      if (outT) PSD_CUDA(cudaMemcpyAsync(srcA, s.dA, bytesA, cudaMemcpyDeviceToHost, s.stream));
+      if (wantZ) PSD_CUDA(cudaMemcpyAsync(dstZ, s.dZ, bytesA, cudaMemcpyDeviceToHost, s.stream));
+      if (dstEig) PSD_CUDA(cudaMemcpyAsync(dstEig, s.dEig, bytesEig, cudaMemcpyDeviceToHost, s.stream));
+      if (dstInfo) PSD_CUDA(cudaMemcpyAsync(dstInfo, s.dInfo, bytesInfo, cudaMemcpyDeviceToHost, s.stream));
+    } else {
+      if (wantZ && (e = ensure_pinned(s.hZ, s.hcapZ, bytesA))) return e;
+      if ((e = ensure_pinned(s.hEig, s.hcapEig, bytesEig))) return e;
+      if ((e = ensure_pinned(s.hInfo, s.hcapInfo, bytesInfo))) return e;
+      if (outT) PSD_CUDA(cudaMemcpyAsync(s.hA, s.dA, bytesA, cudaMemcpyDeviceToHost, s.stream));
+      if (wantZ) PSD_CUDA(cudaMemcpyAsync(s.hZ, s.dZ, bytesA, cudaMemcpyDeviceToHost, s.stream));
+      PSD_CUDA(cudaMemcpyAsync(s.hEig, s.dEig, bytesEig, cudaMemcpyDeviceToHost, s.stream));
+      PSD_CUDA(cudaMemcpyAsync(s.hInfo, s.dInfo, bytesInfo, cudaMemcpyDeviceToHost, s.stream));
+      // pageable destination: drain this slot now and copy out (the other slot keeps the
+      // GPU busy meanwhile)
+      PSD_CUDA(cudaStreamSynchronize(s.stream));
+      if (outT) std::memcpy(srcA, s.hA, bytesA);
+      if (wantZ) std::memcpy(dstZ, s.hZ, bytesA);
+      if (dstEig) std::memcpy(dstEig, s.hEig, bytesEig);
+      if (dstInfo) std::memcpy(dstInfo, s.hInfo, bytesInfo);
+    }
+    *bytes_d2h += (int64_t)((outT ? bytesA : 0) + (wantZ ? bytesA : 0) + bytesEig + bytesInfo);
+  }
+  for (int k = 0; k < kSlotsPerDevice; k++)
+    if (dev.slots[k].stream) PSD_CUDA(cudaStreamSynchronize(dev.slots[k].stream));
+  return rcode;
+}
+
+int run_real_host(psd_handle_t h, const RealCall& rc, int64_t batch, double* A, double* Z, double* eig,
+                  int32_t* info) {
+  if (!h) return fail(PSD_ERR_BAD_ARG, "null handle");
+  if (rc.n < 1 || rc.p < 1 || batch < 0) return fail(PSD_ERR_BAD_ARG, "n, p must be >= 1 and batch >= 0");
+  if (!A) return fail(PSD_ERR_BAD_ARG, "A must not be NULL");
+  if (!rc.reduce_only && (!eig || !info)) return fail(PSD_ERR_BAD_ARG, "eig and info must not be NULL");
+  if (rc.wantZ && !Z) return fail(PSD_ERR_BAD_ARG, "wantZ set but Z is NULL");
+  if (h->devs.empty()) return fail(PSD_ERR_NO_DEVICE, "handle has no CUDA device");
+  std::lock_guard<std::mutex> lock(h->mu);
+  for (auto& s : h->stats) s = 0;
+  if (batch == 0) return PSD_OK;
+  const bool pinned = is_pinned(A) && is_pinned(Z) && is_pinned(eig) && is_pinned(info);
+  const int nd = (int)h->devs.size();
+  std::vector<int> codes(nd, PSD_OK);
+  std::vector<std::string> msgs(nd);
+  std::vector<int64_t> h2d(nd, 0), d2h(nd, 0);
+  auto t0 = std::chrono::steady_clock::now();
+  auto work = [&](int d) {
+    const long long lo = batch * d / nd, hi = batch * (d + 1) / nd;
+    codes[d] = run_real_shard(h, h->devs[d], rc, lo, hi - lo, A, Z, eig, info, pinned, &h2d[d], &d2h[d]);
+    if (codes[d]) msgs[d] = g_err;
+  };
+  if (nd == 1) {
+    work(0);
+  } else {
+    std::vector<std::thread> th;
+    for (int d = 0; d < nd; d++) th.emplace_back(work, d);
+    for (auto& t : th) t.join();
+  }
+  auto t1 = std::chrono::steady_clock::now();
+  for (int d = 0; d < nd; d++) {
+    h->stats[3] += h2d[d];
+    h->stats[4] += d2h[d];
+  }
+  h->stats[5] = std::chrono::duration_cast<std::chrono::microseconds>(t1 - t0).count();
+  for (int d = 0; d < nd; d++)
+    if (codes[d]) return fail(codes[d], msgs[d]);
+  return PSD_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int psd_version(void) { return PSD_VERSION; }
+
+int psd_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+const char* psd_last_error_string(void) { return g_err.c_str(); }
+
+int psd_create(psd_handle_t* handle, int ndev, const int* devices) {
+  if (!handle) return fail(PSD_ERR_BAD_ARG, "handle pointer is NULL");
+  *handle = nullptr;
+  int avail = psd_device_count();
+  if (avail <= 0) return fail(PSD_ERR_NO_DEVICE, "no CUDA device visible (this library has no CPU fallback)");
+  std::vector<int> ords;
+  if (ndev <= 0) {
+    for (int i = 0; i < avail; i++) ords.push_back(i);
+  } else {
+    if (!devices) return fail(PSD_ERR_BAD_ARG, "devices is NULL");
+    for (int i = 0; i < ndev; i++) {
+      if (devices[i] < 0 || devices[i] >= avail) return fail(PSD_ERR_BAD_ARG, "device ordinal out of range");
+      ords.push_back(devices[i]);
+    }
+  }
+  auto* h = new (std::nothrow) psd_handle_s;
+  if (!h) return fail(PSD_ERR_BAD_ARG, "out of host memory");
+  for (int o : ords) {
+    Device d;
+    d.ordinal = o;
+    cudaDeviceProp prop;
+    cudaError_t e = cudaGetDeviceProperties(&prop, o);
+    if (e != cudaSuccess) {
+      delete h;
+      return fail(PSD_ERR_CUDA, std::string("cudaGetDeviceProperties: ") + cudaGetErrorString(e));
+    }
+    if (prop.major < 10) {
+      delete h;
+      return fail(PSD_ERR_NO_DEVICE, "device is not sm_100 class (this library is built for sm_100a only)");
+    }
+    d.sm_count = prop.multiProcessorCount;
+    h->devs.push_back(d);
+  }
+  *handle = h;
+  return PSD_OK;
+}
+
+int psd_destroy(psd_handle_t h) {
+  if (!h) return PSD_OK;
+  for (auto& d : h->devs) {
+    cudaSetDevice(d.ordinal);
+    auto freeSlot = [](Slot& s) {
+      if (s.stream) {
+        cudaStreamSynchronize(s.stream);
+        cudaStreamDestroy(s.stream);
+      }
+      cudaFree(s.dA); cudaFree(s.dZ); cudaFree(s.dEig); cudaFree(s.dInfo);
+      cudaFree(s.dCounter); cudaFree(s.dScratch);
+      cudaFreeHost(s.hA); cudaFreeHost(s.hZ); cudaFreeHost(s.hEig); cudaFreeHost(s.hInfo);
+    };
+    for (auto& s : d.slots) freeSlot(s);
+    freeSlot(d.user);
+  }
+  cudaGetLastError();
+  delete h;
+  return PSD_OK;
+}
+
+int psd_handle_device_count(psd_handle_t h) { return h ? (int)h->devs.size() : 0; }
+
+int psd_rpschur_batched(psd_handle_t h, int n, int p, int64_t batch, int orientation, int wantT,
+                        int wantZ, int maxitfac, double* A, double* Z, double* eig, int32_t* info) {
+  if (orientation != 0 && orientation != 1)
+    return fail(PSD_ERR_BAD_ARG, "orientation argument must be either 0 (:R, right) or 1 (:L, left)");
+  RealCall rc{n, p, orientation, wantT != 0, wantZ != 0, maxitfac, 0, 0};
+  return run_real_host(h, rc, batch, A, Z, eig, info);
+}
+
+int psd_rpschur_hessut_batched(psd_handle_t h, int n, int p, int64_t batch, int wantT, int wantZ,
+                               int maxitfac, double* A, double* Z, double* eig, int32_t* info) {
+  RealCall rc{n, p, 0, wantT != 0, wantZ != 0, maxitfac, 0, 1};
+  return run_real_host(h, rc, batch, A, Z, eig, info);
+}
+
+int psd_rphess_batched(psd_handle_t h, int n, int p, int64_t batch, int wantQ, double* A, double* Q) {
+  RealCall rc{n, p, 0, 1, wantQ != 0, 30, 1, 0};
+  return run_real_host(h, rc, batch, A, Q, nullptr, nullptr);
+}
+
+int psd_rpschur_batched_dev(psd_handle_t h, int dev_index, void* stream, int n, int p, int64_t batch,
+                            int orientation, int wantT, int wantZ, int maxitfac, double* dA,
+                            double* dZ, double* deig, int32_t* dinfo) {
+  if (!h) return fail(PSD_ERR_BAD_ARG, "null handle");
+  if (dev_index < 0 || dev_index >= (int)h->devs.size()) return fail(PSD_ERR_BAD_ARG, "dev_index out of range");
+  if (n < 1 || p < 1 || batch < 0 || !dA || !deig || !dinfo) return fail(PSD_ERR_BAD_ARG, "bad argument");
+  if (orientation != 0 && orientation != 1) return fail(PSD_ERR_BAD_ARG, "bad orientation");
+  if (wantZ && !dZ) return fail(PSD_ERR_BAD_ARG, "wantZ set but dZ is NULL");
+  std::lock_guard<std::mutex> lock(h->mu);
+  Device& dev = h->devs[dev_index];
+  PSD_CUDA(cudaSetDevice(dev.ordinal));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!st) {
+    if (!dev.user.stream) PSD_CUDA(cudaStreamCreateWithFlags(&dev.user.stream, cudaStreamNonBlocking));
+    st = dev.user.stream;
+  }
+  RealCall rc{n, p, orientation, wantT != 0, wantZ != 0, maxitfac, 0, 0};
+  return launch_real(h, dev, dev.user, st, rc, batch, dA, dZ, deig, dinfo);
+}
+
+int psd_last_stats(psd_handle_t h, int64_t stats[8]) {
+  if (!h || !stats) return fail(PSD_ERR_BAD_ARG, "null argument");
+  std::lock_guard<std::mutex> lock(h->mu);
+  for (int i = 0; i < 8; i++) stats[i] = h->stats[i];
+  return PSD_OK;
+}
+
+}  // extern "C"

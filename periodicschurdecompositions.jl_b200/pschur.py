@@ -1,0 +1,195 @@
+"""Host-side mirror of the reference's dense periodic Schur interface.
+
+Reference methods mirrored (file:line relative to the reference repository):
+  pschur(A, lr; kwargs...)                      PeriodicSchurDecompositions.jl:108-113
+  pschur!(A, lr; wantZ, wantT, maxitfac)        PeriodicSchurDecompositions.jl:120-152
+  PeriodicSchur                                  PeriodicSchurDecompositions.jl:59-92
+  char_lr / throw_lr                             PeriodicSchurDecompositions.jl:155-177
+  phessenberg!(A)                                PeriodicSchurDecompositions.jl:213-259
+
+Storage convention: the C ABI takes column-major factors (Julia `Matrix`).  A numpy matrix `M`
+(math orientation) is therefore handed over as `M.T` made C-contiguous; the batched functions
+take/return arrays already in that storage layout, [batch][p][col][row].
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import capi
+from .capi import PsdError, check, lib
+
+
+def char_lr(lr) -> str:
+    """PeriodicSchurDecompositions.jl:155-177"""
+    if lr in ("R", ":R", "r"):
+        return "R"
+    if lr in ("L", ":L", "l"):
+        return "L"
+    raise ValueError("orientation argument must be either :R (right) or :L (left)")
+
+
+@dataclass
+class PeriodicSchur:
+    """Mirror of the reference result struct (PeriodicSchurDecompositions.jl:59-92).
+
+    T1: the quasi-triangular Schur factor T_k, k = schurindex; T: the other p-1 triangular
+    factors in order; Z: the p orthogonal factors; values: eigenvalues of the product.
+    All matrices are numpy arrays in math orientation."""
+    T1: np.ndarray
+    T: List[np.ndarray]
+    Z: List[np.ndarray]
+    values: np.ndarray
+    orientation: str = "R"
+    schurindex: int = 1
+    info: int = 0
+    extra: dict = field(default_factory=dict)
+
+    @property
+    def period(self) -> int:
+        return len(self.T) + 1
+
+
+class Handle:
+    """Owns a psd_handle_t (streams, device workspaces, pinned staging)."""
+
+    def __init__(self, devices: Optional[Sequence[int]] = None):
+        self._h = C.c_void_p()
+        if devices is None:
+            check(lib().psd_create(C.byref(self._h), 0, None))
+        else:
+            arr = (C.c_int * len(devices))(*devices)
+            check(lib().psd_create(C.byref(self._h), len(devices), arr))
+
+    @property
+    def ptr(self):
+        return self._h
+
+    @property
+    def ndev(self) -> int:
+        return int(lib().psd_handle_device_count(self._h))
+
+    def stats(self):
+        s = (C.c_int64 * 8)()
+        check(lib().psd_last_stats(self._h, s))
+        return {"launches": s[0], "problems_smem": s[1], "problems_global": s[2],
+                "h2d_bytes": s[3], "d2h_bytes": s[4], "wall_us": s[5]}
+
+    def close(self):
+        if self._h:
+            lib().psd_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+_default: Optional[Handle] = None
+
+
+def default_handle() -> Handle:
+    global _default
+    if _default is None:
+        _default = Handle()
+    return _default
+
+
+def _vp(a):
+    return None if a is None else C.c_void_p(a.ctypes.data)
+
+
+def pschur_batched(A: np.ndarray, lr="R", wantZ: bool = True, wantT: bool = True,
+                   maxitfac: int = 30, handle: Optional[Handle] = None, overwrite: bool = False):
+    """Batched real periodic Schur decomposition through psd_rpschur_batched.
+
+    A: float64 [batch][p][n][n], each factor column-major (storage layout), user factor order.
+    Returns (T, Z, values, info): T is A overwritten (a copy unless overwrite=True), Z is None
+    when wantZ is False, values complex128 [batch][n], info int32 [batch]."""
+    orient = char_lr(lr)
+    if A.dtype != np.float64 or A.ndim != 4 or A.shape[2] != A.shape[3]:
+        raise ValueError("A must be float64 with shape [batch][p][n][n]")  # DimensionMismatch, :220
+    h = handle or default_handle()
+    batch, p, n, _ = A.shape
+    T = A if (overwrite and A.flags.c_contiguous) else np.ascontiguousarray(A).copy()
+    Z = np.empty_like(T) if wantZ else None
+    vals = np.empty((batch, n), dtype=np.complex128)
+    info = np.empty(batch, dtype=np.int32)
+    check(lib().psd_rpschur_batched(h.ptr, n, p, batch, 1 if orient == "L" else 0, int(wantT),
+                                    int(wantZ), int(maxitfac), _vp(T), _vp(Z), _vp(vals),
+                                    _vp(info)))
+    return T, Z, vals, info
+
+
+def pschur_hessut_batched(H: np.ndarray, wantZ: bool = True, wantT: bool = True, maxitfac: int = 30,
+                          handle: Optional[Handle] = None):
+    """Inner method pschur!(H1, Hs; ...) (PeriodicSchurDecompositions.jl:322) on Hessenberg /
+    triangular input, rightwards order, Z starting from the identity."""
+    h = handle or default_handle()
+    batch, p, n, _ = H.shape
+    T = np.ascontiguousarray(H).copy()
+    Z = np.empty_like(T) if wantZ else None
+    vals = np.empty((batch, n), dtype=np.complex128)
+    info = np.empty(batch, dtype=np.int32)
+    check(lib().psd_rpschur_hessut_batched(h.ptr, n, p, batch, int(wantT), int(wantZ),
+                                           int(maxitfac), _vp(T), _vp(Z), _vp(vals), _vp(info)))
+    return T, Z, vals, info
+
+
+def phessenberg_batched(A: np.ndarray, wantQ: bool = True, handle: Optional[Handle] = None):
+    """phessenberg!(A) + explicit Q (PeriodicSchurDecompositions.jl:213-259, 136-140), batched,
+    storage layout.  Returns (H, Q)."""
+    h = handle or default_handle()
+    batch, p, n, _ = A.shape
+    H = np.ascontiguousarray(A).copy()
+    Q = np.empty_like(H) if wantQ else None
+    check(lib().psd_rphess_batched(h.ptr, n, p, batch, int(wantQ), _vp(H), _vp(Q)))
+    return H, Q
+
+
+def pschur_(A: List[np.ndarray], lr="R", wantZ: bool = True, wantT: bool = True,
+            maxitfac: int = 30, handle: Optional[Handle] = None) -> PeriodicSchur:
+    """pschur!(A, lr; wantZ, wantT, maxitfac) (PeriodicSchurDecompositions.jl:120-152): the input
+    matrices are used as workspace / overwritten with the T factors; T1 aliases A[0] (:R) or
+    A[p-1] (:L) as in the reference (:265, :1078-1093)."""
+    orient = char_lr(lr)
+    p = len(A)
+    if p < 1:
+        raise ValueError("A must hold at least one matrix")
+    n = A[0].shape[0]
+    for Aj in A:
+        if Aj.ndim != 2 or Aj.shape != (n, n):
+            raise ValueError("DimensionMismatch: all factors must be square of equal order")
+        if Aj.dtype != np.float64:
+            raise TypeError("real path takes float64 matrices")
+    stor = np.empty((1, p, n, n), dtype=np.float64)
+    for j in range(p):
+        stor[0, j] = A[j].T
+    T, Z, vals, info = pschur_batched(stor, orient, wantZ, wantT, maxitfac, handle, overwrite=True)
+    if info[0] != 0:
+        raise RuntimeError(f"convergence failed at level {int(info[0])}")  # :891-893
+    for j in range(p):
+        A[j][...] = T[0, j].T
+    if orient == "R":
+        T1 = A[0]
+        Ts = [A[j] for j in range(1, p)]
+        sidx = 1
+    else:
+        T1 = A[p - 1]
+        Ts = [A[j] for j in range(0, p - 1)]
+        sidx = p
+    if wantZ:
+        Zs = [np.ascontiguousarray(Z[0, j].T) for j in range(p)]
+    else:
+        Zs = [np.zeros((0, 0))]  # :1074-1076
+    return PeriodicSchur(T1, Ts, Zs, vals[0].copy(), orient, sidx, int(info[0]))
+
+
+def pschur(A: Sequence[np.ndarray], lr="R", **kwargs) -> PeriodicSchur:
+    """pschur(A, lr; kwargs...) (PeriodicSchurDecompositions.jl:108-113): copying wrapper."""
+    return pschur_([np.array(Aj, dtype=np.float64, copy=True) for Aj in A], lr, **kwargs)

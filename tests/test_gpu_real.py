@@ -1,0 +1,159 @@
+"""GPU parity tests for the real standard periodic Schur path: CUDA library (through the C ABI)
+against the CPU oracle on identical seeded inputs, using the reference's own acceptance
+predicates (test/testfuncs.jl:56-145) and BASELINE.json's gates:
+  eigenvalues matched as a set, rel err <= 100*N*eps*|lambda|max;
+  residual ||Q'AQ - T||/||A|| <= 10*N*eps;  ||Q'Q - I|| <= 10*N*eps;  identical structure.
+"""
+import numpy as np
+import pytest
+
+import psd_checks as K
+
+pytestmark = pytest.mark.gpu
+
+EPS = np.finfo(np.float64).eps
+
+
+def _eig_gate(lam_oracle, lam_gpu, n):
+    scale = np.max(np.abs(lam_oracle))
+    worst = K.match_eigs(lam_oracle, lam_gpu)
+    assert worst <= 100 * n * EPS * scale, f"eigenvalue sets differ: {worst / scale:.3e} rel"
+    # same number of complex pairs (quasi-triangular structure identical)
+    assert np.count_nonzero(lam_oracle.imag > 0) == np.count_nonzero(lam_gpu.imag > 0)
+
+
+def _run_case(psd, oracle, n, p, batch, left, seed=1234, tol=32):
+    A = oracle.gen_real(seed, n, p, batch)
+    To, Zo, lo, io, _ = oracle.rpschur_batched(A, left=left)
+    T, Z, lam, info = psd.pschur_batched(A, "L" if left else "R")
+    assert (info == 0).all() and (io == 0).all()
+    for b in range(batch):
+        K.pschur_check(A[b], T[b], Z[b], lam[b], left=left, tol=tol)
+        _eig_gate(lo[b], lam[b], n)
+    return A, T, Z, lam
+
+
+# reference shapes: test/runtests.jl:89-100 ("Periodic Schur full"), n=5, p in 1,2,3,5, :R and :L
+@pytest.mark.parametrize("p", [1, 2, 3, 5])
+@pytest.mark.parametrize("left", [False, True])
+def test_full_n5(psd, oracle, p, left):
+    _run_case(psd, oracle, 5, p, 16, left)
+
+
+@pytest.mark.parametrize("n,p", [(1, 1), (1, 4), (2, 1), (3, 2), (3, 5), (4, 3), (7, 12), (16, 6)])
+def test_small_shapes(psd, oracle, n, p):
+    _run_case(psd, oracle, n, p, 8, False)
+    _run_case(psd, oracle, n, p, 8, True)
+
+
+# BASELINE configs[0]: real p=3 N=50 :R with Schur vectors
+def test_config1_p3_n50(psd, oracle):
+    _run_case(psd, oracle, 50, 3, 4, False)
+    _run_case(psd, oracle, 50, 3, 2, True)
+
+
+# BASELINE configs[1] shape (p=8, N=32), with T and Z on a sample ...
+def test_config2_shape_with_vectors(psd, oracle):
+    _run_case(psd, oracle, 32, 8, 8, False)
+
+
+# ... and eigenvalues only (the benchmarked mode) on a larger sample, against the oracle
+def test_config2_eigs_only(psd, oracle):
+    n, p, batch = 32, 8, 512
+    A = oracle.gen_real(1234, n, p, batch)
+    _, _, lo, io, _ = oracle.rpschur_batched(A, wantT=False, wantZ=False)
+    _, Z, lam, info = psd.pschur_batched(A, "R", wantZ=False, wantT=False)
+    assert Z is None
+    assert (info == 0).all() and (io == 0).all()
+    for b in range(batch):
+        _eig_gate(lo[b], lam[b], n)
+    # size-independent property: sum of eigenvalues == trace of the product
+    for b in range(0, batch, 37):
+        P = K.M(A[b, 0]).copy()
+        for j in range(1, p):
+            P = P @ K.M(A[b, j])
+        tr = np.trace(P)
+        assert abs(lam[b].sum() - tr) <= 1e-9 * abs(tr)
+
+
+# reference "fast paths" test/runtests.jl:103-132
+@pytest.mark.parametrize("p", [1, 5])
+def test_fast_paths(psd, oracle, p):
+    n = 5
+    A = oracle.gen_real(7, n, p, 8)
+    T2, Z2, lam2, info2 = psd.pschur_batched(A, "R", wantZ=True, wantT=True)
+    T0, Z0, lam0, info0 = psd.pschur_batched(A, "R", wantZ=False, wantT=False)
+    T1, Z1, lam1, info1 = psd.pschur_batched(A, "R", wantZ=False, wantT=True)
+    assert Z0 is None and Z1 is None
+    for b in range(A.shape[0]):
+        K.compare_reigvals(lam2[b], lam0[b], 1000 * EPS)
+        K.compare_reigvals(lam2[b], lam1[b], 1000 * EPS)
+        assert np.linalg.norm(T1[b, 0] - T2[b, 0]) < 20 * EPS * n * max(1.0, np.linalg.norm(T2[b, 0]))
+
+
+# global-memory (L2-resident) variant of the same kernel: factors do not fit in shared memory
+def test_global_mode_n64_p8(psd, oracle):
+    _run_case(psd, oracle, 64, 8, 2, False)
+    st = psd.default_handle().stats()
+    assert st["problems_global"] == 2 and st["problems_smem"] == 0
+
+
+def test_hessut_entry(psd, oracle):
+    # test/runtests.jl:53-66: Hessenberg + upper-triangular input
+    n = 5
+    for p in (1, 2, 3, 5):
+        A = oracle.gen_real(11, n, p, 4)
+        for b in range(4):
+            for j in range(p):
+                Mj = np.triu(K.M(A[b, j]), -1 if j == 0 else 0)
+                A[b, j] = Mj.T
+        T, Z, lam, info = psd.pschur_hessut_batched(A)
+        assert (info == 0).all()
+        for b in range(4):
+            K.pschur_check(A[b], T[b], Z[b], lam[b], left=False)
+            To, Zo, lo, io = oracle.rpschur_hessut(A[b])
+            _eig_gate(lo, lam[b], n)
+
+
+def test_reduction_only(psd, oracle):
+    # test/runtests.jl:14-50 "Periodic Hessenberg"
+    for (n, p) in [(5, 1), (5, 2), (5, 5), (32, 8)]:
+        A = oracle.gen_real(5, n, p, 3)
+        H, Q = psd.phessenberg_batched(A)
+        for b in range(3):
+            for j in range(p):
+                Hj, Qj, Qn, Aj = K.M(H[b, j]), K.M(Q[b, j]), K.M(Q[b, (j + 1) % p]), K.M(A[b, j])
+                assert not np.tril(Hj, -2 if j == 0 else -1).any()
+                assert np.linalg.norm(Qj @ Qj.T - np.eye(n)) < 10 * EPS * n
+                assert np.linalg.norm(Aj - Qj @ Hj @ Qn.T) < 20 * EPS * n * max(1.0, np.linalg.norm(Aj, 1))
+
+
+def test_empty_batch_and_errors(psd):
+    A = np.zeros((0, 3, 4, 4))
+    T, Z, lam, info = psd.pschur_batched(A)
+    assert lam.shape == (0, 4)
+    with pytest.raises(ValueError):
+        psd.pschur_batched(np.zeros((1, 2, 3, 3)), "X")
+    with pytest.raises(ValueError):
+        psd.pschur_batched(np.zeros((1, 2, 3, 4)))
+
+
+def test_struct_api(psd, oracle):
+    # pschur / pschur_ mirror of the reference API incl. aliasing of T1
+    n, p = 6, 3
+    S = oracle.gen_real(3, n, p, 1)[0]
+    A = [np.ascontiguousarray(K.M(S[j])) for j in range(p)]
+    A0 = [a.copy() for a in A]
+    F = psd.pschur_(A, "R")
+    assert F.schurindex == 1 and F.orientation == "R" and F.period == p
+    assert F.T1 is A[0]
+    for j in range(p):
+        Tj = F.T1 if j == 0 else F.T[j - 1]
+        R = F.Z[j] @ Tj @ F.Z[(j + 1) % p].T - A0[j]
+        assert np.linalg.norm(R) < 32 * EPS * np.linalg.norm(A0[j], 1)
+    G = psd.pschur(A0, "L")
+    assert G.schurindex == p and G.orientation == "L"
+    for j in range(p):
+        Tj = G.T1 if j == p - 1 else G.T[j]
+        R = G.Z[(j + 1) % p] @ Tj @ G.Z[j].T - A0[j]
+        assert np.linalg.norm(R) < 32 * EPS * np.linalg.norm(A0[j], 1)
