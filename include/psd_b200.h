@@ -114,6 +114,16 @@ int psd_rpschur_hessut_batched(psd_handle_t handle, int n, int p, int64_t batch,
 int psd_rphess_batched(psd_handle_t handle, int n, int p, int64_t batch, int wantQ, double* A,
                        double* Q);
 
+/* Synthetic inputs (measurement only): uniform [0,1) entries from a
+ * counter-based generator keyed by (seed, problem, factor, row, col), problems
+ * first_b .. first_b+batch-1, written to a host buffer or (asynchronously, on the current
+ * device and `stream`) to a device buffer.  cplx != 0 fills interleaved complex128.
+ * Mirrors rand(T,n,n) under a fixed seed in the reference's tests (test/testfuncs.jl:12). */
+int psd_fill_uniform_host(uint64_t seed, int n, int p, int64_t batch, int64_t first_b, int cplx,
+                          double* A);
+int psd_fill_uniform_dev(void* stream, uint64_t seed, int n, int p, int64_t batch,
+                         int64_t first_b, int cplx, double* dA);
+
 /* Counters of the most recent batched call on this handle (diagnostics; mirrors the
  * reference's niter/maxits reporting, PeriodicSchurDecompositions.jl:458-459,1077):
  * stats[0] = kernel launches, stats[1] = problems solved in shared memory,

@@ -31,10 +31,11 @@ from .pschur import (  # noqa: F401
     pschur_,
     pschur_batched,
     pschur_hessut_batched,
+    shard_bounds,
 )
 
 __all__ = [
     "PsdError", "device_count", "lib", "lib_path", "library_available", "version",
     "PeriodicSchur", "Handle", "default_handle", "phessenberg_batched", "pschur", "pschur_",
-    "pschur_batched", "pschur_hessut_batched",
+    "pschur_batched", "pschur_hessut_batched", "shard_bounds",
 ]

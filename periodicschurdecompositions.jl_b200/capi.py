@@ -22,6 +22,8 @@ EXPORTED_SYMBOLS = [
     "psd_rpschur_hessut_batched",
     "psd_rphess_batched",
     "psd_last_stats",
+    "psd_fill_uniform_host",
+    "psd_fill_uniform_dev",
 ]
 
 
@@ -65,6 +67,10 @@ def lib():
                                                  C.c_int, C.c_int, vp, vp, vp, vp]
         L.psd_rphess_batched.argtypes = [vp, C.c_int, C.c_int, C.c_int64, C.c_int, vp, vp]
         L.psd_last_stats.argtypes = [vp, C.POINTER(C.c_int64)]
+        L.psd_fill_uniform_host.argtypes = [C.c_uint64, C.c_int, C.c_int, C.c_int64, C.c_int64,
+                                            C.c_int, vp]
+        L.psd_fill_uniform_dev.argtypes = [vp, C.c_uint64, C.c_int, C.c_int, C.c_int64,
+                                           C.c_int64, C.c_int, vp]
         for name in EXPORTED_SYMBOLS:
             if name not in ("psd_last_error_string",):
                 getattr(L, name).restype = C.c_int if name != "psd_last_error_string" else C.c_char_p

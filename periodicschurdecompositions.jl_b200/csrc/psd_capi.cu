@@ -9,6 +9,7 @@
 #include <atomic>
 #include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -17,6 +18,7 @@
 
 #include "../../include/psd_b200.h"
 #include "psd_real_kernel.cuh"
+#include "psd_rng.cuh"
 
 namespace {
 
@@ -49,9 +51,11 @@ struct Slot {
   double* hEig = nullptr;
   int32_t* hInfo = nullptr;
   size_t hcapA = 0, hcapZ = 0, hcapEig = 0, hcapInfo = 0;
-  unsigned long long* dCounter = nullptr;
+  unsigned long long* dCounter = nullptr;  // [2]: reduction kernel, QR kernel
   double* dScratch = nullptr;
   size_t capScratch = 0;
+  double* dPacked = nullptr;  // packed Hessenberg-triangular factors between the two kernels
+  size_t capPacked = 0;
 };
 
 struct Device {
@@ -159,15 +163,83 @@ struct RealCall {
   int n, p, left, wantT, wantZ, maxitfac, reduce_only, skip_reduce;
 };
 
+constexpr long long kEigChunk = 65536;  // problems per (reduction, QR) kernel pair
+
+// Eigenvalue-only fast path for n <= 32: reduction kernel -> packed factors -> one warp per
+// problem QR kernel (psd_real_eig32.cuh).
+int launch_real_eig32(psd_handle_s* h, Device& dev, Slot& aux, cudaStream_t stream, const RealCall& rc,
+                      long long batch, double* dA, double* dEig, int32_t* dInfo) {
+  const int n = rc.n, p = rc.p;
+  const size_t nn = (size_t)n * n;
+  const size_t psize = (size_t)psd::pk_problem_size(n, p);
+  const long long chunk = std::min(batch, kEigChunk);
+  int e = ensure_dev(aux.dPacked, aux.capPacked, (size_t)chunk * psize * sizeof(double));
+  if (e) return e;
+  if (!aux.dCounter) PSD_CUDA(cudaMalloc((void**)&aux.dCounter, 2 * sizeof(unsigned long long)));
+  // QR kernel configuration: as many warps (= resident problems) per CTA as shared memory allows
+  cudaFuncAttributes fa;
+  PSD_CUDA(cudaFuncGetAttributes(&fa, psd::rpqr_eig32_kernel));
+  int optin = 0;
+  PSD_CUDA(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev.ordinal));
+  const size_t max_dyn = (size_t)optin - fa.sharedSizeBytes;
+  int wpb = (int)std::min<size_t>(8, max_dyn / (psize * sizeof(double)));
+  if (wpb < 1) return fail(PSD_ERR_UNSUPPORTED, "packed problem does not fit in shared memory");
+  const size_t smem2 = (size_t)wpb * psize * sizeof(double);
+  PSD_CUDA(cudaFuncSetAttribute(psd::rpqr_eig32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)max_dyn));
+  int occ2 = 0;
+  PSD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, psd::rpqr_eig32_kernel, wpb * 32, smem2));
+  if (occ2 < 1) return fail(PSD_ERR_UNSUPPORTED, "QR kernel does not fit on an SM");
+  for (long long off = 0; off < batch; off += chunk) {
+    const long long nb = std::min(chunk, batch - off);
+    RealLaunchPlan pl;
+    e = plan_real(dev, n, p, nb, false, pl);
+    if (e) return e;
+    PSD_CUDA(cudaMemsetAsync(aux.dCounter, 0, 2 * sizeof(unsigned long long), stream));
+    psd::RpschurParams P;
+    P.n = n; P.p = p; P.batch = nb;
+    P.left = rc.left; P.wantT = 0; P.wantZ = 0; P.maxitfac = 30;
+    P.A = dA + (size_t)off * p * nn; P.Z = nullptr; P.eig = nullptr; P.info = nullptr; P.iters = nullptr;
+    P.use_smem = pl.use_smem; P.ldh = pl.ldh;
+    P.reduce_only = 1; P.skip_reduce = rc.skip_reduce;
+    P.counter = aux.dCounter;
+    P.scratch = nullptr; P.scratch_stride = 0;
+    P.packed_out = aux.dPacked;
+    if (!pl.use_smem) return fail(PSD_ERR_UNSUPPORTED, "eig32 path expects shared-memory staging");
+    const int thr1 = std::min(256, std::max(64, ((4 * n + 31) / 32) * 32));
+    int occ1 = 0;
+    PSD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ1, psd::rpschur_kernel, thr1, pl.smem_bytes));
+    const int grid1 = (int)std::max(1LL, std::min((long long)occ1 * dev.sm_count, nb));
+    psd::rpschur_kernel<<<grid1, thr1, pl.smem_bytes, stream>>>(P);
+    PSD_CUDA(cudaGetLastError());
+    psd::EigParams Q;
+    Q.n = n; Q.p = p; Q.batch = nb; Q.maxitfac = rc.maxitfac > 0 ? rc.maxitfac : 30;
+    Q.packed = aux.dPacked;
+    Q.eig = dEig + (size_t)off * 2 * n;
+    Q.info = dInfo + off;
+    Q.iters = nullptr;
+    Q.counter = aux.dCounter + 1;
+    const long long ctas = (nb + wpb - 1) / wpb;
+    const int grid2 = (int)std::max(1LL, std::min((long long)occ2 * dev.sm_count, ctas));
+    psd::rpqr_eig32_kernel<<<grid2, wpb * 32, smem2, stream>>>(Q);
+    PSD_CUDA(cudaGetLastError());
+    __atomic_fetch_add(&h->stats[0], (int64_t)2, __ATOMIC_RELAXED);
+  }
+  __atomic_fetch_add(&h->stats[1], (int64_t)batch, __ATOMIC_RELAXED);
+  return PSD_OK;
+}
+
 // Enqueue the real kernel for `batch` device-resident problems on `stream`.
 int launch_real(psd_handle_s* h, Device& dev, Slot& aux, cudaStream_t stream, const RealCall& rc,
                 long long batch, double* dA, double* dZ, double* dEig, int32_t* dInfo) {
   if (batch == 0) return PSD_OK;
   RealLaunchPlan pl;
   const bool wantZ = rc.wantZ && dZ;
+  if (!rc.wantT && !wantZ && !rc.reduce_only && rc.n <= 32 && !getenv("PSD_DISABLE_EIG32"))
+    return launch_real_eig32(h, dev, aux, stream, rc, batch, dA, dEig, dInfo);
   int e = plan_real(dev, rc.n, rc.p, batch, wantZ, pl);
   if (e) return e;
-  if (!aux.dCounter) PSD_CUDA(cudaMalloc((void**)&aux.dCounter, sizeof(unsigned long long)));
+  if (!aux.dCounter) PSD_CUDA(cudaMalloc((void**)&aux.dCounter, 2 * sizeof(unsigned long long)));
   PSD_CUDA(cudaMemsetAsync(aux.dCounter, 0, sizeof(unsigned long long), stream));
   psd::RpschurParams P;
   P.n = rc.n; P.p = rc.p; P.batch = batch;
@@ -178,6 +250,7 @@ int launch_real(psd_handle_s* h, Device& dev, Slot& aux, cudaStream_t stream, co
   P.reduce_only = rc.reduce_only; P.skip_reduce = rc.skip_reduce;
   P.counter = aux.dCounter;
   P.scratch = nullptr; P.scratch_stride = 0;
+  P.packed_out = nullptr;
   if (pl.scratch) {
     size_t stride = (size_t)psd::rp_small_doubles(rc.n, rc.p);
     e = ensure_dev(aux.dScratch, aux.capScratch, stride * sizeof(double) * pl.grid);
@@ -373,7 +446,7 @@ int psd_destroy(psd_handle_t h) {
         cudaStreamDestroy(s.stream);
       }
       cudaFree(s.dA); cudaFree(s.dZ); cudaFree(s.dEig); cudaFree(s.dInfo);
-      cudaFree(s.dCounter); cudaFree(s.dScratch);
+      cudaFree(s.dCounter); cudaFree(s.dScratch); cudaFree(s.dPacked);
       cudaFreeHost(s.hA); cudaFreeHost(s.hZ); cudaFreeHost(s.hEig); cudaFreeHost(s.hInfo);
     };
     for (auto& s : d.slots) freeSlot(s);
@@ -423,6 +496,63 @@ int psd_rpschur_batched_dev(psd_handle_t h, int dev_index, void* stream, int n, 
   }
   RealCall rc{n, p, orientation, wantT != 0, wantZ != 0, maxitfac, 0, 0};
   return launch_real(h, dev, dev.user, st, rc, batch, dA, dZ, deig, dinfo);
+}
+
+__global__ void fill_uniform_kernel(uint64_t seed, int n, int p, long long batch, long long first_b,
+                                    int cplx, double* A) {
+  const long long nn = (long long)n * n;
+  const long long total = batch * p * nn;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
+       e += (long long)gridDim.x * blockDim.x) {
+    const long long b = e / (p * nn);
+    const long long rem = e - b * p * nn;
+    const int j = (int)(rem / nn);
+    const int c = (int)((rem % nn) / n), r = (int)(rem % n);
+    if (cplx) {
+      A[2 * e] = psd::gen_uniform(seed, (uint64_t)(first_b + b), j, r, c, 0);
+      A[2 * e + 1] = psd::gen_uniform(seed, (uint64_t)(first_b + b), j, r, c, 1);
+    } else {
+      A[e] = psd::gen_uniform(seed, (uint64_t)(first_b + b), j, r, c, 0);
+    }
+  }
+}
+
+int psd_fill_uniform_host(uint64_t seed, int n, int p, int64_t batch, int64_t first_b, int cplx,
+                          double* A) {
+  if (n < 1 || p < 1 || batch < 0 || !A) return fail(PSD_ERR_BAD_ARG, "bad argument");
+  const long long nn = (long long)n * n;
+  unsigned hw = std::thread::hardware_concurrency();
+  int nth = (int)std::max(1u, std::min(hw ? hw : 1u, 64u));
+  if (batch < nth) nth = (int)std::max<int64_t>(1, batch);
+  auto work = [&](int t) {
+    const long long lo = batch * t / nth, hi = batch * (t + 1) / nth;
+    for (long long b = lo; b < hi; b++)
+      for (int j = 0; j < p; j++)
+        for (int c = 0; c < n; c++)
+          for (int r = 0; r < n; r++) {
+            const long long e = (b * p + j) * nn + (long long)c * n + r;
+            if (cplx) {
+              A[2 * e] = psd::gen_uniform(seed, (uint64_t)(first_b + b), j, r, c, 0);
+              A[2 * e + 1] = psd::gen_uniform(seed, (uint64_t)(first_b + b), j, r, c, 1);
+            } else {
+              A[e] = psd::gen_uniform(seed, (uint64_t)(first_b + b), j, r, c, 0);
+            }
+          }
+  };
+  std::vector<std::thread> th;
+  for (int t = 1; t < nth; t++) th.emplace_back(work, t);
+  work(0);
+  for (auto& t : th) t.join();
+  return PSD_OK;
+}
+
+int psd_fill_uniform_dev(void* stream, uint64_t seed, int n, int p, int64_t batch, int64_t first_b,
+                         int cplx, double* dA) {
+  if (n < 1 || p < 1 || batch < 0 || !dA) return fail(PSD_ERR_BAD_ARG, "bad argument");
+  if (batch == 0) return PSD_OK;
+  fill_uniform_kernel<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(seed, n, p, batch, first_b, cplx, dA);
+  PSD_CUDA(cudaGetLastError());
+  return PSD_OK;
 }
 
 int psd_last_stats(psd_handle_t h, int64_t stats[8]) {

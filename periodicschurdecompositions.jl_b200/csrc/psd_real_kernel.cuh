@@ -16,6 +16,7 @@
 // orientation internal j maps to user factor p+1-j (:127-131).
 #pragma once
 #include "psd_device.cuh"
+#include "psd_real_eig32.cuh"
 
 namespace psd {
 
@@ -35,6 +36,8 @@ struct RpschurParams {
   unsigned long long* counter;  // dynamic work queue over problems
   double* scratch;  // per-CTA small arrays when they do not fit in smem (or nullptr)
   long long scratch_stride;
+  double* packed_out;  // reduce_only: write packed Hessenberg-triangular factors here instead
+                       // of A ([batch][pk_problem_size(n,p)], layout of psd_real_eig32.cuh)
 };
 
 // number of doubles of "small" per-problem state
@@ -701,7 +704,18 @@ __global__ void rpschur_kernel(RpschurParams P) {
         if (P.iters) P.iters[b] = niter;
       }
     }
-    if (P.use_smem) {
+    if (P.packed_out) {
+      double* dstb = P.packed_out + (size_t)b * pk_problem_size(n, p);
+      for (int j = 1; j <= p; j++) {
+        const int kl = (j == 1) ? 3 : 1;
+        double* dst = dstb + ((j == 1) ? 0 : pk_size(3, n) + (j - 2) * pk_size(1, n));
+        const double* src = c.Hp(j);
+        for (int e = tid; e < (int)nn; e += nt) {
+          int r = e % n, cc = e / n;
+          if (r <= cc + kl) dst[pk_off(kl, cc) + r] = src[r + (size_t)cc * c.ldh];
+        }
+      }
+    } else if (P.use_smem) {
       if (P.wantT || P.reduce_only) {
         for (int j = 1; j <= p; j++) {
           double* dst = Ab + (size_t)((left ? (p + 1 - j) : j) - 1) * nn;

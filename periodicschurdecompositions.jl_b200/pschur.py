@@ -23,6 +23,12 @@ from . import capi
 from .capi import PsdError, check, lib
 
 
+def shard_bounds(batch: int, world: int, rank: int):
+    """Contiguous batch shard [lo, hi) owned by `rank` of `world`; the same
+    split the C library applies across the devices of a handle (batch*d/nd)."""
+    return batch * rank // world, batch * (rank + 1) // world
+
+
 def char_lr(lr) -> str:
     """PeriodicSchurDecompositions.jl:155-177"""
     if lr in ("R", ":R", "r"):
