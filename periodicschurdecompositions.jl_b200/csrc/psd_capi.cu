@@ -18,6 +18,7 @@
 
 #include "../../include/psd_b200.h"
 #include "psd_real_kernel.cuh"
+#include "psd_real_hess32.cuh"
 #include "psd_rng.cuh"
 
 namespace {
@@ -192,26 +193,48 @@ int launch_real_eig32(psd_handle_s* h, Device& dev, Slot& aux, cudaStream_t stre
   if (occ2 < 1) return fail(PSD_ERR_UNSUPPORTED, "QR kernel does not fit on an SM");
   for (long long off = 0; off < batch; off += chunk) {
     const long long nb = std::min(chunk, batch - off);
-    RealLaunchPlan pl;
-    e = plan_real(dev, n, p, nb, false, pl);
-    if (e) return e;
     PSD_CUDA(cudaMemsetAsync(aux.dCounter, 0, 2 * sizeof(unsigned long long), stream));
-    psd::RpschurParams P;
-    P.n = n; P.p = p; P.batch = nb;
-    P.left = rc.left; P.wantT = 0; P.wantZ = 0; P.maxitfac = 30;
-    P.A = dA + (size_t)off * p * nn; P.Z = nullptr; P.eig = nullptr; P.info = nullptr; P.iters = nullptr;
-    P.use_smem = pl.use_smem; P.ldh = pl.ldh;
-    P.reduce_only = 1; P.skip_reduce = rc.skip_reduce;
-    P.counter = aux.dCounter;
-    P.scratch = nullptr; P.scratch_stride = 0;
-    P.packed_out = aux.dPacked;
-    if (!pl.use_smem) return fail(PSD_ERR_UNSUPPORTED, "eig32 path expects shared-memory staging");
-    const int thr1 = std::min(256, std::max(64, ((4 * n + 31) / 32) * 32));
-    int occ1 = 0;
-    PSD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ1, psd::rpschur_kernel, thr1, pl.smem_bytes));
-    const int grid1 = (int)std::max(1LL, std::min((long long)occ1 * dev.sm_count, nb));
-    psd::rpschur_kernel<<<grid1, thr1, pl.smem_bytes, stream>>>(P);
-    PSD_CUDA(cudaGetLastError());
+    if (rc.skip_reduce) {
+      // input already Hessenberg/triangular: CTA kernel only enforces structure and packs
+      RealLaunchPlan pl;
+      e = plan_real(dev, n, p, nb, false, pl);
+      if (e) return e;
+      if (!pl.use_smem) return fail(PSD_ERR_UNSUPPORTED, "eig32 path expects shared-memory staging");
+      psd::RpschurParams P;
+      P.n = n; P.p = p; P.batch = nb;
+      P.left = rc.left; P.wantT = 0; P.wantZ = 0; P.maxitfac = 30;
+      P.A = dA + (size_t)off * p * nn; P.Z = nullptr; P.eig = nullptr; P.info = nullptr; P.iters = nullptr;
+      P.use_smem = pl.use_smem; P.ldh = pl.ldh;
+      P.reduce_only = 1; P.skip_reduce = 1;
+      P.counter = aux.dCounter;
+      P.scratch = nullptr; P.scratch_stride = 0;
+      P.packed_out = aux.dPacked;
+      psd::rpschur_kernel<<<pl.grid, pl.threads, pl.smem_bytes, stream>>>(P);
+      PSD_CUDA(cudaGetLastError());
+    } else {
+      psd::Hess32Params R;
+      R.n = n; R.p = p; R.batch = nb; R.left = rc.left;
+      R.ld = (n % 2 == 0) ? n + 1 : n;
+      R.A = dA + (size_t)off * p * nn;
+      R.packed_out = aux.dPacked;
+      R.counter = aux.dCounter;
+      cudaFuncAttributes fh;
+      PSD_CUDA(cudaFuncGetAttributes(&fh, psd::rphess_warp32_kernel));
+      const size_t max_dyn1 = (size_t)optin - fh.sharedSizeBytes;
+      const size_t per1 = (size_t)p * R.ld * n * sizeof(double);
+      int wpb1 = (int)std::min<size_t>(8, max_dyn1 / per1);
+      if (wpb1 < 1) return fail(PSD_ERR_UNSUPPORTED, "problem does not fit in shared memory");
+      const size_t smem1 = (size_t)wpb1 * per1;
+      PSD_CUDA(cudaFuncSetAttribute(psd::rphess_warp32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)max_dyn1));
+      int occ1 = 0;
+      PSD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ1, psd::rphess_warp32_kernel, wpb1 * 32, smem1));
+      if (occ1 < 1) return fail(PSD_ERR_UNSUPPORTED, "reduction kernel does not fit on an SM");
+      const long long ctas1 = (nb + wpb1 - 1) / wpb1;
+      const int grid1 = (int)std::max(1LL, std::min((long long)occ1 * dev.sm_count, ctas1));
+      psd::rphess_warp32_kernel<<<grid1, wpb1 * 32, smem1, stream>>>(R);
+      PSD_CUDA(cudaGetLastError());
+    }
     psd::EigParams Q;
     Q.n = n; Q.p = p; Q.batch = nb; Q.maxitfac = rc.maxitfac > 0 ? rc.maxitfac : 30;
     Q.packed = aux.dPacked;
@@ -235,7 +258,7 @@ int launch_real(psd_handle_s* h, Device& dev, Slot& aux, cudaStream_t stream, co
   if (batch == 0) return PSD_OK;
   RealLaunchPlan pl;
   const bool wantZ = rc.wantZ && dZ;
-  if (!rc.wantT && !wantZ && !rc.reduce_only && rc.n <= 32 && !getenv("PSD_DISABLE_EIG32"))
+  if (!rc.wantT && !wantZ && !rc.reduce_only && rc.n <= 32 && rc.p >= 2 && !getenv("PSD_DISABLE_EIG32"))
     return launch_real_eig32(h, dev, aux, stream, rc, batch, dA, dEig, dInfo);
   int e = plan_real(dev, rc.n, rc.p, batch, wantZ, pl);
   if (e) return e;

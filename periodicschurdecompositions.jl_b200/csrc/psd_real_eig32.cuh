@@ -1,4 +1,4 @@
-// Eigenvalue-only real periodic QR for small problems (n <= 32): ONE WARP PER PROBLEM.
+// Eigenvalue-only real periodic QR for small problems (n <= 32, p >= 2): ONE WARP PER PROBLEM.
 //
 // This is the B200 fast path of BASELINE config 2 (p=8, N=32, wantT=wantZ=false).  It
 // implements the same iteration as periodic_qr_cta (PeriodicSchurDecompositions.jl:322-1096
@@ -8,9 +8,14 @@
 //  * lane L owns row L and column L of every factor; a 2- or 3-element reflector is applied
 //    from the left by "column lanes" and from the right by "row lanes", so every update is
 //    lane-local and no reduction is ever needed inside a sweep;
-//  * the entries a reflector is generated from are forwarded with warp shuffles from the
-//    lanes that have just produced them, so the serial chain reflector -> update -> next
-//    reflector never waits on a shared-memory round trip;
+//  * a sweep is a flat sequence of chain links
+//        H1(k) -> factor p -> factor p-1 -> ... -> factor 2 -> H1(k+1) -> ...
+//    Each link's reflectors are computed redundantly by all lanes IN REGISTERS from the 3x3
+//    diagonal block of its matrix (prefetched from shared memory one slot earlier) and the
+//    previous link's reflectors, so the serial dependency chain contains no shuffle and no
+//    shared-memory access; the 3-reflector of link t and the 2-reflector of link t-1 are
+//    computed in the same slot (two independent dependency chains = ILP), and the row/column
+//    updates of link t-1 ("bulk") are applied lane-parallel in that slot as well;
 //  * reflectors are kept un-normalised, H = I + g u u^T with g = -2/(u^T u): one rsqrt and
 //    one reciprocal (MUFU seed + Newton steps) instead of dlarfg's sqrt + three divisions
 //    (householder.jl:66-108); orthogonality of H depends only on g, not on the accuracy of
@@ -48,8 +53,7 @@ struct EigParams {
 
 PSD_DEV double shfl_d(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 
-// MUFU-seeded reciprocal square root / reciprocal with two Newton steps (inputs are kept in
-// a safe range by the caller's power-of-two prescale).
+// MUFU-seeded reciprocal square root / reciprocal with two Newton steps (~20-bit seeds).
 PSD_DEV double fast_rsqrt(double x) {
   double y;
   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
@@ -67,36 +71,37 @@ PSD_DEV double fast_rcp(double x) {
   y = fma(y, e, y);
   e = fma(-x, y, 1.0);
   y = fma(y, e, y);
-  e = fma(-x, y, 1.0);
-  y = fma(y, e, y);
   return y;
 }
 
-// Un-normalised reflector from (x0, x1[, x2]):  H = I + g u u^T, u = (x0 - beta, x1, x2),
-// H x = beta e1.  Returns beta; g = 0 means H = I (householder.jl:76-78).
+// rare path of refl_u: zero tail (H = I, householder.jl:76-78) or out-of-range magnitudes,
+// handled with an exact power-of-two prescale as dlarfg's sfmin loop does (:80-100).
 template <int M>
-PSD_DEV double refl_u(double x0, double x1, double x2, double& u0, double& g) {
+__device__ __noinline__ double refl_u_slow(double x0, double x1, double x2, double* u0, double* g) {
   const double amax = fmax(fabs(x1), (M == 3) ? fabs(x2) : 0.0);
   if (amax == 0.0) {
-    u0 = 0.0;
-    g = 0.0;
+    *u0 = 0.0;
+    *g = 0.0;
     return x0;
   }
   const double m = fmax(amax, fabs(x0));
-  if (m < 1e-140 || m > 1e140) {
-    // rare: fall back to the exactly-scaled dlarfg-style computation
-    const double s = pow2_rescale(m);
-    const double al = x0 * s, y1 = x1 * s, y2 = (M == 3) ? x2 * s : 0.0;
-    const double nrm = sqrt(fma(al, al, fma(y1, y1, y2 * y2)));
-    const double beta = -copysign(nrm, al);
-    const double w0 = al - beta;
-    // u = (w0, y1, y2)/s  ->  g' = -2/(u^T u) = -2 s^2 / (w0^2 + y1^2 + y2^2)
-    u0 = w0 / s;
-    g = (-2.0 * s) * (s / fma(w0, w0, fma(y1, y1, y2 * y2)));
-    return beta / s;
-  }
+  const double s = pow2_rescale(m);
+  const double al = x0 * s, y1 = x1 * s, y2 = (M == 3) ? x2 * s : 0.0;
+  const double nrm = sqrt(fma(al, al, fma(y1, y1, y2 * y2)));
+  const double beta = -copysign(nrm, al);
+  const double w0 = al - beta;
+  *u0 = w0 / s;
+  *g = (-2.0 * s) * (s / fma(w0, w0, fma(y1, y1, y2 * y2)));
+  return beta / s;
+}
+
+// Un-normalised reflector from (x0, x1[, x2]):  H = I + g u u^T, u = (x0 - beta, x1, x2),
+// H x = beta e1.  Returns beta; g = 0 means H = I.
+template <int M>
+PSD_DEV double refl_u(double x0, double x1, double x2, double& u0, double& g) {
   const double ssq = (M == 3) ? fma(x1, x1, x2 * x2) : x1 * x1;
   const double nn = fma(x0, x0, ssq);
+  if (!(ssq > 1e-290 && nn < 1e290)) return refl_u_slow<M>(x0, x1, x2, &u0, &g);
   const double nrm = nn * fast_rsqrt(nn);
   const double beta = -copysign(nrm, x0);
   u0 = x0 - beta;
@@ -104,15 +109,129 @@ PSD_DEV double refl_u(double x0, double x1, double x2, double& u0, double& g) {
   return beta;
 }
 
+// State carried along the chain of links (all values identical in every lane).
+struct ChainState {
+  double u0, u1, u2, g, beta;           // 3-reflector of the previous link
+  double c0, c1, h;                     // 2-reflector of the link before the previous one
+  double n01, n02, n11, n12, n21, n22;  // columns 1,2 of N = X * P3 of the previous link
+  double x00, x01, x02, x10, x11, x12, x22;  // diagonal block prefetched for the current link
+};
+
+// A part: N = X * (I + g u u^T); returns the first column (source of this link's 3-reflector)
+// and stores columns 1,2 for the B part one slot later.
+PSD_DEV void chain_A(const ChainState& c, double& s0, double& s1, double& s2, double& m01,
+                     double& m02, double& m11, double& m12, double& m21, double& m22) {
+  const double d0 = c.g * fma(c.x02, c.u2, fma(c.x01, c.u1, c.x00 * c.u0));
+  const double d1 = c.g * fma(c.x12, c.u2, fma(c.x11, c.u1, c.x10 * c.u0));
+  const double d2 = c.g * (c.x22 * c.u2);
+  s0 = fma(d0, c.u0, c.x00);
+  s1 = fma(d1, c.u0, c.x10);
+  s2 = d2 * c.u0;
+  m01 = fma(d0, c.u1, c.x01);
+  m02 = fma(d0, c.u2, c.x02);
+  m11 = fma(d1, c.u1, c.x11);
+  m12 = fma(d1, c.u2, c.x12);
+  m21 = d2 * c.u1;
+  m22 = fma(d2, c.u2, c.x22);
+}
+
+// B part: 2-reflector of the previous (factor) link from its N, the 2-reflector before it
+// and its own 3-reflector.
+PSD_DEV double chain_B(const ChainState& c, double& b0, double& b1, double& bh) {
+  const double e0 = c.h * fma(c.n02, c.c1, c.n01 * c.c0);
+  const double e1 = c.h * fma(c.n12, c.c1, c.n11 * c.c0);
+  const double e2 = c.h * fma(c.n22, c.c1, c.n21 * c.c0);
+  const double m01 = fma(e0, c.c0, c.n01);
+  const double m11 = fma(e1, c.c0, c.n11);
+  const double m21 = fma(e2, c.c0, c.n21);
+  const double f1 = c.g * fma(c.u2, m21, fma(c.u1, m11, c.u0 * m01));
+  const double y0 = fma(f1, c.u1, m11);
+  b1 = fma(f1, c.u2, m21);
+  return refl_u<2>(y0, b1, 0.0, b0, bh);
+}
+
+// Row pass (right-multiplication by the previous link's reflectors) on a packed matrix at
+// shared-memory index `base`: columns q..q+2 at packed offsets of0..of2, rows l..rmax,
+// KL subdiagonals of storage.  FULLSTORE: store column q for every row (H1) instead of only
+// above the diagonal (triangular factors, whose column q below the diagonal is the bulge that
+// the next column pass overwrites with (beta, 0)).
+template <int KL, bool HAS2>
+PSD_DEV void row_pass(double* sm, int base, int of0, int of1, int of2, int q, int r, int l, int rmax,
+                      bool c2, double u0, double u1, double u2, double g, double b0, double b1,
+                      double bh) {
+  if (r >= l && r <= rmax) {
+    const bool e0x = (KL == 3) || (r <= q + 1);
+    double a0 = e0x ? sm[base + of0 + r] : 0.0;
+    double a1 = sm[base + of1 + r];
+    double a2 = c2 ? sm[base + of2 + r] : 0.0;
+    const double sa = g * fma(a2, u2, fma(a1, u1, a0 * u0));
+    a0 = fma(sa, u0, a0);
+    a1 = fma(sa, u1, a1);
+    a2 = fma(sa, u2, a2);
+    if (HAS2) {
+      const double sb = bh * fma(a2, b1, a1 * b0);
+      a1 = fma(sb, b0, a1);
+      a2 = fma(sb, b1, a2);
+    }
+    if ((KL == 3) || r < q) sm[base + of0 + r] = a0;
+    sm[base + of1 + r] = a1;
+    if (c2) sm[base + of2 + r] = a2;
+  }
+}
+
+// Column pass (left-multiplication) on a triangular factor: column q <- (beta, 0), column
+// q+1 <- (.., beta2, 0), columns > q+1 regular.
+PSD_DEV void col_pass_tri(double* sm, int base, int ocj, int q, int r, int i, bool c2, double u0,
+                          double u1, double u2, double g, double beta, double b0, double b1,
+                          double bh, double beta2) {
+  if (r > q && r <= i) {
+    const int a = base + ocj + q;
+    double a0 = sm[a], a1 = sm[a + 1], a2 = c2 ? sm[a + 2] : 0.0;
+    const double sa = g * fma(u2, a2, fma(u1, a1, u0 * a0));
+    a0 = fma(sa, u0, a0);
+    a1 = fma(sa, u1, a1);
+    a2 = fma(sa, u2, a2);
+    const double sb = bh * fma(b1, a2, b0 * a1);
+    const bool d = (r == q + 1);
+    a1 = d ? beta2 : fma(sb, b0, a1);
+    a2 = d ? 0.0 : fma(sb, b1, a2);
+    sm[a] = a0;
+    sm[a + 1] = a1;
+    if (c2) sm[a + 2] = a2;
+  } else if (r == q) {
+    const int a = base + ocj + q;
+    sm[a] = beta;
+    sm[a + 1] = 0.0;
+  }
+}
+
+// Column pass on H1 with the H1-link's 3-reflector: columns q..i regular, column q-1 <-
+// (beta, 0, 0) (the annihilated bulge), unless this is the first step of the sweep.
+PSD_DEV void col_pass_h1(double* sm, int oc1, int q, int r, int i, int l, bool c2, double u0,
+                         double u1, double u2, double g, double beta) {
+  if (r >= q && r <= i) {
+    const int a = oc1 + q;
+    double a0 = sm[a], a1 = sm[a + 1], a2 = c2 ? sm[a + 2] : 0.0;
+    const double sa = g * fma(u2, a2, fma(u1, a1, u0 * a0));
+    sm[a] = fma(sa, u0, a0);
+    sm[a + 1] = fma(sa, u1, a1);
+    if (c2) sm[a + 2] = fma(sa, u2, a2);
+  } else if (r == q - 1 && q > l) {
+    const int a = oc1 + q;
+    sm[a] = beta;
+    sm[a + 1] = 0.0;
+    if (c2) sm[a + 2] = 0.0;
+  }
+}
+
 extern __shared__ __align__(16) double psd_smem_eig[];
 
 __global__ void __launch_bounds__(256) rpqr_eig32_kernel(EigParams P) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int n = P.n, p = P.p;
-  const int s1 = pk_size(3, n), sj = pk_size(1, n);
-  const int psize = s1 + (p - 1) * sj;
-  double* H1 = psd_smem_eig + (size_t)warp * psize;
-  double* HT = H1 + s1;  // factor j (2..p) at HT + (j-2)*sj
+  const int szh1 = pk_size(3, n), sj = pk_size(1, n);
+  const int psize = szh1 + (p - 1) * sj;
+  double* sm = psd_smem_eig + (size_t)warp * psize;  // H1 at 0, factor j at szh1 + (j-2)*sj
   const int r = lane;
   // this lane's column offsets in the two packed layouts, and those of columns r+1, r+2
   const int oc1 = pk_off(3, r), ocj = pk_off(1, r);
@@ -131,7 +250,7 @@ __global__ void __launch_bounds__(256) rpqr_eig32_kernel(EigParams P) {
     if (b >= P.batch) break;
     {
       const double* src = P.packed + (size_t)b * psize;
-      for (int e = lane; e < psize; e += 32) H1[e] = src[e];
+      for (int e = lane; e < psize; e += 32) sm[e] = src[e];
     }
     __syncwarp();
 
@@ -139,8 +258,8 @@ __global__ void __launch_bounds__(256) rpqr_eig32_kernel(EigParams P) {
     int info = 0, niter = 0;
 
     if (n == 1) {
-      double q = H1[0];
-      for (int j = 2; j <= p; j++) q *= HT[(j - 2) * sj];
+      double q = sm[0];
+      for (int j = 2; j <= p; j++) q *= sm[szh1 + (j - 2) * sj];
       lre = q;
     } else {
       int i = n - 1;
@@ -156,11 +275,12 @@ __global__ void __launch_bounds__(256) rpqr_eig32_kernel(EigParams P) {
           const bool h1b = act && (r + 1 <= i), h2b = act && (r + 2 <= i);
           double q0 = 1.0, q1 = 0.0, q2 = 0.0;
           if (act) {
-            const double* Hj = HT;
-            for (int j = 2; j <= p; j++, Hj += sj) {
-              if (h2b) q2 = q0 * Hj[ocj2 + r] + q1 * Hj[ocj2 + r + 1] + q2 * Hj[ocj2 + r + 2];
-              if (h1b) q1 = q0 * Hj[ocj1 + r] + q1 * Hj[ocj1 + r + 1];
-              q0 *= Hj[ocj + r];
+            int hb = szh1;
+            for (int j = 2; j <= p; j++, hb += sj) {
+              if (h2b)
+                q2 = q0 * sm[hb + ocj2 + r] + q1 * sm[hb + ocj2 + r + 1] + q2 * sm[hb + ocj2 + r + 2];
+              if (h1b) q1 = q0 * sm[hb + ocj1 + r] + q1 * sm[hb + ocj1 + r + 1];
+              q0 *= sm[hb + ocj + r];
             }
           }
           const double t0m = __shfl_up_sync(0xffffffffu, q0, 1);
@@ -168,10 +288,10 @@ __global__ void __launch_bounds__(256) rpqr_eig32_kernel(EigParams P) {
           const double t2m = __shfl_up_sync(0xffffffffu, q2, 1);
           const double t0p = __shfl_down_sync(0xffffffffu, q0, 1);
           if (act) {
-            const double hd = H1[oc1 + r];
-            const double hu = (r < i) ? H1[oc1p + r] : 0.0;
+            const double hd = sm[oc1 + r];
+            const double hu = (r < i) ? sm[oc1p + r] : 0.0;
             if (r > l) {
-              const double hs = H1[oc1m + r];
+              const double hs = sm[oc1m + r];
               hsub = hs * t0m;
               hdiag = hs * t1m + hd * q0;
               if (r < i) hsup = hs * t2m + hd * q1 + hu * t0p;
@@ -193,7 +313,7 @@ __global__ void __launch_bounds__(256) rpqr_eig32_kernel(EigParams P) {
               // opnorm(H1[l:i,l:i], 1) fallback (:536-538): column sums, then warp max
               double cs = 0.0;
               if (act)
-                for (int rr = l; rr <= min(r + 1, i); rr++) cs += fabs(H1[oc1 + rr]);
+                for (int rr = l; rr <= min(r + 1, i); rr++) cs += fabs(sm[oc1 + rr]);
               cs = warp_max(cs);
               if (tst1 == 0.0) tst1 = cs;
             }
@@ -275,166 +395,138 @@ __global__ void __launch_bounds__(256) rpqr_eig32_kernel(EigParams P) {
           }
 
           // ---- double-shift sweep restricted to the window l..i (:806-886) ----
-          // (f0,f1,f2): forwarded source of the next 3-reflector
-          double f0 = v0, f1 = v1, f2 = v2;
-          for (int k = l; k <= i - 1; k++) {
-            const bool three = (k + 2 <= i);
-            const int offk = pk_off(1, k), offk1 = pk_off(1, k + 1), offk2 = pk_off(1, k + 2);
-            const int o3k = pk_off(3, k), o3k1 = pk_off(3, k + 1), o3k2 = pk_off(3, k + 2);
-            double u0, g, beta;
-            // ================= reflector on H1 (left) / H_p (right) =================
-            beta = three ? refl_u<3>(f0, f1, f2, u0, g) : refl_u<2>(f0, f1, 0.0, u0, g);
-            const double u1 = f1, u2 = three ? f2 : 0.0;
-            __syncwarp();
-            if (k > l && r == k - 1) {  // H1[k,k-1] = beta, bulge entries of column k-1 -> 0
-              double* q = H1 + oc1 + k;
-              q[0] = beta;
-              q[1] = 0.0;
-              if (three) q[2] = 0.0;
-            }
-            // left: H1 rows k..k+2, columns k..i (column lanes)
-            if (r >= k && r <= i) {
-              double* q = H1 + oc1 + k;
-              const double a0 = q[0], a1 = q[1], a2 = three ? q[2] : 0.0;
-              const double s = g * fma(u2, a2, fma(u1, a1, u0 * a0));
-              q[0] = fma(s, u0, a0);
-              q[1] = fma(s, u1, a1);
-              if (three) q[2] = fma(s, u2, a2);
-            }
-            if (p == 1) {
-              // right: H1 itself, rows l..min(k+3,i) (row lanes); forward H1[k+1..k+3, k]
-              __syncwarp();
-              const int rmax = min(k + 3, i);
-              double a0n = 0.0;
-              if (r >= l && r <= rmax) {
-                double *q0p = H1 + o3k + r, *q1p = H1 + o3k1 + r, *q2p = H1 + o3k2 + r;
-                const double a0 = *q0p, a1 = *q1p, a2 = three ? *q2p : 0.0;
-                const double s = g * fma(u2, a2, fma(u1, a1, u0 * a0));
-                a0n = fma(s, u0, a0);
-                *q0p = a0n;
-                *q1p = fma(s, u1, a1);
-                if (three) *q2p = fma(s, u2, a2);
-              }
-              f0 = shfl_d(a0n, k + 1);
-              f1 = shfl_d(a0n, min(k + 2, 31));
-              f2 = shfl_d(a0n, min(k + 3, 31));
-              continue;
-            }
-            // right: H_p rows l..k+2, columns k..k+2 (row lanes); forward H_p[k..k+2, k]
-            {
-              double* Hp_ = HT + (p - 2) * sj;
-              const int rmax = three ? k + 2 : k + 1;
-              double a0n = 0.0;
-              if (r >= l && r <= rmax) {
-                double *q0p = Hp_ + offk + r, *q1p = Hp_ + offk1 + r, *q2p = Hp_ + offk2 + r;
-                const double a0 = (r <= k + 1) ? *q0p : 0.0;
-                const double a1 = *q1p, a2 = three ? *q2p : 0.0;
-                const double s = g * fma(u2, a2, fma(u1, a1, u0 * a0));
-                a0n = fma(s, u0, a0);
-                if (r < k) *q0p = a0n;
-                *q1p = fma(s, u1, a1);
-                if (three) *q2p = fma(s, u2, a2);
-              }
-              f0 = shfl_d(a0n, k);
-              f1 = shfl_d(a0n, k + 1);
-              f2 = shfl_d(a0n, min(k + 2, 31));
-            }
-            // ================= factors p..2 =================
-            for (int j = p; j >= 2; j--) {
-              double* Hj = HT + (j - 2) * sj;
-              double* Hm = (j == 2) ? H1 : (Hj - sj);  // H_{j-1}
-              beta = three ? refl_u<3>(f0, f1, f2, u0, g) : refl_u<2>(f0, f1, 0.0, u0, g);
-              const double w1 = f1, w2 = three ? f2 : 0.0;
-              // right: H_{j-1} columns k..k+2 (row lanes) and forward the next source
-              if (j > 2) {
-                const int rmax = three ? k + 2 : k + 1;
-                double a0n = 0.0;
-                if (r >= l && r <= rmax) {
-                  double *q0p = Hm + offk + r, *q1p = Hm + offk1 + r, *q2p = Hm + offk2 + r;
-                  const double a0 = (r <= k + 1) ? *q0p : 0.0;
-                  const double a1 = *q1p, a2 = three ? *q2p : 0.0;
-                  const double s = g * fma(w2, a2, fma(w1, a1, u0 * a0));
-                  a0n = fma(s, u0, a0);
-                  if (r < k) *q0p = a0n;
-                  *q1p = fma(s, w1, a1);
-                  if (three) *q2p = fma(s, w2, a2);
-                }
-                f0 = shfl_d(a0n, k);
-                f1 = shfl_d(a0n, k + 1);
-                f2 = shfl_d(a0n, min(k + 2, 31));
+          {
+            ChainState c;
+            c.c0 = c.c1 = c.h = 0.0;
+            // packed offsets of columns k, k+1, k+2 in both layouts, kept incrementally:
+            // T(kl,c+1) = T(kl,c) + c + 1 + kl
+            int t1a = pk_off(1, l), t1b = pk_off(1, l + 1), t1c = pk_off(1, l + 2);
+            int t3a = pk_off(3, l), t3b = pk_off(3, l + 1), t3c = pk_off(3, l + 2);
+            // previous step's kl=3 offsets (row pass on H1 runs one step late)
+            int p3a = 0, p3b = 0, p3c = 0;
+            double q3u0 = 0, q3u1 = 0, q3u2 = 0, q3g = 0, q3b0 = 0, q3b1 = 0, q3bh = 0, q3beta = 0,
+                   q3beta2 = 0;
+            for (int k = l; k < i; k++) {
+              const bool c2 = (k + 2 <= i);
+              // =============== slot H1(k): 3-reflector of H1 (+ B part / bulk of factor 2, step k-1)
+              double s0, s1, s2, m01, m02, m11, m12, m21, m22;
+              if (k == l) {
+                s0 = v0; s1 = v1; s2 = v2;
               } else {
-                // H1 is Hessenberg: rows l..min(k+3,i); next source is H1[k+1..k+3, k]
-                const int rmax = min(k + 3, i);
-                double a0n = 0.0;
-                if (r >= l && r <= rmax) {
-                  double *q0p = H1 + o3k + r, *q1p = H1 + o3k1 + r, *q2p = H1 + o3k2 + r;
-                  const double a0 = *q0p, a1 = *q1p, a2 = three ? *q2p : 0.0;
-                  const double s = g * fma(w2, a2, fma(w1, a1, u0 * a0));
-                  a0n = fma(s, u0, a0);
-                  *q0p = a0n;
-                  *q1p = fma(s, w1, a1);
-                  if (three) *q2p = fma(s, w2, a2);
-                }
-                f0 = shfl_d(a0n, k + 1);
-                f1 = shfl_d(a0n, min(k + 2, 31));
-                f2 = shfl_d(a0n, min(k + 3, 31));
+                chain_A(c, s0, s1, s2, m01, m02, m11, m12, m21, m22);
+                q3beta2 = chain_B(c, q3b0, q3b1, q3bh);
+                q3u0 = c.u0; q3u1 = c.u1; q3u2 = c.u2; q3g = c.g; q3beta = c.beta;
               }
-              __syncwarp();  // row-lane writes to H_j (previous stage) visible to column lanes
-              // left: H_j rows k..k+2, columns k+1..i (column lanes); column k gets (beta, 0)
-              double y0 = 0.0, y1 = 0.0;
-              if (r == k) {
-                double* q = Hj + ocj + k;
-                q[0] = beta;
-                q[1] = 0.0;
-              } else if (r > k && r <= i) {
-                double* q = Hj + ocj + k;
-                const double a0 = q[0], a1 = q[1], a2 = three ? q[2] : 0.0;
-                const double s = g * fma(w2, a2, fma(w1, a1, u0 * a0));
-                q[0] = fma(s, u0, a0);
-                y0 = fma(s, w1, a1);
-                y1 = three ? fma(s, w2, a2) : 0.0;
-                q[1] = y0;
-                if (three) q[2] = y1;
+              double nu0, ng;
+              double nbeta = refl_u<3>(s0, s1, s2, nu0, ng);
+              __syncwarp();
+              if (k > l) {
+                // bulk of factor 2 at step k-1: row pass on H1, column pass on H2
+                row_pass<3, true>(sm, 0, p3a, p3b, p3c, k - 1, r, l, min(k + 2, i), true, q3u0, q3u1,
+                                  q3u2, q3g, q3b0, q3b1, q3bh);
+                col_pass_tri(sm, szh1, ocj, k - 1, r, i, true, q3u0, q3u1, q3u2, q3g, q3beta, q3b0,
+                             q3b1, q3bh, q3beta2);
               }
-              if (three) {
-                // second reflector, order 2, from H_j[k+1..k+2, k+1] held by column lane k+1
-                y0 = shfl_d(y0, k + 1);
-                y1 = shfl_d(y1, k + 1);
-                double c0, h;
-                const double beta2 = refl_u<2>(y0, y1, 0.0, c0, h);
-                // left: H_j rows k+1,k+2, columns k+2..i
-                if (r == k + 1) {
-                  double* q = Hj + ocj + k + 1;
-                  q[0] = beta2;
-                  q[1] = 0.0;
-                } else if (r > k + 1 && r <= i) {
-                  double* q = Hj + ocj + k + 1;
-                  const double a0 = q[0], a1 = q[1];
-                  const double s = h * fma(y1, a1, c0 * a0);
-                  q[0] = fma(s, c0, a0);
-                  q[1] = fma(s, y1, a1);
-                }
-                // right: H_{j-1} columns k+1,k+2, rows l..k+2 (k+3 for H1)
-                if (j > 2) {
-                  if (r >= l && r <= k + 2) {
-                    double *q1p = Hm + offk1 + r, *q2p = Hm + offk2 + r;
-                    const double a1 = *q1p, a2 = *q2p;
-                    const double s = h * fma(y1, a2, c0 * a1);
-                    *q1p = fma(s, c0, a1);
-                    *q2p = fma(s, y1, a2);
-                  }
+              __syncwarp();
+              // prefetch the diagonal block of factor p at position k
+              {
+                const int hb = szh1 + (p - 2) * sj;
+                c.x00 = sm[hb + t1a + k];
+                c.x01 = sm[hb + t1b + k];
+                c.x02 = c2 ? sm[hb + t1c + k] : 0.0;
+                c.x10 = 0.0;
+                c.x11 = sm[hb + t1b + k + 1];
+                c.x12 = c2 ? sm[hb + t1c + k + 1] : 0.0;
+                c.x22 = c2 ? sm[hb + t1c + k + 2] : 0.0;
+              }
+              c.u0 = nu0; c.u1 = s1; c.u2 = s2; c.g = ng; c.beta = nbeta;
+              // =============== slot factor p: its 3-reflector; bulk of H1(k) ===============
+              {
+                chain_A(c, s0, s1, s2, m01, m02, m11, m12, m21, m22);
+                nbeta = refl_u<3>(s0, s1, s2, nu0, ng);
+                __syncwarp();
+                const int hb = szh1 + (p - 2) * sj;
+                row_pass<1, false>(sm, hb, t1a, t1b, t1c, k, r, l, min(k + 2, i), c2, c.u0, c.u1, c.u2,
+                                   c.g, 0.0, 0.0, 0.0);
+                col_pass_h1(sm, oc1, k, r, i, l, c2, c.u0, c.u1, c.u2, c.g, c.beta);
+                __syncwarp();
+                // prefetch next link's block: factor p-1, or H1 rows k+1..k+3 when p == 2
+                if (p > 2) {
+                  const int hn = hb - sj;
+                  c.x00 = sm[hn + t1a + k];
+                  c.x01 = sm[hn + t1b + k];
+                  c.x02 = c2 ? sm[hn + t1c + k] : 0.0;
+                  c.x10 = 0.0;
+                  c.x11 = sm[hn + t1b + k + 1];
+                  c.x12 = c2 ? sm[hn + t1c + k + 1] : 0.0;
+                  c.x22 = c2 ? sm[hn + t1c + k + 2] : 0.0;
                 } else {
-                  if (r >= l && r <= min(k + 3, i)) {
-                    double *q1p = H1 + o3k1 + r, *q2p = H1 + o3k2 + r;
-                    const double a1 = *q1p, a2 = *q2p;
-                    const double s = h * fma(y1, a2, c0 * a1);
-                    *q1p = fma(s, c0, a1);
-                    *q2p = fma(s, y1, a2);
-                  }
+                  const bool r3 = (k + 3 <= i);
+                  c.x00 = sm[t3a + k + 1];
+                  c.x01 = sm[t3b + k + 1];
+                  c.x02 = c2 ? sm[t3c + k + 1] : 0.0;
+                  c.x10 = c2 ? sm[t3a + k + 2] : 0.0;
+                  c.x11 = c2 ? sm[t3b + k + 2] : 0.0;
+                  c.x12 = c2 ? sm[t3c + k + 2] : 0.0;
+                  c.x22 = r3 ? sm[t3c + k + 3] : 0.0;
                 }
+                c.c0 = 0.0; c.c1 = 0.0; c.h = 0.0;  // the H1 link has no 2-reflector
+                c.u0 = nu0; c.u1 = s1; c.u2 = s2; c.g = ng; c.beta = nbeta;
+                c.n01 = m01; c.n02 = m02; c.n11 = m11; c.n12 = m12; c.n21 = m21; c.n22 = m22;
               }
-            }  // factors
-          }    // k
+              // =============== slots factor p-1 .. 2 ===============
+              for (int j = p - 1; j >= 2; j--) {
+                const int hb = szh1 + (j - 2) * sj;  // this link's matrix; previous link's is hb + sj
+                chain_A(c, s0, s1, s2, m01, m02, m11, m12, m21, m22);
+                double b0, b1, bh;
+                const double beta2 = chain_B(c, b0, b1, bh);
+                nbeta = refl_u<3>(s0, s1, s2, nu0, ng);
+                __syncwarp();
+                row_pass<1, true>(sm, hb, t1a, t1b, t1c, k, r, l, min(k + 2, i), c2, c.u0, c.u1, c.u2,
+                                  c.g, b0, b1, bh);
+                col_pass_tri(sm, hb + sj, ocj, k, r, i, c2, c.u0, c.u1, c.u2, c.g, c.beta, b0, b1, bh,
+                             beta2);
+                __syncwarp();
+                if (j > 2) {
+                  const int hn = hb - sj;
+                  c.x00 = sm[hn + t1a + k];
+                  c.x01 = sm[hn + t1b + k];
+                  c.x02 = c2 ? sm[hn + t1c + k] : 0.0;
+                  c.x10 = 0.0;
+                  c.x11 = sm[hn + t1b + k + 1];
+                  c.x12 = c2 ? sm[hn + t1c + k + 1] : 0.0;
+                  c.x22 = c2 ? sm[hn + t1c + k + 2] : 0.0;
+                } else {
+                  // next link is H1(k+1): rows k+1..k+3, columns k..k+2 of H1
+                  const bool r3 = (k + 3 <= i);
+                  c.x00 = sm[t3a + k + 1];
+                  c.x01 = sm[t3b + k + 1];
+                  c.x02 = c2 ? sm[t3c + k + 1] : 0.0;
+                  c.x10 = c2 ? sm[t3a + k + 2] : 0.0;
+                  c.x11 = c2 ? sm[t3b + k + 2] : 0.0;
+                  c.x12 = c2 ? sm[t3c + k + 2] : 0.0;
+                  c.x22 = r3 ? sm[t3c + k + 3] : 0.0;
+                }
+                c.c0 = b0; c.c1 = b1; c.h = bh;
+                c.u0 = nu0; c.u1 = s1; c.u2 = s2; c.g = ng; c.beta = nbeta;
+                c.n01 = m01; c.n02 = m02; c.n11 = m11; c.n12 = m12; c.n21 = m21; c.n22 = m22;
+              }
+              // advance the packed offsets to step k+1
+              p3a = t3a; p3b = t3b; p3c = t3c;
+              t1a = t1b; t1b = t1c; t1c += (k + 3) + 1;
+              t3a = t3b; t3b = t3c; t3c += (k + 3) + 3;
+            }
+            // flush: B part and bulk of factor 2 at the last step k = i-1
+            {
+              double b0, b1, bh;
+              const double beta2 = chain_B(c, b0, b1, bh);
+              __syncwarp();
+              row_pass<3, true>(sm, 0, p3a, p3b, p3c, i - 1, r, l, i, false, c.u0, c.u1, c.u2, c.g, b0,
+                                b1, bh);
+              col_pass_tri(sm, szh1, ocj, i - 1, r, i, false, c.u0, c.u1, c.u2, c.g, c.beta, b0, b1, bh,
+                           beta2);
+            }
+          }
           __syncwarp();
           its++;
         }  // QR iterations

@@ -1,0 +1,133 @@
+// Periodic Hessenberg-triangular reduction for small problems (n <= 32), no Schur vectors:
+// ONE WARP PER PROBLEM, output in the packed layout consumed by rpqr_eig32_kernel.
+//
+// Same mathematics as phessenberg! (PeriodicSchurDecompositions.jl:229-247): for each column
+// i, factors p..2 get a QR-type reflector (rows i..n-1) that is pushed into the right
+// neighbour from the right, then H_1 gets the Hessenberg reflector (rows i+1..n-1) which is
+// pushed into H_p.  Lane L owns row L / column L; the only cross-lane operation per
+// reflector is one warp-wide sum of squares.  Reflectors are used un-normalised,
+// H = I + g u u^T with g = -2/(u^T u) (see psd_real_eig32.cuh).
+#pragma once
+#include "psd_real_eig32.cuh"
+
+namespace psd {
+
+struct Hess32Params {
+  int n, p;
+  long long batch;
+  int left;             // :L orientation: internal factor j <- user factor p+1-j (:127-131)
+  int ld;               // smem leading dimension (odd)
+  const double* A;      // [batch][p][n*n]
+  double* packed_out;   // [batch][pk_problem_size(n,p)]
+  unsigned long long* counter;
+};
+
+// One reflector step: generate from Aj[r0.., col]; apply from the left to Aj[r0.., col+1..],
+// from the right to Am[:, r0..].  0-based.  All 32 lanes must call.
+PSD_DEV void hess32_step(double* Aj, double* Am, int n, int ld, int r0, int col, int lane) {
+  double* xc = Aj + col * ld;  // source column
+  const double alpha = xc[r0];
+  const double xr = (lane > r0 && lane < n) ? xc[lane] : 0.0;
+  double ssq = warp_sum(xr * xr);
+  if (ssq == 0.0) {
+    // either an exactly zero tail (H = I, householder.jl:76-78) or underflow of the squares
+    const double amax = warp_max(fabs(xr));
+    if (amax == 0.0) return;
+  }
+  double nn = fma(alpha, alpha, ssq);
+  double sc = 1.0;
+  if (!(ssq > 1e-280 && nn < 1e280)) {
+    // rare: rescale by an exact power of two so that the squares are representable
+    const double m = fmax(warp_max(fabs(xr)), fabs(alpha));
+    sc = pow2_rescale(m);
+    const double y = xr * sc;
+    ssq = warp_sum(y * y);
+    nn = fma(alpha * sc, alpha * sc, ssq);
+  }
+  const double al = alpha * sc;
+  const double nrm = sqrt(nn);
+  const double betas = -copysign(nrm, al);
+  const double u0s = al - betas;
+  // H = I + g u u^T with u = (u0s, sc*x[r0+1..]) ; fold sc into the coefficients
+  const double gs = -2.0 / fma(u0s, u0s, ssq);
+  const double g = gs * sc * sc;      // for u = (u0, x) with u0 = u0s/sc
+  const double u0 = u0s / sc;
+  const double beta = betas / sc;
+  // left: columns col+1..n-1 of Aj (lane = column)
+  if (lane > col && lane < n) {
+    double* a = Aj + lane * ld;
+    double d0 = u0 * a[r0], d1 = 0.0;
+    int k = r0 + 1;
+    for (; k + 1 < n; k += 2) {
+      d0 = fma(xc[k], a[k], d0);
+      d1 = fma(xc[k + 1], a[k + 1], d1);
+    }
+    if (k < n) d0 = fma(xc[k], a[k], d0);
+    const double s = g * (d0 + d1);
+    a[r0] = fma(s, u0, a[r0]);
+    for (k = r0 + 1; k < n; k++) a[k] = fma(s, xc[k], a[k]);
+  }
+  if (Am == Aj) __syncwarp();
+  // right: rows 0..n-1 of Am (lane = row), columns r0..n-1
+  if (lane < n) {
+    double* a = Am + lane;
+    double d0 = a[r0 * ld] * u0, d1 = 0.0;
+    int k = r0 + 1;
+    for (; k + 1 < n; k += 2) {
+      d0 = fma(a[k * ld], xc[k], d0);
+      d1 = fma(a[(k + 1) * ld], xc[k + 1], d1);
+    }
+    if (k < n) d0 = fma(a[k * ld], xc[k], d0);
+    const double s = g * (d0 + d1);
+    a[r0 * ld] = fma(s, u0, a[r0 * ld]);
+    for (k = r0 + 1; k < n; k++) a[k * ld] = fma(s, xc[k], a[k * ld]);
+  }
+  __syncwarp();
+  if (lane == r0) xc[lane] = beta;
+  else if (lane > r0 && lane < n) xc[lane] = 0.0;
+  __syncwarp();
+}
+
+extern __shared__ __align__(16) double psd_smem_hess[];
+
+__global__ void __launch_bounds__(256) rphess_warp32_kernel(Hess32Params P) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n = P.n, p = P.p, ld = P.ld;
+  const size_t nn = (size_t)n * n;
+  const int fs = ld * n;  // doubles per staged factor
+  double* S = psd_smem_hess + (size_t)warp * p * fs;
+  const int psize = pk_problem_size(n, p);
+  for (;;) {
+    long long b = 0;
+    if (lane == 0) b = (long long)atomicAdd(P.counter, 1ULL);
+    b = __shfl_sync(0xffffffffu, b, 0);
+    if (b >= P.batch) break;
+    const double* Ab = P.A + (size_t)b * p * nn;
+    for (int j = 0; j < p; j++) {
+      const double* src = Ab + (size_t)(P.left ? (p - 1 - j) : j) * nn;
+      double* dst = S + j * fs;
+      if (lane < n)
+        for (int c = 0; c < n; c++) dst[c * ld + lane] = src[c * n + lane];
+    }
+    __syncwarp();
+    for (int i = 0; i < n - 1; i++) {
+      for (int j = p - 1; j >= 1; j--) hess32_step(S + j * fs, S + (j - 1) * fs, n, ld, i, i, lane);
+      if (n - (i + 1) > 1) hess32_step(S, S + (p - 1) * fs, n, ld, i + 1, i, lane);
+    }
+    // packed output: H1 with 3 subdiagonals of storage, H2..Hp with 1 (zeros below structure)
+    double* dstb = P.packed_out + (size_t)b * psize;
+    for (int j = 0; j < p; j++) {
+      const int kl = (j == 0) ? 3 : 1;
+      const int keep = (j == 0) ? 1 : 0;
+      double* dst = dstb + ((j == 0) ? 0 : pk_size(3, n) + (j - 1) * pk_size(1, n));
+      const double* src = S + j * fs;
+      for (int c = 0; c < n; c++) {
+        const int off = pk_off(kl, c);
+        if (lane <= c + kl && lane < n) dst[off + lane] = (lane <= c + keep) ? src[c * ld + lane] : 0.0;
+      }
+    }
+    __syncwarp();
+  }
+}
+
+}  // namespace psd
