@@ -258,7 +258,7 @@ int launch_real(psd_handle_s* h, Device& dev, Slot& aux, cudaStream_t stream, co
   if (batch == 0) return PSD_OK;
   RealLaunchPlan pl;
   const bool wantZ = rc.wantZ && dZ;
-  if (!rc.wantT && !wantZ && !rc.reduce_only && rc.n <= 32 && rc.p >= 2 && !getenv("PSD_DISABLE_EIG32"))
+  if (!rc.wantT && !wantZ && !rc.reduce_only && rc.n <= 32 && rc.p >= 3 && !getenv("PSD_DISABLE_EIG32"))
     return launch_real_eig32(h, dev, aux, stream, rc, batch, dA, dEig, dInfo);
   int e = plan_real(dev, rc.n, rc.p, batch, wantZ, pl);
   if (e) return e;

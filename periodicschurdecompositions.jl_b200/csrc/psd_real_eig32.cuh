@@ -1,4 +1,4 @@
-// Eigenvalue-only real periodic QR for small problems (n <= 32, p >= 2): ONE WARP PER PROBLEM.
+// Eigenvalue-only real periodic QR for small problems (n <= 32, p >= 3): ONE WARP PER PROBLEM.
 //
 // This is the B200 fast path of BASELINE config 2 (p=8, N=32, wantT=wantZ=false).  It
 // implements the same iteration as periodic_qr_cta (PeriodicSchurDecompositions.jl:322-1096
@@ -76,13 +76,18 @@ PSD_DEV double fast_rcp(double x) {
 
 // rare path of refl_u: zero tail (H = I, householder.jl:76-78) or out-of-range magnitudes,
 // handled with an exact power-of-two prescale as dlarfg's sfmin loop does (:80-100).
+struct ReflOut {
+  double beta, u0, g;
+};
 template <int M>
-__device__ __noinline__ double refl_u_slow(double x0, double x1, double x2, double* u0, double* g) {
+__device__ __noinline__ ReflOut refl_u_slow(double x0, double x1, double x2) {
+  ReflOut o;
   const double amax = fmax(fabs(x1), (M == 3) ? fabs(x2) : 0.0);
   if (amax == 0.0) {
-    *u0 = 0.0;
-    *g = 0.0;
-    return x0;
+    o.u0 = 0.0;
+    o.g = 0.0;
+    o.beta = x0;
+    return o;
   }
   const double m = fmax(amax, fabs(x0));
   const double s = pow2_rescale(m);
@@ -90,23 +95,46 @@ __device__ __noinline__ double refl_u_slow(double x0, double x1, double x2, doub
   const double nrm = sqrt(fma(al, al, fma(y1, y1, y2 * y2)));
   const double beta = -copysign(nrm, al);
   const double w0 = al - beta;
-  *u0 = w0 / s;
-  *g = (-2.0 * s) * (s / fma(w0, w0, fma(y1, y1, y2 * y2)));
-  return beta / s;
+  o.u0 = w0 / s;
+  o.g = (-2.0 * s) * (s / fma(w0, w0, fma(y1, y1, y2 * y2)));
+  o.beta = beta / s;
+  return o;
 }
 
 // Un-normalised reflector from (x0, x1[, x2]):  H = I + g u u^T, u = (x0 - beta, x1, x2),
 // H x = beta e1.  Returns beta; g = 0 means H = I.
-template <int M>
-PSD_DEV double refl_u(double x0, double x1, double x2, double& u0, double& g) {
+// SAFE = false: branch-free (so that the two reflector chains of a slot and the bulk updates
+// can be interleaved by the instruction scheduler); magnitudes outside the range in which
+// the squares are representable set `bad`, and the problem is then redone with SAFE = true,
+// whose rare path rescales exactly like dlarfg (householder.jl:80-100).
+template <int M, bool SAFE>
+PSD_DEV double refl_u(double x0, double x1, double x2, double& u0, double& g, bool& bad) {
   const double ssq = (M == 3) ? fma(x1, x1, x2 * x2) : x1 * x1;
   const double nn = fma(x0, x0, ssq);
-  if (!(ssq > 1e-290 && nn < 1e290)) return refl_u_slow<M>(x0, x1, x2, &u0, &g);
+  const bool ok = (ssq > 1e-290 && nn < 1e290);
+  if (SAFE) {
+    if (!ok) {
+      const ReflOut o = refl_u_slow<M>(x0, x1, x2);
+      u0 = o.u0;
+      g = o.g;
+      return o.beta;
+    }
+  } else {
+    bad = bad || (!ok && ssq != 0.0);
+  }
   const double nrm = nn * fast_rsqrt(nn);
   const double beta = -copysign(nrm, x0);
-  u0 = x0 - beta;
-  g = -2.0 * fast_rcp(fma(u0, u0, ssq));
-  return beta;
+  const double w0 = x0 - beta;
+  const double gg = -2.0 * fast_rcp(fma(w0, w0, ssq));
+  if (SAFE) {
+    u0 = w0;
+    g = gg;
+    return beta;
+  }
+  // zero tail: H = I (householder.jl:76-78)
+  u0 = ok ? w0 : 0.0;
+  g = ok ? gg : 0.0;
+  return ok ? beta : x0;
 }
 
 // State carried along the chain of links (all values identical in every lane).
@@ -137,7 +165,8 @@ PSD_DEV void chain_A(const ChainState& c, double& s0, double& s1, double& s2, do
 
 // B part: 2-reflector of the previous (factor) link from its N, the 2-reflector before it
 // and its own 3-reflector.
-PSD_DEV double chain_B(const ChainState& c, double& b0, double& b1, double& bh) {
+template <bool SAFE>
+PSD_DEV double chain_B(const ChainState& c, double& b0, double& b1, double& bh, bool& bad) {
   const double e0 = c.h * fma(c.n02, c.c1, c.n01 * c.c0);
   const double e1 = c.h * fma(c.n12, c.c1, c.n11 * c.c0);
   const double e2 = c.h * fma(c.n22, c.c1, c.n21 * c.c0);
@@ -147,7 +176,7 @@ PSD_DEV double chain_B(const ChainState& c, double& b0, double& b1, double& bh) 
   const double f1 = c.g * fma(c.u2, m21, fma(c.u1, m11, c.u0 * m01));
   const double y0 = fma(f1, c.u1, m11);
   b1 = fma(f1, c.u2, m21);
-  return refl_u<2>(y0, b1, 0.0, b0, bh);
+  return refl_u<2, SAFE>(y0, b1, 0.0, b0, bh, bad);
 }
 
 // Row pass (right-multiplication by the previous link's reflectors) on a packed matrix at
@@ -159,24 +188,28 @@ template <int KL, bool HAS2>
 PSD_DEV void row_pass(double* sm, int base, int of0, int of1, int of2, int q, int r, int l, int rmax,
                       bool c2, double u0, double u1, double u2, double g, double b0, double b1,
                       double bh) {
-  if (r >= l && r <= rmax) {
-    const bool e0x = (KL == 3) || (r <= q + 1);
-    double a0 = e0x ? sm[base + of0 + r] : 0.0;
-    double a1 = sm[base + of1 + r];
-    double a2 = c2 ? sm[base + of2 + r] : 0.0;
-    const double sa = g * fma(a2, u2, fma(a1, u1, a0 * u0));
-    a0 = fma(sa, u0, a0);
-    a1 = fma(sa, u1, a1);
-    a2 = fma(sa, u2, a2);
-    if (HAS2) {
-      const double sb = bh * fma(a2, b1, a1 * b0);
-      a1 = fma(sb, b0, a1);
-      a2 = fma(sb, b1, a2);
-    }
-    if ((KL == 3) || r < q) sm[base + of0 + r] = a0;
-    sm[base + of1 + r] = a1;
-    if (c2) sm[base + of2 + r] = a2;
+  // branch-free: lanes outside l..rmax compute on a clamped (valid) row and do not store
+  const bool act = (r >= l && r <= rmax);
+  const int rr = min(r, rmax);
+  const bool e0x = (KL == 3) || (rr <= q + 1);
+  const int o2 = c2 ? of2 : of1;
+  double a0 = sm[base + of0 + (e0x ? rr : 0)];
+  double a1 = sm[base + of1 + rr];
+  double a2 = sm[base + o2 + rr];
+  a0 = e0x ? a0 : 0.0;
+  a2 = c2 ? a2 : 0.0;
+  const double sa = g * fma(a2, u2, fma(a1, u1, a0 * u0));
+  a0 = fma(sa, u0, a0);
+  a1 = fma(sa, u1, a1);
+  a2 = fma(sa, u2, a2);
+  if (HAS2) {
+    const double sb = bh * fma(a2, b1, a1 * b0);
+    a1 = fma(sb, b0, a1);
+    a2 = fma(sb, b1, a2);
   }
+  if (act && ((KL == 3) || r < q)) sm[base + of0 + r] = a0;
+  if (act) sm[base + of1 + r] = a1;
+  if (act && c2) sm[base + of2 + r] = a2;
 }
 
 // Column pass (left-multiplication) on a triangular factor: column q <- (beta, 0), column
@@ -184,76 +217,67 @@ PSD_DEV void row_pass(double* sm, int base, int of0, int of1, int of2, int q, in
 PSD_DEV void col_pass_tri(double* sm, int base, int ocj, int q, int r, int i, bool c2, double u0,
                           double u1, double u2, double g, double beta, double b0, double b1,
                           double bh, double beta2) {
-  if (r > q && r <= i) {
-    const int a = base + ocj + q;
-    double a0 = sm[a], a1 = sm[a + 1], a2 = c2 ? sm[a + 2] : 0.0;
-    const double sa = g * fma(u2, a2, fma(u1, a1, u0 * a0));
-    a0 = fma(sa, u0, a0);
-    a1 = fma(sa, u1, a1);
-    a2 = fma(sa, u2, a2);
-    const double sb = bh * fma(b1, a2, b0 * a1);
-    const bool d = (r == q + 1);
-    a1 = d ? beta2 : fma(sb, b0, a1);
-    a2 = d ? 0.0 : fma(sb, b1, a2);
+  const bool act = (r >= q && r <= i);
+  const int a = base + ocj + q;  // rows q.. of this lane's column (valid storage for r >= q)
+  const int as = act ? a : base;  // inactive lanes read a harmless valid location
+  double a0 = sm[as], a1 = sm[as + 1], a2 = sm[as + (c2 ? 2 : 1)];
+  a2 = c2 ? a2 : 0.0;
+  const double sa = g * fma(u2, a2, fma(u1, a1, u0 * a0));
+  a0 = fma(sa, u0, a0);
+  a1 = fma(sa, u1, a1);
+  a2 = fma(sa, u2, a2);
+  const double sb = bh * fma(b1, a2, b0 * a1);
+  const bool d0 = (r == q), d1 = (r == q + 1);
+  a0 = d0 ? beta : a0;
+  a1 = d0 ? 0.0 : (d1 ? beta2 : fma(sb, b0, a1));
+  a2 = d1 ? 0.0 : fma(sb, b1, a2);
+  if (act) {
     sm[a] = a0;
     sm[a + 1] = a1;
-    if (c2) sm[a + 2] = a2;
-  } else if (r == q) {
-    const int a = base + ocj + q;
-    sm[a] = beta;
-    sm[a + 1] = 0.0;
   }
+  if (act && c2 && !d0) sm[a + 2] = a2;
 }
 
 // Column pass on H1 with the H1-link's 3-reflector: columns q..i regular, column q-1 <-
 // (beta, 0, 0) (the annihilated bulge), unless this is the first step of the sweep.
 PSD_DEV void col_pass_h1(double* sm, int oc1, int q, int r, int i, int l, bool c2, double u0,
                          double u1, double u2, double g, double beta) {
-  if (r >= q && r <= i) {
-    const int a = oc1 + q;
-    double a0 = sm[a], a1 = sm[a + 1], a2 = c2 ? sm[a + 2] : 0.0;
-    const double sa = g * fma(u2, a2, fma(u1, a1, u0 * a0));
-    sm[a] = fma(sa, u0, a0);
-    sm[a + 1] = fma(sa, u1, a1);
-    if (c2) sm[a + 2] = fma(sa, u2, a2);
-  } else if (r == q - 1 && q > l) {
-    const int a = oc1 + q;
-    sm[a] = beta;
-    sm[a + 1] = 0.0;
-    if (c2) sm[a + 2] = 0.0;
+  const bool reg = (r >= q && r <= i);
+  const bool src = (r == q - 1 && q > l);
+  const int a = oc1 + q;  // valid storage for r >= q-1 (3 subdiagonals)
+  const int as = (reg || src) ? a : 0;
+  double a0 = sm[as], a1 = sm[as + 1], a2 = sm[as + (c2 ? 2 : 1)];
+  a2 = c2 ? a2 : 0.0;
+  const double sa = g * fma(u2, a2, fma(u1, a1, u0 * a0));
+  a0 = src ? beta : fma(sa, u0, a0);
+  a1 = src ? 0.0 : fma(sa, u1, a1);
+  a2 = src ? 0.0 : fma(sa, u2, a2);
+  if (reg || src) {
+    sm[a] = a0;
+    sm[a + 1] = a1;
   }
+  if ((reg || src) && c2) sm[a + 2] = a2;
 }
 
-extern __shared__ __align__(16) double psd_smem_eig[];
+// Result of one problem: info >= 0 as documented; kNeedSafe = magnitudes left the range the
+// branch-free reflector handles, redo with SAFE = true.
+constexpr int kNeedSafe = -12345;
 
-__global__ void __launch_bounds__(256) rpqr_eig32_kernel(EigParams P) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int n = P.n, p = P.p;
+template <bool SAFE>
+__device__ __forceinline__ int rpqr_problem(double* sm, const int n, const int p, const int maxitfac,
+                                            const int lane, double& lre_out, double& lim_out,
+                                            int& niter_out) {
   const int szh1 = pk_size(3, n), sj = pk_size(1, n);
-  const int psize = szh1 + (p - 1) * sj;
-  double* sm = psd_smem_eig + (size_t)warp * psize;  // H1 at 0, factor j at szh1 + (j-2)*sj
   const int r = lane;
   // this lane's column offsets in the two packed layouts, and those of columns r+1, r+2
   const int oc1 = pk_off(3, r), ocj = pk_off(1, r);
   const int ocj1 = pk_off(1, r + 1), ocj2 = pk_off(1, r + 2);
   const int oc1p = pk_off(3, r + 1), oc1m = (r > 0) ? pk_off(3, r - 1) : 0;
-
   const double dat1 = 0.75, dat2 = -0.4375;
   const double ulp = DBL_EPSILON;
   const double ulpx = ulp * sqrt(sqrt(ulp));
   const double smlnum = DBL_MIN * ((double)n / ulp);
-
-  for (;;) {
-    long long b = 0;
-    if (lane == 0) b = (long long)atomicAdd(P.counter, 1ULL);
-    b = __shfl_sync(0xffffffffu, b, 0);
-    if (b >= P.batch) break;
-    {
-      const double* src = P.packed + (size_t)b * psize;
-      for (int e = lane; e < psize; e += 32) sm[e] = src[e];
-    }
-    __syncwarp();
-
+  bool bad = false;
     double lre = 0.0, lim = 0.0;  // eigenvalue r lives in lane r
     int info = 0, niter = 0;
 
@@ -263,7 +287,7 @@ __global__ void __launch_bounds__(256) rpqr_eig32_kernel(EigParams P) {
       lre = q;
     } else {
       int i = n - 1;
-      int maxitleft = P.maxitfac * n;
+      int maxitleft = maxitfac * n;
       while (i >= 0) {
         int l = 0;
         int its = 1;
@@ -404,72 +428,64 @@ __global__ void __launch_bounds__(256) rpqr_eig32_kernel(EigParams P) {
             int t3a = pk_off(3, l), t3b = pk_off(3, l + 1), t3c = pk_off(3, l + 2);
             // previous step's kl=3 offsets (row pass on H1 runs one step late)
             int p3a = 0, p3b = 0, p3c = 0;
-            double q3u0 = 0, q3u1 = 0, q3u2 = 0, q3g = 0, q3b0 = 0, q3b1 = 0, q3bh = 0, q3beta = 0,
-                   q3beta2 = 0;
             for (int k = l; k < i; k++) {
               const bool c2 = (k + 2 <= i);
-              // =============== slot H1(k): 3-reflector of H1 (+ B part / bulk of factor 2, step k-1)
+              const int rm2 = min(k + 2, i);
               double s0, s1, s2, m01, m02, m11, m12, m21, m22;
-              if (k == l) {
-                s0 = v0; s1 = v1; s2 = v2;
-              } else {
+              double y00, y01, y02, y10, y11, y12, y22;  // block prefetched for the next link
+              // Each slot is ONE scheduling region: sync; prefetch the next link's block; B part
+              // of the previous link; bulk of the previous link; A part + 3-reflector of this
+              // link.  (Requires p >= 3 so that the prefetched block is not touched by the
+              // bulk of the same slot.)
+              // =============== slot H1(k) ===============
+              __syncwarp();
+              {
+                const int hb = szh1 + (p - 2) * sj;  // factor p at position k
+                const int o2 = c2 ? t1c : t1b;
+                y00 = sm[hb + t1a + k];
+                y01 = sm[hb + t1b + k];
+                y02 = sm[hb + o2 + k];
+                y11 = sm[hb + t1b + k + 1];
+                y12 = sm[hb + o2 + k + 1];
+                y22 = sm[hb + o2 + (c2 ? k + 2 : k + 1)];
+                y10 = 0.0;
+                y02 = c2 ? y02 : 0.0; y12 = c2 ? y12 : 0.0; y22 = c2 ? y22 : 0.0;
+              }
+              if (k > l) {
+                double b0, b1, bh;
+                const double beta2 = chain_B<SAFE>(c, b0, b1, bh, bad);
+                // bulk of factor 2 at step k-1: row pass on H1, column pass on H2
+                row_pass<3, true>(sm, 0, p3a, p3b, p3c, k - 1, r, l, min(k + 2, i), true, c.u0, c.u1,
+                                  c.u2, c.g, b0, b1, bh);
+                col_pass_tri(sm, szh1, ocj, k - 1, r, i, true, c.u0, c.u1, c.u2, c.g, c.beta, b0, b1,
+                             bh, beta2);
                 chain_A(c, s0, s1, s2, m01, m02, m11, m12, m21, m22);
-                q3beta2 = chain_B(c, q3b0, q3b1, q3bh);
-                q3u0 = c.u0; q3u1 = c.u1; q3u2 = c.u2; q3g = c.g; q3beta = c.beta;
+              } else {
+                s0 = v0; s1 = v1; s2 = v2;
               }
               double nu0, ng;
-              double nbeta = refl_u<3>(s0, s1, s2, nu0, ng);
-              __syncwarp();
-              if (k > l) {
-                // bulk of factor 2 at step k-1: row pass on H1, column pass on H2
-                row_pass<3, true>(sm, 0, p3a, p3b, p3c, k - 1, r, l, min(k + 2, i), true, q3u0, q3u1,
-                                  q3u2, q3g, q3b0, q3b1, q3bh);
-                col_pass_tri(sm, szh1, ocj, k - 1, r, i, true, q3u0, q3u1, q3u2, q3g, q3beta, q3b0,
-                             q3b1, q3bh, q3beta2);
-              }
-              __syncwarp();
-              // prefetch the diagonal block of factor p at position k
-              {
-                const int hb = szh1 + (p - 2) * sj;
-                c.x00 = sm[hb + t1a + k];
-                c.x01 = sm[hb + t1b + k];
-                c.x02 = c2 ? sm[hb + t1c + k] : 0.0;
-                c.x10 = 0.0;
-                c.x11 = sm[hb + t1b + k + 1];
-                c.x12 = c2 ? sm[hb + t1c + k + 1] : 0.0;
-                c.x22 = c2 ? sm[hb + t1c + k + 2] : 0.0;
-              }
+              double nbeta = refl_u<3, SAFE>(s0, s1, s2, nu0, ng, bad);
+              c.x00 = y00; c.x01 = y01; c.x02 = y02; c.x10 = y10; c.x11 = y11; c.x12 = y12; c.x22 = y22;
               c.u0 = nu0; c.u1 = s1; c.u2 = s2; c.g = ng; c.beta = nbeta;
-              // =============== slot factor p: its 3-reflector; bulk of H1(k) ===============
+              // =============== slot factor p: bulk of H1(k) ===============
+              __syncwarp();
               {
-                chain_A(c, s0, s1, s2, m01, m02, m11, m12, m21, m22);
-                nbeta = refl_u<3>(s0, s1, s2, nu0, ng);
-                __syncwarp();
                 const int hb = szh1 + (p - 2) * sj;
-                row_pass<1, false>(sm, hb, t1a, t1b, t1c, k, r, l, min(k + 2, i), c2, c.u0, c.u1, c.u2,
-                                   c.g, 0.0, 0.0, 0.0);
+                const int hn = hb - sj;  // factor p-1 at position k
+                const int o2 = c2 ? t1c : t1b;
+                y00 = sm[hn + t1a + k];
+                y01 = sm[hn + t1b + k];
+                y02 = sm[hn + o2 + k];
+                y11 = sm[hn + t1b + k + 1];
+                y12 = sm[hn + o2 + k + 1];
+                y22 = sm[hn + o2 + (c2 ? k + 2 : k + 1)];
+                y02 = c2 ? y02 : 0.0; y12 = c2 ? y12 : 0.0; y22 = c2 ? y22 : 0.0;
+                row_pass<1, false>(sm, hb, t1a, t1b, t1c, k, r, l, rm2, c2, c.u0, c.u1, c.u2, c.g, 0.0,
+                                   0.0, 0.0);
                 col_pass_h1(sm, oc1, k, r, i, l, c2, c.u0, c.u1, c.u2, c.g, c.beta);
-                __syncwarp();
-                // prefetch next link's block: factor p-1, or H1 rows k+1..k+3 when p == 2
-                if (p > 2) {
-                  const int hn = hb - sj;
-                  c.x00 = sm[hn + t1a + k];
-                  c.x01 = sm[hn + t1b + k];
-                  c.x02 = c2 ? sm[hn + t1c + k] : 0.0;
-                  c.x10 = 0.0;
-                  c.x11 = sm[hn + t1b + k + 1];
-                  c.x12 = c2 ? sm[hn + t1c + k + 1] : 0.0;
-                  c.x22 = c2 ? sm[hn + t1c + k + 2] : 0.0;
-                } else {
-                  const bool r3 = (k + 3 <= i);
-                  c.x00 = sm[t3a + k + 1];
-                  c.x01 = sm[t3b + k + 1];
-                  c.x02 = c2 ? sm[t3c + k + 1] : 0.0;
-                  c.x10 = c2 ? sm[t3a + k + 2] : 0.0;
-                  c.x11 = c2 ? sm[t3b + k + 2] : 0.0;
-                  c.x12 = c2 ? sm[t3c + k + 2] : 0.0;
-                  c.x22 = r3 ? sm[t3c + k + 3] : 0.0;
-                }
+                chain_A(c, s0, s1, s2, m01, m02, m11, m12, m21, m22);
+                nbeta = refl_u<3, SAFE>(s0, s1, s2, nu0, ng, bad);
+                c.x00 = y00; c.x01 = y01; c.x02 = y02; c.x10 = 0.0; c.x11 = y11; c.x12 = y12; c.x22 = y22;
                 c.c0 = 0.0; c.c1 = 0.0; c.h = 0.0;  // the H1 link has no 2-reflector
                 c.u0 = nu0; c.u1 = s1; c.u2 = s2; c.g = ng; c.beta = nbeta;
                 c.n01 = m01; c.n02 = m02; c.n11 = m11; c.n12 = m12; c.n21 = m21; c.n22 = m22;
@@ -477,36 +493,42 @@ __global__ void __launch_bounds__(256) rpqr_eig32_kernel(EigParams P) {
               // =============== slots factor p-1 .. 2 ===============
               for (int j = p - 1; j >= 2; j--) {
                 const int hb = szh1 + (j - 2) * sj;  // this link's matrix; previous link's is hb + sj
-                chain_A(c, s0, s1, s2, m01, m02, m11, m12, m21, m22);
-                double b0, b1, bh;
-                const double beta2 = chain_B(c, b0, b1, bh);
-                nbeta = refl_u<3>(s0, s1, s2, nu0, ng);
-                __syncwarp();
-                row_pass<1, true>(sm, hb, t1a, t1b, t1c, k, r, l, min(k + 2, i), c2, c.u0, c.u1, c.u2,
-                                  c.g, b0, b1, bh);
-                col_pass_tri(sm, hb + sj, ocj, k, r, i, c2, c.u0, c.u1, c.u2, c.g, c.beta, b0, b1, bh,
-                             beta2);
                 __syncwarp();
                 if (j > 2) {
                   const int hn = hb - sj;
-                  c.x00 = sm[hn + t1a + k];
-                  c.x01 = sm[hn + t1b + k];
-                  c.x02 = c2 ? sm[hn + t1c + k] : 0.0;
-                  c.x10 = 0.0;
-                  c.x11 = sm[hn + t1b + k + 1];
-                  c.x12 = c2 ? sm[hn + t1c + k + 1] : 0.0;
-                  c.x22 = c2 ? sm[hn + t1c + k + 2] : 0.0;
+                  const int o2 = c2 ? t1c : t1b;
+                  y00 = sm[hn + t1a + k];
+                  y01 = sm[hn + t1b + k];
+                  y02 = sm[hn + o2 + k];
+                  y10 = 0.0;
+                  y11 = sm[hn + t1b + k + 1];
+                  y12 = sm[hn + o2 + k + 1];
+                  y22 = sm[hn + o2 + (c2 ? k + 2 : k + 1)];
+                  y02 = c2 ? y02 : 0.0; y12 = c2 ? y12 : 0.0; y22 = c2 ? y22 : 0.0;
                 } else {
                   // next link is H1(k+1): rows k+1..k+3, columns k..k+2 of H1
                   const bool r3 = (k + 3 <= i);
-                  c.x00 = sm[t3a + k + 1];
-                  c.x01 = sm[t3b + k + 1];
-                  c.x02 = c2 ? sm[t3c + k + 1] : 0.0;
-                  c.x10 = c2 ? sm[t3a + k + 2] : 0.0;
-                  c.x11 = c2 ? sm[t3b + k + 2] : 0.0;
-                  c.x12 = c2 ? sm[t3c + k + 2] : 0.0;
-                  c.x22 = r3 ? sm[t3c + k + 3] : 0.0;
+                  const int o2 = c2 ? t3c : t3b;
+                  const int r2i = c2 ? k + 2 : k + 1;
+                  y00 = sm[t3a + k + 1];
+                  y01 = sm[t3b + k + 1];
+                  y02 = sm[o2 + k + 1];
+                  y10 = sm[t3a + r2i];
+                  y11 = sm[t3b + r2i];
+                  y12 = sm[o2 + r2i];
+                  y22 = sm[o2 + (r3 ? k + 3 : k + 1)];
+                  y02 = c2 ? y02 : 0.0; y10 = c2 ? y10 : 0.0; y11 = c2 ? y11 : 0.0;
+                  y12 = c2 ? y12 : 0.0; y22 = r3 ? y22 : 0.0;
                 }
+                double b0, b1, bh;
+                const double beta2 = chain_B<SAFE>(c, b0, b1, bh, bad);
+                row_pass<1, true>(sm, hb, t1a, t1b, t1c, k, r, l, rm2, c2, c.u0, c.u1, c.u2, c.g, b0, b1,
+                                  bh);
+                col_pass_tri(sm, hb + sj, ocj, k, r, i, c2, c.u0, c.u1, c.u2, c.g, c.beta, b0, b1, bh,
+                             beta2);
+                chain_A(c, s0, s1, s2, m01, m02, m11, m12, m21, m22);
+                nbeta = refl_u<3, SAFE>(s0, s1, s2, nu0, ng, bad);
+                c.x00 = y00; c.x01 = y01; c.x02 = y02; c.x10 = y10; c.x11 = y11; c.x12 = y12; c.x22 = y22;
                 c.c0 = b0; c.c1 = b1; c.h = bh;
                 c.u0 = nu0; c.u1 = s1; c.u2 = s2; c.g = ng; c.beta = nbeta;
                 c.n01 = m01; c.n02 = m02; c.n11 = m11; c.n12 = m12; c.n21 = m21; c.n22 = m22;
@@ -518,9 +540,9 @@ __global__ void __launch_bounds__(256) rpqr_eig32_kernel(EigParams P) {
             }
             // flush: B part and bulk of factor 2 at the last step k = i-1
             {
-              double b0, b1, bh;
-              const double beta2 = chain_B(c, b0, b1, bh);
               __syncwarp();
+              double b0, b1, bh;
+              const double beta2 = chain_B<SAFE>(c, b0, b1, bh, bad);
               row_pass<3, true>(sm, 0, p3a, p3b, p3c, i - 1, r, l, i, false, c.u0, c.u1, c.u2, c.g, b0,
                                 b1, bh);
               col_pass_tri(sm, szh1, ocj, i - 1, r, i, false, c.u0, c.u1, c.u2, c.g, c.beta, b0, b1, bh,
@@ -528,6 +550,7 @@ __global__ void __launch_bounds__(256) rpqr_eig32_kernel(EigParams P) {
             }
           }
           __syncwarp();
+          if (!SAFE && bad) return kNeedSafe;
           its++;
         }  // QR iterations
 
@@ -560,8 +583,39 @@ __global__ void __launch_bounds__(256) rpqr_eig32_kernel(EigParams P) {
         i = l - 1;
       }
     }
-    if (r < n) {
-      double* eg = P.eig + ((size_t)b * n + r) * 2;
+    lre_out = lre;
+    lim_out = lim;
+    niter_out = niter;
+    return info;
+}
+
+extern __shared__ __align__(16) double psd_smem_eig[];
+
+__global__ void __launch_bounds__(256) rpqr_eig32_kernel(EigParams P) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n = P.n, p = P.p;
+  const int psize = pk_problem_size(n, p);
+  double* sm = psd_smem_eig + (size_t)warp * psize;  // H1 at 0, factor j at szh1 + (j-2)*sj
+  for (;;) {
+    long long b = 0;
+    if (lane == 0) b = (long long)atomicAdd(P.counter, 1ULL);
+    b = __shfl_sync(0xffffffffu, b, 0);
+    if (b >= P.batch) break;
+    const double* src = P.packed + (size_t)b * psize;
+    for (int e = lane; e < psize; e += 32) sm[e] = src[e];
+    __syncwarp();
+    double lre, lim;
+    int niter;
+    int info = rpqr_problem<false>(sm, n, p, P.maxitfac, lane, lre, lim, niter);
+    if (info == kNeedSafe) {
+      // badly scaled problem: start over with the exactly-rescaling reflector
+      __syncwarp();
+      for (int e = lane; e < psize; e += 32) sm[e] = src[e];
+      __syncwarp();
+      info = rpqr_problem<true>(sm, n, p, P.maxitfac, lane, lre, lim, niter);
+    }
+    if (lane < n) {
+      double* eg = P.eig + ((size_t)b * n + lane) * 2;
       eg[0] = lre;
       eg[1] = lim;
     }

@@ -45,42 +45,68 @@ PSD_DEV void hess32_step(double* Aj, double* Am, int n, int ld, int r0, int col,
     nn = fma(alpha * sc, alpha * sc, ssq);
   }
   const double al = alpha * sc;
-  const double nrm = sqrt(nn);
+  const double nrm = nn * fast_rsqrt(nn);
   const double betas = -copysign(nrm, al);
   const double u0s = al - betas;
   // H = I + g u u^T with u = (u0s, sc*x[r0+1..]) ; fold sc into the coefficients
-  const double gs = -2.0 / fma(u0s, u0s, ssq);
-  const double g = gs * sc * sc;      // for u = (u0, x) with u0 = u0s/sc
-  const double u0 = u0s / sc;
-  const double beta = betas / sc;
-  // left: columns col+1..n-1 of Aj (lane = column)
+  const double gs = -2.0 * fast_rcp(fma(u0s, u0s, ssq));
+  double g = gs, u0 = u0s, beta = betas;
+  if (sc != 1.0) {  // for u = (u0, x) with u0 = u0s/sc
+    g = gs * sc * sc;
+    u0 = u0s / sc;
+    beta = betas / sc;
+  }
+  // left: columns col+1..n-1 of Aj (lane = column).  Loops are unrolled by 4 with independent
+  // accumulators and predicated loads so that the shared-memory loads pipeline.
   if (lane > col && lane < n) {
     double* a = Aj + lane * ld;
-    double d0 = u0 * a[r0], d1 = 0.0;
-    int k = r0 + 1;
-    for (; k + 1 < n; k += 2) {
-      d0 = fma(xc[k], a[k], d0);
-      d1 = fma(xc[k + 1], a[k + 1], d1);
+    double d0 = u0 * a[r0], d1 = 0.0, d2 = 0.0, d3 = 0.0;
+#pragma unroll 2
+    for (int k = r0 + 1; k < n; k += 4) {
+      const bool p1 = k + 1 < n, p2 = k + 2 < n, p3 = k + 3 < n;
+      const double x0 = xc[k], x1 = p1 ? xc[k + 1] : 0.0, x2 = p2 ? xc[k + 2] : 0.0, x3 = p3 ? xc[k + 3] : 0.0;
+      const double a0 = a[k], a1 = p1 ? a[k + 1] : 0.0, a2 = p2 ? a[k + 2] : 0.0, a3 = p3 ? a[k + 3] : 0.0;
+      d0 = fma(x0, a0, d0); d1 = fma(x1, a1, d1); d2 = fma(x2, a2, d2); d3 = fma(x3, a3, d3);
     }
-    if (k < n) d0 = fma(xc[k], a[k], d0);
-    const double s = g * (d0 + d1);
+    const double s = g * ((d0 + d1) + (d2 + d3));
     a[r0] = fma(s, u0, a[r0]);
-    for (k = r0 + 1; k < n; k++) a[k] = fma(s, xc[k], a[k]);
+#pragma unroll 2
+    for (int k = r0 + 1; k < n; k += 4) {
+      const bool p1 = k + 1 < n, p2 = k + 2 < n, p3 = k + 3 < n;
+      const double x0 = xc[k], x1 = p1 ? xc[k + 1] : 0.0, x2 = p2 ? xc[k + 2] : 0.0, x3 = p3 ? xc[k + 3] : 0.0;
+      const double a0 = a[k], a1 = p1 ? a[k + 1] : 0.0, a2 = p2 ? a[k + 2] : 0.0, a3 = p3 ? a[k + 3] : 0.0;
+      a[k] = fma(s, x0, a0);
+      if (p1) a[k + 1] = fma(s, x1, a1);
+      if (p2) a[k + 2] = fma(s, x2, a2);
+      if (p3) a[k + 3] = fma(s, x3, a3);
+    }
   }
   if (Am == Aj) __syncwarp();
   // right: rows 0..n-1 of Am (lane = row), columns r0..n-1
   if (lane < n) {
     double* a = Am + lane;
-    double d0 = a[r0 * ld] * u0, d1 = 0.0;
-    int k = r0 + 1;
-    for (; k + 1 < n; k += 2) {
-      d0 = fma(a[k * ld], xc[k], d0);
-      d1 = fma(a[(k + 1) * ld], xc[k + 1], d1);
+    double d0 = a[r0 * ld] * u0, d1 = 0.0, d2 = 0.0, d3 = 0.0;
+#pragma unroll 2
+    for (int k = r0 + 1; k < n; k += 4) {
+      const bool p1 = k + 1 < n, p2 = k + 2 < n, p3 = k + 3 < n;
+      const double x0 = xc[k], x1 = p1 ? xc[k + 1] : 0.0, x2 = p2 ? xc[k + 2] : 0.0, x3 = p3 ? xc[k + 3] : 0.0;
+      const double a0 = a[k * ld], a1 = p1 ? a[(k + 1) * ld] : 0.0, a2 = p2 ? a[(k + 2) * ld] : 0.0,
+                   a3 = p3 ? a[(k + 3) * ld] : 0.0;
+      d0 = fma(a0, x0, d0); d1 = fma(a1, x1, d1); d2 = fma(a2, x2, d2); d3 = fma(a3, x3, d3);
     }
-    if (k < n) d0 = fma(a[k * ld], xc[k], d0);
-    const double s = g * (d0 + d1);
+    const double s = g * ((d0 + d1) + (d2 + d3));
     a[r0 * ld] = fma(s, u0, a[r0 * ld]);
-    for (k = r0 + 1; k < n; k++) a[k * ld] = fma(s, xc[k], a[k * ld]);
+#pragma unroll 2
+    for (int k = r0 + 1; k < n; k += 4) {
+      const bool p1 = k + 1 < n, p2 = k + 2 < n, p3 = k + 3 < n;
+      const double x0 = xc[k], x1 = p1 ? xc[k + 1] : 0.0, x2 = p2 ? xc[k + 2] : 0.0, x3 = p3 ? xc[k + 3] : 0.0;
+      const double a0 = a[k * ld], a1 = p1 ? a[(k + 1) * ld] : 0.0, a2 = p2 ? a[(k + 2) * ld] : 0.0,
+                   a3 = p3 ? a[(k + 3) * ld] : 0.0;
+      a[k * ld] = fma(s, x0, a0);
+      if (p1) a[(k + 1) * ld] = fma(s, x1, a1);
+      if (p2) a[(k + 2) * ld] = fma(s, x2, a2);
+      if (p3) a[(k + 3) * ld] = fma(s, x3, a3);
+    }
   }
   __syncwarp();
   if (lane == r0) xc[lane] = beta;
