@@ -198,6 +198,8 @@ def run_ours(args):
         for _ in range(args.warmup):
             step_dev()
     barrier()
+    h.set_profiling(True)   # CUDA events around every kernel launch, on the launching stream
+    h.kernel_times()        # drop anything recorded so far
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -212,6 +214,8 @@ def run_ours(args):
             evs.append((e0, e1))
     barrier()
     clocks = sampler.stop() if rank == 0 else None
+    kt = h.kernel_times()
+    h.set_profiling(False)
     kernel_ms = [a.elapsed_time(b) for a, b in evs]
     total_ms = evs[0][0].elapsed_time(evs[-1][1])
     total_ms = max_over_ranks(total_ms)
@@ -242,8 +246,14 @@ def run_ours(args):
         return 0
 
     peak, peak_kind = _peaks()
-    k_ms = sum(kernel_ms) / len(kernel_ms)
-    achieved = BYTES_PER_PROBLEM * B / (k_ms * 1e-3) / 1e9
+    step_ms = sum(kernel_ms) / len(kernel_ms)
+    # dominant kernel: the eigenvalue-only periodic QR iteration (psd::rpqr_eig32_kernel); its
+    # launches each process min(B, 65536) problems.  achieved = SURVEY.md §8(d) bytes per
+    # problem x problems per launch / average launch duration (CUDA events on its stream).
+    n_it = max(1, kt["iterate_launches"])
+    k_ms = kt["iterate_ms"] / n_it
+    units_per_launch = B * args.steps / n_it
+    achieved = BYTES_PER_PROBLEM * units_per_launch / (k_ms * 1e-3) / 1e9
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
@@ -264,11 +274,16 @@ def run_ours(args):
         "e2e": {"value": e2e_value, "unit": "problems/s", "h2d_bytes_per_step": st["h2d_bytes"],
                 "d2h_bytes_per_step": st["d2h_bytes"], "steps": e2e_steps,
                 "matches_device_path": same},
-        "gpu_launches": args.steps,
+        "gpu_launches": kt["iterate_launches"] + kt["reduce_launches"],
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "peak_kind": f"of {peak_kind}",
-                     "kernel": "psd::rpschur_kernel", "kernel_ms": k_ms,
-                     "fp64_gflops_standard_count": FLOPS_PER_PROBLEM * B / (k_ms * 1e-3) / 1e9,
+                     "kernel": "psd::rpqr_eig32_kernel", "kernel_ms": k_ms,
+                     "problems_per_launch": units_per_launch,
+                     "kernel_share_of_step": kt["iterate_ms"] / (kt["iterate_ms"] + kt["reduce_ms"]),
+                     "reduce_kernel": "psd::rphess_warp32_kernel",
+                     "reduce_kernel_ms": kt["reduce_ms"] / max(1, kt["reduce_launches"]),
+                     "step_ms_device": step_ms,
+                     "fp64_gflops_standard_count": FLOPS_PER_PROBLEM * B / (step_ms * 1e-3) / 1e9,
                      "note": "latency-bound serial bulge-chase chain per problem; see DESIGN.md"},
         "clocks": clocks,
         "unconverged": fails,

@@ -131,6 +131,14 @@ int psd_fill_uniform_dev(void* stream, uint64_t seed, int n, int p, int64_t batc
  * stats[4] = D2H bytes, stats[5] = kernel time in microseconds summed over devices. */
 int psd_last_stats(psd_handle_t handle, int64_t stats[8]);
 
+/* Measurement support: with profiling on, every kernel the library launches
+ * is bracketed by CUDA events on its own stream.  psd_kernel_times waits for the recorded
+ * events and returns, accumulated since the previous call, ms[0] = reduction kernels,
+ * ms[1] = QR/QZ iteration kernels (milliseconds of device time), ms[2], ms[3] = how many
+ * launches of each kind were timed. */
+int psd_set_profiling(psd_handle_t handle, int on);
+int psd_kernel_times(psd_handle_t handle, double ms[4]);
+
 #ifdef __cplusplus
 }
 #endif

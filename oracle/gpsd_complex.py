@@ -1,0 +1,541 @@
+"""ORACLE — TEST INFRASTRUCTURE ONLY (see gpsd_common.py header).
+
+numpy restatement of the complex (generalized) periodic Schur path of the reference:
+  pschur!(A, S, lr; wantZ, wantT)         src/generalized.jl:108-148   -> cpschur
+  pschur!(H1, Hs, S; ...) (MB03BZ-style)  src/generalized.jl:166-931   -> cpqz
+  complex standard wrapper                 src/PeriodicSchurDecompositions.jl:1106-1111
+Matrices are numpy complex128 arrays in math orientation; indices in the code are the
+reference's 1-based ones (helpers in gpsd_common.py translate).
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+
+from .gpsd_common import (EPS, FLOATMIN, exceptional_fg, givens, gphessenberg, lmul_g, opnorm1,
+                          phessenberg_householder, rmul_gadj, safeprod)
+
+
+class ConvergenceError(RuntimeError):
+    pass
+
+
+def cpqz(H1, Hs, S, wantZ=True, wantT=True, Q=None, maxitfac=30, rev=False):
+    """generalized.jl:166-931.  H1 upper Hessenberg, Hs list of p-1 upper triangular (all
+    modified in place), S signature with S[0] True.  Returns dict(S, schurindex, T1, T, Z,
+    alpha, beta, alphascale, orientation, info)."""
+    p = len(Hs) + 1
+    n = H1.shape[0]
+    if not S[0]:
+        raise ValueError("Signature entry S[1] must be true")
+    alpha = np.zeros(n, dtype=np.complex128)
+    beta = np.zeros(n, dtype=np.complex128)
+    ascale = np.zeros(n, dtype=np.int64)
+    safmin = FLOATMIN
+    ulp = EPS
+    smlnum = FLOATMIN * (n / ulp)
+    H1[...] = np.triu(H1, -1)  # _gethess! (:195)
+
+    def Hm(l):
+        return H1 if l == 1 else Hs[l - 2]
+
+    ziter = -1 if (p >= math.log2(FLOATMIN) / math.log2(ulp)) else 0
+    if wantZ:
+        Z = [np.eye(n, dtype=np.complex128) for _ in range(p)] if Q is None else Q
+    else:
+        Z = []
+    G = [None] * (n + 2)
+    ilast = n
+    ifirst = -1
+    ifirstm = 1
+    ilastm = n
+    iiter = 1
+    maxit = maxitfac * n
+    nexc = 0
+
+    def check_deflate_hess(ilo, ilast):  # :260-278
+        jlo = ilo
+        for j in range(ilast, ilo, -1):
+            tol = abs(H1[j - 2, j - 2]) + abs(H1[j - 1, j - 1])
+            if tol == 0:
+                tol = opnorm1(H1, ilo, j, ilo, j)
+            tol = max(ulp * tol, smlnum)
+            if abs(H1[j - 1, j - 2]) <= tol:
+                H1[j - 1, j - 2] = 0
+                jlo = j
+                if j == ilast:
+                    return True, jlo
+                break
+        return False, jlo
+
+    def check_deflate_tr(Hl, jlo, ilast):  # :280-299
+        for j in range(ilast, jlo - 1, -1):
+            if j == ilast:
+                tol = abs(Hl[j - 2, j - 1])
+            elif j == jlo:
+                tol = abs(Hl[j - 1, j])
+            else:
+                tol = abs(Hl[j - 2, j - 1]) + abs(Hl[j - 1, j])
+            if tol == 0:
+                tol = opnorm1(Hl, jlo, j, jlo, j, upper=True)
+            tol = max(ulp * tol, smlnum)
+            if abs(Hl[j - 1, j - 1]) <= tol:
+                Hl[j - 1, j - 1] = 0
+                return True, j
+        return False, 0
+
+    done = False
+    info = 0
+    for jiter in range(1, maxit + 1):
+        split1block = False
+        ldeflate = -1
+        jdeflate = -1
+        deflate_pos = False
+        deflate_neg = False
+        doqziter = True
+        jlo = 1
+        while True:  # "for itmp in 1:1" block (:313-449)
+            if ilast == 1:
+                split1block = True
+                break
+            split1block, jlo = check_deflate_hess(1, ilast)
+            if split1block:
+                break
+            for l in range(2, p + 1):  # Test 2 (:327-339)
+                if S[l - 1]:
+                    deflate_pos, jx = check_deflate_tr(Hm(l), jlo, ilast)
+                    if deflate_pos:
+                        ldeflate, jdeflate = l, jx
+                        break
+            # NOTE the reference runs Test 3 even when Test 2 fired and lets it overwrite
+            # ldeflate/jdeflate (:341-353); the if/elseif below then still takes the S+ branch
+            # with the S- indices only if deflate_neg is also set.  Restated literally.
+            deflate_neg = False
+            for l in range(2, p + 1):  # Test 3
+                if not S[l - 1]:
+                    deflate_neg, jx = check_deflate_tr(Hm(l), jlo, ilast)
+                    if deflate_neg:
+                        ldeflate, jdeflate = l, jx
+                        break
+            if ziter >= 7 or ziter < 0:  # Test 4: controlled zero shift (:356-448)
+                for j in range(jlo, ilast):
+                    c, s, r = givens(H1[j - 1, j - 1], H1[j, j - 1])
+                    H1[j - 1, j - 1] = r
+                    H1[j, j - 1] = 0
+                    lmul_g(H1, j, j + 1, c, s, j + 1, ilastm)
+                    G[j] = (c, s)
+                if wantZ:
+                    for j in range(jlo, ilast):
+                        rmul_gadj(Z[0], j, j + 1, G[j][0], G[j][1], 1, n)
+                for l in range(p, 1, -1):
+                    Hl = Hm(l)
+                    if S[l - 1]:
+                        for j in range(jlo, ilast):
+                            c, s = G[j]
+                            if s != 0:
+                                rmul_gadj(Hl, j, j + 1, c, s, ifirstm, j + 1)
+                                tol = abs(Hl[j - 1, j - 1]) + abs(Hl[j, j])
+                                if tol == 0:
+                                    tol = opnorm1(Hl, jlo, j + 1, jlo, j + 1)
+                                tol = max(ulp * tol, smlnum)
+                                if abs(Hl[j, j - 1]) <= tol:
+                                    Hl[j, j - 1] = 0
+                                    G[j] = (1.0, 0j)
+                                else:
+                                    c, s, r = givens(Hl[j - 1, j - 1], Hl[j, j - 1])
+                                    Hl[j - 1, j - 1] = r
+                                    Hl[j, j - 1] = 0
+                                    lmul_g(Hl, j, j + 1, c, s, j + 1, ilastm)
+                                    G[j] = (c, s)
+                    else:
+                        for j in range(jlo, ilast):
+                            c, s = G[j]
+                            if s != 0:
+                                lmul_g(Hl, j, j + 1, c, s, j, ilastm)
+                                tol = abs(Hl[j - 1, j - 1]) + abs(Hl[j, j])
+                                if tol == 0:
+                                    tol = opnorm1(Hl, jlo, j + 1, jlo, j + 1)
+                                tol = max(ulp * tol, smlnum)
+                                if abs(Hl[j, j - 1]) <= tol:
+                                    Hl[j, j - 1] = 0
+                                    G[j] = (1.0, 0j)
+                                else:
+                                    c, s, r = givens(Hl[j, j], Hl[j, j - 1])
+                                    Hl[j, j] = r
+                                    Hl[j, j - 1] = 0
+                                    rmul_gadj(Hl, j + 1, j, c, np.conj(s), ifirstm, j)
+                                    G[j] = (c, -s)
+                    if wantZ:
+                        for j in range(jlo, ilast):
+                            rmul_gadj(Z[l - 1], j, j + 1, G[j][0], G[j][1], 1, n)
+                ziter = 0
+                for j in range(jlo, ilast):
+                    c, s = G[j]
+                    rmul_gadj(H1, j, j + 1, c, s, ifirstm, j + 1)
+                    if s == 0:
+                        ziter = 1
+                doqziter = False
+                break
+            break
+
+        if deflate_pos:  # Case II (:453-566)
+            for j in range(jlo, jdeflate):
+                c, s, r = givens(H1[j - 1, j - 1], H1[j, j - 1])
+                H1[j - 1, j - 1] = r
+                H1[j, j - 1] = 0
+                lmul_g(H1, j, j + 1, c, s, j + 1, ilastm)
+                G[j] = (c, s)
+            if wantZ:
+                for j in range(jlo, jdeflate):
+                    rmul_gadj(Z[0], j, j + 1, G[j][0], G[j][1], 1, n)
+            for l in range(p, 1, -1):
+                ntra = (jdeflate - 2) if l < ldeflate else (jdeflate - 1)
+                Hl = Hm(l)
+                if S[l - 1]:
+                    for j in range(jlo, ntra + 1):
+                        c, s = G[j]
+                        rmul_gadj(Hl, j, j + 1, c, s, ifirstm, j + 1)
+                        c, s, r = givens(Hl[j - 1, j - 1], Hl[j, j - 1])
+                        Hl[j - 1, j - 1] = r
+                        Hl[j, j - 1] = 0
+                        lmul_g(Hl, j, j + 1, c, s, j + 1, ilastm)
+                        G[j] = (c, s)
+                else:
+                    for j in range(jlo, ntra + 1):
+                        c, s = G[j]
+                        lmul_g(Hl, j, j + 1, c, s, j, ilastm)
+                        c, s, r = givens(Hl[j, j], Hl[j, j - 1])
+                        Hl[j, j] = r
+                        Hl[j, j - 1] = 0
+                        rmul_gadj(Hl, j + 1, j, c, np.conj(s), ifirstm, j)
+                        G[j] = (c, -s)
+                if wantZ:
+                    for j in range(jlo, ntra + 1):
+                        rmul_gadj(Z[l - 1], j, j + 1, G[j][0], G[j][1], 1, n)
+            for j in range(jlo, jdeflate - 1):
+                rmul_gadj(H1, j, j + 1, G[j][0], G[j][1], ifirstm, j + 1)
+            # second unshifted step, from the bottom (:512-564)
+            for j in range(ilast, jdeflate, -1):
+                c, s, r = givens(H1[j - 1, j - 1], H1[j - 1, j - 2])
+                H1[j - 1, j - 1] = r
+                H1[j - 1, j - 2] = 0
+                rmul_gadj(H1, j, j - 1, c, np.conj(s), ifirstm, j - 1)
+                G[j] = (c, -s)
+            if wantZ:
+                for j in range(ilast, jdeflate, -1):
+                    rmul_gadj(Z[1 % p], j - 1, j, G[j][0], G[j][1], 1, n)
+            for l in range(2, p + 1):
+                ntra = (jdeflate + 2) if l > ldeflate else (jdeflate + 1)
+                Hl = Hm(l)
+                if not S[l - 1]:
+                    for j in range(ilast, ntra - 1, -1):
+                        c, s = G[j]
+                        rmul_gadj(Hl, j - 1, j, c, s, ifirstm, j)
+                        c, s, r = givens(Hl[j - 2, j - 2], Hl[j - 1, j - 2])
+                        Hl[j - 2, j - 2] = r
+                        Hl[j - 1, j - 2] = 0
+                        lmul_g(Hl, j - 1, j, c, s, j, ilastm)
+                        G[j] = (c, s)
+                else:
+                    for j in range(ilast, ntra - 1, -1):
+                        c, s = G[j]
+                        lmul_g(Hl, j - 1, j, c, s, j - 1, ilastm)
+                        c, s, r = givens(Hl[j - 1, j - 1], Hl[j - 1, j - 2])
+                        Hl[j - 1, j - 1] = r
+                        Hl[j - 1, j - 2] = 0
+                        rmul_gadj(Hl, j, j - 1, c, np.conj(s), ifirstm, j - 1)
+                        G[j] = (c, -s)
+                if wantZ:
+                    ln = (l % p) + 1
+                    for j in range(ilast, ntra - 1, -1):
+                        rmul_gadj(Z[ln - 1], j - 1, j, G[j][0], G[j][1], 1, n)
+            for j in range(ilast, jdeflate + 1, -1):
+                lmul_g(H1, j - 1, j, G[j][0], G[j][1], j - 1, ilastm)
+            doqziter = False
+        elif deflate_neg:  # Case III (:568-740)
+            Hd = Hm(ldeflate)
+            if jdeflate > (ilast - jlo + 1) / 2:  # bottom half: chase the zero down
+                for j1 in range(jdeflate, ilast):
+                    j = j1
+                    c, s, r = givens(Hd[j - 1, j], Hd[j, j])
+                    Hd[j - 1, j] = r
+                    Hd[j, j] = 0
+                    lmul_g(Hd, j, j + 1, c, s, j + 2, ilastm)
+                    ln = (ldeflate % p) + 1
+                    if wantZ:
+                        rmul_gadj(Z[ln - 1], j, j + 1, c, s, 1, n)
+                    gi, gj = j, j + 1
+                    for l in range(1, p):
+                        if ln == 1:
+                            lmul_g(H1, gi, gj, c, s, j - 1, ilastm)
+                            c, s, r = givens(H1[j, j - 1], H1[j, j - 2])
+                            H1[j, j - 1] = r
+                            H1[j, j - 2] = 0
+                            rmul_gadj(H1, j, j - 1, c, np.conj(s), ifirstm, j)
+                            s = -s
+                            gi, gj = j - 1, j
+                            j -= 1
+                        elif S[ln - 1]:
+                            Hln = Hm(ln)
+                            lmul_g(Hln, gi, gj, c, s, j, ilastm)
+                            c, s, r = givens(Hln[j, j], Hln[j, j - 1])
+                            Hln[j, j] = r
+                            Hln[j, j - 1] = 0
+                            rmul_gadj(Hln, j + 1, j, c, np.conj(s), ifirstm, j)
+                            s = -s
+                            gi, gj = j, j + 1
+                        else:
+                            Hln = Hm(ln)
+                            rmul_gadj(Hln, gi, gj, c, s, ifirstm, j + 1)
+                            c, s, r = givens(Hln[j - 1, j - 1], Hln[j, j - 1])
+                            Hln[j - 1, j - 1] = r
+                            Hln[j, j - 1] = 0
+                            lmul_g(Hln, j, j + 1, c, s, j + 1, ilastm)
+                            gi, gj = j, j + 1
+                        ln = (ln % p) + 1
+                        if wantZ:
+                            rmul_gadj(Z[ln - 1], gi, gj, c, s, 1, n)
+                    rmul_gadj(Hd, gi, gj, c, s, ifirstm, j)
+                # deflate last element in Hessenberg (:620-655)
+                j = ilast
+                c, s, r = givens(H1[j - 1, j - 1], H1[j - 1, j - 2])
+                H1[j - 1, j - 1] = r
+                H1[j - 1, j - 2] = 0
+                rmul_gadj(H1, j, j - 1, c, np.conj(s), ifirstm, j - 1)
+                s = -s
+                if wantZ:
+                    rmul_gadj(Z[1 % p], j - 1, j, c, s, 1, n)
+                for l in range(2, ldeflate):
+                    Hl = Hm(l)
+                    if not S[l - 1]:
+                        rmul_gadj(Hl, j - 1, j, c, s, ifirstm, j)
+                        c, s, r = givens(Hl[j - 2, j - 2], Hl[j - 1, j - 2])
+                        Hl[j - 2, j - 2] = r
+                        Hl[j - 1, j - 2] = 0
+                        lmul_g(Hl, j - 1, j, c, s, j, ilastm)
+                    else:
+                        lmul_g(Hl, j - 1, j, c, s, j - 1, ilastm)
+                        c, s, r = givens(Hl[j - 1, j - 1], Hl[j - 1, j - 2])
+                        Hl[j - 1, j - 1] = r
+                        Hl[j - 1, j - 2] = 0
+                        rmul_gadj(Hl, j, j - 1, c, np.conj(s), ifirstm, j - 1)
+                        s = -s
+                    if wantZ:
+                        ln = (l % p) + 1
+                        rmul_gadj(Z[ln - 1], j - 1, j, c, s, 1, n)
+                rmul_gadj(Hd, j - 1, j, c, s, ifirstm, j)
+            else:  # top half: chase the zero up (:656-739)
+                for j1 in range(jdeflate, jlo, -1):
+                    j = j1
+                    c, s, r = givens(Hd[j - 2, j - 1], Hd[j - 2, j - 2])
+                    Hd[j - 2, j - 1] = r
+                    Hd[j - 2, j - 2] = 0
+                    rmul_gadj(Hd, j, j - 1, c, np.conj(s), ifirstm, j - 2)
+                    s = -s
+                    if wantZ:
+                        rmul_gadj(Z[ldeflate - 1], j - 1, j, c, s, 1, n)
+                    gi, gj = j - 1, j
+                    ln = ldeflate - 1
+                    for l in range(1, p):
+                        Hln = Hm(ln)
+                        if ln == 1:
+                            rmul_gadj(Hln, gi, gj, c, s, ifirstm, j + 1)
+                            c, s, r = givens(Hln[j - 1, j - 2], Hln[j, j - 2])
+                            Hln[j - 1, j - 2] = r
+                            Hln[j, j - 2] = 0
+                            lmul_g(Hln, j, j + 1, c, s, j, ilastm)
+                            gi, gj = j, j + 1
+                            j += 1
+                        elif not S[ln - 1]:
+                            lmul_g(Hln, gi, gj, c, s, j - 1, ilastm)
+                            c, s, r = givens(Hln[j - 1, j - 1], Hln[j - 1, j - 2])
+                            Hln[j - 1, j - 1] = r
+                            Hln[j - 1, j - 2] = 0
+                            rmul_gadj(Hln, j, j - 1, c, np.conj(s), ifirstm, j - 1)
+                            s = -s
+                            gi, gj = j - 1, j
+                        else:
+                            rmul_gadj(Hln, gi, gj, c, s, ifirstm, j)
+                            c, s, r = givens(Hln[j - 2, j - 2], Hln[j - 1, j - 2])
+                            Hln[j - 2, j - 2] = r
+                            Hln[j - 1, j - 2] = 0
+                            lmul_g(Hln, j - 1, j, c, s, j, ilastm)
+                            gi, gj = j - 1, j
+                        if wantZ:
+                            rmul_gadj(Z[ln - 1], gi, gj, c, s, 1, n)
+                        ln = p if ln == 1 else ln - 1
+                    lmul_g(Hd, gi, gj, c, s, j, ilastm)
+                # deflate the first element in Hessenberg (:705-738)
+                j = jlo
+                c, s, r = givens(H1[j - 1, j - 1], H1[j, j - 1])
+                H1[j - 1, j - 1] = r
+                H1[j, j - 1] = 0
+                lmul_g(H1, j, j + 1, c, s, j + 1, ilastm)
+                if wantZ:
+                    rmul_gadj(Z[0], j, j + 1, c, s, 1, n)
+                for l in range(p, ldeflate, -1):
+                    Hl = Hm(l)
+                    if S[l - 1]:
+                        rmul_gadj(Hl, j, j + 1, c, s, ifirstm, j + 1)
+                        c, s, r = givens(Hl[j - 1, j - 1], Hl[j, j - 1])
+                        Hl[j - 1, j - 1] = r
+                        Hl[j, j - 1] = 0
+                        lmul_g(Hl, j, j + 1, c, s, j + 1, ilastm)
+                    else:
+                        lmul_g(Hl, j, j + 1, c, s, j, ilastm)
+                        c, s, r = givens(Hl[j, j], Hl[j, j - 1])
+                        Hl[j, j] = r
+                        Hl[j, j - 1] = 0
+                        rmul_gadj(Hl, j + 1, j, c, np.conj(s), ifirstm, j)
+                        s = -s
+                    if wantZ:
+                        rmul_gadj(Z[l - 1], j, j + 1, c, s, 1, n)
+                lmul_g(Hd, j, j + 1, c, s, j + 1, ilastm)
+            doqziter = False
+        elif split1block:  # (:741-762)
+            v4 = [Hs[l][ilast - 1, ilast - 1] for l in range(p - 1)]
+            a, b, sc = safeprod(S, H1[ilast - 1, ilast - 1], v4)
+            alpha[ilast - 1], beta[ilast - 1], ascale[ilast - 1] = a, b, sc
+            ilast -= 1
+            if ilast < 1:
+                done = True
+                break
+            iiter = 0
+            if ziter != -1:
+                ziter = 0
+            if not wantT:
+                ilastm = ilast
+                if ifirstm > ilast:
+                    ifirstm = 1
+            doqziter = False
+        else:
+            ifirst = jlo
+
+        if doqziter:  # (:770-854)
+            iiter += 1
+            ziter += 1
+            if not wantT:
+                ifirstm = ifirst
+            if iiter % 10 == 0:
+                nexc += 1
+                f, g = exceptional_fg(nexc)
+                c, s, _ = givens(f, g)
+            else:
+                c, s, _ = givens(1.0 + 0j, 1.0 + 0j)
+                for l in range(p, 1, -1):
+                    Hl = Hm(l)
+                    if S[l - 1]:
+                        c, s, _ = givens(Hl[ifirst - 1, ifirst - 1] * c,
+                                         Hl[ilast - 1, ilast - 1] * np.conj(s))
+                    else:
+                        c, s, _ = givens(Hl[ilast - 1, ilast - 1] * c,
+                                         -Hl[ifirst - 1, ifirst - 1] * np.conj(s))
+                        s = -s
+                c, s, _ = givens(H1[ifirst - 1, ifirst - 1] * c - H1[ilast - 1, ilast - 1] * np.conj(s),
+                                 H1[ifirst, ifirst - 1] * c)
+            for j1 in range(ifirst - 1, ilast - 1):
+                j = j1 + 1
+                if j1 >= ifirst:
+                    c, s, r = givens(H1[j - 1, j - 2], H1[j, j - 2])
+                    H1[j - 1, j - 2] = r
+                    H1[j, j - 2] = 0
+                lmul_g(H1, j, j + 1, c, s, j, ilastm)
+                if wantZ:
+                    rmul_gadj(Z[0], j, j + 1, c, s, 1, n)
+                for l in range(p, 1, -1):
+                    Hl = Hm(l)
+                    if S[l - 1]:
+                        rmul_gadj(Hl, j, j + 1, c, s, ifirstm, j + 1)
+                        c, s, r = givens(Hl[j - 1, j - 1], Hl[j, j - 1])
+                        Hl[j - 1, j - 1] = r
+                        Hl[j, j - 1] = 0
+                        lmul_g(Hl, j, j + 1, c, s, j + 1, ilastm)
+                    else:
+                        lmul_g(Hl, j, j + 1, c, s, j, ilastm)
+                        c, s, r = givens(Hl[j, j], Hl[j, j - 1])
+                        Hl[j, j] = r
+                        Hl[j, j - 1] = 0
+                        rmul_gadj(Hl, j + 1, j, c, np.conj(s), ifirstm, j)
+                        s = -s
+                    if wantZ:
+                        rmul_gadj(Z[l - 1], j, j + 1, c, s, 1, n)
+                itmp = min(j + 2, ilastm)
+                rmul_gadj(H1, j, j + 1, c, s, ifirstm, itmp)
+    if not done:
+        info = ilast  # "convergence failed at level ilast" (:856-858)
+
+    if wantT and info == 0:  # phase normalisation (:860-908)
+        for l in range(p, 1, -1):
+            Hl = Hm(l)
+            sf = np.ones(n, dtype=np.complex128)
+            if S[l - 1]:
+                for j in range(1, n + 1):
+                    abst = abs(Hl[j - 1, j - 1])
+                    if abst > safmin:
+                        z = np.conj(Hl[j - 1, j - 1] / abst)
+                        Hl[j - 1, j - 1] = abst
+                        if j < n:
+                            Hl[j - 1, j:] *= z
+                    else:
+                        z = 1.0 + 0j
+                    sf[j - 1] = z
+            else:
+                for j in range(1, n + 1):
+                    abst = abs(Hl[j - 1, j - 1])
+                    if abst > safmin:
+                        z = np.conj(Hl[j - 1, j - 1] / abst)
+                        Hl[j - 1, j - 1] = abst
+                        Hl[:j - 1, j - 1] *= z
+                    else:
+                        z = 1.0 + 0j
+                    sf[j - 1] = np.conj(z)
+            if wantZ:
+                for j in range(n):
+                    Z[l - 1][:, j] *= np.conj(sf[j])
+            Hlm1 = Hm(l - 1)
+            if S[l - 2]:
+                for j in range(1, n + 1):
+                    Hlm1[:j, j - 1] *= np.conj(sf[j - 1])
+            else:
+                for j in range(1, n + 1):
+                    Hlm1[j - 1, j - 1:] *= sf[j - 1]
+
+    if rev:  # (:910-927)
+        Zr = ([Z[0]] + [Z[p + 1 - l] for l in range(2, p + 1)]) if wantZ else Z
+        Hr = [Hs[p - 1 - l] for l in range(1, p)]
+        return dict(S=list(reversed(list(S))), schurindex=p, T1=H1, T=Hr, Z=Zr, alpha=alpha,
+                    beta=beta, alphascale=ascale, orientation="L", info=info)
+    return dict(S=list(S), schurindex=1, T1=H1, T=Hs, Z=Z, alpha=alpha, beta=beta,
+                alphascale=ascale, orientation="R", info=info)
+
+
+def cpschur(A, S, lr="R", wantZ=True, wantT=True, maxitfac=30):
+    """generalized.jl:108-148 on a list of complex128 math-orientation matrices (copied)."""
+    p = len(A)
+    A = [np.array(a, dtype=np.complex128) for a in A]
+    S = [bool(x) for x in S]
+    left = lr == "L"
+    if left:
+        Aarg = [A[p - 1 - j] for j in range(p)]
+        Sarg = list(reversed(S))
+    else:
+        Aarg, Sarg = A, S
+    if all(S):
+        Q = phessenberg_householder(Aarg)
+        H1 = np.triu(Aarg[0], -1)
+        Hs = [np.triu(Aarg[j]) for j in range(1, p)]
+    else:
+        if not Sarg[0]:
+            raise ValueError("The leftmost entry in S must be true")
+        Q = gphessenberg(Aarg, Sarg)
+        H1 = Aarg[0]
+        Hs = Aarg[1:]
+    return cpqz(H1, Hs, Sarg, wantZ=wantZ, wantT=wantT, Q=(Q if wantZ else None),
+                maxitfac=maxitfac, rev=left)
+
+
+def values(F):
+    """GeneralizedPeriodicSchur.values (generalized.jl:75-76): alpha ./ beta .* 2^alphascale."""
+    with np.errstate(divide="ignore", invalid="ignore"):
+        return F["alpha"] / F["beta"] * np.exp2(F["alphascale"].astype(np.float64))

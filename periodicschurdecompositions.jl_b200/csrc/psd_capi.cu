@@ -68,10 +68,19 @@ struct Device {
 
 }  // namespace
 
+struct KernelTimer {
+  cudaEvent_t e0, e1;
+  int kind;     // 0 = reduction kernel, 1 = QR/QZ iteration kernel
+  int ordinal;  // device the events belong to
+};
+
 struct psd_handle_s {
   std::vector<Device> devs;
   std::mutex mu;
   int64_t stats[8] = {0};
+  bool profiling = false;           // psd_set_profiling
+  std::vector<KernelTimer> timers;  // pending event pairs (resolved by psd_kernel_times)
+  std::mutex tmu;
 };
 
 namespace {
@@ -107,6 +116,29 @@ bool is_pinned(const void* p) {
   }
   return at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged;
 }
+
+// Bracket a kernel launch with CUDA events on its stream when profiling is enabled.
+struct ScopedKernelTimer {
+  psd_handle_s* h;
+  cudaStream_t st;
+  KernelTimer t;
+  bool on;
+  ScopedKernelTimer(psd_handle_s* h_, const Device& dev, cudaStream_t st_, int kind) : h(h_), st(st_) {
+    on = h->profiling;
+    if (!on) return;
+    t.kind = kind;
+    t.ordinal = dev.ordinal;
+    cudaEventCreate(&t.e0);
+    cudaEventCreate(&t.e1);
+    cudaEventRecord(t.e0, st);
+  }
+  ~ScopedKernelTimer() {
+    if (!on) return;
+    cudaEventRecord(t.e1, st);
+    std::lock_guard<std::mutex> lk(h->tmu);
+    h->timers.push_back(t);
+  }
+};
 
 struct RealLaunchPlan {
   int use_smem = 0;
@@ -232,7 +264,10 @@ int launch_real_eig32(psd_handle_s* h, Device& dev, Slot& aux, cudaStream_t stre
       if (occ1 < 1) return fail(PSD_ERR_UNSUPPORTED, "reduction kernel does not fit on an SM");
       const long long ctas1 = (nb + wpb1 - 1) / wpb1;
       const int grid1 = (int)std::max(1LL, std::min((long long)occ1 * dev.sm_count, ctas1));
-      psd::rphess_warp32_kernel<<<grid1, wpb1 * 32, smem1, stream>>>(R);
+      {
+        ScopedKernelTimer tm(h, dev, stream, 0);
+        psd::rphess_warp32_kernel<<<grid1, wpb1 * 32, smem1, stream>>>(R);
+      }
       PSD_CUDA(cudaGetLastError());
     }
     psd::EigParams Q;
@@ -244,7 +279,10 @@ int launch_real_eig32(psd_handle_s* h, Device& dev, Slot& aux, cudaStream_t stre
     Q.counter = aux.dCounter + 1;
     const long long ctas = (nb + wpb - 1) / wpb;
     const int grid2 = (int)std::max(1LL, std::min((long long)occ2 * dev.sm_count, ctas));
-    psd::rpqr_eig32_kernel<<<grid2, wpb * 32, smem2, stream>>>(Q);
+    {
+      ScopedKernelTimer tm(h, dev, stream, 1);
+      psd::rpqr_eig32_kernel<<<grid2, wpb * 32, smem2, stream>>>(Q);
+    }
     PSD_CUDA(cudaGetLastError());
     __atomic_fetch_add(&h->stats[0], (int64_t)2, __ATOMIC_RELAXED);
   }
@@ -281,7 +319,10 @@ int launch_real(psd_handle_s* h, Device& dev, Slot& aux, cudaStream_t stream, co
     P.scratch = aux.dScratch;
     P.scratch_stride = (long long)stride;
   }
-  psd::rpschur_kernel<<<pl.grid, pl.threads, pl.smem_bytes, stream>>>(P);
+  {
+    ScopedKernelTimer tm(h, dev, stream, 1);
+    psd::rpschur_kernel<<<pl.grid, pl.threads, pl.smem_bytes, stream>>>(P);
+  }
   PSD_CUDA(cudaGetLastError());
   __atomic_fetch_add(&h->stats[0], (int64_t)1, __ATOMIC_RELAXED);
   __atomic_fetch_add(&h->stats[pl.use_smem ? 1 : 2], (int64_t)batch, __ATOMIC_RELAXED);
@@ -575,6 +616,36 @@ int psd_fill_uniform_dev(void* stream, uint64_t seed, int n, int p, int64_t batc
   if (batch == 0) return PSD_OK;
   fill_uniform_kernel<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(seed, n, p, batch, first_b, cplx, dA);
   PSD_CUDA(cudaGetLastError());
+  return PSD_OK;
+}
+
+int psd_set_profiling(psd_handle_t h, int on) {
+  if (!h) return fail(PSD_ERR_BAD_ARG, "null handle");
+  std::lock_guard<std::mutex> lock(h->mu);
+  h->profiling = on != 0;
+  return PSD_OK;
+}
+
+int psd_kernel_times(psd_handle_t h, double ms[4]) {
+  if (!h || !ms) return fail(PSD_ERR_BAD_ARG, "null argument");
+  std::lock_guard<std::mutex> lock(h->mu);
+  std::lock_guard<std::mutex> lk(h->tmu);
+  for (int i = 0; i < 4; i++) ms[i] = 0.0;
+  for (auto& t : h->timers) {
+    cudaSetDevice(t.ordinal);
+    cudaError_t e = cudaEventSynchronize(t.e1);
+    float f = 0.f;
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&f, t.e0, t.e1);
+    cudaEventDestroy(t.e0);
+    cudaEventDestroy(t.e1);
+    if (e != cudaSuccess) {
+      h->timers.clear();
+      return fail(PSD_ERR_CUDA, std::string("kernel timer: ") + cudaGetErrorString(e));
+    }
+    ms[t.kind] += f;
+    ms[2 + t.kind] += 1.0;
+  }
+  h->timers.clear();
   return PSD_OK;
 }
 

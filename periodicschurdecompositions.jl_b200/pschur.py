@@ -84,6 +84,16 @@ class Handle:
         return {"launches": s[0], "problems_smem": s[1], "problems_global": s[2],
                 "h2d_bytes": s[3], "d2h_bytes": s[4], "wall_us": s[5]}
 
+    def set_profiling(self, on: bool):
+        check(lib().psd_set_profiling(self._h, int(on)))
+
+    def kernel_times(self):
+        """Device time (ms) of the kernels launched since the last call, by kind."""
+        ms = (C.c_double * 4)()
+        check(lib().psd_kernel_times(self._h, ms))
+        return {"reduce_ms": ms[0], "iterate_ms": ms[1], "reduce_launches": int(ms[2]),
+                "iterate_launches": int(ms[3])}
+
     def close(self):
         if self._h:
             lib().psd_destroy(self._h)
