@@ -114,6 +114,44 @@ int psd_rpschur_hessut_batched(psd_handle_t handle, int n, int p, int64_t batch,
 int psd_rphess_batched(psd_handle_t handle, int n, int p, int64_t batch, int wantQ, double* A,
                        double* Q);
 
+/* ---------------------------------------------------------------------------------------
+ * Complex (generalized) periodic Schur decomposition, batched.
+ * Replaces pschur!(A::Vector{Matrix{ComplexF64}}, S, lr; wantZ, wantT)
+ *   driver, :L reversal of A and S      generalized.jl:108-148
+ *   generalized Hessenberg-triangular   generalized.jl:988-1082   (_phessenberg!(A, S))
+ *   complex periodic QZ (MB03BZ-style)  generalized.jl:166-931
+ *   scaled eigenvalue representation    generalized.jl:939-976    (_safeprod)
+ * and, with S all true, the complex standard method pschur!(A, lr)
+ * (PeriodicSchurDecompositions.jl:1106-1111), whose glue repackages the result as PeriodicSchur
+ * with values = alpha ./ beta .* 2^alphascale.
+ *   S          in   [p] user order, 1 = factor enters as A_j, 0 = as inv(A_j); the leftmost
+ *                   factor after orientation (S[0] for :R, S[p-1] for :L) must be 1, otherwise
+ *                   PSD_ERR_SIGNATURE ("The leftmost entry in S must be true", generalized.jl:140)
+ *   A          in/out [batch][p][n][n] complex128 (re,im interleaved), user order
+ *   Z          out  [batch][p][n][n] complex128 or NULL when wantZ == 0; indexed as in the
+ *                   reference result (T_l = Z_l' A_l Z_{l+1} for S_l xor :L, else
+ *                   T_l = Z_{l+1}' A_l Z_l; test/testfuncs.jl:175-186)
+ *   alpha,beta out  [batch][n] complex128; alphascale out [batch][n] int64:
+ *                   lambda_k = alpha_k / beta_k * 2^alphascale_k, |alpha| in [1,2) or 0,
+ *                   beta in {0,1} (0 = infinite eigenvalue)
+ *   info       out  [batch]
+ * On return with wantT != 0 the diagonals of all factors except the Schur factor are real and
+ * non-negative (generalized.jl:860-908).  maxitfac <= 0 selects the reference default 30.
+ * ------------------------------------------------------------------------------------- */
+int psd_cpschur_batched(psd_handle_t handle, int n, int p, int64_t batch, int orientation,
+                        const uint8_t* S, int wantT, int wantZ, int maxitfac, double* A,
+                        double* Z, double* alpha, double* beta, int64_t* alphascale,
+                        int32_t* info);
+
+/* Complex periodic QZ iteration on input already in Hessenberg-triangular form, rightwards
+ * order, Z starting from the identity.  Replaces the inner method
+ * pschur!(H1, Hs, S; wantT, wantZ) with Q === nothing (generalized.jl:166-931), which the
+ * reference's tests call directly to keep planted exact zeros (test/testfuncs.jl:384-409,
+ * test/generalized.jl:68-173). */
+int psd_cpschur_hessut_batched(psd_handle_t handle, int n, int p, int64_t batch, const uint8_t* S,
+                               int wantT, int wantZ, int maxitfac, double* A, double* Z,
+                               double* alpha, double* beta, int64_t* alphascale, int32_t* info);
+
 /* Synthetic inputs (measurement only): uniform [0,1) entries from a
  * counter-based generator keyed by (seed, problem, factor, row, col), problems
  * first_b .. first_b+batch-1, written to a host buffer or (asynchronously, on the current

@@ -24,7 +24,12 @@ from .capi import (  # noqa: F401
 )
 from .pschur import (  # noqa: F401
     PeriodicSchur,
+    GeneralizedPeriodicSchur,
     Handle,
+    gpschur,
+    gpschur_,
+    gpschur_batched,
+    gvalues,
     default_handle,
     phessenberg_batched,
     pschur,
@@ -36,6 +41,6 @@ from .pschur import (  # noqa: F401
 
 __all__ = [
     "PsdError", "device_count", "lib", "lib_path", "library_available", "version",
-    "PeriodicSchur", "Handle", "default_handle", "phessenberg_batched", "pschur", "pschur_",
+    "PeriodicSchur", "GeneralizedPeriodicSchur", "gpschur", "gpschur_", "gpschur_batched", "gvalues", "Handle", "default_handle", "phessenberg_batched", "pschur", "pschur_",
     "pschur_batched", "pschur_hessut_batched", "shard_bounds",
 ]

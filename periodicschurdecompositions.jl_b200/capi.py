@@ -21,6 +21,8 @@ EXPORTED_SYMBOLS = [
     "psd_rpschur_batched_dev",
     "psd_rpschur_hessut_batched",
     "psd_rphess_batched",
+    "psd_cpschur_batched",
+    "psd_cpschur_hessut_batched",
     "psd_last_stats",
     "psd_set_profiling",
     "psd_kernel_times",
@@ -68,6 +70,10 @@ def lib():
         L.psd_rpschur_hessut_batched.argtypes = [vp, C.c_int, C.c_int, C.c_int64, C.c_int,
                                                  C.c_int, C.c_int, vp, vp, vp, vp]
         L.psd_rphess_batched.argtypes = [vp, C.c_int, C.c_int, C.c_int64, C.c_int, vp, vp]
+        L.psd_cpschur_batched.argtypes = [vp, C.c_int, C.c_int, C.c_int64, C.c_int, vp, C.c_int,
+                                          C.c_int, C.c_int, vp, vp, vp, vp, vp, vp]
+        L.psd_cpschur_hessut_batched.argtypes = [vp, C.c_int, C.c_int, C.c_int64, vp, C.c_int,
+                                                 C.c_int, C.c_int, vp, vp, vp, vp, vp, vp]
         L.psd_last_stats.argtypes = [vp, C.POINTER(C.c_int64)]
         L.psd_set_profiling.argtypes = [vp, C.c_int]
         L.psd_kernel_times.argtypes = [vp, C.POINTER(C.c_double)]

@@ -19,6 +19,7 @@
 #include "../../include/psd_b200.h"
 #include "psd_real_kernel.cuh"
 #include "psd_real_hess32.cuh"
+#include "psd_cplx_qz.cuh"
 #include "psd_rng.cuh"
 
 namespace {
@@ -57,6 +58,13 @@ struct Slot {
   size_t capScratch = 0;
   double* dPacked = nullptr;  // packed Hessenberg-triangular factors between the two kernels
   size_t capPacked = 0;
+  // generalized paths: alpha, beta, alphascale (device + pinned staging) and the signature
+  void* dX[3] = {nullptr, nullptr, nullptr};
+  size_t capX[3] = {0, 0, 0};
+  void* hX[3] = {nullptr, nullptr, nullptr};
+  size_t hcapX[3] = {0, 0, 0};
+  unsigned char* dS = nullptr;
+  size_t capS = 0;
 };
 
 struct Device {
@@ -446,6 +454,190 @@ int run_real_host(psd_handle_t h, const RealCall& rc, int64_t batch, double* A, 
   return PSD_OK;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Generalized paths (complex periodic QZ; real periodic QZ): same sharding / chunking / slot
+// pipeline as the real standard path, with (alpha, beta, alphascale) instead of eig.
+// ---------------------------------------------------------------------------------------------
+struct GenCall {
+  int n, p, left, wantT, wantZ, maxitfac, skip_reduce;
+  int cplx;                 // 1: complex128 factors, complex beta; 0: real factors, real beta
+  const unsigned char* S;   // host, user order
+};
+
+size_t gen_elem(const GenCall& gc) { return gc.cplx ? 16 : 8; }
+
+int launch_gen(psd_handle_s* h, Device& dev, Slot& aux, cudaStream_t stream, const GenCall& gc, long long batch,
+               void* dA, void* dZ, void* dAlpha, void* dBeta, long long* dScale, int32_t* dInfo) {
+  if (batch == 0) return PSD_OK;
+  const int n = gc.n, p = gc.p;
+  const bool wantZ = gc.wantZ && dZ;
+  int e = ensure_dev(aux.dS, aux.capS, (size_t)p);
+  if (e) return e;
+  PSD_CUDA(cudaMemcpyAsync(aux.dS, gc.S, (size_t)p, cudaMemcpyHostToDevice, stream));
+  if (!aux.dCounter) PSD_CUDA(cudaMalloc((void**)&aux.dCounter, 2 * sizeof(unsigned long long)));
+  PSD_CUDA(cudaMemsetAsync(aux.dCounter, 0, sizeof(unsigned long long), stream));
+  int optin = 0;
+  PSD_CUDA(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev.ordinal));
+  int threads = ((2 * n + 31) / 32) * 32;
+  threads = std::max(64, std::min(threads, 256));
+  if (gc.cplx) {
+    cudaFuncAttributes fa;
+    PSD_CUDA(cudaFuncGetAttributes(&fa, psd::cpschur_kernel));
+    const size_t max_dyn = (size_t)optin - fa.sharedSizeBytes;
+    const size_t small = (size_t)((psd::cq_small_doubles(n, p) + 1) & ~1LL) * sizeof(double);
+    const int ldh = n;
+    const size_t mats = (size_t)p * ldh * n * 16 * (wantZ ? 2 : 1);
+    psd::CpqzParams P;
+    P.n = n; P.p = p; P.batch = batch; P.left = gc.left; P.wantT = gc.wantT; P.wantZ = wantZ ? 1 : 0;
+    P.maxitfac = gc.maxitfac > 0 ? gc.maxitfac : 30;
+    P.skip_reduce = gc.skip_reduce;
+    P.S = aux.dS;
+    P.A = (psd::cplx*)dA; P.Z = wantZ ? (psd::cplx*)dZ : nullptr;
+    P.alpha = (psd::cplx*)dAlpha; P.beta = (psd::cplx*)dBeta; P.scale = dScale; P.info = dInfo;
+    P.counter = aux.dCounter;
+    size_t smem;
+    if (small + mats <= max_dyn) {
+      P.use_smem = 1; P.ldh = ldh; smem = small + mats;
+    } else {
+      if (small > max_dyn) return fail(PSD_ERR_UNSUPPORTED, "n or p too large for the per-CTA state");
+      P.use_smem = 0; P.ldh = n; smem = small;
+    }
+    PSD_CUDA(cudaFuncSetAttribute(psd::cpschur_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_dyn));
+    int occ = 0;
+    PSD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, psd::cpschur_kernel, threads, smem));
+    if (occ < 1) return fail(PSD_ERR_UNSUPPORTED, "kernel does not fit on an SM");
+    const int grid = (int)std::max(1LL, std::min((long long)occ * dev.sm_count, batch));
+    {
+      ScopedKernelTimer tm(h, dev, stream, 1);
+      psd::cpschur_kernel<<<grid, threads, smem, stream>>>(P);
+    }
+    PSD_CUDA(cudaGetLastError());
+    __atomic_fetch_add(&h->stats[0], (int64_t)1, __ATOMIC_RELAXED);
+    __atomic_fetch_add(&h->stats[P.use_smem ? 1 : 2], (int64_t)batch, __ATOMIC_RELAXED);
+    return PSD_OK;
+  }
+  return fail(PSD_ERR_UNSUPPORTED, "real generalized path not built");
+}
+
+int run_gen_shard(psd_handle_s* h, Device& dev, const GenCall& gc, long long first, long long count, char* A,
+                  char* Z, char* alpha, char* beta, int64_t* scale, int32_t* info, bool pinned,
+                  int64_t* bytes_h2d, int64_t* bytes_d2h) {
+  if (count <= 0) return PSD_OK;
+  PSD_CUDA(cudaSetDevice(dev.ordinal));
+  const size_t es = gen_elem(gc);
+  const size_t perB = (size_t)gc.n * gc.n * gc.p * es;  // bytes of factors per problem
+  const size_t xB[3] = {(size_t)gc.n * 16, (size_t)gc.n * es, (size_t)gc.n * 8};
+  const bool wantZ = gc.wantZ && Z;
+  long long chunk = std::max<long long>(1, (512LL << 20) / (long long)perB);
+  chunk = std::min(chunk, count);
+  if (count > chunk) {
+    long long nchunks = (count + chunk - 1) / chunk;
+    chunk = (count + nchunks - 1) / nchunks;
+  }
+  int si = 0;
+  for (long long off = 0; off < count; off += chunk, si = (si + 1) % kSlotsPerDevice) {
+    const long long nb = std::min(chunk, count - off);
+    Slot& s = dev.slots[si];
+    if (!s.stream) PSD_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+    PSD_CUDA(cudaStreamSynchronize(s.stream));
+    int e;
+    const size_t bytesA = nb * perB;
+    if ((e = ensure_dev(s.dA, s.capA, bytesA))) return e;
+    if (wantZ && (e = ensure_dev(s.dZ, s.capZ, bytesA))) return e;
+    for (int k = 0; k < 3; k++)
+      if ((e = ensure_dev(s.dX[k], s.capX[k], nb * xB[k]))) return e;
+    if ((e = ensure_dev(s.dInfo, s.capInfo, nb * sizeof(int32_t)))) return e;
+    char* srcA = A + (size_t)(first + off) * perB;
+    if (pinned) {
+      PSD_CUDA(cudaMemcpyAsync(s.dA, srcA, bytesA, cudaMemcpyHostToDevice, s.stream));
+    } else {
+      if ((e = ensure_pinned(s.hA, s.hcapA, bytesA))) return e;
+      std::memcpy(s.hA, srcA, bytesA);
+      PSD_CUDA(cudaMemcpyAsync(s.dA, s.hA, bytesA, cudaMemcpyHostToDevice, s.stream));
+    }
+    *bytes_h2d += (int64_t)bytesA;
+    e = launch_gen(h, dev, s, s.stream, gc, nb, s.dA, wantZ ? s.dZ : nullptr, s.dX[0], s.dX[1],
+                   (long long*)s.dX[2], s.dInfo);
+    if (e) return e;
+    char* dstZ = wantZ ? Z + (size_t)(first + off) * perB : nullptr;
+    char* dstX[3] = {alpha + (size_t)(first + off) * xB[0], beta + (size_t)(first + off) * xB[1],
+                     (char*)scale + (size_t)(first + off) * xB[2]};
+    int32_t* dstInfo = info + (first + off);
+    const size_t bytesInfo = nb * sizeof(int32_t);
+    if (pinned) {
+      if (gc.wantT) PSD_CUDA(cudaMemcpyAsync(srcA, s.dA, bytesA, cudaMemcpyDeviceToHost, s.stream));
+      if (wantZ) PSD_CUDA(cudaMemcpyAsync(dstZ, s.dZ, bytesA, cudaMemcpyDeviceToHost, s.stream));
+      for (int k = 0; k < 3; k++)
+        PSD_CUDA(cudaMemcpyAsync(dstX[k], s.dX[k], nb * xB[k], cudaMemcpyDeviceToHost, s.stream));
+      PSD_CUDA(cudaMemcpyAsync(dstInfo, s.dInfo, bytesInfo, cudaMemcpyDeviceToHost, s.stream));
+    } else {
+      if (wantZ && (e = ensure_pinned(s.hZ, s.hcapZ, bytesA))) return e;
+      for (int k = 0; k < 3; k++)
+        if ((e = ensure_pinned(s.hX[k], s.hcapX[k], nb * xB[k]))) return e;
+      if ((e = ensure_pinned(s.hInfo, s.hcapInfo, bytesInfo))) return e;
+      if (gc.wantT) PSD_CUDA(cudaMemcpyAsync(s.hA, s.dA, bytesA, cudaMemcpyDeviceToHost, s.stream));
+      if (wantZ) PSD_CUDA(cudaMemcpyAsync(s.hZ, s.dZ, bytesA, cudaMemcpyDeviceToHost, s.stream));
+      for (int k = 0; k < 3; k++)
+        PSD_CUDA(cudaMemcpyAsync(s.hX[k], s.dX[k], nb * xB[k], cudaMemcpyDeviceToHost, s.stream));
+      PSD_CUDA(cudaMemcpyAsync(s.hInfo, s.dInfo, bytesInfo, cudaMemcpyDeviceToHost, s.stream));
+      PSD_CUDA(cudaStreamSynchronize(s.stream));
+      if (gc.wantT) std::memcpy(srcA, s.hA, bytesA);
+      if (wantZ) std::memcpy(dstZ, s.hZ, bytesA);
+      for (int k = 0; k < 3; k++) std::memcpy(dstX[k], s.hX[k], nb * xB[k]);
+      std::memcpy(dstInfo, s.hInfo, bytesInfo);
+    }
+    *bytes_d2h += (int64_t)((gc.wantT ? bytesA : 0) + (wantZ ? bytesA : 0) + nb * (xB[0] + xB[1] + xB[2]) + bytesInfo);
+  }
+  for (int k = 0; k < kSlotsPerDevice; k++)
+    if (dev.slots[k].stream) PSD_CUDA(cudaStreamSynchronize(dev.slots[k].stream));
+  return PSD_OK;
+}
+
+int run_gen_host(psd_handle_t h, const GenCall& gc, int64_t batch, void* A, void* Z, void* alpha, void* beta,
+                 int64_t* scale, int32_t* info) {
+  if (!h) return fail(PSD_ERR_BAD_ARG, "null handle");
+  if (gc.n < 1 || gc.p < 1 || batch < 0) return fail(PSD_ERR_BAD_ARG, "n, p must be >= 1 and batch >= 0");
+  if (!A || !gc.S) return fail(PSD_ERR_BAD_ARG, "A and S must not be NULL");
+  if (!alpha || !beta || !scale || !info) return fail(PSD_ERR_BAD_ARG, "alpha, beta, alphascale and info must not be NULL");
+  if (gc.wantZ && !Z) return fail(PSD_ERR_BAD_ARG, "wantZ set but Z is NULL");
+  // leftmost factor after orientation must have S = true (generalized.jl:140, rgeneralized.jl:37)
+  if (!gc.S[gc.left ? gc.p - 1 : 0]) return fail(PSD_ERR_SIGNATURE, "The leftmost entry in S must be true");
+  if (h->devs.empty()) return fail(PSD_ERR_NO_DEVICE, "handle has no CUDA device");
+  std::lock_guard<std::mutex> lock(h->mu);
+  for (auto& s : h->stats) s = 0;
+  if (batch == 0) return PSD_OK;
+  const bool pinned = is_pinned(A) && is_pinned(Z) && is_pinned(alpha) && is_pinned(beta) && is_pinned(scale) &&
+                      is_pinned(info);
+  const int nd = (int)h->devs.size();
+  std::vector<int> codes(nd, PSD_OK);
+  std::vector<std::string> msgs(nd);
+  std::vector<int64_t> h2d(nd, 0), d2h(nd, 0);
+  auto t0 = std::chrono::steady_clock::now();
+  auto work = [&](int d) {
+    const long long lo = batch * d / nd, hi = batch * (d + 1) / nd;
+    codes[d] = run_gen_shard(h, h->devs[d], gc, lo, hi - lo, (char*)A, (char*)Z, (char*)alpha, (char*)beta, scale,
+                             info, pinned, &h2d[d], &d2h[d]);
+    if (codes[d]) msgs[d] = g_err;
+  };
+  if (nd == 1) {
+    work(0);
+  } else {
+    std::vector<std::thread> th;
+    for (int d = 0; d < nd; d++) th.emplace_back(work, d);
+    for (auto& t : th) t.join();
+  }
+  auto t1 = std::chrono::steady_clock::now();
+  for (int d = 0; d < nd; d++) {
+    h->stats[3] += h2d[d];
+    h->stats[4] += d2h[d];
+  }
+  h->stats[5] = std::chrono::duration_cast<std::chrono::microseconds>(t1 - t0).count();
+  for (int d = 0; d < nd; d++)
+    if (codes[d]) return fail(codes[d], msgs[d]);
+  return PSD_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -510,7 +702,11 @@ int psd_destroy(psd_handle_t h) {
         cudaStreamDestroy(s.stream);
       }
       cudaFree(s.dA); cudaFree(s.dZ); cudaFree(s.dEig); cudaFree(s.dInfo);
-      cudaFree(s.dCounter); cudaFree(s.dScratch); cudaFree(s.dPacked);
+      cudaFree(s.dCounter); cudaFree(s.dScratch); cudaFree(s.dPacked); cudaFree(s.dS);
+      for (int k = 0; k < 3; k++) {
+        cudaFree(s.dX[k]);
+        cudaFreeHost(s.hX[k]);
+      }
       cudaFreeHost(s.hA); cudaFreeHost(s.hZ); cudaFreeHost(s.hEig); cudaFreeHost(s.hInfo);
     };
     for (auto& s : d.slots) freeSlot(s);
@@ -560,6 +756,22 @@ int psd_rpschur_batched_dev(psd_handle_t h, int dev_index, void* stream, int n, 
   }
   RealCall rc{n, p, orientation, wantT != 0, wantZ != 0, maxitfac, 0, 0};
   return launch_real(h, dev, dev.user, st, rc, batch, dA, dZ, deig, dinfo);
+}
+
+int psd_cpschur_batched(psd_handle_t h, int n, int p, int64_t batch, int orientation, const uint8_t* S, int wantT,
+                        int wantZ, int maxitfac, double* A, double* Z, double* alpha, double* beta,
+                        int64_t* alphascale, int32_t* info) {
+  if (orientation != 0 && orientation != 1)
+    return fail(PSD_ERR_BAD_ARG, "orientation argument must be either 0 (:R, right) or 1 (:L, left)");
+  GenCall gc{n, p, orientation, wantT != 0, wantZ != 0, maxitfac, 0, 1, S};
+  return run_gen_host(h, gc, batch, A, Z, alpha, beta, alphascale, info);
+}
+
+int psd_cpschur_hessut_batched(psd_handle_t h, int n, int p, int64_t batch, const uint8_t* S, int wantT, int wantZ,
+                               int maxitfac, double* A, double* Z, double* alpha, double* beta,
+                               int64_t* alphascale, int32_t* info) {
+  GenCall gc{n, p, 0, wantT != 0, wantZ != 0, maxitfac, 1, 1, S};
+  return run_gen_host(h, gc, batch, A, Z, alpha, beta, alphascale, info);
 }
 
 __global__ void fill_uniform_kernel(uint64_t seed, int n, int p, long long batch, long long first_b,

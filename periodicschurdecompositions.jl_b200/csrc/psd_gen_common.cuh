@@ -1,0 +1,603 @@
+// Building blocks of the GENERALIZED periodic Schur kernels (complex and real periodic QZ):
+// scalar types, Givens generation, CTA-parallel rotation / reflector application, the
+// "chase one rotation through every factor" primitive, and the generalized periodic
+// Hessenberg-triangular reduction.
+//
+// Reference semantics restated here (file:line relative to the reference repository):
+//   generalized.jl:988-1082   _phessenberg!(A, S)  Stage 1 (QR / RQ of factors p..2, applied to
+//                             the neighbour factor and to Q[l]) and Stage 2 (Givens Hessenberg
+//                             reduction of A_1, each rotation propagated through all factors)
+//   generalized.jl:808-852    one step of the periodic QZ sweep (same propagation pattern)
+//   generalized.jl:939-976    _safeprod
+//   Julia stdlib givensAlgorithm / lmul!(Givens) / rmul!(., Givens') (LAPACK xLARTG semantics,
+//   source not under the reference tree): [c s; -conj(s) c] [f; g] = [r; 0], c real.
+//
+// Execution model (same as psd_device.cuh): one CTA owns one periodic problem; scalar decisions
+// are computed redundantly in registers by every thread from values read after a CTA barrier;
+// row / column updates are dealt to the threads.
+//
+// The propagation primitive `chase_rotation` is organised around the hardware rather than the
+// reference's loop nest: the rotation that enters factor l and the one that leaves it depend
+// only on the 2x2 diagonal block of that factor, so the whole chain H_1 -> H_p -> ... -> H_2 ->
+// H_1 is evaluated in registers (redundantly per thread), and every row/column update of every
+// factor and of every Z_l touches memory that no other update of the same step reads.  A step
+// therefore needs ONE CTA barrier instead of the 2p+1 of a literal transcription, and the
+// loads of the next diagonal block overlap the updates of the current factor.
+#pragma once
+#include "psd_device.cuh"
+
+namespace psd {
+
+// ------------------------------------------------------------------------------------------
+// complex128 (interleaved re, im: Julia ComplexF64 layout)
+// ------------------------------------------------------------------------------------------
+struct __align__(16) cplx {
+  double x, y;
+};
+PSD_DEV cplx mk(double x, double y) {
+  cplx r;
+  r.x = x;
+  r.y = y;
+  return r;
+}
+PSD_DEV cplx operator+(cplx a, cplx b) { return mk(a.x + b.x, a.y + b.y); }
+PSD_DEV cplx operator-(cplx a, cplx b) { return mk(a.x - b.x, a.y - b.y); }
+PSD_DEV cplx operator-(cplx a) { return mk(-a.x, -a.y); }
+PSD_DEV cplx operator*(cplx a, cplx b) {
+  return mk(fma(a.x, b.x, -a.y * b.y), fma(a.x, b.y, a.y * b.x));
+}
+PSD_DEV cplx operator*(double a, cplx b) { return mk(a * b.x, a * b.y); }
+PSD_DEV cplx operator*(cplx b, double a) { return mk(a * b.x, a * b.y); }
+PSD_DEV cplx conj_(cplx a) { return mk(a.x, -a.y); }
+PSD_DEV double conj_(double a) { return a; }
+PSD_DEV double abs_(cplx a) { return hypot(a.x, a.y); }
+PSD_DEV double abs_(double a) { return fabs(a); }
+PSD_DEV double abs1_(cplx a) { return fabs(a.x) + fabs(a.y); }
+PSD_DEV bool is_zero(cplx a) { return a.x == 0.0 && a.y == 0.0; }
+PSD_DEV bool is_zero(double a) { return a == 0.0; }
+// Smith's complex division
+PSD_DEV cplx operator/(cplx a, cplx b) {
+  if (fabs(b.x) >= fabs(b.y)) {
+    const double r = b.y / b.x, d = b.x + b.y * r;
+    return mk((a.x + a.y * r) / d, (a.y - a.x * r) / d);
+  }
+  const double r = b.x / b.y, d = b.x * r + b.y;
+  return mk((a.x * r + a.y) / d, (a.y * r - a.x) / d);
+}
+PSD_DEV cplx operator/(cplx a, double b) { return mk(a.x / b, a.y / b); }
+
+template <class T>
+struct Scalar;
+template <>
+struct Scalar<double> {
+  static PSD_DEV double zero() { return 0.0; }
+  static PSD_DEV double one() { return 1.0; }
+  static PSD_DEV double from_real(double v) { return v; }
+};
+template <>
+struct Scalar<cplx> {
+  static PSD_DEV cplx zero() { return mk(0.0, 0.0); }
+  static PSD_DEV cplx one() { return mk(1.0, 0.0); }
+  static PSD_DEV cplx from_real(double v) { return mk(v, 0.0); }
+};
+
+// givensAlgorithm(f, g) -> (c, s, r), real: see givens_real in psd_device.cuh.
+PSD_DEV void givens_t(double f, double g, double& c, double& s, double& r) {
+  givens_real(f, g, c, s, r);
+}
+// complex (zlartg semantics): c = |f|/h, s = (f/|f|) conj(g)/h, r = (f/|f|) h, h = hypot(|f|,|g|)
+PSD_DEV void givens_t(cplx f, cplx g, double& c, cplx& s, cplx& r) {
+  if (is_zero(g)) {
+    c = 1.0;
+    s = mk(0.0, 0.0);
+    r = f;
+    return;
+  }
+  if (is_zero(f)) {
+    const double ag = abs_(g);
+    c = 0.0;
+    s = conj_(g) / ag;
+    r = mk(ag, 0.0);
+    return;
+  }
+  double m = fmax(fmax(fabs(f.x), fabs(f.y)), fmax(fabs(g.x), fabs(g.y)));
+  double sc = 1.0;
+  if (m < 1e-140 || m > 1e140) sc = pow2_rescale(m);
+  const cplx fs = sc * f, gs = sc * g;
+  const double f2 = fma(fs.x, fs.x, fs.y * fs.y), g2 = fma(gs.x, gs.x, gs.y * gs.y);
+  if (f2 == 0.0) {  // |f| negligible against |g| even after scaling
+    const double ag = abs_(g);
+    c = 0.0;
+    s = conj_(g) / ag;
+    r = mk(ag, 0.0);
+    return;
+  }
+  const double h2 = f2 + g2;
+  const double f1 = sqrt(f2), h = sqrt(h2);
+  c = f1 / h;
+  const double ifh = 1.0 / (f1 * h);
+  s = (fs * conj_(gs)) * ifh;
+  r = f * (h / f1);
+}
+
+// ------------------------------------------------------------------------------------------
+// Problem context: factor l (1-based, INTERNAL rightwards order) at H + (l-1)*hs, leading
+// dimension ldh; Z_l likewise.  S[l-1] is the internal signature (S[0] is always true).
+// ------------------------------------------------------------------------------------------
+template <class T>
+struct GCtx {
+  int n, p, tid, nt;
+  T* H;
+  long long hs;
+  int ldh;
+  T* Z;
+  long long zs;
+  int ldz;
+  bool wantZ;
+  bool zmap_left;
+  const unsigned char* S;
+  T* stage;  // 4 + 3(p-1) scalars of shared memory: diagonal blocks staged by chase_rotation
+  PSD_DEV T* Hp(int l) const { return H + (long long)(l - 1) * hs; }
+  PSD_DEV T* Zp(int l) const {
+    int s = l;
+    if (zmap_left && l > 1) s = p + 2 - l;  // Zr[l] = Z[p+2-l]  (generalized.jl:913-916)
+    return Z + (long long)(s - 1) * zs;
+  }
+  PSD_DEV bool Sg(int l) const { return S[l - 1] != 0; }
+};
+
+#define PSD_GE(ptr, ld, r, c) (ptr)[((r)-1) + (size_t)((c)-1) * (ld)]
+
+// rows (i1, i2) <- [c s; -conj(s) c] * rows, one column
+template <class T>
+PSD_DEV void rot_pair_rows(T* M, int ld, int i1, int i2, int col, double c, T s) {
+  T* a = &PSD_GE(M, ld, i1, col);
+  T* b = &PSD_GE(M, ld, i2, col);
+  const T a1 = *a, a2 = *b;
+  *a = c * a1 + s * a2;
+  *b = c * a2 - conj_(s) * a1;
+}
+// columns (j1, j2) <- columns * Givens(j1,j2,c,s)', one row
+template <class T>
+PSD_DEV void rot_pair_cols(T* M, int ld, int j1, int j2, int row, double c, T s) {
+  T* a = &PSD_GE(M, ld, row, j1);
+  T* b = &PSD_GE(M, ld, row, j2);
+  const T a1 = *a, a2 = *b;
+  *a = c * a1 + conj_(s) * a2;
+  *b = c * a2 - s * a1;
+}
+
+// ---- simple CTA-synchronous helpers (used on the rarely taken branches) -------------------
+// lmul!(Givens(i1,i2,c,s), view(M, :, c0:c1)); barrier at the end
+template <class T>
+PSD_DEV void g_lmul(const GCtx<T>& cx, T* M, int ld, int i1, int i2, double c, T s, int c0, int c1) {
+  for (int col = c0 + cx.tid; col <= c1; col += cx.nt) rot_pair_rows(M, ld, i1, i2, col, c, s);
+  __syncthreads();
+}
+// rmul!(view(M, r0:r1, :), Givens(j1,j2,c,s)'); barrier at the end
+template <class T>
+PSD_DEV void g_rmul(const GCtx<T>& cx, T* M, int ld, int j1, int j2, double c, T s, int r0, int r1) {
+  for (int row = r0 + cx.tid; row <= r1; row += cx.nt) rot_pair_cols(M, ld, j1, j2, row, c, s);
+  __syncthreads();
+}
+// c, s, r = givensAlgorithm(M[fa], M[ga]); M[fa] = r; M[ga] = 0   (barrier-safe)
+template <class T>
+PSD_DEV void g_gen(const GCtx<T>& cx, T* M, int ld, int fr, int fc, int gr, int gc, double& c, T& s) {
+  const T f = PSD_GE(M, ld, fr, fc), g = PSD_GE(M, ld, gr, gc);
+  T r;
+  givens_t(f, g, c, s, r);
+  __syncthreads();
+  if (cx.tid == 0) {
+    PSD_GE(M, ld, fr, fc) = r;
+    PSD_GE(M, ld, gr, gc) = Scalar<T>::zero();
+  }
+  __syncthreads();
+}
+
+// opnorm(view(M, r0:r1, c0:c1), 1), optionally of the upper triangle of the view (rare
+// fallback of the deflation tolerances; serial, executed by every calling thread).
+template <class T>
+PSD_DEV double g_opnorm1(const T* M, int ld, int r0, int r1, int c0, int c1, bool upper) {
+  double m = 0.0;
+  for (int c = c0; c <= c1; c++) {
+    double s = 0.0;
+    const int rl = upper ? min(r1, r0 + (c - c0)) : r1;
+    for (int r = r0; r <= rl; r++) s += abs_(PSD_GE(M, ld, r, c));
+    m = fmax(m, s);
+  }
+  return m;
+}
+
+// ------------------------------------------------------------------------------------------
+// chase_rotation: apply G1 = Givens(j, j+1, c1, s1) to H_1 from the left (columns h1c0..clast),
+// propagate it through factors p..2 (generalized.jl:823-845 / :1045-1075), apply the rotation
+// that comes out to H_1 from the right (rows rfirst..h1r1) and accumulate every rotation into
+// the Z_l.  If zcol > 0 the generating pair of H_1 is overwritten: H_1[j,zcol] = r1,
+// H_1[j+1,zcol] = 0.  For a factor with S = true the incoming rotation acts on its columns
+// (rows rfirst..j+1) and the outgoing one on its rows (columns j+1..clast); with S = false the
+// incoming one acts on rows (columns j..clast) and the outgoing one on columns (rows rfirst..j).
+// Two barriers: one after the bulk updates (every thread has then consumed the diagonal blocks
+// it read), one after the 2x2 diagonal blocks, staged in shared memory meanwhile, have been
+// written back.  All threads of the CTA must call with identical arguments.
+// ------------------------------------------------------------------------------------------
+template <class T>
+PSD_DEV void chase_rotation(const GCtx<T>& cx, int j, double c1, T s1, int zcol, T r1, int h1c0,
+                            int clast, int rfirst, int h1r1) {
+  const int n = cx.n, p = cx.p, tid = cx.tid, nt = cx.nt;
+  T* H1 = cx.Hp(1);
+  const int ld = cx.ldh;
+  // H_1's 2x2 overlap block and the generating pair are read before anything is written
+  const T ha = PSD_GE(H1, ld, j, j), hb = PSD_GE(H1, ld, j, j + 1);
+  const T hc = PSD_GE(H1, ld, j + 1, j), hd = PSD_GE(H1, ld, j + 1, j + 1);
+  double ci = c1;
+  T si = s1;
+  // prefetch the first factor's diagonal block
+  T b00 = Scalar<T>::zero(), b01 = b00, b11 = b00;
+  if (p > 1) {
+    const T* Hl = cx.Hp(p);
+    b00 = PSD_GE(Hl, ld, j, j);
+    b01 = PSD_GE(Hl, ld, j, j + 1);
+    b11 = PSD_GE(Hl, ld, j + 1, j + 1);
+  }
+  // Z_1 and the left-only part of H_1 (rotation G1); the overlap block is finished at the end
+  {
+    const int nL = (clast - h1c0 + 1) - 2;  // columns h1c0..clast without j, j+1
+    const int nZ = cx.wantZ ? n : 0;
+    T* Z1 = cx.wantZ ? cx.Zp(1) : nullptr;
+    for (int w = tid; w < nL + nZ; w += nt) {
+      if (w < nL) {
+        int col = h1c0 + w;
+        if (col >= j) col += 2;
+        rot_pair_rows(H1, ld, j, j + 1, col, c1, s1);
+      } else {
+        rot_pair_cols(Z1, cx.ldz, j, j + 1, 1 + (w - nL), c1, s1);
+      }
+    }
+  }
+  for (int l = p; l >= 2; l--) {
+    T* Hl = cx.Hp(l);
+    const T c00 = b00, c01 = b01, c11 = b11;
+    if (l > 2) {  // prefetch the next factor's block while this one is processed
+      const T* Hn = cx.Hp(l - 1);
+      b00 = PSD_GE(Hn, ld, j, j);
+      b01 = PSD_GE(Hn, ld, j, j + 1);
+      b11 = PSD_GE(Hn, ld, j + 1, j + 1);
+    }
+    double co;
+    T so, m00, m01, m11;
+    double cR, cL;  // rotation acting on columns (right-only rows) / on rows (left-only columns)
+    T sR, sL;
+    if (cx.Sg(l)) {
+      // block * G_in'  then  G_out * block
+      const T n00 = ci * c00 + conj_(si) * c01;
+      const T n01 = ci * c01 - si * c00;
+      const T n10 = conj_(si) * c11;
+      const T n11 = ci * c11;
+      T r;
+      givens_t(n00, n10, co, so, r);
+      m00 = r;
+      m01 = co * n01 + so * n11;
+      m11 = co * n11 - conj_(so) * n01;
+      cR = ci; sR = si;
+      cL = co; sL = so;
+    } else {
+      // G_in * block  then  block * Givens(j+1, j, co, conj(so))'  (rows rfirst..j only)
+      const T n00 = ci * c00;
+      const T n01 = ci * c01 + si * c11;
+      const T n10 = -(conj_(si) * c00);
+      const T n11 = ci * c11 - conj_(si) * c01;
+      T r;
+      givens_t(n11, n10, co, so, r);
+      m01 = co * n01 + so * n00;
+      m00 = co * n00 - conj_(so) * n01;
+      m11 = r;
+      cL = ci; sL = si;
+      so = -so;  // equivalent Givens(j, j+1, co, -so)  (generalized.jl:839-840)
+      cR = co; sR = so;
+    }
+    {
+      const int nR = j - rfirst;  // rows rfirst..j-1
+      const int nL = clast - (j + 1);  // columns j+2..clast
+      const int nZ = cx.wantZ ? n : 0;
+      T* Zl = cx.wantZ ? cx.Zp(l) : nullptr;
+      for (int w = tid; w < nR + nL + nZ; w += nt) {
+        if (w < nR) {
+          rot_pair_cols(Hl, ld, j, j + 1, rfirst + w, cR, sR);
+        } else if (w < nR + nL) {
+          rot_pair_rows(Hl, ld, j, j + 1, j + 2 + (w - nR), cL, sL);
+        } else {
+          rot_pair_cols(Zl, cx.ldz, j, j + 1, 1 + (w - nR - nL), co, so);
+        }
+      }
+      if (tid == 0) {
+        T* st = cx.stage + 4 + 3 * (l - 2);
+        st[0] = m00;
+        st[1] = m01;
+        st[2] = m11;
+      }
+    }
+    ci = co;
+    si = so;
+  }
+  // right-only rows of H_1 (rotation that came out of factor 2) and the overlap block
+  {
+    const int nR = (h1r1 - rfirst + 1) - 2;  // rows rfirst..h1r1 without j, j+1
+    for (int w = tid; w < nR; w += nt) {
+      int row = rfirst + w;
+      if (row >= j) row += 2;
+      rot_pair_cols(H1, ld, j, j + 1, row, ci, si);
+    }
+    if (tid == 0) {
+      // left with G1, then right with (ci, si)
+      const T a1 = c1 * ha + s1 * hc, b1 = c1 * hb + s1 * hd;
+      const T a2 = c1 * hc - conj_(s1) * ha, b2 = c1 * hd - conj_(s1) * hb;
+      cx.stage[0] = ci * a1 + conj_(si) * b1;
+      cx.stage[1] = ci * b1 - si * a1;
+      cx.stage[2] = ci * a2 + conj_(si) * b2;
+      cx.stage[3] = ci * b2 - si * a2;
+    }
+  }
+  __syncthreads();
+  for (int l = 1 + tid; l <= p; l += nt) {
+    if (l == 1) {
+      PSD_GE(H1, ld, j, j) = cx.stage[0];
+      PSD_GE(H1, ld, j, j + 1) = cx.stage[1];
+      PSD_GE(H1, ld, j + 1, j) = cx.stage[2];
+      PSD_GE(H1, ld, j + 1, j + 1) = cx.stage[3];
+      if (zcol > 0) {
+        PSD_GE(H1, ld, j, zcol) = r1;
+        PSD_GE(H1, ld, j + 1, zcol) = Scalar<T>::zero();
+      }
+    } else {
+      T* Hl = cx.Hp(l);
+      const T* st = cx.stage + 4 + 3 * (l - 2);
+      PSD_GE(Hl, ld, j, j) = st[0];
+      PSD_GE(Hl, ld, j, j + 1) = st[1];
+      PSD_GE(Hl, ld, j + 1, j) = Scalar<T>::zero();
+      PSD_GE(Hl, ld, j + 1, j + 1) = st[2];
+    }
+  }
+  __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------
+// Householder reflectors for Stage 1 (generalized.jl:1009-1028; geqrf!/gerqf! + ormqr!/ormrq!).
+// H = I - tau w w^H.  Each warp recomputes the norm redundantly (no broadcast step).
+// ------------------------------------------------------------------------------------------
+PSD_DEV double sq_(double a) { return a * a; }
+PSD_DEV double sq_(cplx a) { return fma(a.x, a.x, a.y * a.y); }
+PSD_DEV double re_(double a) { return a; }
+PSD_DEV double re_(cplx a) { return a.x; }
+PSD_DEV double im_(double) { return 0.0; }
+PSD_DEV double im_(cplx a) { return a.y; }
+PSD_DEV double amax_(double a) { return fabs(a); }
+PSD_DEV double amax_(cplx a) { return fmax(fabs(a.x), fabs(a.y)); }
+PSD_DEV double rdiv_one(double d) { return 1.0 / d; }
+PSD_DEV cplx rdiv_one(cplx d) { return Scalar<cplx>::one() / d; }
+
+// Reflector from the m-vector x[k*inc], k = 0..m-1 (pivot first).  Returns false when H = I.
+// On return: beta (new pivot value, real), tau, and tv such that w = (1, tv * x[1:]).
+// For complex data with CONJ the reflector is built for conj(x) (row reflectors).
+template <class T, bool CONJ>
+PSD_DEV bool refl_vec(const T* x, long long inc, int m, int lane, double& beta, T& tau, T& tv) {
+  double amax = 0.0;
+  for (int k = 1 + lane; k < m; k += 32) amax = fmax(amax, amax_(x[k * inc]));
+  amax = warp_max(amax);
+  T alpha = x[0];
+  if (CONJ) alpha = conj_(alpha);
+  if (amax == 0.0 && im_(alpha) == 0.0) return false;
+  const double mm = fmax(amax, amax_(alpha));
+  double s = 1.0;
+  if (mm < 1e-140 || mm > 1e140) s = pow2_rescale(mm);
+  double ssq = 0.0;
+  for (int k = 1 + lane; k < m; k += 32) ssq += sq_(s * x[k * inc]);
+  ssq = warp_sum(ssq);
+  const T al = s * alpha;
+  const double b = -copysign(sqrt(sq_(al) + ssq), re_(al));
+  // tau = (beta - alpha)/beta (complex: ((beta-ar)/beta, -ai/beta)); v = x[1:] / (alpha - beta)
+  tau = (Scalar<T>::from_real(b) - al) * (1.0 / b);
+  tv = s * rdiv_one(al - Scalar<T>::from_real(b));
+  beta = b / s;
+  return true;
+}
+
+// QR-type step on column k of Al (S[l] = true): annihilate Al[k+1:n, k]; apply H' to the
+// remaining columns of Al, H to the neighbour factor (from the right if S[l-1], H' from the
+// left otherwise) and to Q_l from the right.
+template <class T>
+PSD_DEV void stage1_qr_step(const GCtx<T>& cx, T* Al, T* Am, bool sm1, T* Ql, int k) {
+  const int n = cx.n, ld = cx.ldh, tid = cx.tid, nt = cx.nt;
+  const int lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
+  const int m = n - k + 1;
+  const T* x = &PSD_GE(Al, ld, k, k);
+  double beta;
+  T tau, tv;
+  if (!refl_vec<T, false>(x, 1, m, lane, beta, tau, tv)) return;  // uniform over the CTA
+  // (a) left on Al columns k+1..n and, when !S[l-1], on all columns of Am: one warp per column
+  const int ncolA = n - k, ncolM = sm1 ? 0 : n;
+  for (int w = warp; w < ncolA + ncolM; w += nw) {
+    T* a = (w < ncolA) ? &PSD_GE(Al, ld, k, k + 1 + w) : &PSD_GE(Am, ld, k, 1 + (w - ncolA));
+    // d = w^H a
+    T d = Scalar<T>::zero();
+    for (int r = lane; r < m; r += 32) {
+      const T wr = (r == 0) ? Scalar<T>::one() : tv * x[r];
+      d = d + conj_(wr) * a[r];
+    }
+    if constexpr (sizeof(T) == sizeof(double)) {
+      d = warp_sum(d);
+    } else {
+      d.x = warp_sum(d.x);
+      d.y = warp_sum(d.y);
+    }
+    d = conj_(tau) * d;  // H' = I - conj(tau) w w^H
+    for (int r = lane; r < m; r += 32) {
+      const T wr = (r == 0) ? Scalar<T>::one() : tv * x[r];
+      a[r] = a[r] - d * wr;
+    }
+  }
+  // (b) right on Am rows (if S[l-1]) and Q_l rows: one thread per row
+  const int nM = sm1 ? n : 0, nQ = cx.wantZ ? n : 0;
+  for (int w = tid; w < nM + nQ; w += nt) {
+    T* a;
+    int lda;
+    if (w < nM) {
+      a = &PSD_GE(Am, ld, 1 + w, k);
+      lda = ld;
+    } else {
+      a = &PSD_GE(Ql, cx.ldz, 1 + (w - nM), k);
+      lda = cx.ldz;
+    }
+    T d = a[0];
+    for (int r = 1; r < m; r++) d = d + a[(size_t)r * lda] * (tv * x[r]);
+    d = tau * d;
+    a[0] = a[0] - d;
+    for (int r = 1; r < m; r++) a[(size_t)r * lda] = a[(size_t)r * lda] - d * conj_(tv * x[r]);
+  }
+  __syncthreads();
+  for (int r = tid; r < m; r += nt)
+    PSD_GE(Al, ld, k + r, k) = (r == 0) ? Scalar<T>::from_real(beta) : Scalar<T>::zero();
+  __syncthreads();
+}
+
+// RQ-type step on row k of Al (S[l] = false): annihilate Al[k, 1:k-1] with a reflector G acting
+// on columns 1..k (pivot = column k); Al <- Al G (rows 1..k-1), neighbour factor Am <- Am G
+// (if S[l-1]) or G' Am (otherwise), Q_l <- Q_l G.
+template <class T>
+PSD_DEV void stage1_rq_step(const GCtx<T>& cx, T* Al, T* Am, bool sm1, T* Ql, int k) {
+  const int n = cx.n, ld = cx.ldh, tid = cx.tid, nt = cx.nt;
+  const int lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
+  const int m = k;
+  // vector conj(Al[k, k]), conj(Al[k, k-1]), ..., conj(Al[k, 1]): pivot first, stride -ld
+  const T* x = &PSD_GE(Al, ld, k, k);
+  const long long inc = -(long long)ld;
+  double beta;
+  T tau, tv;
+  if (!refl_vec<T, true>(x, inc, m, lane, beta, tau, tv)) return;
+  // w_0 = 1 (column k), w_r = tv * conj(x[r*inc]) (column k-r)
+  // (a) right on rows: Al rows 1..k-1, Am rows 1..n (if S[l-1]), Q_l rows 1..n
+  const int nA = k - 1, nM = sm1 ? n : 0, nQ = cx.wantZ ? n : 0;
+  for (int w = tid; w < nA + nM + nQ; w += nt) {
+    T* a;
+    long long lda;
+    if (w < nA) {
+      a = &PSD_GE(Al, ld, 1 + w, k);
+      lda = ld;
+    } else if (w < nA + nM) {
+      a = &PSD_GE(Am, ld, 1 + (w - nA), k);
+      lda = ld;
+    } else {
+      a = &PSD_GE(Ql, cx.ldz, 1 + (w - nA - nM), k);
+      lda = cx.ldz;
+    }
+    // a_r is the entry in column k-r of this row
+    T d = a[0];
+    for (int r = 1; r < m; r++) d = d + a[-(long long)r * lda] * (tv * conj_(x[r * inc]));
+    d = tau * d;
+    a[0] = a[0] - d;
+    for (int r = 1; r < m; r++)
+      a[-(long long)r * lda] = a[-(long long)r * lda] - d * conj_(tv * conj_(x[r * inc]));
+  }
+  // (b) left G' on all columns of Am rows 1..k (if !S[l-1]): one warp per column
+  if (!sm1) {
+    for (int w = warp; w < n; w += nw) {
+      T* a = &PSD_GE(Am, ld, k, 1 + w);  // a[-r] is row k-r
+      T d = Scalar<T>::zero();
+      for (int r = lane; r < m; r += 32) {
+        const T wr = (r == 0) ? Scalar<T>::one() : tv * conj_(x[r * inc]);
+        d = d + conj_(wr) * a[-r];
+      }
+      if constexpr (sizeof(T) == sizeof(double)) {
+        d = warp_sum(d);
+      } else {
+        d.x = warp_sum(d.x);
+        d.y = warp_sum(d.y);
+      }
+      d = conj_(tau) * d;
+      for (int r = lane; r < m; r += 32) {
+        const T wr = (r == 0) ? Scalar<T>::one() : tv * conj_(x[r * inc]);
+        a[-r] = a[-r] - d * wr;
+      }
+    }
+  }
+  __syncthreads();
+  for (int r = tid; r < m; r += nt)
+    PSD_GE(Al, ld, k, k - r) = (r == 0) ? Scalar<T>::from_real(beta) : Scalar<T>::zero();
+  __syncthreads();
+}
+
+// _phessenberg!(A, S) (generalized.jl:988-1082) with the Q accumulation fused in.
+template <class T>
+PSD_DEV void gphessenberg_cta(const GCtx<T>& cx) {
+  const int n = cx.n, p = cx.p, tid = cx.tid, nt = cx.nt, ld = cx.ldh;
+  if (cx.wantZ) {
+    for (int l = 1; l <= p; l++) {
+      T* Zl = cx.Zp(l);
+      for (int e = tid; e < n * n; e += nt) {
+        const int r = e % n, c = e / n;
+        Zl[r + (size_t)c * cx.ldz] = (r == c) ? Scalar<T>::one() : Scalar<T>::zero();
+      }
+    }
+  }
+  __syncthreads();
+  // Stage 1 (:1009-1028)
+  for (int l = p; l >= 2; l--) {
+    T* Al = cx.Hp(l);
+    T* Am = cx.Hp(l - 1);
+    T* Ql = cx.wantZ ? cx.Zp(l) : nullptr;
+    const bool sm1 = cx.Sg(l - 1);
+    if (cx.Sg(l)) {
+      for (int k = 1; k <= n - 1; k++) stage1_qr_step(cx, Al, Am, sm1, Ql, k);
+    } else {
+      for (int k = n; k >= 2; k--) stage1_rq_step(cx, Al, Am, sm1, Ql, k);
+    }
+  }
+  // Stage 2 (:1034-1079): rotation (i-1, i) zeroing A_1[i, jc], chased through all factors
+  T* A1 = cx.Hp(1);
+  for (int jc = 1; jc <= n - 2; jc++) {
+    for (int i = n; i >= jc + 2; i--) {
+      const T f = PSD_GE(A1, ld, i - 1, jc), g = PSD_GE(A1, ld, i, jc);
+      if (is_zero(g)) continue;  // identity rotation (uniform over the CTA)
+      double c;
+      T s, r;
+      givens_t(f, g, c, s, r);
+      chase_rotation(cx, i - 1, c, s, jc, r, jc + 1, n, 1, n);
+    }
+  }
+}
+
+// generalized.jl:939-976 (_safeprod): x_1^{s_1} prod x_l^{s_l} = alpha / beta * 2^scale with
+// |alpha| in [1,2) or 0 and beta in {0,1}.  d[l-1] = diagonal entry of factor l.
+template <class T, class F>
+PSD_DEV void safeprod(int p, const unsigned char* S, F diag_of, T& alpha, int& beta, long long& scale) {
+  alpha = Scalar<T>::one();
+  beta = 1;
+  scale = 0;
+  for (int i = 1; i <= p; i++) {
+    const T xi = diag_of(i);
+    if (S[i - 1]) {
+      alpha = alpha * xi;
+    } else {
+      if (is_zero(xi))
+        beta = 0;
+      else
+        alpha = alpha / xi;
+    }
+    double aa = abs_(alpha);
+    if (aa == 0.0) {
+      alpha = Scalar<T>::zero();
+      scale = 0;
+      if (beta == 0) return;
+    } else if (isfinite(aa)) {
+      int e;
+      (void)frexp(aa, &e);  // aa = f 2^e, f in [0.5,1)  ->  |alpha| 2^-(e-1) in [1,2)
+      alpha = alpha * scalbn(1.0, -(e - 1));
+      // guard against hypot rounding at the boundary
+      aa = abs_(alpha);
+      if (aa >= 2.0) { alpha = alpha * 0.5; e++; }
+      else if (aa < 1.0) { alpha = alpha * 2.0; e--; }
+      scale += (e - 1);
+    }
+  }
+}
+
+}  // namespace psd

@@ -59,6 +59,36 @@ class PeriodicSchur:
         return len(self.T) + 1
 
 
+@dataclass
+class GeneralizedPeriodicSchur:
+    """Mirror of the reference result struct (generalized.jl:31-85): S, schurindex, T1, T, Z,
+    alpha, beta, alphascale, orientation; values = alpha ./ beta .* 2^alphascale (:75-76)."""
+    S: List[bool]
+    schurindex: int
+    T1: np.ndarray
+    T: List[np.ndarray]
+    Z: List[np.ndarray]
+    alpha: np.ndarray
+    beta: np.ndarray
+    alphascale: np.ndarray
+    orientation: str = "R"
+    info: int = 0
+
+    @property
+    def period(self) -> int:
+        return len(self.S)
+
+    @property
+    def values(self) -> np.ndarray:
+        return gvalues(self.alpha, self.beta, self.alphascale)
+
+
+def gvalues(alpha, beta, alphascale):
+    """alpha ./ beta .* 2^alphascale (generalized.jl:75-76); beta == 0 gives a non-finite value."""
+    with np.errstate(divide="ignore", invalid="ignore", over="ignore"):
+        return alpha / beta * np.exp2(np.asarray(alphascale, dtype=np.float64))
+
+
 class Handle:
     """Owns a psd_handle_t (streams, device workspaces, pinned staging)."""
 
@@ -168,6 +198,87 @@ def phessenberg_batched(A: np.ndarray, wantQ: bool = True, handle: Optional[Hand
     return H, Q
 
 
+def _sig(S, p):
+    S = np.ascontiguousarray(np.asarray(S, dtype=bool).astype(np.uint8))
+    if S.shape != (p,):
+        raise ValueError("DimensionMismatch: S must have one entry per factor")
+    return S
+
+
+def gpschur_batched(A: np.ndarray, S, lr="R", wantZ: bool = True, wantT: bool = True,
+                    maxitfac: int = 0, handle: Optional[Handle] = None, hessut: bool = False):
+    """Batched generalized periodic Schur decomposition (psd_cpschur_batched for complex128 A;
+    psd_rgpschur_batched for float64 A).  A: [batch][p][n][n] storage layout, user factor order;
+    S: signature, user order.  hessut=True calls the inner entry point on Hessenberg-triangular
+    input (rightwards order).  Returns (T, Z, alpha, beta, alphascale, info)."""
+    orient = char_lr(lr)
+    if A.ndim != 4 or A.shape[2] != A.shape[3] or A.dtype not in (np.complex128, np.float64):
+        raise ValueError("A must be complex128 or float64 with shape [batch][p][n][n]")
+    h = handle or default_handle()
+    batch, p, n, _ = A.shape
+    Sb = _sig(S, p)
+    cplx = A.dtype == np.complex128
+    T = np.ascontiguousarray(A).copy()
+    Z = np.empty_like(T) if wantZ else None
+    alpha = np.empty((batch, n), dtype=np.complex128)
+    beta = np.empty((batch, n), dtype=np.complex128 if cplx else np.float64)
+    scale = np.empty((batch, n), dtype=np.int64)
+    info = np.empty(batch, dtype=np.int32)
+    L = lib()
+    if hessut:
+        if orient != "R":
+            raise ValueError("the Hessenberg-triangular entry point is rightwards only")
+        f = L.psd_cpschur_hessut_batched if cplx else L.psd_rgpschur_hessut_batched
+        check(f(h.ptr, n, p, batch, _vp(Sb), int(wantT), int(wantZ), int(maxitfac), _vp(T), _vp(Z),
+                _vp(alpha), _vp(beta), _vp(scale), _vp(info)))
+    else:
+        f = L.psd_cpschur_batched if cplx else L.psd_rgpschur_batched
+        check(f(h.ptr, n, p, batch, 1 if orient == "L" else 0, _vp(Sb), int(wantT), int(wantZ),
+                int(maxitfac), _vp(T), _vp(Z), _vp(alpha), _vp(beta), _vp(scale), _vp(info)))
+    return T, Z, alpha, beta, scale, info
+
+
+def gpschur_(A: List[np.ndarray], S, lr="R", wantZ: bool = True, wantT: bool = True,
+             handle: Optional[Handle] = None) -> GeneralizedPeriodicSchur:
+    """pschur!(A, S, lr; wantZ, wantT) (generalized.jl:108-148 complex, rgeneralized.jl:3-45 real):
+    overwrites A with the T factors and returns the reference's result struct."""
+    orient = char_lr(lr)
+    p = len(A)
+    n = A[0].shape[0]
+    dt = A[0].dtype
+    for Aj in A:
+        if Aj.ndim != 2 or Aj.shape != (n, n) or Aj.dtype != dt:
+            raise ValueError("DimensionMismatch: all factors must be square of equal order and type")
+    stor = np.empty((1, p, n, n), dtype=dt)
+    for j in range(p):
+        stor[0, j] = A[j].T
+    try:
+        T, Z, alpha, beta, scale, info = gpschur_batched(stor, S, orient, wantZ, wantT, 0, handle)
+    except PsdError as e:
+        if e.code == -4:
+            raise ValueError("The leftmost entry in S must be true") from e  # ArgumentError
+        raise
+    if info[0] != 0:
+        raise RuntimeError(f"convergence failed at level {int(info[0])}")
+    for j in range(p):
+        A[j][...] = T[0, j].T
+    if orient == "R":
+        T1, Ts, sidx = A[0], [A[j] for j in range(1, p)], 1
+    else:
+        T1, Ts, sidx = A[p - 1], [A[j] for j in range(0, p - 1)], p
+    Zs = [np.ascontiguousarray(Z[0, j].T) for j in range(p)] if wantZ else []
+    return GeneralizedPeriodicSchur([bool(x) for x in S], sidx, T1, Ts, Zs, alpha[0].copy(),
+                                    beta[0].copy(), scale[0].copy(), orient, int(info[0]))
+
+
+def cpschur_std_(A: List[np.ndarray], lr="R", wantZ: bool = True, wantT: bool = True,
+                 handle: Optional[Handle] = None) -> PeriodicSchur:
+    """Complex standard pschur!(A, lr) (PeriodicSchurDecompositions.jl:1106-1111): S = trues,
+    result repackaged as PeriodicSchur with values = alpha ./ beta .* 2^alphascale."""
+    F = gpschur_(A, [True] * len(A), lr, wantZ, wantT, handle)
+    return PeriodicSchur(F.T1, F.T, F.Z, F.values, F.orientation, F.schurindex, F.info)
+
+
 def pschur_(A: List[np.ndarray], lr="R", wantZ: bool = True, wantT: bool = True,
             maxitfac: int = 30, handle: Optional[Handle] = None) -> PeriodicSchur:
     """pschur!(A, lr; wantZ, wantT, maxitfac) (PeriodicSchurDecompositions.jl:120-152): the input
@@ -181,8 +292,13 @@ def pschur_(A: List[np.ndarray], lr="R", wantZ: bool = True, wantT: bool = True,
     for Aj in A:
         if Aj.ndim != 2 or Aj.shape != (n, n):
             raise ValueError("DimensionMismatch: all factors must be square of equal order")
+        if Aj.dtype not in (np.float64, np.complex128):
+            raise TypeError("float64 or complex128 matrices expected")
+    if A[0].dtype == np.complex128:
+        return cpschur_std_(A, orient, wantZ, wantT, handle)
+    for Aj in A:
         if Aj.dtype != np.float64:
-            raise TypeError("real path takes float64 matrices")
+            raise TypeError("all factors must have the same element type")
     stor = np.empty((1, p, n, n), dtype=np.float64)
     for j in range(p):
         stor[0, j] = A[j].T
@@ -208,4 +324,11 @@ def pschur_(A: List[np.ndarray], lr="R", wantZ: bool = True, wantT: bool = True,
 
 def pschur(A: Sequence[np.ndarray], lr="R", **kwargs) -> PeriodicSchur:
     """pschur(A, lr; kwargs...) (PeriodicSchurDecompositions.jl:108-113): copying wrapper."""
-    return pschur_([np.array(Aj, dtype=np.float64, copy=True) for Aj in A], lr, **kwargs)
+    dt = np.complex128 if any(np.iscomplexobj(Aj) for Aj in A) else np.float64
+    return pschur_([np.array(Aj, dtype=dt, copy=True) for Aj in A], lr, **kwargs)
+
+
+def gpschur(A: Sequence[np.ndarray], S, lr="R", **kwargs) -> GeneralizedPeriodicSchur:
+    """pschur(A, S, lr; kwargs...) (generalized.jl:87-91): copying wrapper."""
+    dt = np.complex128 if any(np.iscomplexobj(Aj) for Aj in A) else np.float64
+    return gpschur_([np.array(Aj, dtype=dt, copy=True) for Aj in A], S, lr, **kwargs)

@@ -1,0 +1,96 @@
+"""CPU tests pinning the numpy restatement of the complex generalized periodic Schur path
+(oracle/gpsd_complex.py) with the reference's own predicates and fixtures
+(test/generalized.jl, test/testfuncs.jl:155-235) and eigvals of the explicit product."""
+import numpy as np
+import pytest
+
+import gpsd_cases as GCs
+import psd_checks as K
+from oracle import gpsd as OG
+
+EPS = np.finfo(float).eps
+
+
+def _alt(p):
+    S = [True]
+    for _ in range(1, p):
+        S.append(not S[-1])
+    return S
+
+
+def _check_batch(A, S, out, left=False):
+    T, Z, al, be, sc, info = out
+    assert (info == 0).all()
+    for b in range(A.shape[0]):
+        r = K.gpschur_check(A[b], S, T[b], Z[b], al[b], be[b], sc[b], left=left)
+        lam = r["values"]
+        if all(np.isfinite(lam)):
+            ref = K.gproduct_eigvals(A[b], S, left)
+            worst = K.match_eigs(ref, lam)
+            assert worst <= 1e-9 * np.max(np.abs(ref))
+
+
+# test/generalized.jl:175-222: full complex, p=5 all-true and p=4 alternating, :R and :L
+@pytest.mark.parametrize("p,S,left", [
+    (5, [1] * 5, False), (5, [1] * 5, True),
+    (4, [1, 0, 1, 0], False), (4, [0, 1, 0, 1], True),
+    (1, [1], False), (2, [1, 0], False), (6, [1, 0, 1, 1, 0, 1], False),
+])
+def test_complex_full(p, S, left):
+    A = GCs.rand_storage(1234, 5, p, 3, True)
+    _check_batch(A, S, OG.cpschur_batched(A, S, left=left), left)
+
+
+# test/generalized.jl:224-246 (Hess+UT, all true, with and without hole) and :68-153
+@pytest.mark.parametrize("p", [1, 2, 3, 5])
+def test_complex_hessut_alltrue(p):
+    A = GCs.hessut_storage(77, 5, p, 2, True)
+    _check_batch(A, [1] * p, OG.cpschur_batched(A, [1] * p, hessut=True))
+    if p > 1:
+        A = GCs.hessut_storage(78, 5, p, 2, True, hole=(2, 3))
+        _check_batch(A, [1] * p, OG.cpschur_batched(A, [1] * p, hessut=True))
+
+
+@pytest.mark.parametrize("p", [2, 3, 5])
+def test_complex_hessut_one_minus(p):
+    S = [1, 0] + [1] * (p - 2)
+    A = GCs.hessut_storage(79, 5, p, 2, True)
+    _check_batch(A, S, OG.cpschur_batched(A, S, hessut=True))
+
+
+@pytest.mark.parametrize("S,hole", GCs.HOLE_CASES)
+def test_complex_hole_cases(S, hole):
+    A = GCs.hessut_storage(80 + hole[0] * 10 + hole[1], 5, 5, 2, True, hole=hole)
+    out = OG.cpschur_batched(A, S, hessut=True)
+    _check_batch(A, S, out)
+    lam = K.gpschur_check(A[0], S, out[0][0], out[1][0], out[2][0], out[3][0], out[4][0])["values"]
+    if S[hole[0] - 1]:
+        assert np.count_nonzero(lam == 0) >= 1      # zero eigenvalue of the product
+    else:
+        assert np.count_nonzero(~np.isfinite(lam)) >= 1  # infinite eigenvalue
+
+
+# test/generalized.jl:154-173: moderate N
+@pytest.mark.parametrize("S", [[1, 1, 1, 1], [1, 0, 1, 0]])
+def test_complex_moderate_n(S):
+    A = GCs.hessut_storage(99, 32, 4, 1, True, hole=(2, 3))
+    _check_batch(A, S, OG.cpschur_batched(A, S, hessut=True))
+
+
+def test_complex_fast_paths():
+    """test/generalized.jl:268-303: wantT/wantZ = false give the same eigenvalues."""
+    for p in (1, 5):
+        A = GCs.rand_storage(5, 5, p, 2, True)
+        S = [1] * p
+        full = OG.cpschur_batched(A, S)
+        fast = OG.cpschur_batched(A, S, wantT=False, wantZ=False)
+        for b in range(2):
+            lf = full[2][b] / full[3][b] * np.exp2(full[4][b].astype(float))
+            lq = fast[2][b] / fast[3][b] * np.exp2(fast[4][b].astype(float))
+            assert K.match_eigs(lf, lq) <= 1e-10 * np.max(np.abs(lf))
+
+
+def test_signature_error():
+    A = GCs.rand_storage(1, 4, 3, 1, True)
+    with pytest.raises(ValueError):
+        OG.cpschur_batched(A, [0, 1, 1])
