@@ -55,3 +55,29 @@ def cpschur_batched(A, S, left=False, wantT=True, wantZ=True, hessut=False, maxi
             Z[b] = Zb
         alpha[b], beta[b], scale[b], info[b] = F["alpha"], F["beta"], F["alphascale"], F["info"]
     return T, Z, alpha, beta, scale, info
+
+
+def rgpschur_batched(A, S, left=False, wantT=True, wantZ=True, hessut=False, maxitfac=120):
+    """Real generalized path (rgeneralized.jl:3-45 or, with hessut, the inner :49 entry).
+    Returns (T, Z, alpha, beta, alphascale, info)."""
+    from . import gpsd_real as GR
+    batch, p, n, _ = A.shape
+    T = np.zeros_like(A)
+    Z = np.zeros_like(A) if wantZ else None
+    alpha = np.zeros((batch, n), dtype=np.complex128)
+    beta = np.zeros((batch, n), dtype=np.float64)
+    scale = np.zeros((batch, n), dtype=np.int64)
+    info = np.zeros(batch, dtype=np.int32)
+    for b in range(batch):
+        Am = _math(A[b])
+        if hessut:
+            F = GR.rpqz(Am[0], Am[1:], [bool(x) for x in S], wantZ=wantZ, wantT=wantT,
+                        maxitfac=maxitfac)
+        else:
+            F = GR.rgpschur(Am, S, "L" if left else "R", wantZ=wantZ, wantT=wantT, maxitfac=maxitfac)
+        Tb, Zb = _pack(F, p, n, np.float64, wantZ)
+        T[b] = Tb
+        if wantZ:
+            Z[b] = Zb
+        alpha[b], beta[b], scale[b], info[b] = F["alpha"], F["beta"], F["alphascale"], F["info"]
+    return T, Z, alpha, beta, scale, info

@@ -21,16 +21,23 @@ class ConvergenceError(RuntimeError):
     pass
 
 
-def cpqz(H1, Hs, S, wantZ=True, wantT=True, Q=None, maxitfac=30, rev=False):
+def cpqz(H1, Hs, S, wantZ=True, wantT=True, Q=None, maxitfac=30, rev=False, real_step=None):
     """generalized.jl:166-931.  H1 upper Hessenberg, Hs list of p-1 upper triangular (all
     modified in place), S signature with S[0] True.  Returns dict(S, schurindex, T1, T, Z,
-    alpha, beta, alphascale, orientation, info)."""
+    alpha, beta, alphascale, orientation, info).
+
+    The deflation skeleton (tests 1-4, S+/S- deflation, 1x1 split) is shared verbatim by the
+    real path (rgeneralized.jl:169-648 is the same text with real rotations): gpsd_real.rpqz
+    calls this function with `real_step`, a callback that replaces the single-shift sweep by
+    the real 2x2-block handling and double-shift sweep (rgeneralized.jl:655-1054)."""
     p = len(Hs) + 1
     n = H1.shape[0]
     if not S[0]:
         raise ValueError("Signature entry S[1] must be true")
+    is_real = real_step is not None
+    wdt = np.float64 if is_real else np.complex128
     alpha = np.zeros(n, dtype=np.complex128)
-    beta = np.zeros(n, dtype=np.complex128)
+    beta = np.zeros(n, dtype=wdt)
     ascale = np.zeros(n, dtype=np.int64)
     safmin = FLOATMIN
     ulp = EPS
@@ -42,7 +49,7 @@ def cpqz(H1, Hs, S, wantZ=True, wantT=True, Q=None, maxitfac=30, rev=False):
 
     ziter = -1 if (p >= math.log2(FLOATMIN) / math.log2(ulp)) else 0
     if wantZ:
-        Z = [np.eye(n, dtype=np.complex128) for _ in range(p)] if Q is None else Q
+        Z = [np.eye(n, dtype=wdt) for _ in range(p)] if Q is None else Q
     else:
         Z = []
     G = [None] * (n + 2)
@@ -109,16 +116,17 @@ def cpqz(H1, Hs, S, wantZ=True, wantT=True, Q=None, maxitfac=30, rev=False):
                         ldeflate, jdeflate = l, jx
                         break
             # NOTE the reference runs Test 3 even when Test 2 fired and lets it overwrite
-            # ldeflate/jdeflate (:341-353); the if/elseif below then still takes the S+ branch
-            # with the S- indices only if deflate_neg is also set.  Restated literally.
+            # ldeflate/jdeflate (:341-353), and runs Test 4 regardless; SLICOT MB03BZ jumps to
+            # the handler as soon as a test fires.  The SLICOT order is restated here
+            # (defects on rarely taken branches are not replicated).
             deflate_neg = False
-            for l in range(2, p + 1):  # Test 3
+            for l in (range(2, p + 1) if not deflate_pos else ()):  # Test 3
                 if not S[l - 1]:
                     deflate_neg, jx = check_deflate_tr(Hm(l), jlo, ilast)
                     if deflate_neg:
                         ldeflate, jdeflate = l, jx
                         break
-            if ziter >= 7 or ziter < 0:  # Test 4: controlled zero shift (:356-448)
+            if (ziter >= 7 or ziter < 0) and not (deflate_pos or deflate_neg):  # Test 4 (:356-448)
                 for j in range(jlo, ilast):
                     c, s, r = givens(H1[j - 1, j - 1], H1[j, j - 1])
                     H1[j - 1, j - 1] = r
@@ -141,7 +149,7 @@ def cpqz(H1, Hs, S, wantZ=True, wantT=True, Q=None, maxitfac=30, rev=False):
                                 tol = max(ulp * tol, smlnum)
                                 if abs(Hl[j, j - 1]) <= tol:
                                     Hl[j, j - 1] = 0
-                                    G[j] = (1.0, 0j)
+                                    G[j] = (1.0, 0.0 * s)
                                 else:
                                     c, s, r = givens(Hl[j - 1, j - 1], Hl[j, j - 1])
                                     Hl[j - 1, j - 1] = r
@@ -159,7 +167,7 @@ def cpqz(H1, Hs, S, wantZ=True, wantT=True, Q=None, maxitfac=30, rev=False):
                                 tol = max(ulp * tol, smlnum)
                                 if abs(Hl[j, j - 1]) <= tol:
                                     Hl[j, j - 1] = 0
-                                    G[j] = (1.0, 0j)
+                                    G[j] = (1.0, 0.0 * s)
                                 else:
                                     c, s, r = givens(Hl[j, j], Hl[j, j - 1])
                                     Hl[j, j] = r
@@ -412,7 +420,25 @@ def cpqz(H1, Hs, S, wantZ=True, wantT=True, Q=None, maxitfac=30, rev=False):
         else:
             ifirst = jlo
 
-        if doqziter:  # (:770-854)
+        if doqziter and is_real:  # rgeneralized.jl:655-1054
+            iiter += 1
+            ziter += 1
+            if not wantT:
+                ifirstm = ifirst
+            r = real_step(H1, Hs, S, Z, wantZ, ifirst, ilast, ifirstm, ilastm, alpha, beta, ascale)
+            if r is not None:  # complex 2x2 block split off (:748-790)
+                ilast = ifirst - 1
+                if ilast < 1:
+                    done = True
+                    break
+                iiter = 0
+                if ziter != -1:
+                    ziter = 0
+                if not wantT:
+                    ilastm = ilast
+                    if ifirstm > ilast:
+                        ifirstm = 1
+        elif doqziter:  # (:770-854)
             iiter += 1
             ziter += 1
             if not wantT:
@@ -465,7 +491,7 @@ def cpqz(H1, Hs, S, wantZ=True, wantT=True, Q=None, maxitfac=30, rev=False):
     if not done:
         info = ilast  # "convergence failed at level ilast" (:856-858)
 
-    if wantT and info == 0:  # phase normalisation (:860-908)
+    if wantT and info == 0 and not is_real:  # phase normalisation (:860-908)
         for l in range(p, 1, -1):
             Hl = Hm(l)
             sf = np.ones(n, dtype=np.complex128)

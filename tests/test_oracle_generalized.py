@@ -94,3 +94,62 @@ def test_signature_error():
     A = GCs.rand_storage(1, 4, 3, 1, True)
     with pytest.raises(ValueError):
         OG.cpschur_batched(A, [0, 1, 1])
+
+
+# ------------------------------------------------------------------------------------------
+# real generalized path (oracle/gpsd_real.py): test/generalized.jl:42-153 with T = Float64,
+# predicates test/testfuncs.jl:238-382
+# ------------------------------------------------------------------------------------------
+def _check_real(A, S, out, left=False):
+    T, Z, al, be, sc, info = out
+    assert (info == 0).all()
+    for b in range(A.shape[0]):
+        r = K.gpschur_check(A[b], S, T[b], Z[b], al[b], be[b], sc[b], left=left, real_path=True)
+        lam = r["values"]
+        if all(np.isfinite(lam)):
+            ref = K.gproduct_eigvals(A[b], S, left)
+            assert K.match_eigs(ref, lam) <= 1e-9 * np.max(np.abs(ref))
+        # complex eigenvalues come in adjacent conjugate pairs, positive imaginary part first
+        j = 0
+        while j < len(lam):
+            if np.isfinite(lam[j]) and lam[j].imag != 0:
+                assert lam[j].imag > 0 and lam[j + 1] == np.conj(lam[j])
+                j += 2
+            else:
+                j += 1
+
+
+@pytest.mark.parametrize("p,S,left", [
+    (4, [1, 0, 1, 0], False), (4, [0, 1, 0, 1], True), (1, [1], False), (3, [1, 1, 1], False),
+    (5, [1, 0, 1, 1, 0], False), (3, [0, 1, 1], True),
+])
+def test_real_full(p, S, left):
+    A = GCs.rand_storage(1234, 5, p, 3, False)
+    _check_real(A, S, OG.rgpschur_batched(A, S, left=left), left)
+
+
+@pytest.mark.parametrize("p", [2, 3, 5])
+def test_real_hessut_one_minus(p):
+    S = [1, 0] + [1] * (p - 2)
+    A = GCs.hessut_storage(79, 5, p, 2, False)
+    _check_real(A, S, OG.rgpschur_batched(A, S, hessut=True))
+
+
+@pytest.mark.parametrize("S,hole", GCs.HOLE_CASES)
+def test_real_hole_cases(S, hole):
+    A = GCs.hessut_storage(80 + hole[0] * 10 + hole[1], 5, 5, 2, False, hole=hole)
+    out = OG.rgpschur_batched(A, S, hessut=True)
+    _check_real(A, S, out)
+    lam = K.gpschur_check(A[0], S, out[0][0], out[1][0], out[2][0], out[3][0], out[4][0],
+                          real_path=True)["values"]
+    if S[hole[0] - 1]:
+        assert np.count_nonzero(lam == 0) >= 1
+    else:
+        assert np.count_nonzero(~np.isfinite(lam)) >= 1
+
+
+def test_real_larger():
+    A = GCs.rand_storage(5, 16, 3, 1, False)
+    _check_real(A, [1, 0, 1], OG.rgpschur_batched(A, [1, 0, 1]))
+    A = GCs.rand_storage(6, 12, 4, 1, False)
+    _check_real(A, [0, 1, 0, 1], OG.rgpschur_batched(A, [0, 1, 0, 1], left=True), True)
