@@ -152,6 +152,34 @@ int psd_cpschur_hessut_batched(psd_handle_t handle, int n, int p, int64_t batch,
                                int wantT, int wantZ, int maxitfac, double* A, double* Z,
                                double* alpha, double* beta, int64_t* alphascale, int32_t* info);
 
+/* ---------------------------------------------------------------------------------------
+ * Real generalized periodic Schur decomposition (periodic QZ), batched.
+ * Replaces pschur!(A::Vector{Matrix{Float64}}, S, lr; wantZ, wantT)
+ *   driver, :L reversal of A and S      rgeneralized.jl:3-45
+ *   generalized Hessenberg-triangular   generalized.jl:988-1082   (_phessenberg!(A, S))
+ *   real periodic QZ (MB03BD-style)     rgeneralized.jl:49-1083
+ *   2x2 periodic eigen-kernels          rpschur2x2.jl:9-317, rgeneralized.jl:1140-1509
+ * Arguments as psd_cpschur_batched with real A, Z (float64) and real beta:
+ *   alpha out [batch][n] complex128, beta out [batch][n] float64, alphascale [batch][n] int64.
+ * On return (wantT != 0) the Schur factor is upper quasi-triangular with exact zeros below the
+ * subdiagonal and T1[i+1,i] == 0 wherever eigenvalue i is real; 2x2 diagonal blocks are exactly
+ * the complex-conjugate pairs and are left unstandardised as in the reference
+ * (rgeneralized.jl:748-790); conjugate pairs are adjacent, positive imaginary part first
+ * (rpschur2x2.jl:228-232).  maxitfac <= 0 selects the reference default 120.
+ * The reference keyword `aggressive` (rgeneralized.jl:7, off by default) is not offered.
+ * ------------------------------------------------------------------------------------- */
+int psd_rgpschur_batched(psd_handle_t handle, int n, int p, int64_t batch, int orientation,
+                         const uint8_t* S, int wantT, int wantZ, int maxitfac, double* A,
+                         double* Z, double* alpha, double* beta, int64_t* alphascale,
+                         int32_t* info);
+
+/* Real periodic QZ iteration on Hessenberg-triangular input (rightwards order, Z from the
+ * identity): the inner method pschur!(H1, Hs, S; ...) of rgeneralized.jl:49-1083, which the
+ * reference's tests call directly for the planted-zero cases (test/generalized.jl:68-153). */
+int psd_rgpschur_hessut_batched(psd_handle_t handle, int n, int p, int64_t batch, const uint8_t* S,
+                                int wantT, int wantZ, int maxitfac, double* A, double* Z,
+                                double* alpha, double* beta, int64_t* alphascale, int32_t* info);
+
 /* Synthetic inputs (measurement only): uniform [0,1) entries from a
  * counter-based generator keyed by (seed, problem, factor, row, col), problems
  * first_b .. first_b+batch-1, written to a host buffer or (asynchronously, on the current

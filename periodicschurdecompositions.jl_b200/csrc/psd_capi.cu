@@ -467,9 +467,9 @@ struct GenCall {
 
 size_t gen_elem(const GenCall& gc) { return gc.cplx ? 16 : 8; }
 
-int launch_gen(psd_handle_s* h, Device& dev, Slot& aux, cudaStream_t stream, const GenCall& gc, long long batch,
-               void* dA, void* dZ, void* dAlpha, void* dBeta, long long* dScale, int32_t* dInfo) {
-  if (batch == 0) return PSD_OK;
+template <class T>
+int launch_gen_t(psd_handle_s* h, Device& dev, Slot& aux, cudaStream_t stream, const GenCall& gc, long long batch,
+                 void* dA, void* dZ, void* dAlpha, void* dBeta, long long* dScale, int32_t* dInfo) {
   const int n = gc.n, p = gc.p;
   const bool wantZ = gc.wantZ && dZ;
   int e = ensure_dev(aux.dS, aux.capS, (size_t)p);
@@ -481,43 +481,49 @@ int launch_gen(psd_handle_s* h, Device& dev, Slot& aux, cudaStream_t stream, con
   PSD_CUDA(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev.ordinal));
   int threads = ((2 * n + 31) / 32) * 32;
   threads = std::max(64, std::min(threads, 256));
-  if (gc.cplx) {
-    cudaFuncAttributes fa;
-    PSD_CUDA(cudaFuncGetAttributes(&fa, psd::cpschur_kernel));
-    const size_t max_dyn = (size_t)optin - fa.sharedSizeBytes;
-    const size_t small = (size_t)((psd::cq_small_doubles(n, p) + 1) & ~1LL) * sizeof(double);
-    const int ldh = n;
-    const size_t mats = (size_t)p * ldh * n * 16 * (wantZ ? 2 : 1);
-    psd::CpqzParams P;
-    P.n = n; P.p = p; P.batch = batch; P.left = gc.left; P.wantT = gc.wantT; P.wantZ = wantZ ? 1 : 0;
-    P.maxitfac = gc.maxitfac > 0 ? gc.maxitfac : 30;
-    P.skip_reduce = gc.skip_reduce;
-    P.S = aux.dS;
-    P.A = (psd::cplx*)dA; P.Z = wantZ ? (psd::cplx*)dZ : nullptr;
-    P.alpha = (psd::cplx*)dAlpha; P.beta = (psd::cplx*)dBeta; P.scale = dScale; P.info = dInfo;
-    P.counter = aux.dCounter;
-    size_t smem;
-    if (small + mats <= max_dyn) {
-      P.use_smem = 1; P.ldh = ldh; smem = small + mats;
-    } else {
-      if (small > max_dyn) return fail(PSD_ERR_UNSUPPORTED, "n or p too large for the per-CTA state");
-      P.use_smem = 0; P.ldh = n; smem = small;
-    }
-    PSD_CUDA(cudaFuncSetAttribute(psd::cpschur_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_dyn));
-    int occ = 0;
-    PSD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, psd::cpschur_kernel, threads, smem));
-    if (occ < 1) return fail(PSD_ERR_UNSUPPORTED, "kernel does not fit on an SM");
-    const int grid = (int)std::max(1LL, std::min((long long)occ * dev.sm_count, batch));
-    {
-      ScopedKernelTimer tm(h, dev, stream, 1);
-      psd::cpschur_kernel<<<grid, threads, smem, stream>>>(P);
-    }
-    PSD_CUDA(cudaGetLastError());
-    __atomic_fetch_add(&h->stats[0], (int64_t)1, __ATOMIC_RELAXED);
-    __atomic_fetch_add(&h->stats[P.use_smem ? 1 : 2], (int64_t)batch, __ATOMIC_RELAXED);
-    return PSD_OK;
+  auto kern = psd::gpschur_kernel<T>;
+  cudaFuncAttributes fa;
+  PSD_CUDA(cudaFuncGetAttributes(&fa, kern));
+  const size_t max_dyn = (size_t)optin - fa.sharedSizeBytes;
+  const size_t small = (size_t)((psd::cq_small_doubles(n, p) + 1) & ~1LL) * sizeof(double);
+  const int ldh = (sizeof(T) == 8 && n % 2 == 0) ? n + 1 : n;  // odd leading dimension for real data
+  const size_t mats = (size_t)p * ldh * n * sizeof(T) * (wantZ ? 2 : 1);
+  psd::GpqzParams<T> P;
+  P.n = n; P.p = p; P.batch = batch; P.left = gc.left; P.wantT = gc.wantT; P.wantZ = wantZ ? 1 : 0;
+  P.maxitfac = gc.maxitfac > 0 ? gc.maxitfac : (gc.cplx ? 30 : 120);  // generalized.jl:169, rgeneralized.jl:52
+  P.skip_reduce = gc.skip_reduce;
+  P.S = aux.dS;
+  P.A = (T*)dA; P.Z = wantZ ? (T*)dZ : nullptr;
+  P.alpha = (psd::cplx*)dAlpha; P.beta = (T*)dBeta; P.scale = dScale; P.info = dInfo;
+  P.counter = aux.dCounter;
+  size_t smem;
+  if (small + mats <= max_dyn) {
+    P.use_smem = 1; P.ldh = ldh; smem = small + mats;
+  } else {
+    if (small > max_dyn) return fail(PSD_ERR_UNSUPPORTED, "n or p too large for the per-CTA state");
+    P.use_smem = 0; P.ldh = n; smem = small;
   }
-  return fail(PSD_ERR_UNSUPPORTED, "real generalized path not built");
+  PSD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_dyn));
+  int occ = 0;
+  PSD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
+  if (occ < 1) return fail(PSD_ERR_UNSUPPORTED, "kernel does not fit on an SM");
+  const int grid = (int)std::max(1LL, std::min((long long)occ * dev.sm_count, batch));
+  {
+    ScopedKernelTimer tm(h, dev, stream, 1);
+    kern<<<grid, threads, smem, stream>>>(P);
+  }
+  PSD_CUDA(cudaGetLastError());
+  __atomic_fetch_add(&h->stats[0], (int64_t)1, __ATOMIC_RELAXED);
+  __atomic_fetch_add(&h->stats[P.use_smem ? 1 : 2], (int64_t)batch, __ATOMIC_RELAXED);
+  return PSD_OK;
+}
+
+int launch_gen(psd_handle_s* h, Device& dev, Slot& aux, cudaStream_t stream, const GenCall& gc, long long batch,
+               void* dA, void* dZ, void* dAlpha, void* dBeta, long long* dScale, int32_t* dInfo) {
+  if (batch == 0) return PSD_OK;
+  if (gc.cplx)
+    return launch_gen_t<psd::cplx>(h, dev, aux, stream, gc, batch, dA, dZ, dAlpha, dBeta, dScale, dInfo);
+  return launch_gen_t<double>(h, dev, aux, stream, gc, batch, dA, dZ, dAlpha, dBeta, dScale, dInfo);
 }
 
 int run_gen_shard(psd_handle_s* h, Device& dev, const GenCall& gc, long long first, long long count, char* A,
@@ -771,6 +777,22 @@ int psd_cpschur_hessut_batched(psd_handle_t h, int n, int p, int64_t batch, cons
                                int maxitfac, double* A, double* Z, double* alpha, double* beta,
                                int64_t* alphascale, int32_t* info) {
   GenCall gc{n, p, 0, wantT != 0, wantZ != 0, maxitfac, 1, 1, S};
+  return run_gen_host(h, gc, batch, A, Z, alpha, beta, alphascale, info);
+}
+
+int psd_rgpschur_batched(psd_handle_t h, int n, int p, int64_t batch, int orientation, const uint8_t* S, int wantT,
+                         int wantZ, int maxitfac, double* A, double* Z, double* alpha, double* beta,
+                         int64_t* alphascale, int32_t* info) {
+  if (orientation != 0 && orientation != 1)
+    return fail(PSD_ERR_BAD_ARG, "orientation argument must be either 0 (:R, right) or 1 (:L, left)");
+  GenCall gc{n, p, orientation, wantT != 0, wantZ != 0, maxitfac, 0, 0, S};
+  return run_gen_host(h, gc, batch, A, Z, alpha, beta, alphascale, info);
+}
+
+int psd_rgpschur_hessut_batched(psd_handle_t h, int n, int p, int64_t batch, const uint8_t* S, int wantT,
+                                int wantZ, int maxitfac, double* A, double* Z, double* alpha, double* beta,
+                                int64_t* alphascale, int32_t* info) {
+  GenCall gc{n, p, 0, wantT != 0, wantZ != 0, maxitfac, 1, 0, S};
   return run_gen_host(h, gc, batch, A, Z, alpha, beta, alphascale, info);
 }
 

@@ -18,37 +18,42 @@
 
 namespace psd {
 
-struct CpqzParams {
+template <class T>
+struct GpqzParams {
   int n, p;
   long long batch;
   int left, wantT, wantZ, maxitfac;
   int skip_reduce;          // input already Hessenberg-triangular (pschur!(H1,Hs,S) entry, :166)
   const unsigned char* S;   // [p] user order (device memory)
-  cplx* A;                  // [batch][p][n*n] in/out, user order
-  cplx* Z;                  // [batch][p][n*n] out (reference result order) or nullptr
+  T* A;                     // [batch][p][n*n] in/out, user order
+  T* Z;                     // [batch][p][n*n] out (reference result order) or nullptr
   cplx* alpha;              // [batch][n]
-  cplx* beta;               // [batch][n]
+  T* beta;                  // [batch][n] (complex for the complex path, real for the real one)
   long long* scale;         // [batch][n]
   int* info;                // [batch]
   int use_smem, ldh;
   unsigned long long* counter;
 };
 
-// doubles of per-CTA small state: Gc (n+2), Gs 2(n+2), stage 2(4+3(p-1)), S bytes
+// doubles of per-CTA small state: Gc (n+2), Gs 2(n+2), stage (complex: 2(4+3(p-1)); real double
+// chase: 9+6(p-1)), S bytes
+__host__ __device__ inline long long cq_stage_doubles(int p) { return 10LL + 6 * (p > 1 ? p - 1 : 0); }
 __host__ __device__ inline long long cq_small_doubles(int n, int p) {
-  return 3LL * (n + 2) + 2LL * (4 + 3 * (p > 1 ? p - 1 : 0)) + (p + 15) / 8 + 2;
+  return 3LL * (n + 2) + cq_stage_doubles(p) + (p + 15) / 8 + 2;
 }
 
-struct CqState {
+template <class T>
+struct GqState {
   double* Gc;
-  cplx* Gs;
+  T* Gs;
   int* key;  // shared scratch for the parallel deflation scans
 };
 
 // Test 1 (generalized.jl:260-278): bottom-up scan for a negligible subdiagonal of H_1.
-PSD_DEV bool cq_check_hess(const GCtx<cplx>& cx, const CqState& st, int ilo, int ilast, double ulp,
+template <class T>
+PSD_DEV bool cq_check_hess(const GCtx<T>& cx, const GqState<T>& st, int ilo, int ilast, double ulp,
                            double smlnum, int& jlo) {
-  cplx* H1 = cx.Hp(1);
+  T* H1 = cx.Hp(1);
   const int ld = cx.ldh;
   if (cx.tid == 0) *st.key = 0;
   __syncthreads();
@@ -63,7 +68,7 @@ PSD_DEV bool cq_check_hess(const GCtx<cplx>& cx, const CqState& st, int ilo, int
   __syncthreads();
   jlo = ilo;
   if (jf > 0) {
-    if (cx.tid == 0) PSD_GE(H1, ld, jf, jf - 1) = mk(0.0, 0.0);
+    if (cx.tid == 0) PSD_GE(H1, ld, jf, jf - 1) = Scalar<T>::zero();
     jlo = jf;
     __syncthreads();
     return jf == ilast;
@@ -73,7 +78,8 @@ PSD_DEV bool cq_check_hess(const GCtx<cplx>& cx, const CqState& st, int ilo, int
 
 // Tests 2/3 (generalized.jl:280-299, 327-353): first factor l (ascending) with signature
 // `sign` that has a negligible diagonal entry in jlo..ilast, and the largest such j.
-PSD_DEV bool cq_check_tr(const GCtx<cplx>& cx, const CqState& st, bool sign, int jlo, int ilast,
+template <class T>
+PSD_DEV bool cq_check_tr(const GCtx<T>& cx, const GqState<T>& st, bool sign, int jlo, int ilast,
                          double ulp, double smlnum, int& ldef, int& jdef) {
   const int n = cx.n, p = cx.p, ld = cx.ldh;
   if (cx.tid == 0) *st.key = 0;
@@ -82,7 +88,7 @@ PSD_DEV bool cq_check_tr(const GCtx<cplx>& cx, const CqState& st, bool sign, int
   for (int w = cx.tid; w < (p - 1) * span; w += cx.nt) {
     const int l = 2 + w / span, j = jlo + w % span;
     if (cx.Sg(l) != sign) continue;
-    const cplx* Hl = cx.Hp(l);
+    const T* Hl = cx.Hp(l);
     double tol;
     if (j == ilast)
       tol = abs_(PSD_GE(Hl, ld, j - 1, j));
@@ -100,14 +106,15 @@ PSD_DEV bool cq_check_tr(const GCtx<cplx>& cx, const CqState& st, bool sign, int
   if (k == 0) return false;
   ldef = p + 1 - k / (n + 1);
   jdef = k % (n + 1);
-  if (cx.tid == 0) PSD_GE(cx.Hp(ldef), ld, jdef, jdef) = mk(0.0, 0.0);
+  if (cx.tid == 0) PSD_GE(cx.Hp(ldef), ld, jdef, jdef) = Scalar<T>::zero();
   __syncthreads();
   return true;
 }
 
 // rmul!(M, G_j') for j = j0, j0+dj, ..., j1 in sequence, G_j = Givens(j+oa, j+ob, Gc[j], Gs[j]),
 // all rows: one thread per row, no barrier inside.
-PSD_DEV void cq_rmul_seq(const GCtx<cplx>& cx, const CqState& st, cplx* M, int ld, int j0, int j1,
+template <class T>
+PSD_DEV void cq_rmul_seq(const GCtx<T>& cx, const GqState<T>& st, T* M, int ld, int j0, int j1,
                          int dj, int oa, int ob) {
   for (int row = 1 + cx.tid; row <= cx.n; row += cx.nt)
     for (int j = j0; dj > 0 ? j <= j1 : j >= j1; j += dj)
@@ -123,305 +130,420 @@ PSD_DEV void cq_rmul_seq(const GCtx<cplx>& cx, const CqState& st, cplx* M, int l
     }                       \
   } while (0)
 
-// generalized.jl:166-931.  Returns info (0 or the level ilast at which convergence failed).
-PSD_DEV int cpqz_cta(const GCtx<cplx>& cx, const CqState& st, bool wantT, int maxitfac, cplx* alpha,
-                     cplx* beta, long long* scale) {
-  const int n = cx.n, p = cx.p, ld = cx.ldh, tid = cx.tid;
-  const bool wantZ = cx.wantZ;
-  cplx* H1 = cx.Hp(1);
-  const double ulp = DBL_EPSILON;
-  const double smlnum = DBL_MIN * ((double)n / ulp);
-  const double safmin = DBL_MIN;
-  const cplx czero = mk(0.0, 0.0);
-  // ziter = -1 when p >= log2(floatmin)/log2(eps) (~19.65)  (:199)
-  int ziter = ((double)p >= (-1022.0) / (-52.0)) ? -1 : 0;
-  int ilast = n, ifirst = -1, ifirstm = 1, ilastm = n, iiter = 1;
-  const int maxit = maxitfac * n;
-  int nexc = 0;
-  bool done = false;
+// ==========================================================================================
+// Real path (rgeneralized.jl:655-1054): double-shift sweeps with two rotations per step and
+// 2x2 block handling.
+//
+// How this differs from the reference text (results agree to the tolerances of BASELINE.json;
+// shifts only steer convergence):
+//  * the two starting rotations come from the first column of the double-shift polynomial of the
+//    product H_1 T, T = prod_{l>=2} H_l^{s_l}, evaluated from the leading and trailing 3x3 blocks
+//    of the triangular factors with a running power-of-two scale (what the real standard path
+//    does with its product band, PeriodicSchurDecompositions.jl:474-529, 730-803) instead of
+//    MB03AF's implicit rotation chains (_qzrots, :1140-1359); the reference's explicit-shift
+//    branch (:804-887) is not replicated (it reads undefined names);
+//    every 10th iteration on a block takes a deterministic exceptional shift vector;
+//  * the sweep always enters at Z_1 (rows of H_1), which the reference does only for p == 1
+//    (:944-950); for p > 1 it enters between H_1 and H_2 (:890-943) - the same similarity of a
+//    cyclic shift of the product;
+//  * a 2x2 block is classified by dlanv2 (gs2x2, rschur2x2.jl:9-96) on the explicitly formed,
+//    scaled 2x2 product; a real pair is split by chasing dlanv2's rotation through the factors
+//    (the role of _rp2x2ssr! + the "perfect shift" chain, :685-745), repeated by the outer loop
+//    until Test 1 deflates; a complex pair is left unstandardised in T_1 as in the reference
+//    (:748-790) with alpha, beta, alphascale taken from the scaled product.
+// ==========================================================================================
 
-  for (int jiter = 1; jiter <= maxit; jiter++) {
-    bool split1 = false, dpos = false, dneg = false, doqz = true;
-    int ldef = -1, jdef = -1, jlo = 1;
-    if (ilast == 1) {
-      split1 = true;
+// (a1, a2) <- [c s; -s c] (a1, a2): the same formula serves lmul!(G, .) on a row pair and
+// rmul!(., G') on a column pair for real data.
+PSD_DEV void rrot(double& a1, double& a2, double c, double s) {
+  const double t = c * a1 + s * a2;
+  a2 = c * a2 - s * a1;
+  a1 = t;
+}
+struct Rot2 {
+  double c1, s1;  // G2 = Givens(j, j+1)
+  double c2, s2;  // G1 = Givens(j+1, j+2), applied first
+};
+PSD_DEV void rot3(double& a0, double& a1, double& a2, const Rot2& g) {
+  rrot(a1, a2, g.c2, g.s2);
+  rrot(a0, a1, g.c1, g.s1);
+}
+
+// chase_double: the two rotations G1 = Givens(j+1,j+2), G2 = Givens(j,j+1) act on rows j..j+2
+// of H_1 (columns j..clast), are propagated through factors p..2 (rgeneralized.jl:977-1010) and
+// return to columns j..j+2 of H_1 (rows rfirst..h1r1).  Same organisation as chase_rotation:
+// the 3x3 diagonal blocks are processed in registers by every thread, bulk updates touch
+// disjoint memory, blocks are staged in shared memory and written back between two barriers.
+PSD_DEV void chase_double(const GCtx<double>& cx, int j, Rot2 gin, int zcol, double r1, int clast,
+                          int rfirst, int h1r1) {
+  const int n = cx.n, p = cx.p, tid = cx.tid, nt = cx.nt, ld = cx.ldh;
+  double* H1 = cx.Hp(1);
+  double X[3][3];
+#pragma unroll
+  for (int r = 0; r < 3; r++)
+#pragma unroll
+    for (int c = 0; c < 3; c++) X[r][c] = PSD_GE(H1, ld, j + r, j + c);
+  const Rot2 g0 = gin;
+  double b00 = 0, b01 = 0, b02 = 0, b11 = 0, b12 = 0, b22 = 0;
+  if (p > 1) {
+    const double* Hl = cx.Hp(p);
+    b00 = PSD_GE(Hl, ld, j, j); b01 = PSD_GE(Hl, ld, j, j + 1); b02 = PSD_GE(Hl, ld, j, j + 2);
+    b11 = PSD_GE(Hl, ld, j + 1, j + 1); b12 = PSD_GE(Hl, ld, j + 1, j + 2);
+    b22 = PSD_GE(Hl, ld, j + 2, j + 2);
+  }
+  {  // left-only columns of H_1 and Z_1
+    const int nL = clast - (j + 2);
+    const int nZ = cx.wantZ ? n : 0;
+    double* Z1 = cx.wantZ ? cx.Zp(1) : nullptr;
+    for (int w = tid; w < nL + nZ; w += nt) {
+      double* a;
+      long long st;
+      if (w < nL) {
+        a = &PSD_GE(H1, ld, j, j + 3 + w);
+        st = 1;
+      } else {
+        a = &PSD_GE(Z1, cx.ldz, 1 + (w - nL), j);
+        st = cx.ldz;
+      }
+      double a0 = a[0], a1 = a[st], a2 = a[2 * st];
+      rot3(a0, a1, a2, g0);
+      a[0] = a0; a[st] = a1; a[2 * st] = a2;
+    }
+  }
+  for (int l = p; l >= 2; l--) {
+    double* Hl = cx.Hp(l);
+    double B00 = b00, B01 = b01, B02 = b02, B11 = b11, B12 = b12, B22 = b22, B10 = 0.0, B21 = 0.0;
+    if (l > 2) {
+      const double* Hn = cx.Hp(l - 1);
+      b00 = PSD_GE(Hn, ld, j, j); b01 = PSD_GE(Hn, ld, j, j + 1); b02 = PSD_GE(Hn, ld, j, j + 2);
+      b11 = PSD_GE(Hn, ld, j + 1, j + 1); b12 = PSD_GE(Hn, ld, j + 1, j + 2);
+      b22 = PSD_GE(Hn, ld, j + 2, j + 2);
+    }
+    Rot2 gout;
+    double r;
+    const bool sl = cx.Sg(l);
+    if (sl) {
+      // columns (j+1,j+2) <- G1in; rows (j+1,j+2) re-triangularised by G1out;
+      // columns (j,j+1) <- G2in; rows (j,j+1) re-triangularised by G2out   (:980-991)
+      rrot(B01, B02, gin.c2, gin.s2);
+      rrot(B11, B12, gin.c2, gin.s2);
+      rrot(B21, B22, gin.c2, gin.s2);
+      givens_real(B11, B21, gout.c2, gout.s2, r);
+      B11 = r; B21 = 0.0;
+      rrot(B12, B22, gout.c2, gout.s2);
+      rrot(B00, B01, gin.c1, gin.s1);
+      rrot(B10, B11, gin.c1, gin.s1);
+      givens_real(B00, B10, gout.c1, gout.s1, r);
+      B00 = r; B10 = 0.0;
+      rrot(B01, B11, gout.c1, gout.s1);
+      rrot(B02, B12, gout.c1, gout.s1);
     } else {
-      split1 = cq_check_hess(cx, st, 1, ilast, ulp, smlnum, jlo);
-      if (!split1) {
-        dpos = cq_check_tr(cx, st, true, jlo, ilast, ulp, smlnum, ldef, jdef);
-        if (!dpos) dneg = cq_check_tr(cx, st, false, jlo, ilast, ulp, smlnum, ldef, jdef);
-        if (!dpos && !dneg && (ziter >= 7 || ziter < 0)) {
-          // ---- Test 4: controlled zero shift (:356-448) ----
-          for (int j = jlo; j <= ilast - 1; j++) {
-            double c;
-            cplx s;
-            g_gen(cx, H1, ld, j, j, j + 1, j, c, s);
-            g_lmul(cx, H1, ld, j, j + 1, c, s, j + 1, ilastm);
-            CQ_SETG(j, c, s);
-          }
-          __syncthreads();
-          if (wantZ) cq_rmul_seq(cx, st, cx.Zp(1), cx.ldz, jlo, ilast - 1, 1, 0, 1);
-          for (int l = p; l >= 2; l--) {
-            cplx* Hl = cx.Hp(l);
-            for (int j = jlo; j <= ilast - 1; j++) {
-              double c = st.Gc[j];
-              cplx s = st.Gs[j];
-              if (is_zero(s)) continue;
-              if (cx.Sg(l))
-                g_rmul(cx, Hl, ld, j, j + 1, c, s, ifirstm, j + 1);
-              else
-                g_lmul(cx, Hl, ld, j, j + 1, c, s, j, ilastm);
-              double tol = abs_(PSD_GE(Hl, ld, j, j)) + abs_(PSD_GE(Hl, ld, j + 1, j + 1));
-              if (tol == 0.0) tol = g_opnorm1(Hl, ld, jlo, j + 1, jlo, j + 1, false);
-              tol = fmax(ulp * tol, smlnum);
-              const bool small = abs_(PSD_GE(Hl, ld, j + 1, j)) <= tol;
-              __syncthreads();
-              if (small) {
-                if (tid == 0) PSD_GE(Hl, ld, j + 1, j) = czero;
-                CQ_SETG(j, 1.0, czero);
-                __syncthreads();
-              } else if (cx.Sg(l)) {
-                g_gen(cx, Hl, ld, j, j, j + 1, j, c, s);
-                g_lmul(cx, Hl, ld, j, j + 1, c, s, j + 1, ilastm);
-                CQ_SETG(j, c, s);
-              } else {
-                g_gen(cx, Hl, ld, j + 1, j + 1, j + 1, j, c, s);
-                g_rmul(cx, Hl, ld, j + 1, j, c, conj_(s), ifirstm, j);
-                CQ_SETG(j, c, -s);
-              }
-            }
-            __syncthreads();
-            if (wantZ) cq_rmul_seq(cx, st, cx.Zp(l), cx.ldz, jlo, ilast - 1, 1, 0, 1);
-          }
-          ziter = 0;
-          for (int j = jlo; j <= ilast - 1; j++) {
-            const double c = st.Gc[j];
-            const cplx s = st.Gs[j];
-            g_rmul(cx, H1, ld, j, j + 1, c, s, ifirstm, j + 1);
-            if (is_zero(s)) ziter = 1;
-          }
-          doqz = false;
-        }
-      }
+      // rows (j+1,j+2) <- G1in; columns (j+1,j+2) by G1out (rows <= j+1);
+      // rows (j,j+1) <- G2in; columns (j,j+1) by G2out (rows <= j)           (:993-1004)
+      rrot(B11, B21, gin.c2, gin.s2);
+      rrot(B12, B22, gin.c2, gin.s2);
+      givens_real(B22, -B21, gout.c2, gout.s2, r);
+      B22 = r; B21 = 0.0;
+      rrot(B01, B02, gout.c2, gout.s2);
+      rrot(B11, B12, gout.c2, gout.s2);
+      rrot(B00, B10, gin.c1, gin.s1);
+      rrot(B01, B11, gin.c1, gin.s1);
+      rrot(B02, B12, gin.c1, gin.s1);
+      givens_real(B11, -B10, gout.c1, gout.s1, r);
+      B11 = r; B10 = 0.0;
+      rrot(B00, B01, gout.c1, gout.s1);
     }
-
-    if (dpos) {
-      // ---- Case II: zero on the diagonal of an S+ factor: two unshifted half-sweeps (:453-566)
-      for (int j = jlo; j <= jdef - 1; j++) {
-        double c;
-        cplx s;
-        g_gen(cx, H1, ld, j, j, j + 1, j, c, s);
-        g_lmul(cx, H1, ld, j, j + 1, c, s, j + 1, ilastm);
-        CQ_SETG(j, c, s);
+    {
+      const Rot2 gR = sl ? gin : gout;  // acts on columns (rows above the block)
+      const Rot2 gL = sl ? gout : gin;  // acts on rows (columns right of the block)
+      const int nR = j - rfirst, nL = clast - (j + 2);
+      const int nZ = cx.wantZ ? n : 0;
+      double* Zl = cx.wantZ ? cx.Zp(l) : nullptr;
+      for (int w = tid; w < nR + nL + nZ; w += nt) {
+        double* a;
+        long long st;
+        Rot2 g;
+        if (w < nR) {
+          a = &PSD_GE(Hl, ld, rfirst + w, j);
+          st = ld;
+          g = gR;
+        } else if (w < nR + nL) {
+          a = &PSD_GE(Hl, ld, j, j + 3 + (w - nR));
+          st = 1;
+          g = gL;
+        } else {
+          a = &PSD_GE(Zl, cx.ldz, 1 + (w - nR - nL), j);
+          st = cx.ldz;
+          g = gout;
+        }
+        double a0 = a[0], a1 = a[st], a2 = a[2 * st];
+        rot3(a0, a1, a2, g);
+        a[0] = a0; a[st] = a1; a[2 * st] = a2;
       }
-      __syncthreads();
-      if (wantZ) cq_rmul_seq(cx, st, cx.Zp(1), cx.ldz, jlo, jdef - 1, 1, 0, 1);
-      for (int l = p; l >= 2; l--) {
-        const int ntra = (l < ldef) ? (jdef - 2) : (jdef - 1);
-        cplx* Hl = cx.Hp(l);
-        for (int j = jlo; j <= ntra; j++) {
-          double c = st.Gc[j];
-          cplx s = st.Gs[j];
-          if (cx.Sg(l)) {
-            g_rmul(cx, Hl, ld, j, j + 1, c, s, ifirstm, j + 1);
-            g_gen(cx, Hl, ld, j, j, j + 1, j, c, s);
-            g_lmul(cx, Hl, ld, j, j + 1, c, s, j + 1, ilastm);
-            CQ_SETG(j, c, s);
-          } else {
-            g_lmul(cx, Hl, ld, j, j + 1, c, s, j, ilastm);
-            g_gen(cx, Hl, ld, j + 1, j + 1, j + 1, j, c, s);
-            g_rmul(cx, Hl, ld, j + 1, j, c, conj_(s), ifirstm, j);
-            CQ_SETG(j, c, -s);
-          }
-        }
-        __syncthreads();
-        if (wantZ) cq_rmul_seq(cx, st, cx.Zp(l), cx.ldz, jlo, ntra, 1, 0, 1);
-      }
-      for (int j = jlo; j <= jdef - 2; j++)
-        g_rmul(cx, H1, ld, j, j + 1, st.Gc[j], st.Gs[j], ifirstm, j + 1);
-      // second unshifted step, from the bottom (:512-564)
-      for (int j = ilast; j >= jdef + 1; j--) {
-        double c;
-        cplx s;
-        g_gen(cx, H1, ld, j, j, j, j - 1, c, s);
-        g_rmul(cx, H1, ld, j, j - 1, c, conj_(s), ifirstm, j - 1);
-        CQ_SETG(j, c, -s);
-      }
-      __syncthreads();
-      if (wantZ) cq_rmul_seq(cx, st, cx.Zp(p > 1 ? 2 : 1), cx.ldz, ilast, jdef + 1, -1, -1, 0);
-      for (int l = 2; l <= p; l++) {
-        const int ntra = (l > ldef) ? (jdef + 2) : (jdef + 1);
-        cplx* Hl = cx.Hp(l);
-        for (int j = ilast; j >= ntra; j--) {
-          double c = st.Gc[j];
-          cplx s = st.Gs[j];
-          if (!cx.Sg(l)) {
-            g_rmul(cx, Hl, ld, j - 1, j, c, s, ifirstm, j);
-            g_gen(cx, Hl, ld, j - 1, j - 1, j, j - 1, c, s);
-            g_lmul(cx, Hl, ld, j - 1, j, c, s, j, ilastm);
-            CQ_SETG(j, c, s);
-          } else {
-            g_lmul(cx, Hl, ld, j - 1, j, c, s, j - 1, ilastm);
-            g_gen(cx, Hl, ld, j, j, j, j - 1, c, s);
-            g_rmul(cx, Hl, ld, j, j - 1, c, conj_(s), ifirstm, j - 1);
-            CQ_SETG(j, c, -s);
-          }
-        }
-        __syncthreads();
-        if (wantZ) cq_rmul_seq(cx, st, cx.Zp((l % p) + 1), cx.ldz, ilast, ntra, -1, -1, 0);
-      }
-      for (int j = ilast; j >= jdef + 2; j--)
-        g_lmul(cx, H1, ld, j - 1, j, st.Gc[j], st.Gs[j], j - 1, ilastm);
-      doqz = false;
-    } else if (dneg) {
-      // ---- Case III: zero on the diagonal of an S- factor (:568-740) ----
-      cplx* Hd = cx.Hp(ldef);
-      double c;
-      cplx s;
-      if (2 * jdef > (ilast - jlo + 1)) {  // bottom half: chase the zero down
-        for (int j1 = jdef; j1 <= ilast - 1; j1++) {
-          int j = j1;
-          g_gen(cx, Hd, ld, j, j + 1, j + 1, j + 1, c, s);
-          g_lmul(cx, Hd, ld, j, j + 1, c, s, j + 2, ilastm);
-          int ln = (ldef % p) + 1;
-          if (wantZ) g_rmul(cx, cx.Zp(ln), cx.ldz, j, j + 1, c, s, 1, n);
-          int gi = j, gj = j + 1;
-          for (int l = 1; l <= p - 1; l++) {
-            if (ln == 1) {
-              g_lmul(cx, H1, ld, gi, gj, c, s, j - 1, ilastm);
-              g_gen(cx, H1, ld, j + 1, j, j + 1, j - 1, c, s);
-              g_rmul(cx, H1, ld, j, j - 1, c, conj_(s), ifirstm, j);
-              s = -s;
-              gi = j - 1; gj = j;
-              j -= 1;
-            } else if (cx.Sg(ln)) {
-              cplx* Hn = cx.Hp(ln);
-              g_lmul(cx, Hn, ld, gi, gj, c, s, j, ilastm);
-              g_gen(cx, Hn, ld, j + 1, j + 1, j + 1, j, c, s);
-              g_rmul(cx, Hn, ld, j + 1, j, c, conj_(s), ifirstm, j);
-              s = -s;
-              gi = j; gj = j + 1;
-            } else {
-              cplx* Hn = cx.Hp(ln);
-              g_rmul(cx, Hn, ld, gi, gj, c, s, ifirstm, j + 1);
-              g_gen(cx, Hn, ld, j, j, j + 1, j, c, s);
-              g_lmul(cx, Hn, ld, j, j + 1, c, s, j + 1, ilastm);
-              gi = j; gj = j + 1;
-            }
-            ln = (ln % p) + 1;
-            if (wantZ) g_rmul(cx, cx.Zp(ln), cx.ldz, gi, gj, c, s, 1, n);
-          }
-          g_rmul(cx, Hd, ld, gi, gj, c, s, ifirstm, j);
-        }
-        // deflate the last element in the Hessenberg factor (:620-655)
-        const int j = ilast;
-        g_gen(cx, H1, ld, j, j, j, j - 1, c, s);
-        g_rmul(cx, H1, ld, j, j - 1, c, conj_(s), ifirstm, j - 1);
-        s = -s;
-        if (wantZ) g_rmul(cx, cx.Zp(p > 1 ? 2 : 1), cx.ldz, j - 1, j, c, s, 1, n);
-        for (int l = 2; l <= ldef - 1; l++) {
-          cplx* Hl = cx.Hp(l);
-          if (!cx.Sg(l)) {
-            g_rmul(cx, Hl, ld, j - 1, j, c, s, ifirstm, j);
-            g_gen(cx, Hl, ld, j - 1, j - 1, j, j - 1, c, s);
-            g_lmul(cx, Hl, ld, j - 1, j, c, s, j, ilastm);
-          } else {
-            g_lmul(cx, Hl, ld, j - 1, j, c, s, j - 1, ilastm);
-            g_gen(cx, Hl, ld, j, j, j, j - 1, c, s);
-            g_rmul(cx, Hl, ld, j, j - 1, c, conj_(s), ifirstm, j - 1);
-            s = -s;
-          }
-          if (wantZ) g_rmul(cx, cx.Zp((l % p) + 1), cx.ldz, j - 1, j, c, s, 1, n);
-        }
-        g_rmul(cx, Hd, ld, j - 1, j, c, s, ifirstm, j);
-      } else {  // top half: chase the zero up (:656-739)
-        for (int j1 = jdef; j1 >= jlo + 1; j1--) {
-          int j = j1;
-          g_gen(cx, Hd, ld, j - 1, j, j - 1, j - 1, c, s);
-          g_rmul(cx, Hd, ld, j, j - 1, c, conj_(s), ifirstm, j - 2);
-          s = -s;
-          if (wantZ) g_rmul(cx, cx.Zp(ldef), cx.ldz, j - 1, j, c, s, 1, n);
-          int gi = j - 1, gj = j;
-          int ln = ldef - 1;
-          for (int l = 1; l <= p - 1; l++) {
-            cplx* Hn = cx.Hp(ln);
-            if (ln == 1) {
-              g_rmul(cx, Hn, ld, gi, gj, c, s, ifirstm, j + 1);
-              g_gen(cx, Hn, ld, j, j - 1, j + 1, j - 1, c, s);
-              g_lmul(cx, Hn, ld, j, j + 1, c, s, j, ilastm);
-              gi = j; gj = j + 1;
-              j += 1;
-            } else if (!cx.Sg(ln)) {
-              g_lmul(cx, Hn, ld, gi, gj, c, s, j - 1, ilastm);
-              g_gen(cx, Hn, ld, j, j, j, j - 1, c, s);
-              g_rmul(cx, Hn, ld, j, j - 1, c, conj_(s), ifirstm, j - 1);
-              s = -s;
-              gi = j - 1; gj = j;
-            } else {
-              g_rmul(cx, Hn, ld, gi, gj, c, s, ifirstm, j);
-              g_gen(cx, Hn, ld, j - 1, j - 1, j, j - 1, c, s);
-              g_lmul(cx, Hn, ld, j - 1, j, c, s, j, ilastm);
-              gi = j - 1; gj = j;
-            }
-            if (wantZ) g_rmul(cx, cx.Zp(ln), cx.ldz, gi, gj, c, s, 1, n);
-            ln = (ln == 1) ? p : (ln - 1);
-          }
-          g_lmul(cx, Hd, ld, gi, gj, c, s, j, ilastm);
-        }
-        // deflate the first element in the Hessenberg factor (:705-738)
-        const int j = jlo;
-        g_gen(cx, H1, ld, j, j, j + 1, j, c, s);
-        g_lmul(cx, H1, ld, j, j + 1, c, s, j + 1, ilastm);
-        if (wantZ) g_rmul(cx, cx.Zp(1), cx.ldz, j, j + 1, c, s, 1, n);
-        for (int l = p; l >= ldef + 1; l--) {
-          cplx* Hl = cx.Hp(l);
-          if (cx.Sg(l)) {
-            g_rmul(cx, Hl, ld, j, j + 1, c, s, ifirstm, j + 1);
-            g_gen(cx, Hl, ld, j, j, j + 1, j, c, s);
-            g_lmul(cx, Hl, ld, j, j + 1, c, s, j + 1, ilastm);
-          } else {
-            g_lmul(cx, Hl, ld, j, j + 1, c, s, j, ilastm);
-            g_gen(cx, Hl, ld, j + 1, j + 1, j + 1, j, c, s);
-            g_rmul(cx, Hl, ld, j + 1, j, c, conj_(s), ifirstm, j);
-            s = -s;
-          }
-          if (wantZ) g_rmul(cx, cx.Zp(l), cx.ldz, j, j + 1, c, s, 1, n);
-        }
-        g_lmul(cx, Hd, ld, j, j + 1, c, s, j + 1, ilastm);
-      }
-      doqz = false;
-    } else if (split1) {
-      // ---- 1x1 block split off (:741-762) ----
       if (tid == 0) {
-        cplx a;
-        int b;
-        long long sc;
-        safeprod<cplx>(p, cx.S, [&](int l) { return PSD_GE(cx.Hp(l), ld, ilast, ilast); }, a, b, sc);
-        alpha[ilast - 1] = a;
-        beta[ilast - 1] = mk((double)b, 0.0);
-        scale[ilast - 1] = sc;
+        double* sg = cx.stage + 9 + 6 * (l - 2);
+        sg[0] = B00; sg[1] = B01; sg[2] = B02; sg[3] = B11; sg[4] = B12; sg[5] = B22;
       }
-      ilast -= 1;
-      if (ilast < 1) {
-        done = true;
-        break;
-      }
-      iiter = 0;
-      if (ziter != -1) ziter = 0;
-      if (!wantT) {
-        ilastm = ilast;
-        if (ifirstm > ilast) ifirstm = 1;
-      }
-      doqz = false;
-    } else if (doqz) {
-      ifirst = jlo;
     }
+    gin = gout;
+  }
+  {  // right-only rows of H_1 and its 3x3 overlap block
+    const int nR = (h1r1 - rfirst + 1) - 3;
+    for (int w = tid; w < nR; w += nt) {
+      int row = rfirst + w;
+      if (row >= j) row += 3;
+      double* a = &PSD_GE(H1, ld, row, j);
+      double a0 = a[0], a1 = a[ld], a2 = a[2 * (size_t)ld];
+      rot3(a0, a1, a2, gin);
+      a[0] = a0; a[ld] = a1; a[2 * (size_t)ld] = a2;
+    }
+    if (tid == 0) {
+#pragma unroll
+      for (int c = 0; c < 3; c++) rot3(X[0][c], X[1][c], X[2][c], g0);
+#pragma unroll
+      for (int r = 0; r < 3; r++) rot3(X[r][0], X[r][1], X[r][2], gin);
+#pragma unroll
+      for (int r = 0; r < 3; r++)
+#pragma unroll
+        for (int c = 0; c < 3; c++) cx.stage[3 * r + c] = X[r][c];
+    }
+  }
+  __syncthreads();
+  for (int l = 1 + tid; l <= p; l += nt) {
+    if (l == 1) {
+      for (int r = 0; r < 3; r++)
+        for (int c = 0; c < 3; c++) PSD_GE(H1, ld, j + r, j + c) = cx.stage[3 * r + c];
+      if (zcol > 0) {
+        PSD_GE(H1, ld, j, zcol) = r1;
+        PSD_GE(H1, ld, j + 1, zcol) = 0.0;
+        PSD_GE(H1, ld, j + 2, zcol) = 0.0;
+      }
+    } else {
+      double* Hl = cx.Hp(l);
+      const double* sg = cx.stage + 9 + 6 * (l - 2);
+      PSD_GE(Hl, ld, j, j) = sg[0]; PSD_GE(Hl, ld, j, j + 1) = sg[1]; PSD_GE(Hl, ld, j, j + 2) = sg[2];
+      PSD_GE(Hl, ld, j + 1, j) = 0.0; PSD_GE(Hl, ld, j + 1, j + 1) = sg[3]; PSD_GE(Hl, ld, j + 1, j + 2) = sg[4];
+      PSD_GE(Hl, ld, j + 2, j) = 0.0; PSD_GE(Hl, ld, j + 2, j + 1) = 0.0; PSD_GE(Hl, ld, j + 2, j + 2) = sg[5];
+    }
+  }
+  __syncthreads();
+}
 
-    if (doqz) {
-      // ---- single-shift periodic QZ sweep (:770-854) ----
-      iiter++;
-      ziter++;
-      if (!wantT) ifirstm = ifirst;
+// Scaled product of the KxK (K = 2 or 3) diagonal blocks at rows/cols i0..i0+K-1 of the
+// triangular factors: Tm 2^e = prod_{l=2..p} H_l[blk]^{s_l} (upper triangular).  A zero
+// diagonal of an inverted factor gives sing = true.
+template <int K>
+PSD_DEV void tri_block_product(const GCtx<double>& cx, int i0, double (&Tm)[K][K], int& e, bool& sing) {
+  const int p = cx.p, ld = cx.ldh;
+#pragma unroll
+  for (int r = 0; r < K; r++)
+#pragma unroll
+    for (int c = 0; c < K; c++) Tm[r][c] = (r == c) ? 1.0 : 0.0;
+  e = 0;
+  sing = false;
+  for (int l = 2; l <= p; l++) {
+    const double* Hl = cx.Hp(l);
+    double U[K][K];
+#pragma unroll
+    for (int r = 0; r < K; r++)
+#pragma unroll
+      for (int c = 0; c < K; c++) U[r][c] = (c >= r) ? PSD_GE(Hl, ld, i0 + r, i0 + c) : 0.0;
+    double N[K][K];
+    if (cx.Sg(l)) {
+      // N = Tm * U
+#pragma unroll
+      for (int r = 0; r < K; r++)
+#pragma unroll
+        for (int c = 0; c < K; c++) {
+          double acc = 0.0;
+#pragma unroll
+          for (int k = 0; k < K; k++)
+            if (k >= r && k <= c) acc = fma(Tm[r][k], U[k][c], acc);
+          N[r][c] = acc;
+        }
+    } else {
+      // N = Tm * inv(U): solve N U = Tm row by row (forward substitution over columns)
+#pragma unroll
+      for (int r = 0; r < K; r++)
+#pragma unroll
+        for (int c = 0; c < K; c++) {
+          if (c < r) {
+            N[r][c] = 0.0;
+            continue;
+          }
+          double acc = Tm[r][c];
+#pragma unroll
+          for (int k = 0; k < K; k++)
+            if (k >= r && k < c) acc = fma(-N[r][k], U[k][c], acc);
+          if (U[c][c] == 0.0) {
+            sing = true;
+            N[r][c] = acc;
+          } else {
+            N[r][c] = acc / U[c][c];
+          }
+        }
+    }
+    double m = 0.0;
+#pragma unroll
+    for (int r = 0; r < K; r++)
+#pragma unroll
+      for (int c = 0; c < K; c++) m = fmax(m, fabs(N[r][c]));
+    int ex = 0;
+    if (m > 0.0 && isfinite(m)) (void)frexp(m, &ex);
+    const double sc = scalbn(1.0, -ex);
+#pragma unroll
+    for (int r = 0; r < K; r++)
+#pragma unroll
+      for (int c = 0; c < K; c++) Tm[r][c] = N[r][c] * sc;
+    e += ex;
+  }
+}
+
+// 2x2 active block at rows j, j+1 (j = ifirst).  Returns true when the block has been split off
+// as a complex pair (eigenvalues written); false after a rotation chain that drives
+// H_1[j+1,j] towards zero (real pair).  `force`: accept the block as it stands.
+PSD_DEV bool rq_block2x2(const GCtx<double>& cx, int j, int ifirstm, int ilastm, bool force, cplx* alpha,
+                         double* beta, long long* scale) {
+  const int ld = cx.ldh;
+  double* H1 = cx.Hp(1);
+  double Tm[2][2];
+  int e;
+  bool sing;
+  tri_block_product<2>(cx, j, Tm, e, sing);
+  const double h11 = PSD_GE(H1, ld, j, j), h12 = PSD_GE(H1, ld, j, j + 1);
+  const double h21 = PSD_GE(H1, ld, j + 1, j), h22 = PSD_GE(H1, ld, j + 1, j + 1);
+  // M = H1blk * Tm (Tm upper triangular)
+  double a = h11 * Tm[0][0], b = fma(h11, Tm[0][1], h12 * Tm[1][1]);
+  double c = h21 * Tm[0][0], d = fma(h21, Tm[0][1], h22 * Tm[1][1]);
+  double cs, sn, w1r, w1i, w2r, w2i;
+  gs2x2(a, b, c, d, cs, sn, w1r, w1i, w2r, w2i);
+  if (w1i == 0.0 && !force) {
+    // real pair: rotate rows j, j+1 of H_1 by dlanv2's rotation and chase it round the cycle
+    chase_rotation<double>(cx, j, cs, sn, 0, 0.0, j, ilastm, ifirstm, min(j + 2, ilastm));
+    return false;
+  }
+  __syncthreads();
+  if (cx.tid == 0) {
+    const double lr[2] = {w1r, w2r}, li[2] = {w1i, w2i};
+    for (int k = 0; k < 2; k++) {
+      const double m = hypot(lr[k], li[k]);
+      if (m == 0.0 || !isfinite(m)) {
+        alpha[j - 1 + k] = mk(lr[k], li[k]);
+        scale[j - 1 + k] = 0;
+      } else {
+        int ex;
+        (void)frexp(m, &ex);
+        const double sc = scalbn(1.0, -(ex - 1));
+        alpha[j - 1 + k] = mk(lr[k] * sc, li[k] * sc);
+        scale[j - 1 + k] = (long long)e + (ex - 1);
+      }
+      beta[j - 1 + k] = sing ? 0.0 : 1.0;
+    }
+    if (w1i == 0.0) PSD_GE(H1, ld, j + 1, j) = 0.0;  // forced acceptance of a real pair
+  }
+  __syncthreads();
+  return true;
+}
+
+// One double-shift sweep on the active block ifirst..ilast (order >= 3).
+PSD_DEV void rq_double_shift_sweep(const GCtx<double>& cx, int ifirst, int ilast, int ifirstm, int ilastm,
+                                   int iiter, int& nexc) {
+  const int ld = cx.ldh;
+  double* H1 = cx.Hp(1);
+  double v0, v1, v2;
+  if (iiter % 10 == 0) {
+    nexc++;
+    const double g = 0.6180339887498949;
+    double fr[3];
+    for (int m = 0; m < 3; m++) {
+      const double x = (double)(3 * nexc + m + 1) * g;
+      fr[m] = x - floor(x);
+    }
+    v0 = fr[0] + 0.25; v1 = fr[1] - 0.5; v2 = 0.5 * fr[2];
+  } else {
+    double Tl[3][3], Tt[3][3];
+    int el, et;
+    bool s1, s2;
+    tri_block_product<3>(cx, ifirst, Tl, el, s1);
+    tri_block_product<3>(cx, ilast - 2, Tt, et, s2);
+    const int i = ifirst, k = ilast - 2, m = ilast - 1, nn = ilast;
+    // leading entries of the product band (scale 2^el)
+    const double a11 = PSD_GE(H1, ld, i, i), a12 = PSD_GE(H1, ld, i, i + 1);
+    const double a21 = PSD_GE(H1, ld, i + 1, i), a22 = PSD_GE(H1, ld, i + 1, i + 1);
+    const double a32 = PSD_GE(H1, ld, i + 2, i + 1);
+    const double h11 = a11 * Tl[0][0], h21 = a21 * Tl[0][0];
+    const double h12 = fma(a11, Tl[0][1], a12 * Tl[1][1]), h22 = fma(a21, Tl[0][1], a22 * Tl[1][1]);
+    const double h32 = a32 * Tl[1][1];
+    // trailing 2x2 of the product (scale 2^et), brought to the leading scale
+    const double amk = PSD_GE(H1, ld, m, k), amm = PSD_GE(H1, ld, m, m), amn = PSD_GE(H1, ld, m, nn);
+    const double anm = PSD_GE(H1, ld, nn, m), ann = PSD_GE(H1, ld, nn, nn);
+    const double sc = scalbn(1.0, max(-600, min(600, et - el)));
+    double h33 = fma(amk, Tt[0][1], amm * Tt[1][1]) * sc;
+    double h34 = fma(amk, Tt[0][2], fma(amm, Tt[1][2], amn * Tt[2][2])) * sc;
+    double h43 = anm * Tt[1][1] * sc;
+    double h44 = fma(anm, Tt[1][2], ann * Tt[2][2]) * sc;
+    // dlahqr-style shifts (PeriodicSchurDecompositions.jl:730-762) and first column (:768-803)
+    double rt1r, rt2r, rt1i, rt2i;
+    double s = fabs(h33) + fabs(h34) + fabs(h43) + fabs(h44);
+    if (s == 0.0 || !isfinite(s)) {
+      rt1r = rt2r = rt1i = rt2i = 0.0;
+    } else {
+      h33 /= s; h44 /= s; h34 /= s; h43 /= s;
+      const double trc = (h33 + h44) * 0.5;
+      const double disc = (h33 - trc) * (h44 - trc) - h34 * h43;
+      const double rtdisc = sqrt(fabs(disc));
+      if (disc >= 0.0) {
+        rt1r = trc * s; rt2r = rt1r; rt1i = rtdisc * s; rt2i = -rt1i;
+      } else {
+        rt1r = trc + rtdisc;
+        rt2r = trc - rtdisc;
+        rt1r = (fabs(rt1r - h44) <= fabs(rt2r - h44)) ? (rt1r * s) : (rt2r * s);
+        rt2r = rt1r;
+        rt1i = rt2i = 0.0;
+      }
+    }
+    s = fabs(h11 - rt2r) + fabs(rt2i) + fabs(h21);
+    if (s == 0.0 || !isfinite(s)) {
+      v0 = 1.0; v1 = 1.0; v2 = 1.0;
+    } else {
+      const double h21s = h21 / s;
+      v0 = h21s * h12 + (h11 - rt1r) * ((h11 - rt2r) / s) - rt1i * (rt2i / s);
+      v1 = h21s * (h11 + h22 - rt1r - rt2r);
+      v2 = h21s * h32;
+    }
+  }
+  {
+    const double s = fabs(v0) + fabs(v1) + fabs(v2);
+    if (s > 0.0 && isfinite(s)) { v0 /= s; v1 /= s; v2 /= s; } else { v0 = v1 = v2 = 1.0; }
+  }
+  Rot2 g;
+  double r2, r1;
+  givens_real(v1, v2, g.c2, g.s2, r2);
+  givens_real(v0, r2, g.c1, g.s1, r1);
+  for (int j = ifirst; j <= ilast - 2; j++) {
+    int zcol = 0;
+    if (j > ifirst) {
+      givens_real(PSD_GE(H1, ld, j + 1, j - 1), PSD_GE(H1, ld, j + 2, j - 1), g.c2, g.s2, r2);
+      givens_real(PSD_GE(H1, ld, j, j - 1), r2, g.c1, g.s1, r1);
+      zcol = j - 1;
+    }
+    chase_double(cx, j, g, zcol, r1, ilastm, ifirstm, min(j + 3, ilastm));
+  }
+  // trailing single rotation (:1015-1048)
+  {
+    const int j = ilast - 1;
+    double c, s, r;
+    givens_real(PSD_GE(H1, ld, j, j - 1), PSD_GE(H1, ld, j + 1, j - 1), c, s, r);
+    chase_rotation<double>(cx, j, c, s, j - 1, r, j, ilastm, ifirstm, min(j + 2, ilastm));
+  }
+}
+
+// Single-shift sweep of the complex periodic QZ iteration (generalized.jl:770-854).
+PSD_DEV void cq_single_shift_sweep(const GCtx<cplx>& cx, int ifirst, int ilast, int ifirstm, int ilastm,
+                                   int iiter, int& nexc) {
+  const int p = cx.p, ld = cx.ldh;
+  cplx* H1 = cx.Hp(1);
+
       double c;
       cplx s, r;
       if (iiter % 10 == 0) {
@@ -457,11 +579,341 @@ PSD_DEV int cpqz_cta(const GCtx<cplx>& cx, const CqState& st, bool wantT, int ma
         }
         chase_rotation(cx, j, c, s, zcol, r, j, ilastm, ifirstm, min(j + 2, ilastm));
       }
+}
+
+// generalized.jl:166-931.  Returns info (0 or the level ilast at which convergence failed).
+template <class T>
+PSD_DEV int gpqz_cta(const GCtx<T>& cx, const GqState<T>& st, bool wantT, int maxitfac, cplx* alpha,
+                     T* beta, long long* scale) {
+  constexpr bool kCplx = (sizeof(T) == sizeof(cplx));
+  const int n = cx.n, p = cx.p, ld = cx.ldh, tid = cx.tid;
+  const bool wantZ = cx.wantZ;
+  T* H1 = cx.Hp(1);
+  const double ulp = DBL_EPSILON;
+  const double smlnum = DBL_MIN * ((double)n / ulp);
+  const double safmin = DBL_MIN;
+  const T czero = Scalar<T>::zero();
+  // ziter = -1 when p >= log2(floatmin)/log2(eps) (~19.65)  (:199)
+  int ziter = ((double)p >= (-1022.0) / (-52.0)) ? -1 : 0;
+  int ilast = n, ifirst = -1, ifirstm = 1, ilastm = n, iiter = 1;
+  int n2x2 = 0;  // consecutive attempts on the same 2x2 block (real path)
+  const int maxit = maxitfac * n;
+  int nexc = 0;
+  bool done = false;
+
+  for (int jiter = 1; jiter <= maxit; jiter++) {
+    bool split1 = false, dpos = false, dneg = false, doqz = true;
+    int ldef = -1, jdef = -1, jlo = 1;
+    if (ilast == 1) {
+      split1 = true;
+    } else {
+      split1 = cq_check_hess(cx, st, 1, ilast, ulp, smlnum, jlo);
+      if (!split1) {
+        dpos = cq_check_tr(cx, st, true, jlo, ilast, ulp, smlnum, ldef, jdef);
+        if (!dpos) dneg = cq_check_tr(cx, st, false, jlo, ilast, ulp, smlnum, ldef, jdef);
+        if (!dpos && !dneg && (ziter >= 7 || ziter < 0)) {
+          // ---- Test 4: controlled zero shift (:356-448) ----
+          for (int j = jlo; j <= ilast - 1; j++) {
+            double c;
+            T s;
+            g_gen(cx, H1, ld, j, j, j + 1, j, c, s);
+            g_lmul(cx, H1, ld, j, j + 1, c, s, j + 1, ilastm);
+            CQ_SETG(j, c, s);
+          }
+          __syncthreads();
+          if (wantZ) cq_rmul_seq(cx, st, cx.Zp(1), cx.ldz, jlo, ilast - 1, 1, 0, 1);
+          for (int l = p; l >= 2; l--) {
+            T* Hl = cx.Hp(l);
+            for (int j = jlo; j <= ilast - 1; j++) {
+              double c = st.Gc[j];
+              T s = st.Gs[j];
+              if (is_zero(s)) continue;
+              if (cx.Sg(l))
+                g_rmul(cx, Hl, ld, j, j + 1, c, s, ifirstm, j + 1);
+              else
+                g_lmul(cx, Hl, ld, j, j + 1, c, s, j, ilastm);
+              double tol = abs_(PSD_GE(Hl, ld, j, j)) + abs_(PSD_GE(Hl, ld, j + 1, j + 1));
+              if (tol == 0.0) tol = g_opnorm1(Hl, ld, jlo, j + 1, jlo, j + 1, false);
+              tol = fmax(ulp * tol, smlnum);
+              const bool small = abs_(PSD_GE(Hl, ld, j + 1, j)) <= tol;
+              __syncthreads();
+              if (small) {
+                if (tid == 0) PSD_GE(Hl, ld, j + 1, j) = czero;
+                CQ_SETG(j, 1.0, czero);
+                __syncthreads();
+              } else if (cx.Sg(l)) {
+                g_gen(cx, Hl, ld, j, j, j + 1, j, c, s);
+                g_lmul(cx, Hl, ld, j, j + 1, c, s, j + 1, ilastm);
+                CQ_SETG(j, c, s);
+              } else {
+                g_gen(cx, Hl, ld, j + 1, j + 1, j + 1, j, c, s);
+                g_rmul(cx, Hl, ld, j + 1, j, c, conj_(s), ifirstm, j);
+                CQ_SETG(j, c, -s);
+              }
+            }
+            __syncthreads();
+            if (wantZ) cq_rmul_seq(cx, st, cx.Zp(l), cx.ldz, jlo, ilast - 1, 1, 0, 1);
+          }
+          ziter = 0;
+          for (int j = jlo; j <= ilast - 1; j++) {
+            const double c = st.Gc[j];
+            const T s = st.Gs[j];
+            g_rmul(cx, H1, ld, j, j + 1, c, s, ifirstm, j + 1);
+            if (is_zero(s)) ziter = 1;
+          }
+          doqz = false;
+        }
+      }
+    }
+
+    if (dpos) {
+      // ---- Case II: zero on the diagonal of an S+ factor: two unshifted half-sweeps (:453-566)
+      for (int j = jlo; j <= jdef - 1; j++) {
+        double c;
+        T s;
+        g_gen(cx, H1, ld, j, j, j + 1, j, c, s);
+        g_lmul(cx, H1, ld, j, j + 1, c, s, j + 1, ilastm);
+        CQ_SETG(j, c, s);
+      }
+      __syncthreads();
+      if (wantZ) cq_rmul_seq(cx, st, cx.Zp(1), cx.ldz, jlo, jdef - 1, 1, 0, 1);
+      for (int l = p; l >= 2; l--) {
+        const int ntra = (l < ldef) ? (jdef - 2) : (jdef - 1);
+        T* Hl = cx.Hp(l);
+        for (int j = jlo; j <= ntra; j++) {
+          double c = st.Gc[j];
+          T s = st.Gs[j];
+          if (cx.Sg(l)) {
+            g_rmul(cx, Hl, ld, j, j + 1, c, s, ifirstm, j + 1);
+            g_gen(cx, Hl, ld, j, j, j + 1, j, c, s);
+            g_lmul(cx, Hl, ld, j, j + 1, c, s, j + 1, ilastm);
+            CQ_SETG(j, c, s);
+          } else {
+            g_lmul(cx, Hl, ld, j, j + 1, c, s, j, ilastm);
+            g_gen(cx, Hl, ld, j + 1, j + 1, j + 1, j, c, s);
+            g_rmul(cx, Hl, ld, j + 1, j, c, conj_(s), ifirstm, j);
+            CQ_SETG(j, c, -s);
+          }
+        }
+        __syncthreads();
+        if (wantZ) cq_rmul_seq(cx, st, cx.Zp(l), cx.ldz, jlo, ntra, 1, 0, 1);
+      }
+      for (int j = jlo; j <= jdef - 2; j++)
+        g_rmul(cx, H1, ld, j, j + 1, st.Gc[j], st.Gs[j], ifirstm, j + 1);
+      // second unshifted step, from the bottom (:512-564)
+      for (int j = ilast; j >= jdef + 1; j--) {
+        double c;
+        T s;
+        g_gen(cx, H1, ld, j, j, j, j - 1, c, s);
+        g_rmul(cx, H1, ld, j, j - 1, c, conj_(s), ifirstm, j - 1);
+        CQ_SETG(j, c, -s);
+      }
+      __syncthreads();
+      if (wantZ) cq_rmul_seq(cx, st, cx.Zp(p > 1 ? 2 : 1), cx.ldz, ilast, jdef + 1, -1, -1, 0);
+      for (int l = 2; l <= p; l++) {
+        const int ntra = (l > ldef) ? (jdef + 2) : (jdef + 1);
+        T* Hl = cx.Hp(l);
+        for (int j = ilast; j >= ntra; j--) {
+          double c = st.Gc[j];
+          T s = st.Gs[j];
+          if (!cx.Sg(l)) {
+            g_rmul(cx, Hl, ld, j - 1, j, c, s, ifirstm, j);
+            g_gen(cx, Hl, ld, j - 1, j - 1, j, j - 1, c, s);
+            g_lmul(cx, Hl, ld, j - 1, j, c, s, j, ilastm);
+            CQ_SETG(j, c, s);
+          } else {
+            g_lmul(cx, Hl, ld, j - 1, j, c, s, j - 1, ilastm);
+            g_gen(cx, Hl, ld, j, j, j, j - 1, c, s);
+            g_rmul(cx, Hl, ld, j, j - 1, c, conj_(s), ifirstm, j - 1);
+            CQ_SETG(j, c, -s);
+          }
+        }
+        __syncthreads();
+        if (wantZ) cq_rmul_seq(cx, st, cx.Zp((l % p) + 1), cx.ldz, ilast, ntra, -1, -1, 0);
+      }
+      for (int j = ilast; j >= jdef + 2; j--)
+        g_lmul(cx, H1, ld, j - 1, j, st.Gc[j], st.Gs[j], j - 1, ilastm);
+      doqz = false;
+    } else if (dneg) {
+      // ---- Case III: zero on the diagonal of an S- factor (:568-740) ----
+      T* Hd = cx.Hp(ldef);
+      double c;
+      T s;
+      if (2 * jdef > (ilast - jlo + 1)) {  // bottom half: chase the zero down
+        for (int j1 = jdef; j1 <= ilast - 1; j1++) {
+          int j = j1;
+          g_gen(cx, Hd, ld, j, j + 1, j + 1, j + 1, c, s);
+          g_lmul(cx, Hd, ld, j, j + 1, c, s, j + 2, ilastm);
+          int ln = (ldef % p) + 1;
+          if (wantZ) g_rmul(cx, cx.Zp(ln), cx.ldz, j, j + 1, c, s, 1, n);
+          int gi = j, gj = j + 1;
+          for (int l = 1; l <= p - 1; l++) {
+            if (ln == 1) {
+              g_lmul(cx, H1, ld, gi, gj, c, s, j - 1, ilastm);
+              g_gen(cx, H1, ld, j + 1, j, j + 1, j - 1, c, s);
+              g_rmul(cx, H1, ld, j, j - 1, c, conj_(s), ifirstm, j);
+              s = -s;
+              gi = j - 1; gj = j;
+              j -= 1;
+            } else if (cx.Sg(ln)) {
+              T* Hn = cx.Hp(ln);
+              g_lmul(cx, Hn, ld, gi, gj, c, s, j, ilastm);
+              g_gen(cx, Hn, ld, j + 1, j + 1, j + 1, j, c, s);
+              g_rmul(cx, Hn, ld, j + 1, j, c, conj_(s), ifirstm, j);
+              s = -s;
+              gi = j; gj = j + 1;
+            } else {
+              T* Hn = cx.Hp(ln);
+              g_rmul(cx, Hn, ld, gi, gj, c, s, ifirstm, j + 1);
+              g_gen(cx, Hn, ld, j, j, j + 1, j, c, s);
+              g_lmul(cx, Hn, ld, j, j + 1, c, s, j + 1, ilastm);
+              gi = j; gj = j + 1;
+            }
+            ln = (ln % p) + 1;
+            if (wantZ) g_rmul(cx, cx.Zp(ln), cx.ldz, gi, gj, c, s, 1, n);
+          }
+          g_rmul(cx, Hd, ld, gi, gj, c, s, ifirstm, j);
+        }
+        // deflate the last element in the Hessenberg factor (:620-655)
+        const int j = ilast;
+        g_gen(cx, H1, ld, j, j, j, j - 1, c, s);
+        g_rmul(cx, H1, ld, j, j - 1, c, conj_(s), ifirstm, j - 1);
+        s = -s;
+        if (wantZ) g_rmul(cx, cx.Zp(p > 1 ? 2 : 1), cx.ldz, j - 1, j, c, s, 1, n);
+        for (int l = 2; l <= ldef - 1; l++) {
+          T* Hl = cx.Hp(l);
+          if (!cx.Sg(l)) {
+            g_rmul(cx, Hl, ld, j - 1, j, c, s, ifirstm, j);
+            g_gen(cx, Hl, ld, j - 1, j - 1, j, j - 1, c, s);
+            g_lmul(cx, Hl, ld, j - 1, j, c, s, j, ilastm);
+          } else {
+            g_lmul(cx, Hl, ld, j - 1, j, c, s, j - 1, ilastm);
+            g_gen(cx, Hl, ld, j, j, j, j - 1, c, s);
+            g_rmul(cx, Hl, ld, j, j - 1, c, conj_(s), ifirstm, j - 1);
+            s = -s;
+          }
+          if (wantZ) g_rmul(cx, cx.Zp((l % p) + 1), cx.ldz, j - 1, j, c, s, 1, n);
+        }
+        g_rmul(cx, Hd, ld, j - 1, j, c, s, ifirstm, j);
+      } else {  // top half: chase the zero up (:656-739)
+        for (int j1 = jdef; j1 >= jlo + 1; j1--) {
+          int j = j1;
+          g_gen(cx, Hd, ld, j - 1, j, j - 1, j - 1, c, s);
+          g_rmul(cx, Hd, ld, j, j - 1, c, conj_(s), ifirstm, j - 2);
+          s = -s;
+          if (wantZ) g_rmul(cx, cx.Zp(ldef), cx.ldz, j - 1, j, c, s, 1, n);
+          int gi = j - 1, gj = j;
+          int ln = ldef - 1;
+          for (int l = 1; l <= p - 1; l++) {
+            T* Hn = cx.Hp(ln);
+            if (ln == 1) {
+              g_rmul(cx, Hn, ld, gi, gj, c, s, ifirstm, j + 1);
+              g_gen(cx, Hn, ld, j, j - 1, j + 1, j - 1, c, s);
+              g_lmul(cx, Hn, ld, j, j + 1, c, s, j, ilastm);
+              gi = j; gj = j + 1;
+              j += 1;
+            } else if (!cx.Sg(ln)) {
+              g_lmul(cx, Hn, ld, gi, gj, c, s, j - 1, ilastm);
+              g_gen(cx, Hn, ld, j, j, j, j - 1, c, s);
+              g_rmul(cx, Hn, ld, j, j - 1, c, conj_(s), ifirstm, j - 1);
+              s = -s;
+              gi = j - 1; gj = j;
+            } else {
+              g_rmul(cx, Hn, ld, gi, gj, c, s, ifirstm, j);
+              g_gen(cx, Hn, ld, j - 1, j - 1, j, j - 1, c, s);
+              g_lmul(cx, Hn, ld, j - 1, j, c, s, j, ilastm);
+              gi = j - 1; gj = j;
+            }
+            if (wantZ) g_rmul(cx, cx.Zp(ln), cx.ldz, gi, gj, c, s, 1, n);
+            ln = (ln == 1) ? p : (ln - 1);
+          }
+          g_lmul(cx, Hd, ld, gi, gj, c, s, j, ilastm);
+        }
+        // deflate the first element in the Hessenberg factor (:705-738)
+        const int j = jlo;
+        g_gen(cx, H1, ld, j, j, j + 1, j, c, s);
+        g_lmul(cx, H1, ld, j, j + 1, c, s, j + 1, ilastm);
+        if (wantZ) g_rmul(cx, cx.Zp(1), cx.ldz, j, j + 1, c, s, 1, n);
+        for (int l = p; l >= ldef + 1; l--) {
+          T* Hl = cx.Hp(l);
+          if (cx.Sg(l)) {
+            g_rmul(cx, Hl, ld, j, j + 1, c, s, ifirstm, j + 1);
+            g_gen(cx, Hl, ld, j, j, j + 1, j, c, s);
+            g_lmul(cx, Hl, ld, j, j + 1, c, s, j + 1, ilastm);
+          } else {
+            g_lmul(cx, Hl, ld, j, j + 1, c, s, j, ilastm);
+            g_gen(cx, Hl, ld, j + 1, j + 1, j + 1, j, c, s);
+            g_rmul(cx, Hl, ld, j + 1, j, c, conj_(s), ifirstm, j);
+            s = -s;
+          }
+          if (wantZ) g_rmul(cx, cx.Zp(l), cx.ldz, j, j + 1, c, s, 1, n);
+        }
+        g_lmul(cx, Hd, ld, j, j + 1, c, s, j + 1, ilastm);
+      }
+      doqz = false;
+    } else if (split1) {
+      // ---- 1x1 block split off (:741-762) ----
+      if (tid == 0) {
+        T a;
+        int b;
+        long long sc;
+        safeprod<T>(p, cx.S, [&](int l) { return PSD_GE(cx.Hp(l), ld, ilast, ilast); }, a, b, sc);
+        alpha[ilast - 1] = mk(re_(a), im_(a));
+        beta[ilast - 1] = Scalar<T>::from_real((double)b);
+        scale[ilast - 1] = sc;
+      }
+      ilast -= 1;
+      if (ilast < 1) {
+        done = true;
+        break;
+      }
+      iiter = 0;
+      if (ziter != -1) ziter = 0;
+      if (!wantT) {
+        ilastm = ilast;
+        if (ifirstm > ilast) ifirstm = 1;
+      }
+      doqz = false;
+    } else if (doqz) {
+      ifirst = jlo;
+    }
+
+    if (doqz) {
+      iiter++;
+      ziter++;
+      if (!wantT) ifirstm = ifirst;
+      if constexpr (kCplx) {
+        cq_single_shift_sweep(cx, ifirst, ilast, ifirstm, ilastm, iiter, nexc);
+      } else {
+        // ---- real path: 2x2 block handling / double-shift sweep (rgeneralized.jl:655-1054) ----
+        if (ifirst + 1 == ilast) {
+          n2x2++;
+          if (rq_block2x2(cx, ifirst, ifirstm, ilastm, n2x2 > 20, alpha, beta, scale)) {
+            // complex pair (or accepted block) split off (:748-790)
+            n2x2 = 0;
+            ilast = ifirst - 1;
+            if (ilast < 1) {
+              done = true;
+              break;
+            }
+            iiter = 0;
+            if (ziter != -1) ziter = 0;
+            if (!wantT) {
+              ilastm = ilast;
+              if (ifirstm > ilast) ifirstm = 1;
+            }
+          }
+        } else {
+          n2x2 = 0;
+          rq_double_shift_sweep(cx, ifirst, ilast, ifirstm, ilastm, iiter, nexc);
+        }
+      }
     }
   }
   if (!done) return ilast;  // "convergence failed at level ilast" (:856-858)
 
-  if (wantT) {
+  if constexpr (kCplx) {
+   if (wantT) {
     // ---- make diag(H_l), l >= 2, real non-negative (:860-908) ----
     for (int l = p; l >= 2; l--) {
       cplx* Hl = cx.Hp(l);
@@ -499,32 +951,35 @@ PSD_DEV int cpqz_cta(const GCtx<cplx>& cx, const CqState& st, bool wantT, int ma
       __syncthreads();
     }
   }
+  }
   return 0;
 }
 
 extern __shared__ __align__(16) double psd_smem_cq[];
 
-__global__ void cpschur_kernel(CpqzParams P) {
+template <class T>
+__global__ void gpschur_kernel(GpqzParams<T> P) {
   const int n = P.n, p = P.p, tid = threadIdx.x, nt = blockDim.x;
   const size_t nn = (size_t)n * n;
   __shared__ long long s_b;
   __shared__ int s_key;
 
   double* small = psd_smem_cq;
-  CqState st;
+  GqState<T> st;
   st.Gc = small;
-  st.Gs = reinterpret_cast<cplx*>(small + (n + 2) + ((n + 2) & 1));
-  cplx* stage = st.Gs + (n + 2);
-  unsigned char* Sint = reinterpret_cast<unsigned char*>(stage + 4 + 3 * (p > 1 ? p - 1 : 0));
+  st.Gs = reinterpret_cast<T*>(small + (n + 2) + ((n + 2) & 1));
+  T* stage = reinterpret_cast<T*>(small + (n + 2) + ((n + 2) & 1) + 2 * (n + 2));
+  unsigned char* Sint = reinterpret_cast<unsigned char*>(small + (n + 2) + ((n + 2) & 1) + 2 * (n + 2) +
+                                                         cq_stage_doubles(p));
   st.key = &s_key;
-  cplx* mats = reinterpret_cast<cplx*>(psd_smem_cq + ((cq_small_doubles(n, p) + 1) & ~1LL));
+  T* mats = reinterpret_cast<T*>(psd_smem_cq + ((cq_small_doubles(n, p) + 1) & ~1LL));
 
   const bool left = P.left != 0;
   // internal signature: reversed for :L (generalized.jl:114-123)
   for (int l = tid; l < p; l += nt) Sint[l] = P.S[left ? (p - 1 - l) : l];
   __syncthreads();
 
-  GCtx<cplx> cx;
+  GCtx<T> cx;
   cx.n = n; cx.p = p; cx.tid = tid; cx.nt = nt;
   cx.wantZ = P.wantZ && P.Z;
   cx.S = Sint;
@@ -536,16 +991,16 @@ __global__ void cpschur_kernel(CpqzParams P) {
     const long long b = s_b;
     __syncthreads();
     if (b >= P.batch) break;
-    cplx* Ab = P.A + (size_t)b * p * nn;
-    cplx* Zb = cx.wantZ ? (P.Z + (size_t)b * p * nn) : nullptr;
+    T* Ab = P.A + (size_t)b * p * nn;
+    T* Zb = cx.wantZ ? (P.Z + (size_t)b * p * nn) : nullptr;
     if (P.use_smem) {
       cx.ldh = P.ldh; cx.ldz = P.ldh;
       cx.H = mats; cx.hs = (long long)P.ldh * n;
       cx.Z = mats + (size_t)p * P.ldh * n; cx.zs = (long long)P.ldh * n;
       cx.zmap_left = false;
       for (int l = 1; l <= p; l++) {
-        const cplx* src = Ab + (size_t)((left ? (p + 1 - l) : l) - 1) * nn;
-        cplx* dst = cx.Hp(l);
+        const T* src = Ab + (size_t)((left ? (p + 1 - l) : l) - 1) * nn;
+        T* dst = cx.Hp(l);
         for (int e = tid; e < (int)nn; e += nt) dst[(e % n) + (size_t)(e / n) * cx.ldh] = src[e];
       }
     } else {
@@ -565,43 +1020,43 @@ __global__ void cpschur_kernel(CpqzParams P) {
     } else {
       if (cx.wantZ) {
         for (int l = 1; l <= p; l++) {
-          cplx* Zl = cx.Zp(l);
+          T* Zl = cx.Zp(l);
           for (int e = tid; e < (int)nn; e += nt)
-            Zl[(e % n) + (size_t)(e / n) * cx.ldz] = ((e % n) == (e / n)) ? mk(1.0, 0.0) : mk(0.0, 0.0);
+            Zl[(e % n) + (size_t)(e / n) * cx.ldz] = ((e % n) == (e / n)) ? Scalar<T>::one() : Scalar<T>::zero();
         }
       }
     }
     // enforce exact Hessenberg / triangular structure (_gethess!, :195; triu! :1027)
     for (int l = 1; l <= p; l++) {
-      cplx* Hl = cx.Hp(l);
+      T* Hl = cx.Hp(l);
       const int keep = (l == 1) ? 1 : 0;
       for (int e = tid; e < (int)nn; e += nt) {
         const int r = e % n, c = e / n;
-        if (r > c + keep) Hl[r + (size_t)c * cx.ldh] = mk(0.0, 0.0);
+        if (r > c + keep) Hl[r + (size_t)c * cx.ldh] = Scalar<T>::zero();
       }
     }
     __syncthreads();
 
     cplx* al = P.alpha + (size_t)b * n;
-    cplx* be = P.beta + (size_t)b * n;
+    T* be = P.beta + (size_t)b * n;
     long long* sc = P.scale + (size_t)b * n;
-    const int info = cpqz_cta(cx, st, P.wantT != 0, P.maxitfac, al, be, sc);
+    const int info = gpqz_cta<T>(cx, st, P.wantT != 0, P.maxitfac, al, be, sc);
     if (tid == 0) P.info[b] = info;
     __syncthreads();
 
     if (P.use_smem) {
       if (P.wantT) {
         for (int l = 1; l <= p; l++) {
-          cplx* dst = Ab + (size_t)((left ? (p + 1 - l) : l) - 1) * nn;
-          const cplx* src = cx.Hp(l);
+          T* dst = Ab + (size_t)((left ? (p + 1 - l) : l) - 1) * nn;
+          const T* src = cx.Hp(l);
           for (int e = tid; e < (int)nn; e += nt) dst[e] = src[(e % n) + (size_t)(e / n) * cx.ldh];
         }
       }
       if (cx.wantZ) {
         for (int l = 1; l <= p; l++) {
           const int s = (left && l > 1) ? (p + 2 - l) : l;
-          cplx* dst = Zb + (size_t)(s - 1) * nn;
-          const cplx* src = cx.Zp(l);
+          T* dst = Zb + (size_t)(s - 1) * nn;
+          const T* src = cx.Zp(l);
           for (int e = tid; e < (int)nn; e += nt) dst[e] = src[(e % n) + (size_t)(e / n) * cx.ldz];
         }
       }
