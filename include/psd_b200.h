@@ -180,6 +180,17 @@ int psd_rgpschur_hessut_batched(psd_handle_t handle, int n, int p, int64_t batch
                                 int wantT, int wantZ, int maxitfac, double* A, double* Z,
                                 double* alpha, double* beta, int64_t* alphascale, int32_t* info);
 
+/* Row-wise periodic Hessenberg reduction for the left orientation, batched.
+ * Replaces _rphessenberg!(Ap, A, Q) (rhessx.jl:53-109; RHouseholder rhessx.jl:7-50), whose only
+ * caller is the Krylov-Schur restart (krylov.jl:800-832).  For the product Ap A_{p-1} ... A_1:
+ *   Ap  in/out [batch][m][n] column-major, m = n + (extra_row != 0): on return upper Hessenberg
+ *               (the extra Arnoldi foot row, if present, is reduced to its last entry)
+ *   A   in/out [batch][p-1][n][n]: on return upper triangular (NULL when p == 1)
+ *   Q   in/out [batch][p][qrows][n] or NULL: Q_l <- Q_l H' for every reflector applied to the
+ *               columns of factor l (l = p is Ap) */
+int psd_rphess_rowwise_batched(psd_handle_t handle, int n, int extra_row, int p, int qrows,
+                               int64_t batch, double* Ap, double* A, double* Q);
+
 /* Synthetic inputs (measurement only): uniform [0,1) entries from a
  * counter-based generator keyed by (seed, problem, factor, row, col), problems
  * first_b .. first_b+batch-1, written to a host buffer or (asynchronously, on the current

@@ -25,6 +25,7 @@ EXPORTED_SYMBOLS = [
     "psd_cpschur_hessut_batched",
     "psd_rgpschur_batched",
     "psd_rgpschur_hessut_batched",
+    "psd_rphess_rowwise_batched",
     "psd_last_stats",
     "psd_set_profiling",
     "psd_kernel_times",
@@ -78,6 +79,8 @@ def lib():
                                                  C.c_int, C.c_int, vp, vp, vp, vp, vp, vp]
         L.psd_rgpschur_batched.argtypes = L.psd_cpschur_batched.argtypes
         L.psd_rgpschur_hessut_batched.argtypes = L.psd_cpschur_hessut_batched.argtypes
+        L.psd_rphess_rowwise_batched.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64,
+                                                 vp, vp, vp]
         L.psd_last_stats.argtypes = [vp, C.POINTER(C.c_int64)]
         L.psd_set_profiling.argtypes = [vp, C.c_int]
         L.psd_kernel_times.argtypes = [vp, C.POINTER(C.c_double)]

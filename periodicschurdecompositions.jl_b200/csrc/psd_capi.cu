@@ -20,6 +20,7 @@
 #include "psd_real_kernel.cuh"
 #include "psd_real_hess32.cuh"
 #include "psd_cplx_qz.cuh"
+#include "psd_rowhess.cuh"
 #include "psd_rng.cuh"
 
 namespace {
@@ -794,6 +795,51 @@ int psd_rgpschur_hessut_batched(psd_handle_t h, int n, int p, int64_t batch, con
                                 int64_t* alphascale, int32_t* info) {
   GenCall gc{n, p, 0, wantT != 0, wantZ != 0, maxitfac, 1, 0, S};
   return run_gen_host(h, gc, batch, A, Z, alpha, beta, alphascale, info);
+}
+
+int psd_rphess_rowwise_batched(psd_handle_t h, int n, int extra_row, int p, int qrows, int64_t batch, double* Ap,
+                               double* A, double* Q) {
+  if (!h) return fail(PSD_ERR_BAD_ARG, "null handle");
+  if (n < 1 || p < 1 || batch < 0 || !Ap || (p > 1 && !A) || (Q && qrows < 1))
+    return fail(PSD_ERR_BAD_ARG, "bad argument");
+  if (h->devs.empty()) return fail(PSD_ERR_NO_DEVICE, "handle has no CUDA device");
+  std::lock_guard<std::mutex> lock(h->mu);
+  for (auto& s : h->stats) s = 0;
+  if (batch == 0) return PSD_OK;
+  Device& dev = h->devs[0];
+  PSD_CUDA(cudaSetDevice(dev.ordinal));
+  Slot& s = dev.slots[0];
+  if (!s.stream) PSD_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+  const int m = n + (extra_row ? 1 : 0);
+  const size_t bAp = (size_t)batch * m * n * sizeof(double);
+  const size_t bA = (size_t)batch * (p - 1) * n * n * sizeof(double);
+  const size_t bQ = Q ? (size_t)batch * p * qrows * n * sizeof(double) : 0;
+  int e;
+  if ((e = ensure_dev(s.dA, s.capA, bAp))) return e;
+  if (bA && (e = ensure_dev(s.dZ, s.capZ, bA))) return e;
+  if (bQ && (e = ensure_dev(s.dX[0], s.capX[0], bQ))) return e;
+  PSD_CUDA(cudaMemcpyAsync(s.dA, Ap, bAp, cudaMemcpyHostToDevice, s.stream));
+  if (bA) PSD_CUDA(cudaMemcpyAsync(s.dZ, A, bA, cudaMemcpyHostToDevice, s.stream));
+  if (bQ) PSD_CUDA(cudaMemcpyAsync(s.dX[0], Q, bQ, cudaMemcpyHostToDevice, s.stream));
+  psd::RowHessParams<double> P;
+  P.n = n; P.m = m; P.p = p; P.qrows = qrows; P.batch = batch;
+  P.Ap = s.dA; P.A = bA ? s.dZ : nullptr; P.Q = bQ ? (double*)s.dX[0] : nullptr;
+  const int threads = std::max(64, std::min(256, ((std::max(n, qrows) + 31) / 32) * 32));
+  const int grid = (int)std::min<long long>(batch, (long long)dev.sm_count * 4);
+  {
+    ScopedKernelTimer tm(h, dev, s.stream, 0);
+    psd::rowhess_kernel<double><<<grid, threads, 0, s.stream>>>(P);
+  }
+  PSD_CUDA(cudaGetLastError());
+  PSD_CUDA(cudaMemcpyAsync(Ap, s.dA, bAp, cudaMemcpyDeviceToHost, s.stream));
+  if (bA) PSD_CUDA(cudaMemcpyAsync(A, s.dZ, bA, cudaMemcpyDeviceToHost, s.stream));
+  if (bQ) PSD_CUDA(cudaMemcpyAsync(Q, s.dX[0], bQ, cudaMemcpyDeviceToHost, s.stream));
+  PSD_CUDA(cudaStreamSynchronize(s.stream));
+  h->stats[0] = 1;
+  h->stats[2] = batch;
+  h->stats[3] = (int64_t)(bAp + bA + bQ);
+  h->stats[4] = (int64_t)(bAp + bA + bQ);
+  return PSD_OK;
 }
 
 __global__ void fill_uniform_kernel(uint64_t seed, int n, int p, long long batch, long long first_b,

@@ -198,6 +198,25 @@ def phessenberg_batched(A: np.ndarray, wantQ: bool = True, handle: Optional[Hand
     return H, Q
 
 
+def rphessenberg_rowwise_batched(Ap: np.ndarray, A: Optional[np.ndarray], Q: Optional[np.ndarray],
+                                 handle: Optional[Handle] = None):
+    """_rphessenberg!(Ap, A, Q) (rhessx.jl:53-109), batched, storage layout:
+    Ap [batch][n][m] (column-major m x n, m = n or n+1), A [batch][p-1][n][n] or None,
+    Q [batch][p][n][qrows] or None.  Returns updated copies (Ap, A, Q)."""
+    h = handle or default_handle()
+    batch, n, m = Ap.shape
+    if m not in (n, n + 1):
+        raise ValueError("only implemented for square or 1 extra row")  # rhessx.jl:60
+    p = 1 if A is None else A.shape[1] + 1
+    Ap2 = np.ascontiguousarray(Ap, dtype=np.float64).copy()
+    A2 = None if A is None else np.ascontiguousarray(A, dtype=np.float64).copy()
+    Q2 = None if Q is None else np.ascontiguousarray(Q, dtype=np.float64).copy()
+    qrows = 0 if Q is None else Q.shape[3]
+    check(lib().psd_rphess_rowwise_batched(h.ptr, n, int(m == n + 1), p, qrows, batch, _vp(Ap2),
+                                           _vp(A2), _vp(Q2)))
+    return Ap2, A2, Q2
+
+
 def _sig(S, p):
     S = np.ascontiguousarray(np.asarray(S, dtype=bool).astype(np.uint8))
     if S.shape != (p,):
