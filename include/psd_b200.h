@@ -191,6 +191,16 @@ int psd_rgpschur_hessut_batched(psd_handle_t handle, int n, int p, int64_t batch
 int psd_rphess_rowwise_batched(psd_handle_t handle, int n, int extra_row, int p, int qrows,
                                int64_t batch, double* Ap, double* A, double* Q);
 
+/* Test / measurement hook for the FP64 tensor-core (DMMA) GEMM that carries the large-N blocked
+ * updates (csrc/psd_dgemm.cuh): C <- alpha*op(A)*op(B) + beta*C on host buffers, column-major,
+ * BLAS dgemm argument meaning (transA/transB: 0 = 'N', 1 = 'T').  With reps > 0 the kernel alone
+ * is additionally timed on resident operands (CUDA events, 3 warm-up launches) and the average
+ * milliseconds per launch are returned in *ms.  Replaces the BLAS calls the reference reaches
+ * through householder.jl:199-218,252 once they are blocked. */
+int psd_dgemm_host(psd_handle_t handle, int transA, int transB, int M, int N, int K, double alpha,
+                   const double* A, int lda, const double* B, int ldb, double beta, double* C,
+                   int ldc, int reps, double* ms);
+
 /* Synthetic inputs (measurement only): uniform [0,1) entries from a
  * counter-based generator keyed by (seed, problem, factor, row, col), problems
  * first_b .. first_b+batch-1, written to a host buffer or (asynchronously, on the current

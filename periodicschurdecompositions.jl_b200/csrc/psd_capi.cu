@@ -21,6 +21,7 @@
 #include "psd_real_hess32.cuh"
 #include "psd_cplx_qz.cuh"
 #include "psd_rowhess.cuh"
+#include "psd_dgemm.cuh"
 #include "psd_rng.cuh"
 
 namespace {
@@ -839,6 +840,51 @@ int psd_rphess_rowwise_batched(psd_handle_t h, int n, int extra_row, int p, int 
   h->stats[2] = batch;
   h->stats[3] = (int64_t)(bAp + bA + bQ);
   h->stats[4] = (int64_t)(bAp + bA + bQ);
+  return PSD_OK;
+}
+
+int psd_dgemm_host(psd_handle_t h, int transA, int transB, int M, int N, int K, double alpha, const double* A,
+                   int lda, const double* B, int ldb, double beta, double* C, int ldc, int reps, double* ms) {
+  if (!h) return fail(PSD_ERR_BAD_ARG, "null handle");
+  if (M < 0 || N < 0 || K < 0 || !A || !B || !C) return fail(PSD_ERR_BAD_ARG, "bad argument");
+  if (h->devs.empty()) return fail(PSD_ERR_NO_DEVICE, "handle has no CUDA device");
+  std::lock_guard<std::mutex> lock(h->mu);
+  Device& dev = h->devs[0];
+  PSD_CUDA(cudaSetDevice(dev.ordinal));
+  Slot& s = dev.slots[0];
+  if (!s.stream) PSD_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+  const size_t bA = (size_t)lda * (transA ? M : K) * 8, bB = (size_t)ldb * (transB ? K : N) * 8;
+  const size_t bC = (size_t)ldc * N * 8;
+  int e;
+  if ((e = ensure_dev(s.dA, s.capA, bA))) return e;
+  if ((e = ensure_dev(s.dZ, s.capZ, bB))) return e;
+  if ((e = ensure_dev(s.dX[0], s.capX[0], bC))) return e;
+  PSD_CUDA(cudaMemcpyAsync(s.dA, A, bA, cudaMemcpyHostToDevice, s.stream));
+  PSD_CUDA(cudaMemcpyAsync(s.dZ, B, bB, cudaMemcpyHostToDevice, s.stream));
+  PSD_CUDA(cudaMemcpyAsync(s.dX[0], C, bC, cudaMemcpyHostToDevice, s.stream));
+  psd::GemmArgs g;
+  g.M = M; g.N = N; g.K = K;
+  g.A = s.dA; g.rsA = transA ? lda : 1; g.csA = transA ? 1 : lda;
+  g.B = s.dZ; g.rsB = transB ? ldb : 1; g.csB = transB ? 1 : ldb;
+  g.C = (double*)s.dX[0]; g.ldc = ldc; g.alpha = alpha; g.beta = beta; g.splitK = 1;
+  PSD_CUDA(psd::dgemm_launch(s.stream, dev.sm_count, g));
+  PSD_CUDA(cudaMemcpyAsync(C, s.dX[0], bC, cudaMemcpyDeviceToHost, s.stream));
+  PSD_CUDA(cudaStreamSynchronize(s.stream));
+  if (reps > 0 && ms) {
+    cudaEvent_t e0, e1;
+    PSD_CUDA(cudaEventCreate(&e0));
+    PSD_CUDA(cudaEventCreate(&e1));
+    for (int w = 0; w < 3; w++) PSD_CUDA(psd::dgemm_launch(s.stream, dev.sm_count, g));
+    PSD_CUDA(cudaEventRecord(e0, s.stream));
+    for (int r = 0; r < reps; r++) PSD_CUDA(psd::dgemm_launch(s.stream, dev.sm_count, g));
+    PSD_CUDA(cudaEventRecord(e1, s.stream));
+    PSD_CUDA(cudaEventSynchronize(e1));
+    float f = 0.f;
+    PSD_CUDA(cudaEventElapsedTime(&f, e0, e1));
+    *ms = f / reps;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+  }
   return PSD_OK;
 }
 
