@@ -222,9 +222,10 @@ int psd_last_stats(psd_handle_t handle, int64_t stats[8]);
  * is bracketed by CUDA events on its own stream.  psd_kernel_times waits for the recorded
  * events and returns, accumulated since the previous call, ms[0] = reduction kernels,
  * ms[1] = QR/QZ iteration kernels (milliseconds of device time), ms[2], ms[3] = how many
- * launches of each kind were timed. */
+ * launches of each kind were timed; for the large-N blocked reduction ms[4] = panel kernels,
+ * ms[5] = FP64 tensor-core GEMM updates (milliseconds), ms[6] = GEMM flops issued; ms[7] = 0. */
 int psd_set_profiling(psd_handle_t handle, int on);
-int psd_kernel_times(psd_handle_t handle, double ms[4]);
+int psd_kernel_times(psd_handle_t handle, double ms[8]);
 
 #ifdef __cplusplus
 }

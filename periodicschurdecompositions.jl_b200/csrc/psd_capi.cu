@@ -22,6 +22,7 @@
 #include "psd_cplx_qz.cuh"
 #include "psd_rowhess.cuh"
 #include "psd_dgemm.cuh"
+#include "psd_large_hess.cuh"
 #include "psd_rng.cuh"
 
 namespace {
@@ -80,7 +81,7 @@ struct Device {
 
 struct KernelTimer {
   cudaEvent_t e0, e1;
-  int kind;     // 0 = reduction kernel, 1 = QR/QZ iteration kernel
+  int kind;     // 0 = reduction kernel, 1 = QR/QZ iteration kernel, 2 = large-N panel, 3 = large-N GEMMs
   int ordinal;  // device the events belong to
 };
 
@@ -90,6 +91,7 @@ struct psd_handle_s {
   int64_t stats[8] = {0};
   bool profiling = false;           // psd_set_profiling
   std::vector<KernelTimer> timers;  // pending event pairs (resolved by psd_kernel_times)
+  double gemm_flops = 0.0;          // FP64 GEMM flops issued by the large-N reduction since then
   std::mutex tmu;
 };
 
@@ -189,7 +191,7 @@ int plan_real(const Device& dev, int n, int p, long long batch, bool wantZ, Real
   // one row or column per thread for the left, right and Z updates
   int want = n * (wantZ ? 3 : 2);
   int threads = ((want + 31) / 32) * 32;
-  threads = std::max(32, std::min(threads, pl.use_smem ? 256 : 512));
+  threads = std::max(32, std::min(threads, 256));  // 254 registers per thread: 256 threads fill an SM's file
   pl.threads = threads;
   PSD_CUDA(cudaFuncSetAttribute(psd::rpschur_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)max_dyn));
@@ -204,7 +206,10 @@ int plan_real(const Device& dev, int n, int p, long long batch, bool wantZ, Real
 
 struct RealCall {
   int n, p, left, wantT, wantZ, maxitfac, reduce_only, skip_reduce;
+  int z_preset = 0;
 };
+
+constexpr int kLargeN = 192;  // from here on the reduction runs blocked on the whole GPU
 
 constexpr long long kEigChunk = 65536;  // problems per (reduction, QR) kernel pair
 
@@ -247,7 +252,7 @@ int launch_real_eig32(psd_handle_s* h, Device& dev, Slot& aux, cudaStream_t stre
       P.left = rc.left; P.wantT = 0; P.wantZ = 0; P.maxitfac = 30;
       P.A = dA + (size_t)off * p * nn; P.Z = nullptr; P.eig = nullptr; P.info = nullptr; P.iters = nullptr;
       P.use_smem = pl.use_smem; P.ldh = pl.ldh;
-      P.reduce_only = 1; P.skip_reduce = 1;
+      P.reduce_only = 1; P.skip_reduce = 1; P.z_preset = 0;
       P.counter = aux.dCounter;
       P.scratch = nullptr; P.scratch_stride = 0;
       P.packed_out = aux.dPacked;
@@ -300,12 +305,20 @@ int launch_real_eig32(psd_handle_s* h, Device& dev, Slot& aux, cudaStream_t stre
   return PSD_OK;
 }
 
+
+// Large-N path: blocked periodic Hessenberg-triangular reduction on the whole GPU (one problem at
+// a time), then the periodic QR iteration on the reduced factors with Z preset to the Q_j.
+int launch_real_large(psd_handle_s* h, Device& dev, Slot& aux, cudaStream_t stream, const RealCall& rc,
+                      long long batch, double* dA, double* dZ, double* dEig, int32_t* dInfo);
+
 // Enqueue the real kernel for `batch` device-resident problems on `stream`.
 int launch_real(psd_handle_s* h, Device& dev, Slot& aux, cudaStream_t stream, const RealCall& rc,
                 long long batch, double* dA, double* dZ, double* dEig, int32_t* dInfo) {
   if (batch == 0) return PSD_OK;
   RealLaunchPlan pl;
   const bool wantZ = rc.wantZ && dZ;
+  if (rc.n >= kLargeN && rc.p <= psd::LH_MAXP && !rc.skip_reduce && !getenv("PSD_DISABLE_LARGE"))
+    return launch_real_large(h, dev, aux, stream, rc, batch, dA, dZ, dEig, dInfo);
   if (!rc.wantT && !wantZ && !rc.reduce_only && rc.n <= 32 && rc.p >= 3 && !getenv("PSD_DISABLE_EIG32"))
     return launch_real_eig32(h, dev, aux, stream, rc, batch, dA, dEig, dInfo);
   int e = plan_real(dev, rc.n, rc.p, batch, wantZ, pl);
@@ -318,7 +331,7 @@ int launch_real(psd_handle_s* h, Device& dev, Slot& aux, cudaStream_t stream, co
   P.maxitfac = rc.maxitfac > 0 ? rc.maxitfac : 30;
   P.A = dA; P.Z = wantZ ? dZ : nullptr; P.eig = dEig; P.info = dInfo; P.iters = nullptr;
   P.use_smem = pl.use_smem; P.ldh = pl.ldh;
-  P.reduce_only = rc.reduce_only; P.skip_reduce = rc.skip_reduce;
+  P.reduce_only = rc.reduce_only; P.skip_reduce = rc.skip_reduce; P.z_preset = rc.z_preset;
   P.counter = aux.dCounter;
   P.scratch = nullptr; P.scratch_stride = 0;
   P.packed_out = nullptr;
@@ -337,6 +350,68 @@ int launch_real(psd_handle_s* h, Device& dev, Slot& aux, cudaStream_t stream, co
   __atomic_fetch_add(&h->stats[0], (int64_t)1, __ATOMIC_RELAXED);
   __atomic_fetch_add(&h->stats[pl.use_smem ? 1 : 2], (int64_t)batch, __ATOMIC_RELAXED);
   return PSD_OK;
+}
+
+
+int launch_real_large(psd_handle_s* h, Device& dev, Slot& aux, cudaStream_t stream, const RealCall& rc,
+                      long long batch, double* dA, double* dZ, double* dEig, int32_t* dInfo) {
+  const int n = rc.n, p = rc.p;
+  const size_t nn = (size_t)n * n;
+  const bool wantZ = rc.wantZ && dZ;
+  int e = ensure_dev(aux.dScratch, aux.capScratch,
+                     (psd::lh_work_doubles(n, p) + (size_t)psd::rp_small_doubles(n, p) * 2) * sizeof(double));
+  if (e) return e;
+  double* work = aux.dScratch + (size_t)psd::rp_small_doubles(n, p) * 2;  // QR scratch lives in front
+  for (long long b = 0; b < batch; b++) {
+    double* Ab = dA + (size_t)b * p * nn;
+    double* Zb = wantZ ? dZ + (size_t)b * p * nn : nullptr;
+    double* Ap[psd::LH_MAXP];
+    double* Qp[psd::LH_MAXP];
+    for (int j = 1; j <= p; j++) {
+      Ap[j - 1] = Ab + (size_t)((rc.left ? (p + 1 - j) : j) - 1) * nn;
+      const int s = (rc.left && j > 1) ? (p + 2 - j) : j;
+      Qp[j - 1] = Zb ? Zb + (size_t)(s - 1) * nn : nullptr;
+    }
+    double fl = 0.0;
+    std::vector<ScopedKernelTimer*> open(4, nullptr);
+    auto mark = [&](int kind, int phase) {
+      if (phase == 0) {
+        open[kind] = new ScopedKernelTimer(h, dev, stream, kind);
+      } else {
+        delete open[kind];
+        open[kind] = nullptr;
+      }
+    };
+    long long* dprof = nullptr;
+    if (getenv("PSD_PANEL_PROF")) {
+      if (!aux.dCounter) PSD_CUDA(cudaMalloc((void**)&aux.dCounter, 2 * sizeof(unsigned long long)));
+      static long long* s_prof = nullptr;
+      if (!s_prof) PSD_CUDA(cudaMalloc((void**)&s_prof, 8 * sizeof(long long)));
+      PSD_CUDA(cudaMemsetAsync(s_prof, 0, 8 * sizeof(long long), stream));
+      dprof = s_prof;
+    }
+    cudaError_t ce = psd::rphess_large(stream, dev.sm_count, n, p, Ap, Zb ? Qp : nullptr, work, &fl, mark, dprof);
+    if (dprof) {
+      long long hp[8];
+      PSD_CUDA(cudaMemcpyAsync(hp, dprof, sizeof(hp), cudaMemcpyDeviceToHost, stream));
+      PSD_CUDA(cudaStreamSynchronize(stream));
+      fprintf(stderr, "[psd panel cycles, CTA 0] s1+s2 %lld | wait S2 %lld | s3 %lld | wait S3 %lld | s4 head+gemv %lld | s4 tail %lld\n",
+              hp[0], hp[1], hp[2], hp[3], hp[4], hp[5]);
+    }
+    for (auto* t : open) delete t;
+    if (ce != cudaSuccess) return fail(PSD_ERR_CUDA, std::string("large-N reduction: ") + cudaGetErrorString(ce));
+    h->gemm_flops += fl;
+    __atomic_fetch_add(&h->stats[0], (int64_t)((n + 63) / 64) * (1 + 7 * p), __ATOMIC_RELAXED);
+  }
+  if (rc.reduce_only) {
+    __atomic_fetch_add(&h->stats[2], (int64_t)batch, __ATOMIC_RELAXED);
+    return PSD_OK;
+  }
+  // periodic QR iteration on the Hessenberg-triangular factors, Z preset to Q
+  RealCall rq = rc;
+  rq.skip_reduce = 1;
+  rq.z_preset = 1;
+  return launch_real(h, dev, aux, stream, rq, batch, dA, dZ, dEig, dInfo);
 }
 
 // One device's share of a host-buffer batched call.
@@ -952,11 +1027,13 @@ int psd_set_profiling(psd_handle_t h, int on) {
   return PSD_OK;
 }
 
-int psd_kernel_times(psd_handle_t h, double ms[4]) {
+int psd_kernel_times(psd_handle_t h, double ms[8]) {
   if (!h || !ms) return fail(PSD_ERR_BAD_ARG, "null argument");
   std::lock_guard<std::mutex> lock(h->mu);
   std::lock_guard<std::mutex> lk(h->tmu);
-  for (int i = 0; i < 4; i++) ms[i] = 0.0;
+  for (int i = 0; i < 8; i++) ms[i] = 0.0;
+  ms[6] = h->gemm_flops;
+  h->gemm_flops = 0.0;
   for (auto& t : h->timers) {
     cudaSetDevice(t.ordinal);
     cudaError_t e = cudaEventSynchronize(t.e1);
@@ -968,8 +1045,12 @@ int psd_kernel_times(psd_handle_t h, double ms[4]) {
       h->timers.clear();
       return fail(PSD_ERR_CUDA, std::string("kernel timer: ") + cudaGetErrorString(e));
     }
-    ms[t.kind] += f;
-    ms[2 + t.kind] += 1.0;
+    if (t.kind < 2) {
+      ms[t.kind] += f;
+      ms[2 + t.kind] += 1.0;
+    } else {
+      ms[2 + t.kind] += f;  // ms[4] = panel kernels, ms[5] = GEMM groups
+    }
   }
   h->timers.clear();
   return PSD_OK;

@@ -33,6 +33,7 @@ struct RpschurParams {
   int ldh;          // leading dimension of staged matrices
   int reduce_only;  // 1: stop after the Hessenberg-triangular reduction (psd_rphess_batched)
   int skip_reduce;  // 1: input is already Hessenberg/triangular (pschur!(H1,Hs) entry, :322)
+  int z_preset;     // with skip_reduce: Z already holds the Q_j of an earlier reduction (Q kwarg, :326)
   unsigned long long* counter;  // dynamic work queue over problems
   double* scratch;  // per-CTA small arrays when they do not fit in smem (or nullptr)
   long long scratch_stride;
@@ -668,7 +669,7 @@ __global__ void rpschur_kernel(RpschurParams P) {
     if (!P.skip_reduce) {
       phessenberg_cta(c, wantZ);
     } else {
-      if (wantZ) {
+      if (wantZ && !P.z_preset) {
         for (int j = 1; j <= p; j++) {
           double* Zj = c.Zp(j);
           for (int e = tid; e < (int)nn; e += nt) {

@@ -119,10 +119,11 @@ class Handle:
 
     def kernel_times(self):
         """Device time (ms) of the kernels launched since the last call, by kind."""
-        ms = (C.c_double * 4)()
+        ms = (C.c_double * 8)()
         check(lib().psd_kernel_times(self._h, ms))
         return {"reduce_ms": ms[0], "iterate_ms": ms[1], "reduce_launches": int(ms[2]),
-                "iterate_launches": int(ms[3])}
+                "iterate_launches": int(ms[3]), "large_panel_ms": ms[4], "large_gemm_ms": ms[5],
+                "large_gemm_flops": ms[6]}
 
     def close(self):
         if self._h:

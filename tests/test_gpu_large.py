@@ -1,0 +1,49 @@
+"""GPU tests of the large-N path: blocked periodic Hessenberg-triangular reduction
+(panel kernel + FP64 tensor-core GEMM updates, csrc/psd_large_hess.cuh) against the reference's
+"Periodic Hessenberg" predicates (test/runtests.jl:14-50) and the CPU oracle, and the full
+pschur! on top of it."""
+import numpy as np
+import pytest
+
+import psd_checks as K
+
+pytestmark = pytest.mark.gpu
+EPS = np.finfo(float).eps
+
+
+def _check_hess(A, H, Q):
+    p, n, _ = A.shape
+    for j in range(p):
+        Hj, Aj, Qj, Qn = K.M(H[j]), K.M(A[j]), K.M(Q[j]), K.M(Q[(j + 1) % p])
+        assert not np.tril(Hj, -2 if j == 0 else -1).any(), f"factor {j} structure"
+        assert np.linalg.norm(Qj @ Qj.T - np.eye(n)) < 10 * EPS * n
+        res = np.linalg.norm(Aj - Qj @ Hj @ Qn.T)
+        assert res < 20 * EPS * n * max(1.0, np.linalg.norm(Aj) / n ** 0.5), (j, res / (EPS * n))
+
+
+@pytest.mark.parametrize("n,p", [(192, 1), (200, 3), (256, 4), (333, 2)])
+def test_large_reduction(psd, oracle, n, p):
+    A = oracle.gen_real(1234, n, p, 1)
+    H, Q = psd.phessenberg_batched(A)
+    _check_hess(A[0], H[0], Q[0])
+    # same factors as the unblocked oracle up to the signs of rows/columns
+    Ho, _ = oracle.rphess_batched(A)
+    for j in range(p):
+        assert np.allclose(np.abs(H[0, j]), np.abs(Ho[0, j]), atol=1e-9 * max(1.0, np.abs(Ho[0, j]).max()))
+    # without Q
+    H2, Q2 = psd.phessenberg_batched(A, wantQ=False)
+    assert Q2 is None and np.allclose(H2, H, atol=1e-12 * np.abs(H).max())
+
+
+def test_large_pschur(psd, oracle):
+    """full decomposition at N = 256 (blocked reduction, then the periodic QR iteration with Z
+    preset to the accumulated Q)"""
+    n, p = 256, 3
+    A = oracle.gen_real(77, n, p, 1)
+    for lr in ("R", "L"):
+        T, Z, lam, info = psd.pschur_batched(A, lr)
+        assert info[0] == 0
+        K.pschur_check(A[0], T[0], Z[0], lam[0], left=(lr == "L"), tol=64, check_lambda=False)
+        tr = np.trace(np.linalg.multi_dot([K.M(A[0, j]) for j in (range(p) if lr == "R" else range(p - 1, -1, -1))])
+                      ) if p > 1 else np.trace(K.M(A[0, 0]))
+        assert abs(lam[0].sum() - tr) <= 1e-8 * abs(tr)
