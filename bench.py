@@ -98,24 +98,33 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def host_cores() -> int:
+    """Host threads this process may use (torchrun exports OMP_NUM_THREADS=1, so the OpenMP
+    default cannot be trusted: the thread count is always passed explicitly)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_reference_rate(sample: int, nthreads: int = 0):
     """Time the CPU restatement of the reference (oracle, OpenMP over the batch) on `sample`
     problems of the same workload.  Returns (problems/s, cores, seconds)."""
     from oracle import oracle as O
+    nthreads = nthreads or host_cores()
     A = O.gen_real(SEED, N_ORDER, PERIOD, sample)
     t0 = time.perf_counter()
     _, _, _, info, _ = O.rpschur_batched(A, left=False, wantT=False, wantZ=False, nthreads=nthreads)
     dt = time.perf_counter() - t0
     assert (info == 0).all()
-    return sample / dt, (nthreads or O.max_threads()), dt
+    return sample / dt, nthreads, dt
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    from oracle import oracle as O
-    cores = O.max_threads()
+    cores = host_cores()
     # bounded sample per step: ~2-4 s of CPU work
     probe_rate, _, _ = cpu_reference_rate(max(64, 32 * cores))
     sample = int(max(256, min(args.batch, probe_rate * 3.0)))
@@ -259,7 +268,7 @@ def run_ours(args):
     if os.path.exists(tpath):
         try:
             with open(tpath) as f:
-                traffic = json.load(f).get("rpschur_c2_bytes_per_launch")
+                traffic = json.load(f).get("rpqr_eig32_dram_bytes_per_problem")
         except Exception:
             traffic = None
     line = {
@@ -276,7 +285,9 @@ def run_ours(args):
                 "matches_device_path": same},
         "gpu_launches": kt["iterate_launches"] + kt["reduce_launches"],
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": traffic, "peak_kind": f"of {peak_kind}",
+                     "frac": achieved / peak,
+                     "traffic": (traffic * units_per_launch) if traffic else None,
+                     "peak_kind": f"of {peak_kind}",
                      "kernel": "psd::rpqr_eig32_kernel", "kernel_ms": k_ms,
                      "problems_per_launch": units_per_launch,
                      "kernel_share_of_step": kt["iterate_ms"] / (kt["iterate_ms"] + kt["reduce_ms"]),
@@ -290,7 +301,7 @@ def run_ours(args):
     }
     if world == 1:
         # bounded CPU sample: ~10-20 s on the box's host cores
-        probe, cores, _ = cpu_reference_rate(max(64, 32 * (os.cpu_count() or 8)))
+        probe, cores, _ = cpu_reference_rate(max(64, 32 * host_cores()))
         sample = int(max(512, min(B, probe * 12.0)))
         rate, cores, dt = cpu_reference_rate(sample)
         line["cpu_baseline"] = {
@@ -299,6 +310,15 @@ def run_ours(args):
                       f"the reference (Julia unavailable), OpenMP over the batch"}
     print(json.dumps(line))
     return 0
+
+
+def _shutdown():
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            dist.destroy_process_group()
+    except Exception:
+        pass
 
 
 def main():
@@ -311,7 +331,10 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
-    return run_ours(args)
+    try:
+        return run_ours(args)
+    finally:
+        _shutdown()
 
 
 if __name__ == "__main__":
