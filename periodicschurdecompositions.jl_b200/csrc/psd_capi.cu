@@ -221,7 +221,7 @@ int launch_real_eig32(psd_handle_s* h, Device& dev, Slot& aux, cudaStream_t stre
   const size_t nn = (size_t)n * n;
   const size_t psize = (size_t)psd::pk_problem_size(n, p);
   const long long chunk = std::min(batch, kEigChunk);
-  int e = ensure_dev(aux.dPacked, aux.capPacked, (size_t)chunk * psize * sizeof(double));
+  int e = ensure_dev(aux.dPacked, aux.capPacked, (size_t)chunk * (psize + 1) * sizeof(double));
   if (e) return e;
   if (!aux.dCounter) PSD_CUDA(cudaMalloc((void**)&aux.dCounter, 2 * sizeof(unsigned long long)));
   // QR kernel configuration: as many warps (= resident problems) per CTA as shared memory allows
@@ -292,6 +292,7 @@ int launch_real_eig32(psd_handle_s* h, Device& dev, Slot& aux, cudaStream_t stre
     Q.info = dInfo + off;
     Q.iters = nullptr;
     Q.counter = aux.dCounter + 1;
+    Q.force_safe = getenv("PSD_EIG32_SAFE") ? 1 : 0;
     const long long ctas = (nb + wpb - 1) / wpb;
     const int grid2 = (int)std::max(1LL, std::min((long long)occ2 * dev.sm_count, ctas));
     {
@@ -573,6 +574,7 @@ int launch_gen_t(psd_handle_s* h, Device& dev, Slot& aux, cudaStream_t stream, c
   P.A = (T*)dA; P.Z = wantZ ? (T*)dZ : nullptr;
   P.alpha = (psd::cplx*)dAlpha; P.beta = (T*)dBeta; P.scale = dScale; P.info = dInfo;
   P.counter = aux.dCounter;
+  P.debug = getenv("PSD_GEN_PROF") ? 1 : 0;
   size_t smem;
   if (small + mats <= max_dyn) {
     P.use_smem = 1; P.ldh = ldh; smem = small + mats;
@@ -904,7 +906,7 @@ int psd_rphess_rowwise_batched(psd_handle_t h, int n, int extra_row, int p, int 
   const int grid = (int)std::min<long long>(batch, (long long)dev.sm_count * 4);
   {
     ScopedKernelTimer tm(h, dev, s.stream, 0);
-    psd::rowhess_kernel<double><<<grid, threads, 0, s.stream>>>(P);
+    psd::rowhess_kernel<double><<<grid, threads, (size_t)(n + 2) * sizeof(double), s.stream>>>(P);
   }
   PSD_CUDA(cudaGetLastError());
   PSD_CUDA(cudaMemcpyAsync(Ap, s.dA, bAp, cudaMemcpyDeviceToHost, s.stream));

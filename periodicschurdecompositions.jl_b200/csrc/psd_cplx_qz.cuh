@@ -32,6 +32,7 @@ struct GpqzParams {
   long long* scale;         // [batch][n]
   int* info;                // [batch]
   int use_smem, ldh;
+  int debug;                // print a phase breakdown (cycles) for the problems of CTA 0
   unsigned long long* counter;
 };
 
@@ -39,7 +40,7 @@ struct GpqzParams {
 // chase: 9+6(p-1)), S bytes
 __host__ __device__ inline long long cq_stage_doubles(int p) { return 10LL + 6 * (p > 1 ? p - 1 : 0); }
 __host__ __device__ inline long long cq_small_doubles(int n, int p) {
-  return 3LL * (n + 2) + cq_stage_doubles(p) + (p + 15) / 8 + 2;
+  return 5LL * (n + 2) + 2 * cq_stage_doubles(p) + (p + 15) / 8 + 2;
 }
 
 template <class T>
@@ -169,56 +170,92 @@ PSD_DEV void rot3(double& a0, double& a1, double& a2, const Rot2& g) {
   rrot(a0, a1, g.c1, g.s1);
 }
 
+// Independent 3-element items (a[0], a[st], a[2 st]) <- rot3(., g[sel]); BULK_U of them are loaded
+// before any is stored (memory-latency bound at the larger sizes, see bulk_rot2).
+template <class Item>
+PSD_DEV void bulk_rot3(int tid, int nt, int total, const Rot2 (&g)[3], Item&& item) {
+  for (int w0 = tid; w0 < total; w0 += BULK_U * nt) {
+    double* pa[BULK_U];
+    long long st[BULK_U];
+    int sel[BULK_U];
+    double v0[BULK_U], v1[BULK_U], v2[BULK_U];
+#pragma unroll
+    for (int u = 0; u < BULK_U; u++) {
+      const int w = w0 + u * nt;
+      pa[u] = nullptr;
+      if (w < total) item(w, pa[u], st[u], sel[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < BULK_U; u++)
+      if (pa[u]) {
+        v0[u] = pa[u][0];
+        v1[u] = pa[u][st[u]];
+        v2[u] = pa[u][2 * st[u]];
+      }
+#pragma unroll
+    for (int u = 0; u < BULK_U; u++)
+      if (pa[u]) {
+        const Rot2 gg = (sel[u] == 0) ? g[0] : (sel[u] == 1) ? g[1] : g[2];
+        rot3(v0[u], v1[u], v2[u], gg);
+        pa[u][0] = v0[u];
+        pa[u][st[u]] = v1[u];
+        pa[u][2 * st[u]] = v2[u];
+      }
+  }
+}
+
 // chase_double: the two rotations G1 = Givens(j+1,j+2), G2 = Givens(j,j+1) act on rows j..j+2
 // of H_1 (columns j..clast), are propagated through factors p..2 (rgeneralized.jl:977-1010) and
 // return to columns j..j+2 of H_1 (rows rfirst..h1r1).  Same organisation as chase_rotation:
 // the 3x3 diagonal blocks are processed in registers by every thread, bulk updates touch
 // disjoint memory, blocks are staged in shared memory and written back between two barriers.
-PSD_DEV void chase_double(const GCtx<double>& cx, int j, Rot2 gin, int zcol, double r1, int clast,
+__device__ __noinline__ void chase_double(const GCtx<double>& cx, int j, Rot2 gin, int zcol, double r1, int clast,
                           int rfirst, int h1r1) {
   const int n = cx.n, p = cx.p, tid = cx.tid, nt = cx.nt, ld = cx.ldh;
   double* H1 = cx.Hp(1);
+  // one parallel load of every 3x3 diagonal block (H_1: 9 entries, factor l: 6 at 9+6(l-2))
+  {
+    double* in = cx.stage_in;
+    for (int e = tid; e < 9 + 6 * (p - 1); e += nt) {
+      if (e < 9) {
+        in[e] = PSD_GE(H1, ld, j + e / 3, j + e % 3);
+      } else {
+        const int l = 2 + (e - 9) / 6, w = (e - 9) % 6;
+        const int rr = (w < 3) ? 0 : (w < 5) ? 1 : 2;
+        const int cc = (w < 3) ? w : (w < 5) ? (w - 2) : 2;
+        in[e] = PSD_GE(cx.Hp(l), ld, j + rr, j + cc);
+      }
+    }
+    __syncthreads();
+  }
+  const double* bin = cx.stage_in;
   double X[3][3];
 #pragma unroll
   for (int r = 0; r < 3; r++)
 #pragma unroll
-    for (int c = 0; c < 3; c++) X[r][c] = PSD_GE(H1, ld, j + r, j + c);
+    for (int c = 0; c < 3; c++) X[r][c] = bin[3 * r + c];
   const Rot2 g0 = gin;
-  double b00 = 0, b01 = 0, b02 = 0, b11 = 0, b12 = 0, b22 = 0;
-  if (p > 1) {
-    const double* Hl = cx.Hp(p);
-    b00 = PSD_GE(Hl, ld, j, j); b01 = PSD_GE(Hl, ld, j, j + 1); b02 = PSD_GE(Hl, ld, j, j + 2);
-    b11 = PSD_GE(Hl, ld, j + 1, j + 1); b12 = PSD_GE(Hl, ld, j + 1, j + 2);
-    b22 = PSD_GE(Hl, ld, j + 2, j + 2);
-  }
   {  // left-only columns of H_1 and Z_1
     const int nL = clast - (j + 2);
     const int nZ = cx.wantZ ? n : 0;
     double* Z1 = cx.wantZ ? cx.Zp(1) : nullptr;
-    for (int w = tid; w < nL + nZ; w += nt) {
-      double* a;
-      long long st;
+    const Rot2 gs[3] = {g0, g0, g0};
+    const int ldz = cx.ldz;
+    bulk_rot3(tid, nt, nL + nZ, gs, [&](int w, double*& a, long long& st, int& sel) {
+      sel = 0;
       if (w < nL) {
         a = &PSD_GE(H1, ld, j, j + 3 + w);
         st = 1;
       } else {
-        a = &PSD_GE(Z1, cx.ldz, 1 + (w - nL), j);
-        st = cx.ldz;
+        a = &PSD_GE(Z1, ldz, 1 + (w - nL), j);
+        st = ldz;
       }
-      double a0 = a[0], a1 = a[st], a2 = a[2 * st];
-      rot3(a0, a1, a2, g0);
-      a[0] = a0; a[st] = a1; a[2 * st] = a2;
-    }
+    });
   }
   for (int l = p; l >= 2; l--) {
     double* Hl = cx.Hp(l);
-    double B00 = b00, B01 = b01, B02 = b02, B11 = b11, B12 = b12, B22 = b22, B10 = 0.0, B21 = 0.0;
-    if (l > 2) {
-      const double* Hn = cx.Hp(l - 1);
-      b00 = PSD_GE(Hn, ld, j, j); b01 = PSD_GE(Hn, ld, j, j + 1); b02 = PSD_GE(Hn, ld, j, j + 2);
-      b11 = PSD_GE(Hn, ld, j + 1, j + 1); b12 = PSD_GE(Hn, ld, j + 1, j + 2);
-      b22 = PSD_GE(Hn, ld, j + 2, j + 2);
-    }
+    const double* bl = bin + 9 + 6 * (l - 2);
+    double B00 = bl[0], B01 = bl[1], B02 = bl[2], B11 = bl[3], B12 = bl[4], B22 = bl[5], B10 = 0.0, B21 = 0.0;
     Rot2 gout;
     double r;
     const bool sl = cx.Sg(l);
@@ -259,27 +296,23 @@ PSD_DEV void chase_double(const GCtx<double>& cx, int j, Rot2 gin, int zcol, dou
       const int nR = j - rfirst, nL = clast - (j + 2);
       const int nZ = cx.wantZ ? n : 0;
       double* Zl = cx.wantZ ? cx.Zp(l) : nullptr;
-      for (int w = tid; w < nR + nL + nZ; w += nt) {
-        double* a;
-        long long st;
-        Rot2 g;
+      const Rot2 gs[3] = {gR, gL, gout};
+      const int ldz = cx.ldz;
+      bulk_rot3(tid, nt, nR + nL + nZ, gs, [&](int w, double*& a, long long& st, int& sel) {
         if (w < nR) {
           a = &PSD_GE(Hl, ld, rfirst + w, j);
           st = ld;
-          g = gR;
+          sel = 0;
         } else if (w < nR + nL) {
           a = &PSD_GE(Hl, ld, j, j + 3 + (w - nR));
           st = 1;
-          g = gL;
+          sel = 1;
         } else {
-          a = &PSD_GE(Zl, cx.ldz, 1 + (w - nR - nL), j);
-          st = cx.ldz;
-          g = gout;
+          a = &PSD_GE(Zl, ldz, 1 + (w - nR - nL), j);
+          st = ldz;
+          sel = 2;
         }
-        double a0 = a[0], a1 = a[st], a2 = a[2 * st];
-        rot3(a0, a1, a2, g);
-        a[0] = a0; a[st] = a1; a[2 * st] = a2;
-      }
+      });
       if (tid == 0) {
         double* sg = cx.stage + 9 + 6 * (l - 2);
         sg[0] = B00; sg[1] = B01; sg[2] = B02; sg[3] = B11; sg[4] = B12; sg[5] = B22;
@@ -289,14 +322,14 @@ PSD_DEV void chase_double(const GCtx<double>& cx, int j, Rot2 gin, int zcol, dou
   }
   {  // right-only rows of H_1 and its 3x3 overlap block
     const int nR = (h1r1 - rfirst + 1) - 3;
-    for (int w = tid; w < nR; w += nt) {
+    const Rot2 gs[3] = {gin, gin, gin};
+    bulk_rot3(tid, nt, nR, gs, [&](int w, double*& a, long long& st, int& sel) {
       int row = rfirst + w;
       if (row >= j) row += 3;
-      double* a = &PSD_GE(H1, ld, row, j);
-      double a0 = a[0], a1 = a[ld], a2 = a[2 * (size_t)ld];
-      rot3(a0, a1, a2, gin);
-      a[0] = a0; a[ld] = a1; a[2 * (size_t)ld] = a2;
-    }
+      a = &PSD_GE(H1, ld, row, j);
+      st = ld;
+      sel = 0;
+    });
     if (tid == 0) {
 #pragma unroll
       for (int c = 0; c < 3; c++) rot3(X[0][c], X[1][c], X[2][c], g0);
@@ -969,8 +1002,10 @@ __global__ void gpschur_kernel(GpqzParams<T> P) {
   st.Gc = small;
   st.Gs = reinterpret_cast<T*>(small + (n + 2) + ((n + 2) & 1));
   T* stage = reinterpret_cast<T*>(small + (n + 2) + ((n + 2) & 1) + 2 * (n + 2));
-  unsigned char* Sint = reinterpret_cast<unsigned char*>(small + (n + 2) + ((n + 2) & 1) + 2 * (n + 2) +
-                                                         cq_stage_doubles(p));
+  T* stage_in = reinterpret_cast<T*>(small + (n + 2) + ((n + 2) & 1) + 2 * (n + 2) + cq_stage_doubles(p));
+  T* wvec = reinterpret_cast<T*>(small + (n + 2) + ((n + 2) & 1) + 2 * (n + 2) + 2 * cq_stage_doubles(p));
+  unsigned char* Sint = reinterpret_cast<unsigned char*>(small + (n + 2) + ((n + 2) & 1) + 4 * (n + 2) +
+                                                         2 * cq_stage_doubles(p));
   st.key = &s_key;
   T* mats = reinterpret_cast<T*>(psd_smem_cq + ((cq_small_doubles(n, p) + 1) & ~1LL));
 
@@ -984,6 +1019,10 @@ __global__ void gpschur_kernel(GpqzParams<T> P) {
   cx.wantZ = P.wantZ && P.Z;
   cx.S = Sint;
   cx.stage = stage;
+  cx.stage_in = stage_in;
+  cx.wvec = wvec;
+  __shared__ long long s_prof[4];
+  cx.prof = P.debug ? s_prof : nullptr;
 
   for (;;) {
     if (tid == 0) s_b = (long long)atomicAdd(P.counter, 1ULL);
@@ -1015,6 +1054,7 @@ __global__ void gpschur_kernel(GpqzParams<T> P) {
     }
     __syncthreads();
 
+    const long long tstart = clock64();
     if (!P.skip_reduce) {
       gphessenberg_cta(cx);
     } else {
@@ -1040,7 +1080,11 @@ __global__ void gpschur_kernel(GpqzParams<T> P) {
     cplx* al = P.alpha + (size_t)b * n;
     T* be = P.beta + (size_t)b * n;
     long long* sc = P.scale + (size_t)b * n;
+    const long long tred = clock64();
     const int info = gpqz_cta<T>(cx, st, P.wantT != 0, P.maxitfac, al, be, sc);
+    if (P.debug && tid == 0 && blockIdx.x == 0)
+      printf("[psd gpschur b=%lld] stage1 %lld  stage2 %lld  qz %lld cycles\n", b,
+             P.skip_reduce ? 0LL : s_prof[0] - tstart, P.skip_reduce ? 0LL : tred - s_prof[0], clock64() - tred);
     if (tid == 0) P.info[b] = info;
     __syncthreads();
 

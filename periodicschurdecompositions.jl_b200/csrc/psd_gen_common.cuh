@@ -136,7 +136,10 @@ struct GCtx {
   bool wantZ;
   bool zmap_left;
   const unsigned char* S;
-  T* stage;  // 4 + 3(p-1) scalars of shared memory: diagonal blocks staged by chase_rotation
+  T* stage;     // 4 + 3(p-1) scalars of shared memory: diagonal blocks staged by chase_rotation
+  T* stage_in;  // same size: the diagonal blocks of all factors, fetched with ONE parallel load
+  long long* prof;  // phase time stamps (debug), or nullptr
+  T* wvec;          // n scalars of shared memory: the reflector being applied (Stage 1)
   PSD_DEV T* Hp(int l) const { return H + (long long)(l - 1) * hs; }
   PSD_DEV T* Zp(int l) const {
     int s = l;
@@ -165,6 +168,40 @@ PSD_DEV void rot_pair_cols(T* M, int ld, int j1, int j2, int row, double c, T s)
   const T a1 = *a, a2 = *b;
   *a = c * a1 + conj_(s) * a2;
   *b = c * a2 - s * a1;
+}
+
+// Apply a list of independent 2-element rotations, dealt round-robin to the threads: item w is
+// decoded by `item(w, a, b, c, s)` into two element pointers and the rotation
+// (a, b) <- (c a + s b, c b - conj(s) a)   [rows: s; columns (right-multiplication by G'): conj(s)].
+// All items touch disjoint memory, so BULK_U of them are loaded before any is stored: the loop is
+// bound by memory latency (factors in L2 / HBM at the larger sizes), not by arithmetic.
+constexpr int BULK_U = 4;
+template <class T, class Item>
+PSD_DEV void bulk_rot2(int tid, int nt, int total, Item&& item) {
+  for (int w0 = tid; w0 < total; w0 += BULK_U * nt) {
+    T* pa[BULK_U];
+    T* pb[BULK_U];
+    double cc[BULK_U];
+    T ss[BULK_U], va[BULK_U], vb[BULK_U];
+#pragma unroll
+    for (int u = 0; u < BULK_U; u++) {
+      const int w = w0 + u * nt;
+      pa[u] = nullptr;
+      if (w < total) item(w, pa[u], pb[u], cc[u], ss[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < BULK_U; u++)
+      if (pa[u]) {
+        va[u] = *pa[u];
+        vb[u] = *pb[u];
+      }
+#pragma unroll
+    for (int u = 0; u < BULK_U; u++)
+      if (pa[u]) {
+        *pa[u] = cc[u] * va[u] + ss[u] * vb[u];
+        *pb[u] = cc[u] * vb[u] - conj_(ss[u]) * va[u];
+      }
+  }
 }
 
 // ---- simple CTA-synchronous helpers (used on the rarely taken branches) -------------------
@@ -221,48 +258,58 @@ PSD_DEV double g_opnorm1(const T* M, int ld, int r0, int r1, int c0, int c1, boo
 // written back.  All threads of the CTA must call with identical arguments.
 // ------------------------------------------------------------------------------------------
 template <class T>
-PSD_DEV void chase_rotation(const GCtx<T>& cx, int j, double c1, T s1, int zcol, T r1, int h1c0,
+__device__ __noinline__ void chase_rotation(const GCtx<T>& cx, int j, double c1, T s1, int zcol, T r1, int h1c0,
                             int clast, int rfirst, int h1r1) {
   const int n = cx.n, p = cx.p, tid = cx.tid, nt = cx.nt;
   T* H1 = cx.Hp(1);
   const int ld = cx.ldh;
-  // H_1's 2x2 overlap block and the generating pair are read before anything is written
-  const T ha = PSD_GE(H1, ld, j, j), hb = PSD_GE(H1, ld, j, j + 1);
-  const T hc = PSD_GE(H1, ld, j + 1, j), hd = PSD_GE(H1, ld, j + 1, j + 1);
+  // All 2x2 diagonal blocks (H_1: 4 entries at [0..3], factor l: 3 entries at 4+3(l-2)) are
+  // fetched by one parallel load into shared memory: the chain below then costs one memory
+  // latency per step instead of one per factor.
+  {
+    T* in = cx.stage_in;
+    for (int e = tid; e < 4 + 3 * (p - 1); e += nt) {
+      if (e < 4) {
+        in[e] = PSD_GE(H1, ld, j + (e >> 1), j + (e & 1));
+      } else {
+        const int l = 2 + (e - 4) / 3, w = (e - 4) % 3;
+        in[e] = PSD_GE(cx.Hp(l), ld, j + (w == 2 ? 1 : 0), j + (w == 0 ? 0 : 1));
+      }
+    }
+    __syncthreads();
+  }
+  const T* bin = cx.stage_in;
+  const T ha = bin[0], hb = bin[1], hc = bin[2], hd = bin[3];
   double ci = c1;
   T si = s1;
-  // prefetch the first factor's diagonal block
   T b00 = Scalar<T>::zero(), b01 = b00, b11 = b00;
-  if (p > 1) {
-    const T* Hl = cx.Hp(p);
-    b00 = PSD_GE(Hl, ld, j, j);
-    b01 = PSD_GE(Hl, ld, j, j + 1);
-    b11 = PSD_GE(Hl, ld, j + 1, j + 1);
-  }
   // Z_1 and the left-only part of H_1 (rotation G1); the overlap block is finished at the end
   {
     const int nL = (clast - h1c0 + 1) - 2;  // columns h1c0..clast without j, j+1
     const int nZ = cx.wantZ ? n : 0;
     T* Z1 = cx.wantZ ? cx.Zp(1) : nullptr;
-    for (int w = tid; w < nL + nZ; w += nt) {
+    const int ldz = cx.ldz;
+    bulk_rot2<T>(tid, nt, nL + nZ, [&](int w, T*& a, T*& b, double& c, T& s) {
+      c = c1;
       if (w < nL) {
         int col = h1c0 + w;
         if (col >= j) col += 2;
-        rot_pair_rows(H1, ld, j, j + 1, col, c1, s1);
+        a = &PSD_GE(H1, ld, j, col);
+        b = a + 1;
+        s = s1;
       } else {
-        rot_pair_cols(Z1, cx.ldz, j, j + 1, 1 + (w - nL), c1, s1);
+        a = &PSD_GE(Z1, ldz, 1 + (w - nL), j);
+        b = a + ldz;
+        s = conj_(s1);
       }
-    }
+    });
   }
   for (int l = p; l >= 2; l--) {
     T* Hl = cx.Hp(l);
+    b00 = bin[4 + 3 * (l - 2)];
+    b01 = bin[5 + 3 * (l - 2)];
+    b11 = bin[6 + 3 * (l - 2)];
     const T c00 = b00, c01 = b01, c11 = b11;
-    if (l > 2) {  // prefetch the next factor's block while this one is processed
-      const T* Hn = cx.Hp(l - 1);
-      b00 = PSD_GE(Hn, ld, j, j);
-      b01 = PSD_GE(Hn, ld, j, j + 1);
-      b11 = PSD_GE(Hn, ld, j + 1, j + 1);
-    }
     double co;
     T so, m00, m01, m11;
     double cR, cL;  // rotation acting on columns (right-only rows) / on rows (left-only columns)
@@ -300,15 +347,25 @@ PSD_DEV void chase_rotation(const GCtx<T>& cx, int j, double c1, T s1, int zcol,
       const int nL = clast - (j + 1);  // columns j+2..clast
       const int nZ = cx.wantZ ? n : 0;
       T* Zl = cx.wantZ ? cx.Zp(l) : nullptr;
-      for (int w = tid; w < nR + nL + nZ; w += nt) {
+      const int ldz = cx.ldz;
+      bulk_rot2<T>(tid, nt, nR + nL + nZ, [&](int w, T*& a, T*& b, double& c, T& s) {
         if (w < nR) {
-          rot_pair_cols(Hl, ld, j, j + 1, rfirst + w, cR, sR);
+          a = &PSD_GE(Hl, ld, rfirst + w, j);
+          b = a + ld;
+          c = cR;
+          s = conj_(sR);
         } else if (w < nR + nL) {
-          rot_pair_rows(Hl, ld, j, j + 1, j + 2 + (w - nR), cL, sL);
+          a = &PSD_GE(Hl, ld, j, j + 2 + (w - nR));
+          b = a + 1;
+          c = cL;
+          s = sL;
         } else {
-          rot_pair_cols(Zl, cx.ldz, j, j + 1, 1 + (w - nR - nL), co, so);
+          a = &PSD_GE(Zl, ldz, 1 + (w - nR - nL), j);
+          b = a + ldz;
+          c = co;
+          s = conj_(so);
         }
-      }
+      });
       if (tid == 0) {
         T* st = cx.stage + 4 + 3 * (l - 2);
         st[0] = m00;
@@ -322,11 +379,14 @@ PSD_DEV void chase_rotation(const GCtx<T>& cx, int j, double c1, T s1, int zcol,
   // right-only rows of H_1 (rotation that came out of factor 2) and the overlap block
   {
     const int nR = (h1r1 - rfirst + 1) - 2;  // rows rfirst..h1r1 without j, j+1
-    for (int w = tid; w < nR; w += nt) {
+    bulk_rot2<T>(tid, nt, nR, [&](int w, T*& a, T*& b, double& c, T& s) {
       int row = rfirst + w;
       if (row >= j) row += 2;
-      rot_pair_cols(H1, ld, j, j + 1, row, ci, si);
-    }
+      a = &PSD_GE(H1, ld, row, j);
+      b = a + ld;
+      c = ci;
+      s = conj_(si);
+    });
     if (tid == 0) {
       // left with G1, then right with (ci, si)
       const T a1 = c1 * ha + s1 * hc, b1 = c1 * hb + s1 * hd;
@@ -401,6 +461,69 @@ PSD_DEV bool refl_vec(const T* x, long long inc, int m, int lane, double& beta, 
   return true;
 }
 
+// ---- reflector application with memory-level parallelism ------------------------------------
+// The reflector w (w_0 = 1) is placed in shared memory once; every loop below then loads HH_U
+// matrix entries before using any of them.  (A literal "d += a[r] * w[r]" loop that reads w from
+// the matrix it updates is fully latency-exposed: the compiler must assume the stores alias it.)
+constexpr int HH_U = 8;
+
+// a[0], a[st], ..., a[(m-1) st]  <-  (I - coef w w^H)-type update of one row/column vector:
+//   d = sum_r f(w_r) a_r;  a_r -= (coef d) g(w_r)
+// RIGHT = true:  d = sum a_r w_r,        a_r -= (tau d) conj(w_r)     (A H,   one thread per row)
+template <class T>
+PSD_DEV void hh_right_one(T* a, long long st, int m, const T* w, T tau) {
+  T d = Scalar<T>::zero();
+  int r = 0;
+  for (; r + HH_U <= m; r += HH_U) {
+    T v[HH_U];
+#pragma unroll
+    for (int u = 0; u < HH_U; u++) v[u] = a[(long long)(r + u) * st];
+#pragma unroll
+    for (int u = 0; u < HH_U; u++) d = d + v[u] * w[r + u];
+  }
+  for (; r < m; r++) d = d + a[(long long)r * st] * w[r];
+  d = tau * d;
+  r = 0;
+  for (; r + HH_U <= m; r += HH_U) {
+    T v[HH_U];
+#pragma unroll
+    for (int u = 0; u < HH_U; u++) v[u] = a[(long long)(r + u) * st];
+#pragma unroll
+    for (int u = 0; u < HH_U; u++) a[(long long)(r + u) * st] = v[u] - d * conj_(w[r + u]);
+  }
+  for (; r < m; r++) a[(long long)r * st] = a[(long long)r * st] - d * conj_(w[r]);
+}
+
+// H' A on one column handled by a warp: a_r at a[r*st], r < m; d = conj(tau) sum conj(w_r) a_r;
+// a_r -= d w_r.  Lanes stride over r; up to 4 strided chunks are loaded at once.
+template <class T>
+PSD_DEV void hh_left_warp(T* a, long long st, int m, const T* w, T tau, int lane) {
+  T d = Scalar<T>::zero();
+  for (int r = lane; r < m; r += 128) {
+    T v[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) v[u] = (r + 32 * u < m) ? a[(long long)(r + 32 * u) * st] : Scalar<T>::zero();
+#pragma unroll
+    for (int u = 0; u < 4; u++)
+      if (r + 32 * u < m) d = d + conj_(w[r + 32 * u]) * v[u];
+  }
+  if constexpr (sizeof(T) == sizeof(double)) {
+    d = warp_sum(d);
+  } else {
+    d.x = warp_sum(d.x);
+    d.y = warp_sum(d.y);
+  }
+  d = conj_(tau) * d;
+  for (int r = lane; r < m; r += 128) {
+    T v[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) v[u] = (r + 32 * u < m) ? a[(long long)(r + 32 * u) * st] : Scalar<T>::zero();
+#pragma unroll
+    for (int u = 0; u < 4; u++)
+      if (r + 32 * u < m) a[(long long)(r + 32 * u) * st] = v[u] - d * w[r + 32 * u];
+  }
+}
+
 // QR-type step on column k of Al (S[l] = true): annihilate Al[k+1:n, k]; apply H' to the
 // remaining columns of Al, H to the neighbour factor (from the right if S[l-1], H' from the
 // left otherwise) and to Q_l from the right.
@@ -409,49 +532,26 @@ PSD_DEV void stage1_qr_step(const GCtx<T>& cx, T* Al, T* Am, bool sm1, T* Ql, in
   const int n = cx.n, ld = cx.ldh, tid = cx.tid, nt = cx.nt;
   const int lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
   const int m = n - k + 1;
-  const T* x = &PSD_GE(Al, ld, k, k);
+  T* xg = &PSD_GE(Al, ld, k, k);
   double beta;
   T tau, tv;
-  if (!refl_vec<T, false>(x, 1, m, lane, beta, tau, tv)) return;  // uniform over the CTA
+  if (!refl_vec<T, false>(xg, 1, m, lane, beta, tau, tv)) return;  // uniform over the CTA
+  T* w = cx.wvec;  // w_0 = 1, w_r = tv x_r  (rows k..n)
+  for (int r = tid; r < m; r += nt) w[r] = (r == 0) ? Scalar<T>::one() : tv * xg[r];
+  __syncthreads();
   // (a) left on Al columns k+1..n and, when !S[l-1], on all columns of Am: one warp per column
   const int ncolA = n - k, ncolM = sm1 ? 0 : n;
-  for (int w = warp; w < ncolA + ncolM; w += nw) {
-    T* a = (w < ncolA) ? &PSD_GE(Al, ld, k, k + 1 + w) : &PSD_GE(Am, ld, k, 1 + (w - ncolA));
-    // d = w^H a
-    T d = Scalar<T>::zero();
-    for (int r = lane; r < m; r += 32) {
-      const T wr = (r == 0) ? Scalar<T>::one() : tv * x[r];
-      d = d + conj_(wr) * a[r];
-    }
-    if constexpr (sizeof(T) == sizeof(double)) {
-      d = warp_sum(d);
-    } else {
-      d.x = warp_sum(d.x);
-      d.y = warp_sum(d.y);
-    }
-    d = conj_(tau) * d;  // H' = I - conj(tau) w w^H
-    for (int r = lane; r < m; r += 32) {
-      const T wr = (r == 0) ? Scalar<T>::one() : tv * x[r];
-      a[r] = a[r] - d * wr;
-    }
+  for (int c = warp; c < ncolA + ncolM; c += nw) {
+    T* a = (c < ncolA) ? &PSD_GE(Al, ld, k, k + 1 + c) : &PSD_GE(Am, ld, k, 1 + (c - ncolA));
+    hh_left_warp<T>(a, 1, m, w, tau, lane);
   }
   // (b) right on Am rows (if S[l-1]) and Q_l rows: one thread per row
   const int nM = sm1 ? n : 0, nQ = cx.wantZ ? n : 0;
-  for (int w = tid; w < nM + nQ; w += nt) {
-    T* a;
-    int lda;
-    if (w < nM) {
-      a = &PSD_GE(Am, ld, 1 + w, k);
-      lda = ld;
-    } else {
-      a = &PSD_GE(Ql, cx.ldz, 1 + (w - nM), k);
-      lda = cx.ldz;
-    }
-    T d = a[0];
-    for (int r = 1; r < m; r++) d = d + a[(size_t)r * lda] * (tv * x[r]);
-    d = tau * d;
-    a[0] = a[0] - d;
-    for (int r = 1; r < m; r++) a[(size_t)r * lda] = a[(size_t)r * lda] - d * conj_(tv * x[r]);
+  for (int c = tid; c < nM + nQ; c += nt) {
+    if (c < nM)
+      hh_right_one<T>(&PSD_GE(Am, ld, 1 + c, k), ld, m, w, tau);
+    else
+      hh_right_one<T>(&PSD_GE(Ql, cx.ldz, 1 + (c - nM), k), cx.ldz, m, w, tau);
   }
   __syncthreads();
   for (int r = tid; r < m; r += nt)
@@ -468,57 +568,27 @@ PSD_DEV void stage1_rq_step(const GCtx<T>& cx, T* Al, T* Am, bool sm1, T* Ql, in
   const int lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
   const int m = k;
   // vector conj(Al[k, k]), conj(Al[k, k-1]), ..., conj(Al[k, 1]): pivot first, stride -ld
-  const T* x = &PSD_GE(Al, ld, k, k);
+  T* xg = &PSD_GE(Al, ld, k, k);
   const long long inc = -(long long)ld;
   double beta;
   T tau, tv;
-  if (!refl_vec<T, true>(x, inc, m, lane, beta, tau, tv)) return;
-  // w_0 = 1 (column k), w_r = tv * conj(x[r*inc]) (column k-r)
+  if (!refl_vec<T, true>(xg, inc, m, lane, beta, tau, tv)) return;
+  T* w = cx.wvec;  // w_0 = 1 (column k), w_r = tv conj(x_r) (column k-r)
+  for (int r = tid; r < m; r += nt) w[r] = (r == 0) ? Scalar<T>::one() : tv * conj_(xg[r * inc]);
+  __syncthreads();
   // (a) right on rows: Al rows 1..k-1, Am rows 1..n (if S[l-1]), Q_l rows 1..n
   const int nA = k - 1, nM = sm1 ? n : 0, nQ = cx.wantZ ? n : 0;
-  for (int w = tid; w < nA + nM + nQ; w += nt) {
-    T* a;
-    long long lda;
-    if (w < nA) {
-      a = &PSD_GE(Al, ld, 1 + w, k);
-      lda = ld;
-    } else if (w < nA + nM) {
-      a = &PSD_GE(Am, ld, 1 + (w - nA), k);
-      lda = ld;
-    } else {
-      a = &PSD_GE(Ql, cx.ldz, 1 + (w - nA - nM), k);
-      lda = cx.ldz;
-    }
-    // a_r is the entry in column k-r of this row
-    T d = a[0];
-    for (int r = 1; r < m; r++) d = d + a[-(long long)r * lda] * (tv * conj_(x[r * inc]));
-    d = tau * d;
-    a[0] = a[0] - d;
-    for (int r = 1; r < m; r++)
-      a[-(long long)r * lda] = a[-(long long)r * lda] - d * conj_(tv * conj_(x[r * inc]));
+  for (int c = tid; c < nA + nM + nQ; c += nt) {
+    if (c < nA)
+      hh_right_one<T>(&PSD_GE(Al, ld, 1 + c, k), -(long long)ld, m, w, tau);
+    else if (c < nA + nM)
+      hh_right_one<T>(&PSD_GE(Am, ld, 1 + (c - nA), k), -(long long)ld, m, w, tau);
+    else
+      hh_right_one<T>(&PSD_GE(Ql, cx.ldz, 1 + (c - nA - nM), k), -(long long)cx.ldz, m, w, tau);
   }
   // (b) left G' on all columns of Am rows 1..k (if !S[l-1]): one warp per column
-  if (!sm1) {
-    for (int w = warp; w < n; w += nw) {
-      T* a = &PSD_GE(Am, ld, k, 1 + w);  // a[-r] is row k-r
-      T d = Scalar<T>::zero();
-      for (int r = lane; r < m; r += 32) {
-        const T wr = (r == 0) ? Scalar<T>::one() : tv * conj_(x[r * inc]);
-        d = d + conj_(wr) * a[-r];
-      }
-      if constexpr (sizeof(T) == sizeof(double)) {
-        d = warp_sum(d);
-      } else {
-        d.x = warp_sum(d.x);
-        d.y = warp_sum(d.y);
-      }
-      d = conj_(tau) * d;
-      for (int r = lane; r < m; r += 32) {
-        const T wr = (r == 0) ? Scalar<T>::one() : tv * conj_(x[r * inc]);
-        a[-r] = a[-r] - d * wr;
-      }
-    }
-  }
+  if (!sm1)
+    for (int c = warp; c < n; c += nw) hh_left_warp<T>(&PSD_GE(Am, ld, k, 1 + c), -1, m, w, tau, lane);
   __syncthreads();
   for (int r = tid; r < m; r += nt)
     PSD_GE(Al, ld, k, k - r) = (r == 0) ? Scalar<T>::from_real(beta) : Scalar<T>::zero();
@@ -551,6 +621,7 @@ PSD_DEV void gphessenberg_cta(const GCtx<T>& cx) {
       for (int k = n; k >= 2; k--) stage1_rq_step(cx, Al, Am, sm1, Ql, k);
     }
   }
+  if (cx.prof && tid == 0) cx.prof[0] = clock64();
   // Stage 2 (:1034-1079): rotation (i-1, i) zeroing A_1[i, jc], chased through all factors
   T* A1 = cx.Hp(1);
   for (int jc = 1; jc <= n - 2; jc++) {

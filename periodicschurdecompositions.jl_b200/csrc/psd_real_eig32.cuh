@@ -40,15 +40,22 @@ __host__ __device__ inline int pk_problem_size(int n, int p) {
   return pk_size(3, n) + (p - 1) * pk_size(1, n);
 }
 
+// Stride between packed problems: the factors plus one slot holding the power-of-two exponent E
+// by which the product was scaled down (every factor is normalised to max |entry| in [0.5, 1) by
+// an exact power of two before the iteration, because the un-normalised reflectors
+// H = I + g u u^T square the entries; eigenvalues are multiplied by 2^E at the end).
+__host__ __device__ inline int pk_problem_stride(int n, int p) { return pk_problem_size(n, p) + 1; }
+
 struct EigParams {
   int n, p;
   long long batch;
   int maxitfac;
-  const double* packed;  // [batch][pk_problem_size]
+  const double* packed;  // [batch][pk_problem_stride]
   double* eig;           // [batch][n][2]
   int* info;
   int* iters;
   unsigned long long* counter;
+  int force_safe;  // debug: skip the branch-free first attempt
 };
 
 PSD_DEV double shfl_d(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
@@ -601,12 +608,13 @@ __global__ void __launch_bounds__(256) rpqr_eig32_kernel(EigParams P) {
     if (lane == 0) b = (long long)atomicAdd(P.counter, 1ULL);
     b = __shfl_sync(0xffffffffu, b, 0);
     if (b >= P.batch) break;
-    const double* src = P.packed + (size_t)b * psize;
+    const double* src = P.packed + (size_t)b * (psize + 1);
+    const int escale = (int)src[psize];
     for (int e = lane; e < psize; e += 32) sm[e] = src[e];
     __syncwarp();
     double lre, lim;
     int niter;
-    int info = rpqr_problem<false>(sm, n, p, P.maxitfac, lane, lre, lim, niter);
+    int info = P.force_safe ? kNeedSafe : rpqr_problem<false>(sm, n, p, P.maxitfac, lane, lre, lim, niter);
     if (info == kNeedSafe) {
       // badly scaled problem: start over with the exactly-rescaling reflector
       __syncwarp();
@@ -616,8 +624,8 @@ __global__ void __launch_bounds__(256) rpqr_eig32_kernel(EigParams P) {
     }
     if (lane < n) {
       double* eg = P.eig + ((size_t)b * n + lane) * 2;
-      eg[0] = lre;
-      eg[1] = lim;
+      eg[0] = scalbn(lre, escale);
+      eg[1] = scalbn(lim, escale);
     }
     if (lane == 0) {
       P.info[b] = info;

@@ -18,7 +18,7 @@ struct Hess32Params {
   int left;             // :L orientation: internal factor j <- user factor p+1-j (:127-131)
   int ld;               // smem leading dimension (odd)
   const double* A;      // [batch][p][n*n]
-  double* packed_out;   // [batch][pk_problem_size(n,p)]
+  double* packed_out;   // [batch][pk_problem_stride(n,p)]
   unsigned long long* counter;
 };
 
@@ -136,12 +136,33 @@ __global__ void __launch_bounds__(256) rphess_warp32_kernel(Hess32Params P) {
         for (int c = 0; c < n; c++) dst[c * ld + lane] = src[c * n + lane];
     }
     __syncwarp();
+    // normalise every factor by an exact power of two (see pk_problem_stride)
+    int escale = 0;
+    for (int j = 0; j < p; j++) {
+      double* dst = S + j * fs;
+      double m = 0.0;
+      if (lane < n)
+        for (int c = 0; c < n; c++) m = fmax(m, fabs(dst[c * ld + lane]));
+      m = warp_max(m);
+      if (m > 0.0 && m < 1.7e308) {
+        int e;
+        (void)frexp(m, &e);
+        if (e != 0) {
+          const double sc = scalbn(1.0, -e);
+          if (lane < n)
+            for (int c = 0; c < n; c++) dst[c * ld + lane] *= sc;
+          escale += e;
+        }
+      }
+    }
+    __syncwarp();
     for (int i = 0; i < n - 1; i++) {
       for (int j = p - 1; j >= 1; j--) hess32_step(S + j * fs, S + (j - 1) * fs, n, ld, i, i, lane);
       if (n - (i + 1) > 1) hess32_step(S, S + (p - 1) * fs, n, ld, i + 1, i, lane);
     }
     // packed output: H1 with 3 subdiagonals of storage, H2..Hp with 1 (zeros below structure)
-    double* dstb = P.packed_out + (size_t)b * psize;
+    double* dstb = P.packed_out + (size_t)b * (psize + 1);
+    if (lane == 0) dstb[psize] = (double)escale;
     for (int j = 0; j < p; j++) {
       const int kl = (j == 0) ? 3 : 1;
       const int keep = (j == 0) ? 1 : 0;

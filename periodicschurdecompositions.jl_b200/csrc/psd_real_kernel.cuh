@@ -706,16 +706,38 @@ __global__ void rpschur_kernel(RpschurParams P) {
       }
     }
     if (P.packed_out) {
-      double* dstb = P.packed_out + (size_t)b * pk_problem_size(n, p);
+      // packed factors, each normalised by an exact power of two (see pk_problem_stride)
+      double* dstb = P.packed_out + (size_t)b * pk_problem_stride(n, p);
+      for (int j = 1 + tid; j <= p; j += nt) c.hnorms[j] = 0.0;
+      __syncthreads();
+      for (int j = 1; j <= p; j++) {
+        const double* src = c.Hp(j);
+        double m = 0.0;
+        for (int e = tid; e < (int)nn; e += nt) m = fmax(m, fabs(src[(e % n) + (size_t)(e / n) * c.ldh]));
+        m = warp_max(m);
+        if ((tid & 31) == 0)
+          atomicMax((unsigned long long*)&c.hnorms[j], (unsigned long long)__double_as_longlong(m));
+      }
+      __syncthreads();
+      int escale = 0;
       for (int j = 1; j <= p; j++) {
         const int kl = (j == 1) ? 3 : 1;
         double* dst = dstb + ((j == 1) ? 0 : pk_size(3, n) + (j - 2) * pk_size(1, n));
         const double* src = c.Hp(j);
+        const double m = c.hnorms[j];
+        double sc = 1.0;
+        if (m > 0.0 && m < 1.7e308) {
+          int e;
+          (void)frexp(m, &e);
+          sc = scalbn(1.0, -e);
+          escale += e;
+        }
         for (int e = tid; e < (int)nn; e += nt) {
           int r = e % n, cc = e / n;
-          if (r <= cc + kl) dst[pk_off(kl, cc) + r] = src[r + (size_t)cc * c.ldh];
+          if (r <= cc + kl) dst[pk_off(kl, cc) + r] = src[r + (size_t)cc * c.ldh] * sc;
         }
       }
+      if (tid == 0) dstb[pk_problem_size(n, p)] = (double)escale;
     } else if (P.use_smem) {
       if (P.wantT || P.reduce_only) {
         for (int j = 1; j <= p; j++) {

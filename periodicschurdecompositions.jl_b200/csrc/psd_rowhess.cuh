@@ -35,47 +35,22 @@ PSD_DEV void rowhess_step(T* X, int ldx, int xrows, int k, int kc, T* Qm, int ld
   double beta;
   T tau, tv;
   if (!refl_vec<T, true>(x, inc, m, lane, beta, tau, tv)) return;
+  extern __shared__ __align__(16) double rowhess_smem[];
+  T* w = reinterpret_cast<T*>(rowhess_smem);  // w_0 = 1 (column kc), w_r = tv conj(x_r) (column kc-r)
+  for (int r = tid; r < m; r += nt) w[r] = (r == 0) ? Scalar<T>::one() : tv * conj_(x[r * inc]);
+  __syncthreads();
   const int nX = xrows, nQ = Qm ? qrows : 0;
-  for (int w = tid; w < nX + nQ; w += nt) {
-    T* a;
-    long long lda;
-    if (w < nX) {
-      if (w + 1 == k) continue;  // the source row is finalised below
-      a = &PSD_GE(X, ldx, 1 + w, kc);
-      lda = ldx;
+  for (int c = tid; c < nX + nQ; c += nt) {
+    if (c < nX) {
+      if (c + 1 == k) continue;  // the source row is finalised below
+      hh_right_one<T>(&PSD_GE(X, ldx, 1 + c, kc), -(long long)ldx, m, w, tau);
     } else {
-      a = &PSD_GE(Qm, ldq, 1 + (w - nX), kc);
-      lda = ldq;
+      hh_right_one<T>(&PSD_GE(Qm, ldq, 1 + (c - nX), kc), -(long long)ldq, m, w, tau);
     }
-    T d = a[0];
-    for (int r = 1; r < m; r++) d = d + a[-(long long)r * lda] * (tv * conj_(x[r * inc]));
-    d = tau * d;
-    a[0] = a[0] - d;
-    for (int r = 1; r < m; r++)
-      a[-(long long)r * lda] = a[-(long long)r * lda] - d * conj_(tv * conj_(x[r * inc]));
   }
   if (L == X) __syncthreads();  // p == 1: both sides act on Ap, one after the other
-  if (L) {
-    for (int w = warp; w < ncolL; w += nw) {
-      T* a = &PSD_GE(L, ldl, kc, 1 + w);  // a[-r] is row kc-r
-      T d = Scalar<T>::zero();
-      for (int r = lane; r < m; r += 32) {
-        const T wr = (r == 0) ? Scalar<T>::one() : tv * conj_(x[r * inc]);
-        d = d + conj_(wr) * a[-r];
-      }
-      if constexpr (sizeof(T) == sizeof(double)) {
-        d = warp_sum(d);
-      } else {
-        d.x = warp_sum(d.x);
-        d.y = warp_sum(d.y);
-      }
-      d = conj_(tau) * d;
-      for (int r = lane; r < m; r += 32) {
-        const T wr = (r == 0) ? Scalar<T>::one() : tv * conj_(x[r * inc]);
-        a[-r] = a[-r] - d * wr;
-      }
-    }
-  }
+  if (L)
+    for (int c = warp; c < ncolL; c += nw) hh_left_warp<T>(&PSD_GE(L, ldl, kc, 1 + c), -1, m, w, tau, lane);
   __syncthreads();
   for (int r = tid; r < m; r += nt)
     PSD_GE(X, ldx, k, kc - r) = (r == 0) ? Scalar<T>::from_real(beta) : Scalar<T>::zero();
