@@ -16,8 +16,8 @@
 //     V_j' v follows without a third barrier).
 //   trailing update (FP64 tensor-core GEMMs, psd_dgemm.cuh), per factor j:
 //       A_j[:, c1:]   -= Y_j V_{j+1}[c1:, :]'
-//       A_j[c0:, c1:] -= V_j (T_j' (V_j' A_j[c0:, c1:]))
-//       Q_j[:, c0:]   -= ((Q_j[:, c0:] V_j) T_j) V_j'
+//       A_j[c0:, c1:] -= V_j (X_j' A_j[c0:, c1:]),   X_j = V_j T_j (formed by the panel kernel)
+//       Q_j[:, c0:]   -= (Q_j[:, c0:] X_j) V_j'
 //
 // During the reduction the factors are kept TRANSPOSED in memory (A_j[r,c] at At[c + r*n]): the
 // matrix-vector products then read each owned row as one contiguous run (sequential DRAM
@@ -50,6 +50,7 @@ struct PanelParams {
   double* V;           // [p][n*nb]
   double* Y;           // [p][n*nb]
   double* T;           // [p][nb*nb], upper triangular, zero-initialised per panel
+  double* X;           // [p][n*nb]  X_j = V_j T_j (written at the end of the panel)
   double* abuf;        // [n]
   double* wbuf;        // [2][nb] (zero on entry)
   double* zbuf;        // [2][nb] (zero on entry)
@@ -128,6 +129,7 @@ __global__ void __launch_bounds__(LH_THREADS, 1) rphess_panel_kernel(PanelParams
       {
         const int qnew = kk - 1;
         double p0 = 0.0, p1 = 0.0;
+#pragma unroll 4
         for (int q = warp; q < kk; q += LH_NW) {
           const double vq = (q == qnew) ? 1.0 : Vn[i + (size_t)q * n];
           if (ra) p0 = fma(Yj[r0 + tx + (size_t)q * n], vq, p0);
@@ -142,6 +144,7 @@ __global__ void __launch_bounds__(LH_THREADS, 1) rphess_panel_kernel(PanelParams
       }
       // ---- s2: w = V_j[:, 0:k]' a  (partial over own rows) ----
       if (have && r1 > c0) {
+#pragma unroll 4
         for (int q = warp; q < k; q += LH_NW) {
           double d = 0.0;
           if (ra) d = Vj[r0 + tx + (size_t)q * n] * a_s[tx];
@@ -170,7 +173,8 @@ __global__ void __launch_bounds__(LH_THREADS, 1) rphess_panel_kernel(PanelParams
       {
         double p0 = 0.0, p1 = 0.0;
         if (have && r1 > c0) {
-          for (int q = warp; q < k; q += LH_NW) {
+  #pragma unroll 4
+        for (int q = warp; q < k; q += LH_NW) {
             const double uq = u_s[q];
             if (ra) p0 = fma(Vj[r0 + tx + (size_t)q * n], uq, p0);
             if (rb) p1 = fma(Vj[r0 + tx + 32 + (size_t)q * n], uq, p1);
@@ -192,7 +196,8 @@ __global__ void __launch_bounds__(LH_THREADS, 1) rphess_panel_kernel(PanelParams
         }
         __syncthreads();
         if (have && r1 > piv + 1) {
-          for (int q = warp; q < k; q += LH_NW) {
+  #pragma unroll 4
+        for (int q = warp; q < k; q += LH_NW) {
             double d = 0.0;
             if (ra && r0 + tx > piv) d = Vj[r0 + tx + (size_t)q * n] * a_s[tx];
             if (rb && r0 + tx + 32 > piv) d = fma(Vj[r0 + tx + 32 + (size_t)q * n], a_s[tx + 32], d);
@@ -257,7 +262,8 @@ __global__ void __launch_bounds__(LH_THREADS, 1) rphess_panel_kernel(PanelParams
       {
         double p0 = 0.0, p1 = 0.0;
         if (have) {
-          for (int q = warp; q < k; q += LH_NW) {
+  #pragma unroll 4
+        for (int q = warp; q < k; q += LH_NW) {
             const double zq = z_s[q];
             if (ra) p0 = fma(Ym[r0 + tx + (size_t)q * n], zq, p0);
             if (rb) p1 = fma(Ym[r0 + tx + 32 + (size_t)q * n], zq, p1);
@@ -284,6 +290,19 @@ __global__ void __launch_bounds__(LH_THREADS, 1) rphess_panel_kernel(PanelParams
         __syncthreads();
         LH_TICK(5)
       }
+    }
+  }
+  // X_j = V_j T_j for the own rows: the trailing updates then need no multiplication by T
+  if (have) {
+    const int nrow = r1 - r0;
+    for (int e = tid; e < p * nrow * kb; e += LH_THREADS) {
+      const int j = e / (nrow * kb), rem = e % (nrow * kb);
+      const int q = rem / nrow, r = r0 + rem % nrow;
+      const double* Vj = P.V + (size_t)j * nnb;
+      const double* Tj = Ts + (size_t)j * nb * nb;
+      double acc = 0.0;
+      for (int t = 0; t <= q; t++) acc = fma(Vj[r + (size_t)t * n], Tj[t + q * nb], acc);
+      P.X[(size_t)j * nnb + r + (size_t)q * n] = acc;
     }
   }
   if (prof)
@@ -334,7 +353,7 @@ inline int lh_panel_width(int p) {
 }
 inline size_t lh_work_doubles(int n, int p) {
   const int nb = lh_panel_width(p);
-  return 2 * (size_t)p * n * nb + (size_t)p * nb * nb + 2 * (size_t)n * nb + n + 4 * nb + 8;
+  return 3 * (size_t)p * n * nb + (size_t)p * nb * nb + 2 * (size_t)n * nb + n + 4 * nb + 8;
 }
 
 // Reduce the p factors A[0..p-1] (internal rightwards order, device pointers) in place and, when
@@ -350,7 +369,8 @@ inline cudaError_t rphess_large(cudaStream_t st, int sm_count, int n, int p, dou
   const int nb = lh_panel_width(p);
   double* V = work;
   double* Y = V + (size_t)p * n * nb;
-  double* T = Y + (size_t)p * n * nb;
+  double* X = Y + (size_t)p * n * nb;
+  double* T = X + (size_t)p * n * nb;
   double* W = T + (size_t)p * nb * nb;
   double* W2 = W + (size_t)n * nb;
   double* small = W2 + (size_t)n * nb;  // abuf[n], wbuf[nb], zbuf[nb], sc[2]
@@ -375,7 +395,7 @@ inline cudaError_t rphess_large(cudaStream_t st, int sm_count, int n, int p, dou
     PanelParams P;
     P.n = n; P.p = p; P.c0 = c0; P.kb = kb; P.nb = nb;
     for (int j = 0; j < p; j++) P.A[j] = A[j];
-    P.V = V; P.Y = Y; P.T = T;
+    P.V = V; P.Y = Y; P.T = T; P.X = X;
     P.abuf = small; P.wbuf = small + n; P.zbuf = small + n + 2 * nb; P.sc = small + n + 4 * nb;
     P.R = R;
     P.prof = prof_cycles;
@@ -392,36 +412,30 @@ inline cudaError_t rphess_large(cudaStream_t st, int sm_count, int n, int p, dou
       const double* Vj = V + (size_t)(j - 1) * n * nb;
       const double* Vn = V + (size_t)(jn - 1) * n * nb;
       const double* Yj = Y + (size_t)(j - 1) * n * nb;
-      const double* Tj = T + (size_t)(j - 1) * nb * nb;
+      const double* Xj = X + (size_t)(j - 1) * n * nb;
       GemmArgs g;
       if (ncols > 0) {
         // transposed storage: At = A_j', an n x n column-major array with At[c, r] = A_j[r, c]
         // (1) A_j[:, c1:] -= Y_j V_jn[c1:, :]'        <=>  At[c1:, :] -= V_jn[c1:, :] Y_j'
         g = GemmArgs{ncols, n, kb, Vn + c1, 1, n, Yj, n, 1, Aj + c1, n, -1.0, 1.0, 1};
         if ((e = dgemm_launch(st, sm_count, g)) != cudaSuccess) return e;
-        // (2) W = V_j[c0:, :]' A_j[c0:, c1:]          <=>  Wt = At[c1:, c0:] V_j[c0:, :]
-        g = GemmArgs{ncols, kb, n - c0, Aj + c1 + (size_t)c0 * n, 1, n, Vj + c0, 1, n, W, n, 1.0, 0.0, 1};
-        if ((e = dgemm_launch(st, sm_count, g)) != cudaSuccess) return e;
-        // (2b) W2 = T_j' W                            <=>  W2t = Wt T_j
-        g = GemmArgs{ncols, kb, kb, W, 1, n, Tj, 1, nb, W2, n, 1.0, 0.0, 1};
+        // (2) W2 = T_j' V_j[c0:, :]' A_j[c0:, c1:]    <=>  W2t = At[c1:, c0:] X_j[c0:, :]
+        g = GemmArgs{ncols, kb, n - c0, Aj + c1 + (size_t)c0 * n, 1, n, Xj + c0, 1, n, W2, n, 1.0, 0.0, 1};
         if ((e = dgemm_launch(st, sm_count, g)) != cudaSuccess) return e;
         // (3) A_j[c0:, c1:] -= V_j[c0:, :] W2         <=>  At[c1:, c0:] -= W2t V_j[c0:, :]'
         g = GemmArgs{ncols, n - c0, kb, W2, 1, n, Vj + c0, n, 1, Aj + c1 + (size_t)c0 * n, n, -1.0, 1.0, 1};
         if ((e = dgemm_launch(st, sm_count, g)) != cudaSuccess) return e;
-        fl += 2.0 * kb * ncols * ((double)n + 2.0 * (n - c0) + kb);
+        fl += 2.0 * kb * ncols * ((double)n + 2.0 * (n - c0));
       }
       if (Q) {
         double* Qj = Q[j - 1];
-        // (4) W = Q_j[:, c0:] V_j[c0:, :]   (n x kb, leading dimension n)
-        g = GemmArgs{n, kb, n - c0, Qj + (size_t)c0 * n, 1, n, Vj + c0, 1, n, W, n, 1.0, 0.0, 1};
-        if ((e = dgemm_launch(st, sm_count, g)) != cudaSuccess) return e;
-        // (4b) W2 = W T_j
-        g = GemmArgs{n, kb, kb, W, 1, n, Tj, 1, nb, W2, n, 1.0, 0.0, 1};
+        // (4) W2 = Q_j[:, c0:] X_j[c0:, :]   (n x kb, leading dimension n)
+        g = GemmArgs{n, kb, n - c0, Qj + (size_t)c0 * n, 1, n, Xj + c0, 1, n, W2, n, 1.0, 0.0, 1};
         if ((e = dgemm_launch(st, sm_count, g)) != cudaSuccess) return e;
         // (5) Q_j[:, c0:] -= W2 V_j[c0:, :]'
         g = GemmArgs{n, n - c0, kb, W2, 1, n, Vj + c0, n, 1, Qj + (size_t)c0 * n, n, -1.0, 1.0, 1};
         if ((e = dgemm_launch(st, sm_count, g)) != cudaSuccess) return e;
-        fl += 2.0 * kb * n * (2.0 * (n - c0) + kb);
+        fl += 2.0 * kb * n * (2.0 * (n - c0));
       }
     }
     mark(3, 1);
