@@ -1,0 +1,48 @@
+"""Shape / signature fuzzing of the three GPU paths against the reference's predicates
+(new-suite plan item 3): random N in 1..40, p in 1..7, random signature with
+S[leftmost] = true, both orientations, optional planted zeros.  Seeded, so failures reproduce."""
+import numpy as np
+import pytest
+
+import gpsd_cases as GCs
+import psd_checks as K
+
+pytestmark = pytest.mark.gpu
+EPS = np.finfo(float).eps
+
+
+def _cases(seed, count):
+    rng = np.random.default_rng(seed)
+    for _ in range(count):
+        n = int(rng.integers(1, 41))
+        p = int(rng.integers(1, 8))
+        left = bool(rng.integers(0, 2))
+        S = [int(x) for x in rng.integers(0, 2, size=p)]
+        S[p - 1 if left else 0] = 1
+        yield n, p, left, S, int(rng.integers(0, 2 ** 31))
+
+
+@pytest.mark.parametrize("case", list(_cases(20261018, 24)))
+def test_fuzz_real_standard(psd, oracle, case):
+    n, p, left, _, seed = case
+    A = oracle.gen_real(seed, n, p, 2)
+    T, Z, lam, info = psd.pschur_batched(A, "L" if left else "R")
+    assert (info == 0).all()
+    _, _, lam0, info0 = psd.pschur_batched(A, "L" if left else "R", wantT=False, wantZ=False)
+    assert (info0 == 0).all()
+    for b in range(2):
+        K.pschur_check(A[b], T[b], Z[b], lam[b], left=left, tol=64)
+        scale = max(np.max(np.abs(lam[b])), 1e-300)
+        assert K.match_eigs(lam[b], lam0[b]) <= 1000 * n * EPS * scale
+
+
+@pytest.mark.parametrize("cplx", [False, True])
+@pytest.mark.parametrize("case", list(_cases(77, 16)))
+def test_fuzz_generalized(psd, case, cplx):
+    n, p, left, S, seed = case
+    A = GCs.rand_storage(seed % 100000, n, p, 2, cplx)
+    T, Z, al, be, sc, info = psd.gpschur_batched(A, S, "L" if left else "R")
+    assert (info == 0).all()
+    for b in range(2):
+        K.gpschur_check(A[b], S, T[b], Z[b], al[b], be[b], sc[b], left=left, real_path=not cplx,
+                        tol=200)
