@@ -180,6 +180,14 @@ int psd_rgpschur_hessut_batched(psd_handle_t handle, int n, int p, int64_t batch
                                 int wantT, int wantZ, int maxitfac, double* A, double* Z,
                                 double* alpha, double* beta, int64_t* alphascale, int32_t* info);
 
+/* Generalized periodic Hessenberg-triangular reduction only, batched (cplx != 0: complex128).
+ * Replaces _phessenberg!(A, S; wantQ) (generalized.jl:988-1082, exercised directly by
+ * test/generalized.jl:2-40): on return A_1 is upper Hessenberg, A_2..A_p upper triangular (exact
+ * zeros below), Q (or NULL) the explicit Q_l with  A_l = Q_l H_l Q_{l+1}'  for S_l = true and
+ * A_l = Q_{l+1} H_l Q_l'  for S_l = false.  Rightwards order; S[0] must be 1. */
+int psd_gphess_batched(psd_handle_t handle, int cplx, int n, int p, int64_t batch, const uint8_t* S,
+                       int wantQ, double* A, double* Q);
+
 /* Row-wise periodic Hessenberg reduction for the left orientation, batched.
  * Replaces _rphessenberg!(Ap, A, Q) (rhessx.jl:53-109; RHouseholder rhessx.jl:7-50), whose only
  * caller is the Krylov-Schur restart (krylov.jl:800-832).  For the product Ap A_{p-1} ... A_1:

@@ -29,6 +29,7 @@ from .pschur import (  # noqa: F401
     gpschur,
     gpschur_,
     gpschur_batched,
+    gphessenberg_batched,
     gvalues,
     default_handle,
     phessenberg_batched,
@@ -42,6 +43,6 @@ from .pschur import (  # noqa: F401
 
 __all__ = [
     "PsdError", "device_count", "lib", "lib_path", "library_available", "version",
-    "PeriodicSchur", "GeneralizedPeriodicSchur", "gpschur", "gpschur_", "gpschur_batched", "gvalues", "Handle", "default_handle", "phessenberg_batched", "rphessenberg_rowwise_batched", "pschur", "pschur_",
+    "PeriodicSchur", "GeneralizedPeriodicSchur", "gpschur", "gpschur_", "gpschur_batched", "gphessenberg_batched", "gvalues", "Handle", "default_handle", "phessenberg_batched", "rphessenberg_rowwise_batched", "pschur", "pschur_",
     "pschur_batched", "pschur_hessut_batched", "shard_bounds",
 ]

@@ -26,6 +26,7 @@ EXPORTED_SYMBOLS = [
     "psd_rgpschur_batched",
     "psd_rgpschur_hessut_batched",
     "psd_rphess_rowwise_batched",
+    "psd_gphess_batched",
     "psd_dgemm_host",
     "psd_last_stats",
     "psd_set_profiling",
@@ -85,6 +86,7 @@ def lib():
         L.psd_dgemm_host.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double,
                                      vp, C.c_int, vp, C.c_int, C.c_double, vp, C.c_int, C.c_int,
                                      C.POINTER(C.c_double)]
+        L.psd_gphess_batched.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int64, vp, C.c_int, vp, vp]
         L.psd_last_stats.argtypes = [vp, C.POINTER(C.c_int64)]
         L.psd_set_profiling.argtypes = [vp, C.c_int]
         L.psd_kernel_times.argtypes = [vp, C.POINTER(C.c_double)]

@@ -541,6 +541,7 @@ struct GenCall {
   int n, p, left, wantT, wantZ, maxitfac, skip_reduce;
   int cplx;                 // 1: complex128 factors, complex beta; 0: real factors, real beta
   const unsigned char* S;   // host, user order
+  int reduce_only = 0;
 };
 
 size_t gen_elem(const GenCall& gc) { return gc.cplx ? 16 : 8; }
@@ -570,6 +571,7 @@ int launch_gen_t(psd_handle_s* h, Device& dev, Slot& aux, cudaStream_t stream, c
   P.n = n; P.p = p; P.batch = batch; P.left = gc.left; P.wantT = gc.wantT; P.wantZ = wantZ ? 1 : 0;
   P.maxitfac = gc.maxitfac > 0 ? gc.maxitfac : (gc.cplx ? 30 : 120);  // generalized.jl:169, rgeneralized.jl:52
   P.skip_reduce = gc.skip_reduce;
+  P.reduce_only = gc.reduce_only;
   P.S = aux.dS;
   P.A = (T*)dA; P.Z = wantZ ? (T*)dZ : nullptr;
   P.alpha = (psd::cplx*)dAlpha; P.beta = (T*)dBeta; P.scale = dScale; P.info = dInfo;
@@ -646,16 +648,17 @@ int run_gen_shard(psd_handle_s* h, Device& dev, const GenCall& gc, long long fir
                    (long long*)s.dX[2], s.dInfo);
     if (e) return e;
     char* dstZ = wantZ ? Z + (size_t)(first + off) * perB : nullptr;
-    char* dstX[3] = {alpha + (size_t)(first + off) * xB[0], beta + (size_t)(first + off) * xB[1],
-                     (char*)scale + (size_t)(first + off) * xB[2]};
-    int32_t* dstInfo = info + (first + off);
+    const bool ev = !gc.reduce_only;
+    char* dstX[3] = {ev ? alpha + (size_t)(first + off) * xB[0] : nullptr, ev ? beta + (size_t)(first + off) * xB[1] : nullptr,
+                     ev ? (char*)scale + (size_t)(first + off) * xB[2] : nullptr};
+    int32_t* dstInfo = ev ? info + (first + off) : nullptr;
     const size_t bytesInfo = nb * sizeof(int32_t);
     if (pinned) {
       if (gc.wantT) PSD_CUDA(cudaMemcpyAsync(srcA, s.dA, bytesA, cudaMemcpyDeviceToHost, s.stream));
       if (wantZ) PSD_CUDA(cudaMemcpyAsync(dstZ, s.dZ, bytesA, cudaMemcpyDeviceToHost, s.stream));
-      for (int k = 0; k < 3; k++)
+      for (int k = 0; k < 3 && ev; k++)
         PSD_CUDA(cudaMemcpyAsync(dstX[k], s.dX[k], nb * xB[k], cudaMemcpyDeviceToHost, s.stream));
-      PSD_CUDA(cudaMemcpyAsync(dstInfo, s.dInfo, bytesInfo, cudaMemcpyDeviceToHost, s.stream));
+      if (ev) PSD_CUDA(cudaMemcpyAsync(dstInfo, s.dInfo, bytesInfo, cudaMemcpyDeviceToHost, s.stream));
     } else {
       if (wantZ && (e = ensure_pinned(s.hZ, s.hcapZ, bytesA))) return e;
       for (int k = 0; k < 3; k++)
@@ -669,8 +672,8 @@ int run_gen_shard(psd_handle_s* h, Device& dev, const GenCall& gc, long long fir
       PSD_CUDA(cudaStreamSynchronize(s.stream));
       if (gc.wantT) std::memcpy(srcA, s.hA, bytesA);
       if (wantZ) std::memcpy(dstZ, s.hZ, bytesA);
-      for (int k = 0; k < 3; k++) std::memcpy(dstX[k], s.hX[k], nb * xB[k]);
-      std::memcpy(dstInfo, s.hInfo, bytesInfo);
+      for (int k = 0; k < 3 && ev; k++) std::memcpy(dstX[k], s.hX[k], nb * xB[k]);
+      if (ev) std::memcpy(dstInfo, s.hInfo, bytesInfo);
     }
     *bytes_d2h += (int64_t)((gc.wantT ? bytesA : 0) + (wantZ ? bytesA : 0) + nb * (xB[0] + xB[1] + xB[2]) + bytesInfo);
   }
@@ -684,7 +687,8 @@ int run_gen_host(psd_handle_t h, const GenCall& gc, int64_t batch, void* A, void
   if (!h) return fail(PSD_ERR_BAD_ARG, "null handle");
   if (gc.n < 1 || gc.p < 1 || batch < 0) return fail(PSD_ERR_BAD_ARG, "n, p must be >= 1 and batch >= 0");
   if (!A || !gc.S) return fail(PSD_ERR_BAD_ARG, "A and S must not be NULL");
-  if (!alpha || !beta || !scale || !info) return fail(PSD_ERR_BAD_ARG, "alpha, beta, alphascale and info must not be NULL");
+  if (!gc.reduce_only && (!alpha || !beta || !scale || !info))
+    return fail(PSD_ERR_BAD_ARG, "alpha, beta, alphascale and info must not be NULL");
   if (gc.wantZ && !Z) return fail(PSD_ERR_BAD_ARG, "wantZ set but Z is NULL");
   // leftmost factor after orientation must have S = true (generalized.jl:140, rgeneralized.jl:37)
   if (!gc.S[gc.left ? gc.p - 1 : 0]) return fail(PSD_ERR_SIGNATURE, "The leftmost entry in S must be true");
@@ -857,6 +861,13 @@ int psd_cpschur_hessut_batched(psd_handle_t h, int n, int p, int64_t batch, cons
                                int64_t* alphascale, int32_t* info) {
   GenCall gc{n, p, 0, wantT != 0, wantZ != 0, maxitfac, 1, 1, S};
   return run_gen_host(h, gc, batch, A, Z, alpha, beta, alphascale, info);
+}
+
+int psd_gphess_batched(psd_handle_t h, int cplx, int n, int p, int64_t batch, const uint8_t* S, int wantQ, double* A,
+                       double* Q) {
+  GenCall gc{n, p, 0, 1, wantQ != 0, 0, 0, cplx != 0, S};
+  gc.reduce_only = 1;
+  return run_gen_host(h, gc, batch, A, Q, nullptr, nullptr, nullptr, nullptr);
 }
 
 int psd_rgpschur_batched(psd_handle_t h, int n, int p, int64_t batch, int orientation, const uint8_t* S, int wantT,

@@ -24,6 +24,7 @@ struct GpqzParams {
   long long batch;
   int left, wantT, wantZ, maxitfac;
   int skip_reduce;          // input already Hessenberg-triangular (pschur!(H1,Hs,S) entry, :166)
+  int reduce_only;          // stop after _phessenberg!(A, S): A <- H factors, Z <- Q (no eigenvalues)
   const unsigned char* S;   // [p] user order (device memory)
   T* A;                     // [batch][p][n*n] in/out, user order
   T* Z;                     // [batch][p][n*n] out (reference result order) or nullptr
@@ -1081,7 +1082,7 @@ __global__ void gpschur_kernel(GpqzParams<T> P) {
     T* be = P.beta + (size_t)b * n;
     long long* sc = P.scale + (size_t)b * n;
     const long long tred = clock64();
-    const int info = gpqz_cta<T>(cx, st, P.wantT != 0, P.maxitfac, al, be, sc);
+    const int info = P.reduce_only ? 0 : gpqz_cta<T>(cx, st, P.wantT != 0, P.maxitfac, al, be, sc);
     if (P.debug && tid == 0 && blockIdx.x == 0)
       printf("[psd gpschur b=%lld] stage1 %lld  stage2 %lld  qz %lld cycles\n", b,
              P.skip_reduce ? 0LL : s_prof[0] - tstart, P.skip_reduce ? 0LL : tred - s_prof[0], clock64() - tred);

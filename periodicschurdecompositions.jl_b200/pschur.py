@@ -225,6 +225,24 @@ def _sig(S, p):
     return S
 
 
+def gphessenberg_batched(A: np.ndarray, S, wantQ: bool = True, handle: Optional[Handle] = None):
+    """_phessenberg!(A, S; wantQ) (generalized.jl:988-1082), batched, storage layout, float64 or
+    complex128.  Returns (H, Q)."""
+    h = handle or default_handle()
+    batch, p, n, _ = A.shape
+    Sb = _sig(S, p)
+    H = np.ascontiguousarray(A).copy()
+    Q = np.empty_like(H) if wantQ else None
+    try:
+        check(lib().psd_gphess_batched(h.ptr, int(A.dtype == np.complex128), n, p, batch, _vp(Sb),
+                                       int(wantQ), _vp(H), _vp(Q)))
+    except PsdError as e:
+        if e.code == -4:
+            raise ValueError("The first entry in S must be true") from e  # generalized.jl:990
+        raise
+    return H, Q
+
+
 def gpschur_batched(A: np.ndarray, S, lr="R", wantZ: bool = True, wantT: bool = True,
                     maxitfac: int = 0, handle: Optional[Handle] = None, hessut: bool = False):
     """Batched generalized periodic Schur decomposition (psd_cpschur_batched for complex128 A;

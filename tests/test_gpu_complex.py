@@ -136,3 +136,26 @@ def test_signature_error(psd):
     assert ei.value.code == -4
     with pytest.raises(psd.PsdError):
         psd.gpschur_batched(A, [1, 1, 0], "L")
+
+
+# test/generalized.jl:2-40 ("Generalized Periodic Hessenberg"): alternating S, p in {2,5}, n = 5,
+# real and complex; also larger shapes
+@pytest.mark.parametrize("cplx", [False, True])
+@pytest.mark.parametrize("n,p", [(5, 2), (5, 5), (1, 2), (17, 4), (40, 3)])
+def test_generalized_hessenberg(psd, cplx, n, p):
+    S = [True]
+    for _ in range(1, p):
+        S.append(not S[-1])
+    A = GCs.rand_storage(4321, n, p, 3, cplx)
+    H, Q = psd.gphessenberg_batched(A, S)
+    for b in range(3):
+        for j in range(p):
+            Hj, Aj, Qj, Qn = K.M(H[b, j]), K.M(A[b, j]), K.M(Q[b, j]), K.M(Q[b, (j + 1) % p])
+            assert not np.tril(Hj, -2 if j == 0 else -1).any()
+            assert np.linalg.norm(Qj @ Qj.conj().T - np.eye(n)) < 10 * EPS * n
+            Ax = Qj @ Hj @ Qn.conj().T if S[j] else Qn @ Hj @ Qj.conj().T
+            assert np.linalg.norm(Aj - Ax) < 20 * EPS * n * max(1.0, np.linalg.norm(Aj) / n ** 0.5)
+    H2, Q2 = psd.gphessenberg_batched(A, S, wantQ=False)
+    assert Q2 is None and np.allclose(H2, H, atol=1e-13)
+    with pytest.raises(ValueError):
+        psd.gphessenberg_batched(A, [False] + S[1:])
