@@ -241,21 +241,29 @@ int launch_real_eig32(psd_handle_s* h, Device& dev, Slot& aux, cudaStream_t stre
   for (long long off = 0; off < batch; off += chunk) {
     const long long nb = std::min(chunk, batch - off);
     PSD_CUDA(cudaMemsetAsync(aux.dCounter, 0, 2 * sizeof(unsigned long long), stream));
-    if (rc.skip_reduce) {
+    const char* hess_cta = getenv("PSD_HESS_CTA");  // experiment: CTA-per-problem reduction, N threads
+    if (rc.skip_reduce || hess_cta) {
       // input already Hessenberg/triangular: CTA kernel only enforces structure and packs
       RealLaunchPlan pl;
       e = plan_real(dev, n, p, nb, false, pl);
       if (e) return e;
+      if (hess_cta) {
+        pl.threads = atoi(hess_cta);
+        int occ = 0;
+        PSD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, psd::rpschur_kernel, pl.threads, pl.smem_bytes));
+        pl.grid = (int)std::max(1LL, std::min((long long)occ * dev.sm_count, nb));
+      }
       if (!pl.use_smem) return fail(PSD_ERR_UNSUPPORTED, "eig32 path expects shared-memory staging");
       psd::RpschurParams P;
       P.n = n; P.p = p; P.batch = nb;
       P.left = rc.left; P.wantT = 0; P.wantZ = 0; P.maxitfac = 30;
       P.A = dA + (size_t)off * p * nn; P.Z = nullptr; P.eig = nullptr; P.info = nullptr; P.iters = nullptr;
       P.use_smem = pl.use_smem; P.ldh = pl.ldh;
-      P.reduce_only = 1; P.skip_reduce = 1; P.z_preset = 0;
+      P.reduce_only = 1; P.skip_reduce = rc.skip_reduce; P.z_preset = 0;
       P.counter = aux.dCounter;
       P.scratch = nullptr; P.scratch_stride = 0;
       P.packed_out = aux.dPacked;
+      ScopedKernelTimer tm(h, dev, stream, 0);
       psd::rpschur_kernel<<<pl.grid, pl.threads, pl.smem_bytes, stream>>>(P);
       PSD_CUDA(cudaGetLastError());
     } else {

@@ -56,6 +56,47 @@ PSD_DEV void hess32_step(double* Aj, double* Am, int n, int ld, int r0, int col,
     u0 = u0s / sc;
     beta = betas / sc;
   }
+  if (Am != Aj) {
+    // Left update of Aj (lane = column, columns col+1..n-1) and right update of Am (lane = row)
+    // touch different matrices: both dot products and both updates run in the same loops, so the
+    // two dependent chains overlap (instruction-level parallelism within the warp).
+    const bool la = (lane > col && lane < n), rw = (lane < n);
+    double* cl = Aj + (la ? lane : col + 1 < n ? col + 1 : col) * ld;  // inactive lanes read a valid column
+    double* ar = Am + (rw ? lane : 0);
+    double dl0 = u0 * cl[r0], dl1 = 0.0, dr0 = ar[r0 * ld] * u0, dr1 = 0.0;
+#pragma unroll 2
+    for (int k = r0 + 1; k < n; k += 2) {
+      const bool p1 = k + 1 < n;
+      const double x0 = xc[k], x1 = p1 ? xc[k + 1] : 0.0;
+      const double l0 = cl[k], l1 = p1 ? cl[k + 1] : 0.0;
+      const double q0 = ar[k * ld], q1 = p1 ? ar[(k + 1) * ld] : 0.0;
+      dl0 = fma(x0, l0, dl0); dl1 = fma(x1, l1, dl1);
+      dr0 = fma(q0, x0, dr0); dr1 = fma(q1, x1, dr1);
+    }
+    const double sl = g * (dl0 + dl1), sr = g * (dr0 + dr1);
+    if (la) cl[r0] = fma(sl, u0, cl[r0]);
+    if (rw) ar[r0 * ld] = fma(sr, u0, ar[r0 * ld]);
+#pragma unroll 2
+    for (int k = r0 + 1; k < n; k += 2) {
+      const bool p1 = k + 1 < n;
+      const double x0 = xc[k], x1 = p1 ? xc[k + 1] : 0.0;
+      const double l0 = cl[k], l1 = p1 ? cl[k + 1] : 0.0;
+      const double q0 = ar[k * ld], q1 = p1 ? ar[(k + 1) * ld] : 0.0;
+      if (la) {
+        cl[k] = fma(sl, x0, l0);
+        if (p1) cl[k + 1] = fma(sl, x1, l1);
+      }
+      if (rw) {
+        ar[k * ld] = fma(sr, x0, q0);
+        if (p1) ar[(k + 1) * ld] = fma(sr, x1, q1);
+      }
+    }
+    __syncwarp();
+    if (lane == r0) xc[lane] = beta;
+    else if (lane > r0 && lane < n) xc[lane] = 0.0;
+    __syncwarp();
+    return;
+  }
   // left: columns col+1..n-1 of Aj (lane = column).  Loops are unrolled by 4 with independent
   // accumulators and predicated loads so that the shared-memory loads pipeline.
   if (lane > col && lane < n) {
@@ -129,12 +170,18 @@ __global__ void __launch_bounds__(256) rphess_warp32_kernel(Hess32Params P) {
     b = __shfl_sync(0xffffffffu, b, 0);
     if (b >= P.batch) break;
     const double* Ab = P.A + (size_t)b * p * nn;
+    // stage the whole problem with asynchronous 8-byte copies (LDGSTS): every load of the
+    // problem is in flight before the first one is waited for
     for (int j = 0; j < p; j++) {
       const double* src = Ab + (size_t)(P.left ? (p - 1 - j) : j) * nn;
       double* dst = S + j * fs;
       if (lane < n)
-        for (int c = 0; c < n; c++) dst[c * ld + lane] = src[c * n + lane];
+        for (int c = 0; c < n; c++) {
+          const unsigned sa = (unsigned)__cvta_generic_to_shared(dst + c * ld + lane);
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(src + c * n + lane));
+        }
     }
+    asm volatile("cp.async.wait_all;" ::: "memory");
     __syncwarp();
     // normalise every factor by an exact power of two (see pk_problem_stride)
     int escale = 0;
