@@ -416,7 +416,44 @@ int launch_real_large(psd_handle_s* h, Device& dev, Slot& aux, cudaStream_t stre
     __atomic_fetch_add(&h->stats[2], (int64_t)batch, __ATOMIC_RELAXED);
     return PSD_OK;
   }
-  // periodic QR iteration on the Hessenberg-triangular factors, Z preset to Q
+  // Periodic QR iteration on the Hessenberg-triangular factors, Z preset to Q.  For large N a
+  // single CTA per problem is hopeless (~N^2.8); the generalized double-shift kernel with S = trues
+  // runs instead as a cooperative team on the whole GPU, one problem at a time.  Its 2x2 blocks
+  // are left unstandardised (as the reference's real generalized path does, rgeneralized.jl:748-790);
+  // consumers only test T1[j+1,j] != 0 (rordschur.jl:56).
+  if (!getenv("PSD_DISABLE_TEAM")) {
+    const size_t cnt = (size_t)batch * n;
+    if ((e = ensure_dev(aux.dX[0], aux.capX[0], cnt * 16))) return e;
+    if ((e = ensure_dev(aux.dX[1], aux.capX[1], cnt * 8))) return e;
+    if ((e = ensure_dev(aux.dX[2], aux.capX[2], cnt * 8))) return e;
+    psd::GpqzParams<double> P;
+    P.n = n; P.p = p; P.batch = batch; P.left = rc.left; P.wantT = rc.wantT; P.wantZ = wantZ ? 1 : 0;
+    P.maxitfac = 4 * (rc.maxitfac > 0 ? rc.maxitfac : 30);  // QZ loop counts deflation steps too (rgeneralized.jl:52)
+    P.skip_reduce = 1; P.reduce_only = 0;
+    P.S = nullptr;
+    P.A = dA; P.Z = wantZ ? dZ : nullptr;
+    P.alpha = (psd::cplx*)aux.dX[0]; P.beta = (double*)aux.dX[1]; P.scale = (long long*)aux.dX[2];
+    P.info = dInfo;
+    P.use_smem = 0; P.ldh = n; P.debug = 0; P.counter = nullptr;
+    auto kern = psd::gpschur_team_kernel<double>;
+    const size_t smem = (size_t)((psd::cq_small_doubles(n, p) + 1) & ~1LL) * sizeof(double);
+    PSD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    PSD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, smem));
+    if (occ < 1) return fail(PSD_ERR_UNSUPPORTED, "team kernel does not fit on an SM");
+    int zp = 1;
+    void* args[] = {&P, &zp};
+    {
+      ScopedKernelTimer tm(h, dev, stream, 1);
+      PSD_CUDA(cudaLaunchCooperativeKernel((void*)kern, dim3(dev.sm_count), dim3(256), args, smem, stream));
+    }
+    psd::gvalues_kernel<<<std::min<long long>(1024, (long long)(cnt + 255) / 256), 256, 0, stream>>>(
+        (const psd::cplx*)aux.dX[0], (const double*)aux.dX[1], (const long long*)aux.dX[2], dEig, (long long)cnt);
+    PSD_CUDA(cudaGetLastError());
+    __atomic_fetch_add(&h->stats[0], (int64_t)2, __ATOMIC_RELAXED);
+    __atomic_fetch_add(&h->stats[2], (int64_t)batch, __ATOMIC_RELAXED);
+    return PSD_OK;
+  }
   RealCall rq = rc;
   rq.skip_reduce = 1;
   rq.z_preset = 1;

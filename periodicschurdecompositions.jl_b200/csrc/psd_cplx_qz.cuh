@@ -70,9 +70,10 @@ PSD_DEV bool cq_check_hess(const GCtx<T>& cx, const GqState<T>& st, int ilo, int
   __syncthreads();
   jlo = ilo;
   if (jf > 0) {
-    if (cx.tid == 0) PSD_GE(H1, ld, jf, jf - 1) = Scalar<T>::zero();
+    if (cx.team) cx.sync();  // every CTA has finished its (redundant) scan
+    if (cx.lead && cx.tid == 0) PSD_GE(H1, ld, jf, jf - 1) = Scalar<T>::zero();
     jlo = jf;
-    __syncthreads();
+    cx.sync();
     return jf == ilast;
   }
   return false;
@@ -108,8 +109,9 @@ PSD_DEV bool cq_check_tr(const GCtx<T>& cx, const GqState<T>& st, bool sign, int
   if (k == 0) return false;
   ldef = p + 1 - k / (n + 1);
   jdef = k % (n + 1);
-  if (cx.tid == 0) PSD_GE(cx.Hp(ldef), ld, jdef, jdef) = Scalar<T>::zero();
-  __syncthreads();
+  if (cx.team) cx.sync();
+  if (cx.lead && cx.tid == 0) PSD_GE(cx.Hp(ldef), ld, jdef, jdef) = Scalar<T>::zero();
+  cx.sync();
   return true;
 }
 
@@ -118,10 +120,10 @@ PSD_DEV bool cq_check_tr(const GCtx<T>& cx, const GqState<T>& st, bool sign, int
 template <class T>
 PSD_DEV void cq_rmul_seq(const GCtx<T>& cx, const GqState<T>& st, T* M, int ld, int j0, int j1,
                          int dj, int oa, int ob) {
-  for (int row = 1 + cx.tid; row <= cx.n; row += cx.nt)
+  for (int row = 1 + cx.wtid; row <= cx.n; row += cx.wnt)
     for (int j = j0; dj > 0 ? j <= j1 : j >= j1; j += dj)
       rot_pair_cols(M, ld, j + oa, j + ob, row, st.Gc[j], st.Gs[j]);
-  __syncthreads();
+  cx.sync();
 }
 
 #define CQ_SETG(j, c, s)    \
@@ -242,7 +244,7 @@ __device__ __noinline__ void chase_double(const GCtx<double>& cx, int j, Rot2 gi
     double* Z1 = cx.wantZ ? cx.Zp(1) : nullptr;
     const Rot2 gs[3] = {g0, g0, g0};
     const int ldz = cx.ldz;
-    bulk_rot3(tid, nt, nL + nZ, gs, [&](int w, double*& a, long long& st, int& sel) {
+    bulk_rot3(cx.wtid, cx.wnt, nL + nZ, gs, [&](int w, double*& a, long long& st, int& sel) {
       sel = 0;
       if (w < nL) {
         a = &PSD_GE(H1, ld, j, j + 3 + w);
@@ -299,7 +301,7 @@ __device__ __noinline__ void chase_double(const GCtx<double>& cx, int j, Rot2 gi
       double* Zl = cx.wantZ ? cx.Zp(l) : nullptr;
       const Rot2 gs[3] = {gR, gL, gout};
       const int ldz = cx.ldz;
-      bulk_rot3(tid, nt, nR + nL + nZ, gs, [&](int w, double*& a, long long& st, int& sel) {
+      bulk_rot3(cx.wtid, cx.wnt, nR + nL + nZ, gs, [&](int w, double*& a, long long& st, int& sel) {
         if (w < nR) {
           a = &PSD_GE(Hl, ld, rfirst + w, j);
           st = ld;
@@ -324,7 +326,7 @@ __device__ __noinline__ void chase_double(const GCtx<double>& cx, int j, Rot2 gi
   {  // right-only rows of H_1 and its 3x3 overlap block
     const int nR = (h1r1 - rfirst + 1) - 3;
     const Rot2 gs[3] = {gin, gin, gin};
-    bulk_rot3(tid, nt, nR, gs, [&](int w, double*& a, long long& st, int& sel) {
+    bulk_rot3(cx.wtid, cx.wnt, nR, gs, [&](int w, double*& a, long long& st, int& sel) {
       int row = rfirst + w;
       if (row >= j) row += 3;
       a = &PSD_GE(H1, ld, row, j);
@@ -342,8 +344,8 @@ __device__ __noinline__ void chase_double(const GCtx<double>& cx, int j, Rot2 gi
         for (int c = 0; c < 3; c++) cx.stage[3 * r + c] = X[r][c];
     }
   }
-  __syncthreads();
-  for (int l = 1 + tid; l <= p; l += nt) {
+  cx.sync();
+  for (int l = 1 + tid; cx.lead && l <= p; l += nt) {
     if (l == 1) {
       for (int r = 0; r < 3; r++)
         for (int c = 0; c < 3; c++) PSD_GE(H1, ld, j + r, j + c) = cx.stage[3 * r + c];
@@ -360,7 +362,7 @@ __device__ __noinline__ void chase_double(const GCtx<double>& cx, int j, Rot2 gi
       PSD_GE(Hl, ld, j + 2, j) = 0.0; PSD_GE(Hl, ld, j + 2, j + 1) = 0.0; PSD_GE(Hl, ld, j + 2, j + 2) = sg[5];
     }
   }
-  __syncthreads();
+  cx.sync();
 }
 
 // Scaled product of the KxK (K = 2 or 3) diagonal blocks at rows/cols i0..i0+K-1 of the
@@ -456,8 +458,8 @@ PSD_DEV bool rq_block2x2(const GCtx<double>& cx, int j, int ifirstm, int ilastm,
     chase_rotation<double>(cx, j, cs, sn, 0, 0.0, j, ilastm, ifirstm, min(j + 2, ilastm));
     return false;
   }
-  __syncthreads();
-  if (cx.tid == 0) {
+  cx.sync();
+  if (cx.lead && cx.tid == 0) {
     const double lr[2] = {w1r, w2r}, li[2] = {w1i, w2i};
     for (int k = 0; k < 2; k++) {
       const double m = hypot(lr[k], li[k]);
@@ -475,7 +477,7 @@ PSD_DEV bool rq_block2x2(const GCtx<double>& cx, int j, int ifirstm, int ilastm,
     }
     if (w1i == 0.0) PSD_GE(H1, ld, j + 1, j) = 0.0;  // forced acceptance of a real pair
   }
-  __syncthreads();
+  cx.sync();
   return true;
 }
 
@@ -670,11 +672,11 @@ PSD_DEV int gpqz_cta(const GCtx<T>& cx, const GqState<T>& st, bool wantT, int ma
               if (tol == 0.0) tol = g_opnorm1(Hl, ld, jlo, j + 1, jlo, j + 1, false);
               tol = fmax(ulp * tol, smlnum);
               const bool small = abs_(PSD_GE(Hl, ld, j + 1, j)) <= tol;
-              __syncthreads();
+              cx.sync();
               if (small) {
-                if (tid == 0) PSD_GE(Hl, ld, j + 1, j) = czero;
+                if (cx.lead && tid == 0) PSD_GE(Hl, ld, j + 1, j) = czero;
                 CQ_SETG(j, 1.0, czero);
-                __syncthreads();
+                cx.sync();
               } else if (cx.Sg(l)) {
                 g_gen(cx, Hl, ld, j, j, j + 1, j, c, s);
                 g_lmul(cx, Hl, ld, j, j + 1, c, s, j + 1, ilastm);
@@ -887,7 +889,7 @@ PSD_DEV int gpqz_cta(const GCtx<T>& cx, const GqState<T>& st, bool wantT, int ma
       doqz = false;
     } else if (split1) {
       // ---- 1x1 block split off (:741-762) ----
-      if (tid == 0) {
+      if (cx.lead && tid == 0) {
         T a;
         int b;
         long long sc;
@@ -964,7 +966,7 @@ PSD_DEV int gpqz_cta(const GCtx<T>& cx, const GqState<T>& st, bool wantT, int ma
         st.Gc[j] = (abst > safmin) ? abst : -1.0;
       }
       __syncthreads();
-      for (int e = tid; e < n * n; e += cx.nt) {
+      for (int e = cx.wtid; e < n * n; e += cx.wnt) {
         const int r0 = 1 + e % n, c0 = 1 + e / n;
         // this factor
         if (sl) {
@@ -982,7 +984,7 @@ PSD_DEV int gpqz_cta(const GCtx<T>& cx, const GqState<T>& st, bool wantT, int ma
           if (c0 >= r0) PSD_GE(Hm, ld, r0, c0) = PSD_GE(Hm, ld, r0, c0) * st.Gs[r0];
         }
       }
-      __syncthreads();
+      cx.sync();
     }
   }
   }
@@ -1022,6 +1024,7 @@ __global__ void gpschur_kernel(GpqzParams<T> P) {
   cx.stage = stage;
   cx.stage_in = stage_in;
   cx.wvec = wvec;
+  cx.wtid = tid; cx.wnt = nt; cx.lead = true; cx.team = false;
   __shared__ long long s_prof[4];
   cx.prof = P.debug ? s_prof : nullptr;
 
@@ -1107,6 +1110,89 @@ __global__ void gpschur_kernel(GpqzParams<T> P) {
       }
     }
     __syncthreads();
+  }
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Team kernel: ONE large problem at a time on the whole GPU (cooperative launch, one CTA per SM).
+// Input must already be in Hessenberg-triangular form (the blocked reduction of
+// psd_large_hess.cuh, or the inner pschur!(H1, Hs, S) entry); Z is either preset (the Q_j of the
+// reduction) or initialised to the identity here.  Every CTA executes gpqz_cta redundantly; see
+// GCtx for how the work is shared.  Factors and Z stay in place in global memory.
+// ---------------------------------------------------------------------------------------------
+template <class T>
+__global__ void gpschur_team_kernel(GpqzParams<T> P, int z_preset) {
+  namespace cgx = cooperative_groups;
+  cgx::grid_group grid = cgx::this_grid();
+  const int n = P.n, p = P.p, tid = threadIdx.x, nt = blockDim.x;
+  const size_t nn = (size_t)n * n;
+  __shared__ int s_key;
+  double* small = psd_smem_cq;
+  GqState<T> st;
+  st.Gc = small;
+  st.Gs = reinterpret_cast<T*>(small + (n + 2) + ((n + 2) & 1));
+  T* stage = reinterpret_cast<T*>(small + (n + 2) + ((n + 2) & 1) + 2 * (n + 2));
+  T* stage_in = reinterpret_cast<T*>(small + (n + 2) + ((n + 2) & 1) + 2 * (n + 2) + cq_stage_doubles(p));
+  T* wvec = reinterpret_cast<T*>(small + (n + 2) + ((n + 2) & 1) + 2 * (n + 2) + 2 * cq_stage_doubles(p));
+  unsigned char* Sint = reinterpret_cast<unsigned char*>(small + (n + 2) + ((n + 2) & 1) + 4 * (n + 2) +
+                                                         2 * cq_stage_doubles(p));
+  st.key = &s_key;
+  const bool left = P.left != 0;
+  for (int l = tid; l < p; l += nt) Sint[l] = P.S ? P.S[left ? (p - 1 - l) : l] : 1;
+  __syncthreads();
+  GCtx<T> cx;
+  cx.n = n; cx.p = p; cx.tid = tid; cx.nt = nt;
+  cx.wantZ = P.wantZ && P.Z;
+  cx.S = Sint;
+  cx.stage = stage; cx.stage_in = stage_in; cx.wvec = wvec; cx.prof = nullptr;
+  cx.wtid = blockIdx.x * nt + tid; cx.wnt = gridDim.x * nt;
+  cx.lead = blockIdx.x == 0; cx.team = true;
+  cx.ldh = n; cx.ldz = n;
+  for (long long b = 0; b < P.batch; b++) {
+    T* Ab = P.A + (size_t)b * p * nn;
+    T* Zb = cx.wantZ ? (P.Z + (size_t)b * p * nn) : nullptr;
+    if (left) {
+      cx.H = Ab + (size_t)(p - 1) * nn; cx.hs = -(long long)nn;
+    } else {
+      cx.H = Ab; cx.hs = (long long)nn;
+    }
+    cx.Z = Zb; cx.zs = (long long)nn;
+    cx.zmap_left = left;
+    if (cx.wantZ && !z_preset)
+      for (int l = 1; l <= p; l++) {
+        T* Zl = cx.Zp(l);
+        for (long long e = cx.wtid; e < (long long)nn; e += cx.wnt)
+          Zl[e] = ((e % n) == (e / n)) ? Scalar<T>::one() : Scalar<T>::zero();
+      }
+    for (int l = 1; l <= p; l++) {
+      T* Hl = cx.Hp(l);
+      const int keep = (l == 1) ? 1 : 0;
+      for (long long e = cx.wtid; e < (long long)nn; e += cx.wnt) {
+        const int r = (int)(e % n), c = (int)(e / n);
+        if (r > c + keep) Hl[e] = Scalar<T>::zero();
+      }
+    }
+    grid.sync();
+    const int info = gpqz_cta<T>(cx, st, P.wantT != 0, P.maxitfac, P.alpha + (size_t)b * n,
+                                 P.beta + (size_t)b * n, P.scale + (size_t)b * n);
+    if (cx.lead && tid == 0) P.info[b] = info;
+    grid.sync();
+  }
+}
+
+// (alpha, beta, alphascale) -> eigenvalue alpha / beta * 2^alphascale (generalized.jl:75-76); used
+// when the real standard path runs its iteration on the generalized team kernel with S = trues.
+__global__ void gvalues_kernel(const cplx* alpha, const double* beta, const long long* scale, double* eig,
+                               long long count) {
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < count;
+       e += (long long)gridDim.x * blockDim.x) {
+    const long long sc = scale[e];
+    const int s1 = (int)(sc / 2), s2 = (int)(sc - sc / 2);
+    const double re = scalbn(scalbn(alpha[e].x / beta[e], s1), s2);
+    const double im = scalbn(scalbn(alpha[e].y / beta[e], s1), s2);
+    eig[2 * e] = re;
+    eig[2 * e + 1] = (alpha[e].y == 0.0) ? 0.0 : im;
   }
 }
 

@@ -24,6 +24,8 @@
 // therefore needs ONE CTA barrier instead of the 2p+1 of a literal transcription, and the
 // loads of the next diagonal block overlap the updates of the current factor.
 #pragma once
+#include <cooperative_groups.h>
+
 #include "psd_device.cuh"
 
 namespace psd {
@@ -140,6 +142,19 @@ struct GCtx {
   T* stage_in;  // same size: the diagonal blocks of all factors, fetched with ONE parallel load
   long long* prof;  // phase time stamps (debug), or nullptr
   T* wvec;          // n scalars of shared memory: the reflector being applied (Stage 1)
+  // Team mode (one large problem on the whole GPU, cooperative launch): every CTA runs the same
+  // scalar control flow redundantly on values read from global memory after a grid barrier, the
+  // row/column/Z updates are dealt to all threads of the grid (wtid of wnt), single-writer stores
+  // are done by the leading CTA, and sync() is the grid barrier.  For a single CTA wtid = tid,
+  // wnt = nt, lead = true and sync() is __syncthreads().
+  int wtid, wnt;
+  bool lead, team;
+  PSD_DEV void sync() const {
+    if (team)
+      cooperative_groups::this_grid().sync();
+    else
+      __syncthreads();
+  }
   PSD_DEV T* Hp(int l) const { return H + (long long)(l - 1) * hs; }
   PSD_DEV T* Zp(int l) const {
     int s = l;
@@ -208,14 +223,14 @@ PSD_DEV void bulk_rot2(int tid, int nt, int total, Item&& item) {
 // lmul!(Givens(i1,i2,c,s), view(M, :, c0:c1)); barrier at the end
 template <class T>
 PSD_DEV void g_lmul(const GCtx<T>& cx, T* M, int ld, int i1, int i2, double c, T s, int c0, int c1) {
-  for (int col = c0 + cx.tid; col <= c1; col += cx.nt) rot_pair_rows(M, ld, i1, i2, col, c, s);
-  __syncthreads();
+  for (int col = c0 + cx.wtid; col <= c1; col += cx.wnt) rot_pair_rows(M, ld, i1, i2, col, c, s);
+  cx.sync();
 }
 // rmul!(view(M, r0:r1, :), Givens(j1,j2,c,s)'); barrier at the end
 template <class T>
 PSD_DEV void g_rmul(const GCtx<T>& cx, T* M, int ld, int j1, int j2, double c, T s, int r0, int r1) {
-  for (int row = r0 + cx.tid; row <= r1; row += cx.nt) rot_pair_cols(M, ld, j1, j2, row, c, s);
-  __syncthreads();
+  for (int row = r0 + cx.wtid; row <= r1; row += cx.wnt) rot_pair_cols(M, ld, j1, j2, row, c, s);
+  cx.sync();
 }
 // c, s, r = givensAlgorithm(M[fa], M[ga]); M[fa] = r; M[ga] = 0   (barrier-safe)
 template <class T>
@@ -223,12 +238,12 @@ PSD_DEV void g_gen(const GCtx<T>& cx, T* M, int ld, int fr, int fc, int gr, int 
   const T f = PSD_GE(M, ld, fr, fc), g = PSD_GE(M, ld, gr, gc);
   T r;
   givens_t(f, g, c, s, r);
-  __syncthreads();
-  if (cx.tid == 0) {
+  cx.sync();
+  if (cx.lead && cx.tid == 0) {
     PSD_GE(M, ld, fr, fc) = r;
     PSD_GE(M, ld, gr, gc) = Scalar<T>::zero();
   }
-  __syncthreads();
+  cx.sync();
 }
 
 // opnorm(view(M, r0:r1, c0:c1), 1), optionally of the upper triangle of the view (rare
@@ -289,7 +304,7 @@ __device__ __noinline__ void chase_rotation(const GCtx<T>& cx, int j, double c1,
     const int nZ = cx.wantZ ? n : 0;
     T* Z1 = cx.wantZ ? cx.Zp(1) : nullptr;
     const int ldz = cx.ldz;
-    bulk_rot2<T>(tid, nt, nL + nZ, [&](int w, T*& a, T*& b, double& c, T& s) {
+    bulk_rot2<T>(cx.wtid, cx.wnt, nL + nZ, [&](int w, T*& a, T*& b, double& c, T& s) {
       c = c1;
       if (w < nL) {
         int col = h1c0 + w;
@@ -348,7 +363,7 @@ __device__ __noinline__ void chase_rotation(const GCtx<T>& cx, int j, double c1,
       const int nZ = cx.wantZ ? n : 0;
       T* Zl = cx.wantZ ? cx.Zp(l) : nullptr;
       const int ldz = cx.ldz;
-      bulk_rot2<T>(tid, nt, nR + nL + nZ, [&](int w, T*& a, T*& b, double& c, T& s) {
+      bulk_rot2<T>(cx.wtid, cx.wnt, nR + nL + nZ, [&](int w, T*& a, T*& b, double& c, T& s) {
         if (w < nR) {
           a = &PSD_GE(Hl, ld, rfirst + w, j);
           b = a + ld;
@@ -379,7 +394,7 @@ __device__ __noinline__ void chase_rotation(const GCtx<T>& cx, int j, double c1,
   // right-only rows of H_1 (rotation that came out of factor 2) and the overlap block
   {
     const int nR = (h1r1 - rfirst + 1) - 2;  // rows rfirst..h1r1 without j, j+1
-    bulk_rot2<T>(tid, nt, nR, [&](int w, T*& a, T*& b, double& c, T& s) {
+    bulk_rot2<T>(cx.wtid, cx.wnt, nR, [&](int w, T*& a, T*& b, double& c, T& s) {
       int row = rfirst + w;
       if (row >= j) row += 2;
       a = &PSD_GE(H1, ld, row, j);
@@ -397,8 +412,8 @@ __device__ __noinline__ void chase_rotation(const GCtx<T>& cx, int j, double c1,
       cx.stage[3] = ci * b2 - si * a2;
     }
   }
-  __syncthreads();
-  for (int l = 1 + tid; l <= p; l += nt) {
+  cx.sync();
+  for (int l = 1 + tid; cx.lead && l <= p; l += nt) {
     if (l == 1) {
       PSD_GE(H1, ld, j, j) = cx.stage[0];
       PSD_GE(H1, ld, j, j + 1) = cx.stage[1];
@@ -417,7 +432,7 @@ __device__ __noinline__ void chase_rotation(const GCtx<T>& cx, int j, double c1,
       PSD_GE(Hl, ld, j + 1, j + 1) = st[2];
     }
   }
-  __syncthreads();
+  cx.sync();
 }
 
 // ------------------------------------------------------------------------------------------
