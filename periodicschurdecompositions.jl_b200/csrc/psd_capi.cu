@@ -443,9 +443,11 @@ int launch_real_large(psd_handle_s* h, Device& dev, Slot& aux, cudaStream_t stre
     if (occ < 1) return fail(PSD_ERR_UNSUPPORTED, "team kernel does not fit on an SM");
     int zp = 1;
     void* args[] = {&P, &zp};
+    int ctas = dev.sm_count;
+    if (const char* ev = getenv("PSD_TEAM_CTAS")) ctas = std::max(1, std::min(atoi(ev), dev.sm_count * occ));
     {
       ScopedKernelTimer tm(h, dev, stream, 1);
-      PSD_CUDA(cudaLaunchCooperativeKernel((void*)kern, dim3(dev.sm_count), dim3(256), args, smem, stream));
+      PSD_CUDA(cudaLaunchCooperativeKernel((void*)kern, dim3(ctas), dim3(256), args, smem, stream));
     }
     psd::gvalues_kernel<<<std::min<long long>(1024, (long long)(cnt + 255) / 256), 256, 0, stream>>>(
         (const psd::cplx*)aux.dX[0], (const double*)aux.dX[1], (const long long*)aux.dX[2], dEig, (long long)cnt);
