@@ -47,3 +47,24 @@ def test_large_pschur(psd, oracle):
         tr = np.trace(np.linalg.multi_dot([K.M(A[0, j]) for j in (range(p) if lr == "R" else range(p - 1, -1, -1))])
                       ) if p > 1 else np.trace(K.M(A[0, 0]))
         assert abs(lam[0].sum() - tr) <= 1e-8 * abs(tr)
+
+
+def test_large_fast_paths_and_batch(psd, oracle):
+    """team-mode iteration: eigenvalues-only and T-only variants agree with the full run
+    (test/runtests.jl:103-132 at a large-N shape), and a small batch of large problems is solved
+    one after the other by the team"""
+    n, p = 200, 2
+    A = oracle.gen_real(31, n, p, 3)
+    T, Z, lam, info = psd.pschur_batched(A, "R")
+    assert (info == 0).all()
+    _, Z0, lam0, info0 = psd.pschur_batched(A, "R", wantT=False, wantZ=False)
+    T1, Z1, lam1, info1 = psd.pschur_batched(A, "L", wantT=True, wantZ=False)
+    assert Z0 is None and Z1 is None and (info0 == 0).all() and (info1 == 0).all()
+    for b in range(3):
+        K.pschur_check(A[b], T[b], Z[b], lam[b], tol=64, check_lambda=False)
+        scale = np.max(np.abs(lam[b]))
+        assert K.match_eigs(lam[b], lam0[b]) <= 1000 * n * EPS * scale
+        ref = np.linalg.eigvals(K.M(A[b, 0]) @ K.M(A[b, 1]))
+        assert K.match_eigs(ref, lam[b]) <= 1e-8 * scale
+        refl = np.linalg.eigvals(K.M(A[b, 1]) @ K.M(A[b, 0]))
+        assert K.match_eigs(refl, lam1[b]) <= 1e-8 * scale
