@@ -256,7 +256,7 @@ def run_ours(args):
 
     peak, peak_kind = _peaks()
     step_ms = sum(kernel_ms) / len(kernel_ms)
-    # dominant kernel: the eigenvalue-only periodic QR iteration (psd::rpqr_eig32_kernel); its
+    # dominant kernel: the eigenvalue-only periodic QR iteration (psd::rpqr_eig32_kernel_t); its
     # launches each process min(B, 65536) problems.  achieved = SURVEY.md §8(d) bytes per
     # problem x problems per launch / average launch duration (CUDA events on its stream).
     n_it = max(1, kt["iterate_launches"])
@@ -288,10 +288,10 @@ def run_ours(args):
                      "frac": achieved / peak,
                      "traffic": (traffic * units_per_launch) if traffic else None,
                      "peak_kind": f"of {peak_kind}",
-                     "kernel": "psd::rpqr_eig32_kernel", "kernel_ms": k_ms,
+                     "kernel": "psd::rpqr_eig32_kernel_t<32,8>", "kernel_ms": k_ms,
                      "problems_per_launch": units_per_launch,
                      "kernel_share_of_step": kt["iterate_ms"] / (kt["iterate_ms"] + kt["reduce_ms"]),
-                     "reduce_kernel": "psd::rphess_warp32_kernel",
+                     "reduce_kernel": "psd::rphess_warp32_kernel_t<32,8>",
                      "reduce_kernel_ms": kt["reduce_ms"] / max(1, kt["reduce_launches"]),
                      "step_ms_device": step_ms,
                      "fp64_gflops_standard_count": FLOPS_PER_PROBLEM * B / (step_ms * 1e-3) / 1e9,

@@ -225,18 +225,20 @@ int launch_real_eig32(psd_handle_s* h, Device& dev, Slot& aux, cudaStream_t stre
   if (e) return e;
   if (!aux.dCounter) PSD_CUDA(cudaMalloc((void**)&aux.dCounter, 2 * sizeof(unsigned long long)));
   // QR kernel configuration: as many warps (= resident problems) per CTA as shared memory allows
+  void (*qrk)(psd::EigParams) = (n == 32 && p == 8 && !getenv("PSD_NO_SPECIAL")) ? psd::rpqr_eig32_kernel_t<32, 8>
+                                                                                : psd::rpqr_eig32_kernel_t<0, 0>;
   cudaFuncAttributes fa;
-  PSD_CUDA(cudaFuncGetAttributes(&fa, psd::rpqr_eig32_kernel));
+  PSD_CUDA(cudaFuncGetAttributes(&fa, qrk));
   int optin = 0;
   PSD_CUDA(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev.ordinal));
   const size_t max_dyn = (size_t)optin - fa.sharedSizeBytes;
   int wpb = (int)std::min<size_t>(8, max_dyn / (psize * sizeof(double)));
   if (wpb < 1) return fail(PSD_ERR_UNSUPPORTED, "packed problem does not fit in shared memory");
   const size_t smem2 = (size_t)wpb * psize * sizeof(double);
-  PSD_CUDA(cudaFuncSetAttribute(psd::rpqr_eig32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  PSD_CUDA(cudaFuncSetAttribute(qrk, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)max_dyn));
   int occ2 = 0;
-  PSD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, psd::rpqr_eig32_kernel, wpb * 32, smem2));
+  PSD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, qrk, wpb * 32, smem2));
   if (occ2 < 1) return fail(PSD_ERR_UNSUPPORTED, "QR kernel does not fit on an SM");
   for (long long off = 0; off < batch; off += chunk) {
     const long long nb = std::min(chunk, batch - off);
@@ -273,23 +275,26 @@ int launch_real_eig32(psd_handle_s* h, Device& dev, Slot& aux, cudaStream_t stre
       R.A = dA + (size_t)off * p * nn;
       R.packed_out = aux.dPacked;
       R.counter = aux.dCounter;
+      void (*hk)(psd::Hess32Params) = (n == 32 && p == 8 && !getenv("PSD_NO_SPECIAL"))
+                                          ? psd::rphess_warp32_kernel_t<32, 8>
+                                          : psd::rphess_warp32_kernel_t<0, 0>;
       cudaFuncAttributes fh;
-      PSD_CUDA(cudaFuncGetAttributes(&fh, psd::rphess_warp32_kernel));
+      PSD_CUDA(cudaFuncGetAttributes(&fh, hk));
       const size_t max_dyn1 = (size_t)optin - fh.sharedSizeBytes;
       const size_t per1 = (size_t)p * R.ld * n * sizeof(double);
       int wpb1 = (int)std::min<size_t>(8, max_dyn1 / per1);
       if (wpb1 < 1) return fail(PSD_ERR_UNSUPPORTED, "problem does not fit in shared memory");
       const size_t smem1 = (size_t)wpb1 * per1;
-      PSD_CUDA(cudaFuncSetAttribute(psd::rphess_warp32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+      PSD_CUDA(cudaFuncSetAttribute(hk, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)max_dyn1));
       int occ1 = 0;
-      PSD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ1, psd::rphess_warp32_kernel, wpb1 * 32, smem1));
+      PSD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ1, hk, wpb1 * 32, smem1));
       if (occ1 < 1) return fail(PSD_ERR_UNSUPPORTED, "reduction kernel does not fit on an SM");
       const long long ctas1 = (nb + wpb1 - 1) / wpb1;
       const int grid1 = (int)std::max(1LL, std::min((long long)occ1 * dev.sm_count, ctas1));
       {
         ScopedKernelTimer tm(h, dev, stream, 0);
-        psd::rphess_warp32_kernel<<<grid1, wpb1 * 32, smem1, stream>>>(R);
+        hk<<<grid1, wpb1 * 32, smem1, stream>>>(R);
       }
       PSD_CUDA(cudaGetLastError());
     }
@@ -305,7 +310,7 @@ int launch_real_eig32(psd_handle_s* h, Device& dev, Slot& aux, cudaStream_t stre
     const int grid2 = (int)std::max(1LL, std::min((long long)occ2 * dev.sm_count, ctas));
     {
       ScopedKernelTimer tm(h, dev, stream, 1);
-      psd::rpqr_eig32_kernel<<<grid2, wpb * 32, smem2, stream>>>(Q);
+      qrk<<<grid2, wpb * 32, smem2, stream>>>(Q);
     }
     PSD_CUDA(cudaGetLastError());
     __atomic_fetch_add(&h->stats[0], (int64_t)2, __ATOMIC_RELAXED);

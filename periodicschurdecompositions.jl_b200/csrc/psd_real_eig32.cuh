@@ -598,9 +598,12 @@ __device__ __forceinline__ int rpqr_problem(double* sm, const int n, const int p
 
 extern __shared__ __align__(16) double psd_smem_eig[];
 
-__global__ void __launch_bounds__(256) rpqr_eig32_kernel(EigParams P) {
+// NN, PP > 0 fix the order and period at compile time (the headline shape N = 32, p = 8 gets its
+// own instantiation: packed offsets and strides fold into constants); 0 = taken from the params.
+template <int NN, int PP>
+__global__ void __launch_bounds__(256) rpqr_eig32_kernel_t(EigParams P) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int n = P.n, p = P.p;
+  const int n = NN ? NN : P.n, p = PP ? PP : P.p;
   const int psize = pk_problem_size(n, p);
   double* sm = psd_smem_eig + (size_t)warp * psize;  // H1 at 0, factor j at szh1 + (j-2)*sj
   for (;;) {

@@ -157,9 +157,10 @@ PSD_DEV void hess32_step(double* Aj, double* Am, int n, int ld, int r0, int col,
 
 extern __shared__ __align__(16) double psd_smem_hess[];
 
-__global__ void __launch_bounds__(256) rphess_warp32_kernel(Hess32Params P) {
+template <int NN, int PP>
+__global__ void __launch_bounds__(256) rphess_warp32_kernel_t(Hess32Params P) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int n = P.n, p = P.p, ld = P.ld;
+  const int n = NN ? NN : P.n, p = PP ? PP : P.p, ld = NN ? (NN % 2 == 0 ? NN + 1 : NN) : P.ld;
   const size_t nn = (size_t)n * n;
   const int fs = ld * n;  // doubles per staged factor
   double* S = psd_smem_hess + (size_t)warp * p * fs;
