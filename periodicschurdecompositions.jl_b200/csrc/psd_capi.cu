@@ -243,18 +243,11 @@ int launch_real_eig32(psd_handle_s* h, Device& dev, Slot& aux, cudaStream_t stre
   for (long long off = 0; off < batch; off += chunk) {
     const long long nb = std::min(chunk, batch - off);
     PSD_CUDA(cudaMemsetAsync(aux.dCounter, 0, 2 * sizeof(unsigned long long), stream));
-    const char* hess_cta = getenv("PSD_HESS_CTA");  // experiment: CTA-per-problem reduction, N threads
-    if (rc.skip_reduce || hess_cta) {
+    if (rc.skip_reduce) {
       // input already Hessenberg/triangular: CTA kernel only enforces structure and packs
       RealLaunchPlan pl;
       e = plan_real(dev, n, p, nb, false, pl);
       if (e) return e;
-      if (hess_cta) {
-        pl.threads = atoi(hess_cta);
-        int occ = 0;
-        PSD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, psd::rpschur_kernel, pl.threads, pl.smem_bytes));
-        pl.grid = (int)std::max(1LL, std::min((long long)occ * dev.sm_count, nb));
-      }
       if (!pl.use_smem) return fail(PSD_ERR_UNSUPPORTED, "eig32 path expects shared-memory staging");
       psd::RpschurParams P;
       P.n = n; P.p = p; P.batch = nb;
