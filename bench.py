@@ -283,12 +283,13 @@ def run_ours(args):
         "e2e": {"value": e2e_value, "unit": "problems/s", "h2d_bytes_per_step": st["h2d_bytes"],
                 "d2h_bytes_per_step": st["d2h_bytes"], "steps": e2e_steps,
                 "matches_device_path": same},
-        "gpu_launches": kt["iterate_launches"] + kt["reduce_launches"],
+        "gpu_launches": kt["iterate_launches"] + kt["reduce_launches"] + kt["extra_launches"],
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak,
                      "traffic": (traffic * units_per_launch) if traffic else None,
                      "peak_kind": f"of {peak_kind}",
-                     "kernel": "psd::rpqr_eig32_kernel_t<32,8>", "kernel_ms": k_ms,
+                     "kernel": "psd::rpqr_eig32_kernel_t (six occupancy phases, orders 32..12, timed together)",
+                     "kernel_ms": k_ms,
                      "problems_per_launch": units_per_launch,
                      "kernel_share_of_step": kt["iterate_ms"] / (kt["iterate_ms"] + kt["reduce_ms"]),
                      "reduce_kernel": "psd::rphess_warp32_kernel_t<32,8>",

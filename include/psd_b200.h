@@ -231,7 +231,9 @@ int psd_last_stats(psd_handle_t handle, int64_t stats[8]);
  * events and returns, accumulated since the previous call, ms[0] = reduction kernels,
  * ms[1] = QR/QZ iteration kernels (milliseconds of device time), ms[2], ms[3] = how many
  * launches of each kind were timed; for the large-N blocked reduction ms[4] = panel kernels,
- * ms[5] = FP64 tensor-core GEMM updates (milliseconds), ms[6] = GEMM flops issued; ms[7] = 0. */
+ * ms[5] = FP64 tensor-core GEMM updates (milliseconds), ms[6] = GEMM flops issued; ms[7] = kernel
+ * launches not counted in ms[2..3] because one timer brackets several (the occupancy phases of the
+ * eigenvalue-only iteration). */
 int psd_set_profiling(psd_handle_t handle, int on);
 int psd_kernel_times(psd_handle_t handle, double ms[8]);
 

@@ -61,6 +61,9 @@ struct Slot {
   size_t capScratch = 0;
   double* dPacked = nullptr;  // packed Hessenberg-triangular factors between the two kernels
   size_t capPacked = 0;
+  double* dPk[8] = {nullptr};  // packed leading parts handed to the later occupancy phases
+  size_t capPk[8] = {0};
+  unsigned long long* dPhaseCtr = nullptr;  // work counters of the phase launches
   // generalized paths: alpha, beta, alphascale (device + pinned staging) and the signature
   void* dX[3] = {nullptr, nullptr, nullptr};
   size_t capX[3] = {0, 0, 0};
@@ -92,6 +95,7 @@ struct psd_handle_s {
   bool profiling = false;           // psd_set_profiling
   std::vector<KernelTimer> timers;  // pending event pairs (resolved by psd_kernel_times)
   double gemm_flops = 0.0;          // FP64 GEMM flops issued by the large-N reduction since then
+  double extra_launches = 0.0;      // kernel launches covered by a timer that brackets several
   std::mutex tmu;
 };
 
@@ -221,25 +225,68 @@ int launch_real_eig32(psd_handle_s* h, Device& dev, Slot& aux, cudaStream_t stre
   const size_t nn = (size_t)n * n;
   const size_t psize = (size_t)psd::pk_problem_size(n, p);
   const long long chunk = std::min(batch, kEigChunk);
-  int e = ensure_dev(aux.dPacked, aux.capPacked, (size_t)chunk * (psize + 1) * sizeof(double));
+  int e = ensure_dev(aux.dPacked, aux.capPacked, (size_t)chunk * psd::pk_problem_stride(n, p) * sizeof(double));
   if (e) return e;
   if (!aux.dCounter) PSD_CUDA(cudaMalloc((void**)&aux.dCounter, 2 * sizeof(unsigned long long)));
-  // QR kernel configuration: as many warps (= resident problems) per CTA as shared memory allows
-  void (*qrk)(psd::EigParams) = (n == 32 && p == 8 && !getenv("PSD_NO_SPECIAL")) ? psd::rpqr_eig32_kernel_t<32, 8>
-                                                                                : psd::rpqr_eig32_kernel_t<0, 0>;
-  cudaFuncAttributes fa;
-  PSD_CUDA(cudaFuncGetAttributes(&fa, qrk));
+  if (!aux.dPhaseCtr) PSD_CUDA(cudaMalloc((void**)&aux.dPhaseCtr, 16 * sizeof(unsigned long long)));
   int optin = 0;
   PSD_CUDA(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev.ordinal));
-  const size_t max_dyn = (size_t)optin - fa.sharedSizeBytes;
-  int wpb = (int)std::min<size_t>(8, max_dyn / (psize * sizeof(double)));
-  if (wpb < 1) return fail(PSD_ERR_UNSUPPORTED, "packed problem does not fit in shared memory");
-  const size_t smem2 = (size_t)wpb * psize * sizeof(double);
-  PSD_CUDA(cudaFuncSetAttribute(qrk, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)max_dyn));
-  int occ2 = 0;
-  PSD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, qrk, wpb * 32, smem2));
-  if (occ2 < 1) return fail(PSD_ERR_UNSUPPORTED, "QR kernel does not fit on an SM");
+  // occupancy phases of the iteration (see rpqr_eig32_kernel_t): orders n, 7n/8, ..., 3n/8
+  struct Phase {
+    int n, stop, wpb, grid;
+    size_t smem;
+    void (*kern)(psd::EigParams);
+  };
+  std::vector<Phase> phases;
+  {
+    std::vector<int> orders{n};
+    if (n >= 24 && !getenv("PSD_NO_PHASES"))
+      for (int k = 1; k <= 5; k++) orders.push_back(n - k * (n / 8));  // n = 32: 28, 24, 20, 16, 12
+    bool special = (n == 32 && p == 8 && !getenv("PSD_NO_SPECIAL"));
+    if (const char* ev = getenv("PSD_PHASES")) {  // experiment: comma-separated decreasing orders after n
+      orders.assign(1, n);
+      special = false;
+      for (const char* c = ev; *c;) {
+        int v = atoi(c);
+        if (v > 1 && v < orders.back()) orders.push_back(v);
+        while (*c && *c != ',') c++;
+        if (*c == ',') c++;
+      }
+    }
+    for (size_t k = 0; k < orders.size(); k++) {
+      Phase ph;
+      ph.n = orders[k];
+      ph.stop = (k + 1 < orders.size()) ? orders[k + 1] : 0;
+      ph.kern = psd::rpqr_eig32_kernel_t<0, 0>;
+      if (special && k == 0) ph.kern = psd::rpqr_eig32_kernel_t<32, 8>;
+      cudaFuncAttributes fa;
+      PSD_CUDA(cudaFuncGetAttributes(&fa, ph.kern));
+      const size_t max_dyn = (size_t)optin - fa.sharedSizeBytes;
+      const size_t pbytes = (size_t)psd::pk_problem_size(ph.n, p) * sizeof(double);
+      PSD_CUDA(cudaFuncSetAttribute(ph.kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_dyn));
+      // warps per CTA: the split that gives the most resident warps per SM (<= 8 warps per CTA)
+      int best_w = 0, best_total = 0;
+      for (int w = 1; w <= 8; w++) {
+        if ((size_t)w * pbytes > max_dyn) break;
+        int occ = 0;
+        PSD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ph.kern, w * 32, (size_t)w * pbytes));
+        if (occ * w > best_total || (occ * w == best_total && w > best_w)) {
+          best_total = occ * w;
+          best_w = w;
+        }
+      }
+      if (best_w < 1) return fail(PSD_ERR_UNSUPPORTED, "packed problem does not fit in shared memory");
+      ph.wpb = best_w;
+      ph.smem = (size_t)best_w * pbytes;
+      ph.grid = (best_total / best_w) * dev.sm_count;
+      phases.push_back(ph);
+    }
+    if (phases.size() > 9) return fail(PSD_ERR_BAD_ARG, "too many phases");
+    for (size_t k = 1; k < phases.size(); k++)
+      if ((e = ensure_dev(aux.dPk[k - 1], aux.capPk[k - 1],
+                          (size_t)chunk * psd::pk_problem_stride(phases[k].n, p) * sizeof(double))))
+        return e;
+  }
   for (long long off = 0; off < batch; off += chunk) {
     const long long nb = std::min(chunk, batch - off);
     PSD_CUDA(cudaMemsetAsync(aux.dCounter, 0, 2 * sizeof(unsigned long long), stream));
@@ -291,21 +338,28 @@ int launch_real_eig32(psd_handle_s* h, Device& dev, Slot& aux, cudaStream_t stre
       }
       PSD_CUDA(cudaGetLastError());
     }
-    psd::EigParams Q;
-    Q.n = n; Q.p = p; Q.batch = nb; Q.maxitfac = rc.maxitfac > 0 ? rc.maxitfac : 30;
-    Q.packed = aux.dPacked;
-    Q.eig = dEig + (size_t)off * 2 * n;
-    Q.info = dInfo + off;
-    Q.iters = nullptr;
-    Q.counter = aux.dCounter + 1;
-    Q.force_safe = getenv("PSD_EIG32_SAFE") ? 1 : 0;
-    const long long ctas = (nb + wpb - 1) / wpb;
-    const int grid2 = (int)std::max(1LL, std::min((long long)occ2 * dev.sm_count, ctas));
+    PSD_CUDA(cudaMemsetAsync(aux.dPhaseCtr, 0, 16 * sizeof(unsigned long long), stream));
     {
-      ScopedKernelTimer tm(h, dev, stream, 1);
-      qrk<<<grid2, wpb * 32, smem2, stream>>>(Q);
+      ScopedKernelTimer tm(h, dev, stream, 1);  // the phase launches are timed as one iteration
+      for (size_t k = 0; k < phases.size(); k++) {
+        const Phase& ph = phases[k];
+        psd::EigParams Q;
+        Q.n = ph.n; Q.p = p; Q.batch = nb; Q.maxitfac = rc.maxitfac > 0 ? rc.maxitfac : 30;
+        Q.packed = (k == 0) ? aux.dPacked : aux.dPk[k - 1];
+        Q.packed_next = (k + 1 < phases.size()) ? aux.dPk[k] : nullptr;
+        Q.n_full = n; Q.stop = ph.stop; Q.first_phase = (k == 0) ? 1 : 0;
+        Q.eig = dEig + (size_t)off * 2 * n;
+        Q.info = dInfo + off;
+        Q.iters = nullptr;
+        Q.counter = aux.dPhaseCtr + k;
+        Q.force_safe = getenv("PSD_EIG32_SAFE") ? 1 : 0;
+        const long long ctas = (nb + ph.wpb - 1) / ph.wpb;
+        const int grid2 = (int)std::max(1LL, std::min((long long)ph.grid, ctas));
+        ph.kern<<<grid2, ph.wpb * 32, ph.smem, stream>>>(Q);
+      }
     }
     PSD_CUDA(cudaGetLastError());
+    h->extra_launches += (double)(phases.size() - 1);
     __atomic_fetch_add(&h->stats[0], (int64_t)2, __ATOMIC_RELAXED);
   }
   __atomic_fetch_add(&h->stats[1], (int64_t)batch, __ATOMIC_RELAXED);
@@ -837,6 +891,8 @@ int psd_destroy(psd_handle_t h) {
       }
       cudaFree(s.dA); cudaFree(s.dZ); cudaFree(s.dEig); cudaFree(s.dInfo);
       cudaFree(s.dCounter); cudaFree(s.dScratch); cudaFree(s.dPacked); cudaFree(s.dS);
+      for (int k = 0; k < 8; k++) cudaFree(s.dPk[k]);
+      cudaFree(s.dPhaseCtr);
       for (int k = 0; k < 3; k++) {
         cudaFree(s.dX[k]);
         cudaFreeHost(s.hX[k]);
@@ -1092,6 +1148,8 @@ int psd_kernel_times(psd_handle_t h, double ms[8]) {
   for (int i = 0; i < 8; i++) ms[i] = 0.0;
   ms[6] = h->gemm_flops;
   h->gemm_flops = 0.0;
+  ms[7] = h->extra_launches;
+  h->extra_launches = 0.0;
   for (auto& t : h->timers) {
     cudaSetDevice(t.ordinal);
     cudaError_t e = cudaEventSynchronize(t.e1);

@@ -44,14 +44,22 @@ __host__ __device__ inline int pk_problem_size(int n, int p) {
 // by which the product was scaled down (every factor is normalised to max |entry| in [0.5, 1) by
 // an exact power of two before the iteration, because the un-normalised reflectors
 // H = I + g u u^T square the entries; eigenvalues are multiplied by 2^E at the end).
-__host__ __device__ inline int pk_problem_stride(int n, int p) { return pk_problem_size(n, p) + 1; }
+// The slots behind the factors hold the state that travels between the occupancy phases of the
+// iteration (see rpqr_eig32_kernel_t): [0] E, [1] current bottom index i (-1: finished or failed),
+// [2] iterations left of the shared budget (:442-443), [3] iterations used so far.
+constexpr int PK_STATE = 4;
+__host__ __device__ inline int pk_problem_stride(int n, int p) { return pk_problem_size(n, p) + PK_STATE; }
 
 struct EigParams {
   int n, p;
   long long batch;
   int maxitfac;
-  const double* packed;  // [batch][pk_problem_stride]
-  double* eig;           // [batch][n][2]
+  const double* packed;  // [batch][pk_problem_stride(n, p)]
+  double* packed_next;   // [batch][pk_problem_stride(stop, p)] or nullptr (last phase)
+  int n_full;            // order of the original problems (row stride of eig)
+  int stop;              // this phase works while the bottom index i >= stop
+  int first_phase;       // state slots [1..3] are not set yet: start at i = n-1 with the full budget
+  double* eig;           // [batch][n_full][2]
   int* info;
   int* iters;
   unsigned long long* counter;
@@ -271,9 +279,10 @@ PSD_DEV void col_pass_h1(double* sm, int oc1, int q, int r, int i, int l, bool c
 constexpr int kNeedSafe = -12345;
 
 template <bool SAFE>
-__device__ __forceinline__ int rpqr_problem(double* sm, const int n, const int p, const int maxitfac,
-                                            const int lane, double& lre_out, double& lim_out,
-                                            int& niter_out) {
+__device__ __forceinline__ int rpqr_problem(double* sm, const int n, const int p, const int i0,
+                                            const int ml0, const int stop, const int lane,
+                                            double& lre_out, double& lim_out, int& niter_out,
+                                            int& i_end, int& ml_end) {
   const int szh1 = pk_size(3, n), sj = pk_size(1, n);
   const int r = lane;
   // this lane's column offsets in the two packed layouts, and those of columns r+1, r+2
@@ -288,14 +297,16 @@ __device__ __forceinline__ int rpqr_problem(double* sm, const int n, const int p
     double lre = 0.0, lim = 0.0;  // eigenvalue r lives in lane r
     int info = 0, niter = 0;
 
+    i_end = -1;
+    ml_end = 0;
     if (n == 1) {
       double q = sm[0];
       for (int j = 2; j <= p; j++) q *= sm[szh1 + (j - 2) * sj];
       lre = q;
     } else {
-      int i = n - 1;
-      int maxitleft = maxitfac * n;
-      while (i >= 0) {
+      int i = i0;
+      int maxitleft = ml0;
+      while (i >= stop) {
         int l = 0;
         int its = 1;
         bool splitting = false;
@@ -589,6 +600,8 @@ __device__ __forceinline__ int rpqr_problem(double* sm, const int n, const int p
         niter += its;
         i = l - 1;
       }
+      i_end = i;
+      ml_end = maxitleft;
     }
     lre_out = lre;
     lim_out = lim;
@@ -600,39 +613,90 @@ extern __shared__ __align__(16) double psd_smem_eig[];
 
 // NN, PP > 0 fix the order and period at compile time (the headline shape N = 32, p = 8 gets its
 // own instantiation: packed offsets and strides fold into constants); 0 = taken from the params.
+// The iteration runs in up to three OCCUPANCY PHASES.  With wantT = false everything right of /
+// below the current bottom index i is dead, so a problem whose bottom index has dropped below
+// `stop` only needs the leading stop x stop part of every factor - which is a PREFIX of each
+// packed array (column c always occupies c+1+kl slots).  A phase therefore works on problems of
+// order n while i >= stop, writes the prefixes plus the loop state to the next phase's buffer,
+// and the next launch treats them as problems of order `stop` with a smaller shared-memory
+// footprint: more resident warps per SM where the latency-bound chain needs them
+// (p = 8: order 32 -> 6 warps/SM, 24 -> 10; from there on the register file caps it).  Measured
+// gain on the headline shape: 8-10 % (the iteration is only partly latency-bound).
+// NN, PP > 0 fix the order and period at compile time (packed offsets and strides fold into
+// constants); 0 = taken from the params.
 template <int NN, int PP>
 __global__ void __launch_bounds__(256) rpqr_eig32_kernel_t(EigParams P) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int n = NN ? NN : P.n, p = PP ? PP : P.p;
   const int psize = pk_problem_size(n, p);
+  const int stop = P.stop;
   double* sm = psd_smem_eig + (size_t)warp * psize;  // H1 at 0, factor j at szh1 + (j-2)*sj
   for (;;) {
     long long b = 0;
     if (lane == 0) b = (long long)atomicAdd(P.counter, 1ULL);
     b = __shfl_sync(0xffffffffu, b, 0);
     if (b >= P.batch) break;
-    const double* src = P.packed + (size_t)b * (psize + 1);
+    const double* src = P.packed + (size_t)b * (psize + PK_STATE);
     const int escale = (int)src[psize];
+    int i0, ml0, nit0;
+    if (P.first_phase) {
+      i0 = n - 1;
+      ml0 = P.maxitfac * n;
+      nit0 = 0;
+    } else {
+      i0 = (int)src[psize + 1];
+      ml0 = (int)src[psize + 2];
+      nit0 = (int)src[psize + 3];
+    }
+    double* nxt = P.packed_next ? P.packed_next + (size_t)b * pk_problem_stride(stop, p) : nullptr;
+    if (i0 < 0) {  // finished or failed in an earlier phase
+      if (nxt && lane == 0) nxt[pk_problem_size(stop, p) + 1] = -1.0;
+      continue;
+    }
     for (int e = lane; e < psize; e += 32) sm[e] = src[e];
     __syncwarp();
     double lre, lim;
-    int niter;
-    int info = P.force_safe ? kNeedSafe : rpqr_problem<false>(sm, n, p, P.maxitfac, lane, lre, lim, niter);
+    int niter, i_end, ml_end;
+    int info = P.force_safe ? kNeedSafe
+                            : rpqr_problem<false>(sm, n, p, i0, ml0, stop, lane, lre, lim, niter, i_end, ml_end);
     if (info == kNeedSafe) {
-      // badly scaled problem: start over with the exactly-rescaling reflector
+      // badly scaled problem: redo this phase with the exactly-rescaling reflector
       __syncwarp();
       for (int e = lane; e < psize; e += 32) sm[e] = src[e];
       __syncwarp();
-      info = rpqr_problem<true>(sm, n, p, P.maxitfac, lane, lre, lim, niter);
+      info = rpqr_problem<true>(sm, n, p, i0, ml0, stop, lane, lre, lim, niter, i_end, ml_end);
     }
-    if (lane < n) {
-      double* eg = P.eig + ((size_t)b * n + lane) * 2;
+    // eigenvalues found in this phase: indices i_end+1 .. i0 (all of 0..i0 after a failure, as the
+    // single-phase kernel reports them)
+    if (lane <= i0 && (lane > i_end || info != 0)) {
+      double* eg = P.eig + ((size_t)b * P.n_full + lane) * 2;
       eg[0] = scalbn(lre, escale);
       eg[1] = scalbn(lim, escale);
     }
+    const bool more = (info == 0 && i_end >= 0 && nxt != nullptr);
     if (lane == 0) {
-      P.info[b] = info;
-      if (P.iters) P.iters[b] = niter;
+      if (!more) {
+        P.info[b] = info;
+        if (P.iters) P.iters[b] = nit0 + niter;
+      }
+    }
+    if (nxt) {
+      __syncwarp();
+      if (more) {
+        // prefixes of the packed factors = the leading stop x stop problem
+        const int s3 = pk_size(3, stop), s1 = pk_size(1, stop);
+        const int szh1 = pk_size(3, n), sj = pk_size(1, n);
+        for (int e = lane; e < s3; e += 32) nxt[e] = sm[e];
+        for (int j = 2; j <= p; j++)
+          for (int e = lane; e < s1; e += 32) nxt[s3 + (j - 2) * s1 + e] = sm[szh1 + (j - 2) * sj + e];
+      }
+      if (lane == 0) {
+        double* stt = nxt + pk_problem_size(stop, p);
+        stt[0] = (double)escale;
+        stt[1] = more ? (double)i_end : -1.0;
+        stt[2] = (double)ml_end;
+        stt[3] = (double)(nit0 + niter);
+      }
     }
     __syncwarp();
   }

@@ -209,7 +209,7 @@ __global__ void __launch_bounds__(256) rphess_warp32_kernel_t(Hess32Params P) {
       if (n - (i + 1) > 1) hess32_step(S, S + (p - 1) * fs, n, ld, i + 1, i, lane);
     }
     // packed output: H1 with 3 subdiagonals of storage, H2..Hp with 1 (zeros below structure)
-    double* dstb = P.packed_out + (size_t)b * (psize + 1);
+    double* dstb = P.packed_out + (size_t)b * (psize + PK_STATE);
     if (lane == 0) dstb[psize] = (double)escale;
     for (int j = 0; j < p; j++) {
       const int kl = (j == 0) ? 3 : 1;

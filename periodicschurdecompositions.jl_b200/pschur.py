@@ -123,7 +123,7 @@ class Handle:
         check(lib().psd_kernel_times(self._h, ms))
         return {"reduce_ms": ms[0], "iterate_ms": ms[1], "reduce_launches": int(ms[2]),
                 "iterate_launches": int(ms[3]), "large_panel_ms": ms[4], "large_gemm_ms": ms[5],
-                "large_gemm_flops": ms[6]}
+                "large_gemm_flops": ms[6], "extra_launches": int(ms[7])}
 
     def close(self):
         if self._h:
