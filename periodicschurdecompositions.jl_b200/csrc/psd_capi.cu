@@ -224,7 +224,9 @@ int launch_real_eig32(psd_handle_s* h, Device& dev, Slot& aux, cudaStream_t stre
   const int n = rc.n, p = rc.p;
   const size_t nn = (size_t)n * n;
   const size_t psize = (size_t)psd::pk_problem_size(n, p);
-  const long long chunk = std::min(batch, kEigChunk);
+  long long chunk_max = kEigChunk;
+  if (const char* ev = getenv("PSD_EIG_CHUNK")) chunk_max = std::max(1LL, atoll(ev));
+  const long long chunk = std::min(batch, chunk_max);
   int e = ensure_dev(aux.dPacked, aux.capPacked, (size_t)chunk * psd::pk_problem_stride(n, p) * sizeof(double));
   if (e) return e;
   if (!aux.dCounter) PSD_CUDA(cudaMalloc((void**)&aux.dCounter, 2 * sizeof(unsigned long long)));
@@ -524,8 +526,9 @@ int run_real_shard(psd_handle_s* h, Device& dev, const RealCall& rc, long long f
   const size_t per = nn * rc.p;  // doubles per problem
   const bool wantZ = rc.wantZ && Z;
   const bool outT = rc.wantT || rc.reduce_only;
-  // chunk: at most ~512 MiB of factors per slot, at least one wave of CTAs
-  long long chunk = std::max<long long>(1, (512LL << 20) / (long long)(per * sizeof(double)));
+  // chunk: at most ~1 GiB of factors per slot (larger chunks amortise the tail of the persistent
+  // kernels, smaller ones shorten the un-overlapped first copy; 1 GiB measured best for config 2)
+  long long chunk = std::max<long long>(1, (1024LL << 20) / (long long)(per * sizeof(double)));
   chunk = std::min(chunk, count);
   if (count > chunk) {
     // balance chunk sizes
@@ -534,8 +537,12 @@ int run_real_shard(psd_handle_s* h, Device& dev, const RealCall& rc, long long f
   }
   int si = 0;
   int rcode = PSD_OK;
-  for (long long off = 0; off < count && rcode == PSD_OK; off += chunk, si = (si + 1) % kSlotsPerDevice) {
-    const long long nb = std::min(chunk, count - off);
+  // the first chunk is an eighth of the others: its host-to-device copy is the only one that no
+  // kernel overlaps
+  const long long first_chunk = (count > chunk) ? std::max<long long>(1, chunk / 8) : chunk;
+  long long nb = 0;
+  for (long long off = 0; off < count && rcode == PSD_OK; off += nb, si = (si + 1) % kSlotsPerDevice) {
+    nb = std::min(off == 0 ? first_chunk : chunk, count - off);
     Slot& s = dev.slots[si];
     if (!s.stream) PSD_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
     // the slot's previous chunk must have fully drained before its buffers are reused
