@@ -261,26 +261,47 @@ int launch_real_eig32(psd_handle_s* h, Device& dev, Slot& aux, cudaStream_t stre
       ph.stop = (k + 1 < orders.size()) ? orders[k + 1] : 0;
       ph.kern = psd::rpqr_eig32_kernel_t<0, 0>;
       if (special && k == 0) ph.kern = psd::rpqr_eig32_kernel_t<32, 8>;
+      int wmax = 8;
+      if (k > 0) {
+        const char* lr = getenv("PSD_LOWREG");
+        const int mode = lr ? atoi(lr) : 168;
+        if (mode == 168) { ph.kern = psd::rpqr_eig32_kernel_r168; wmax = 3; }
+        if (mode == 128) { ph.kern = psd::rpqr_eig32_kernel_r128; wmax = 4; }
+      }
       cudaFuncAttributes fa;
       PSD_CUDA(cudaFuncGetAttributes(&fa, ph.kern));
       const size_t max_dyn = (size_t)optin - fa.sharedSizeBytes;
       const size_t pbytes = (size_t)psd::pk_problem_size(ph.n, p) * sizeof(double);
       PSD_CUDA(cudaFuncSetAttribute(ph.kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_dyn));
+      // several CTAs per SM only fit with the largest shared-memory carve-out
+      PSD_CUDA(cudaFuncSetAttribute(ph.kern, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                    (int)cudaSharedmemCarveoutMaxShared));
       // warps per CTA: the split that gives the most resident warps per SM (<= 8 warps per CTA)
       int best_w = 0, best_total = 0;
-      for (int w = 1; w <= 8; w++) {
+      for (int w = 1; w <= wmax; w++) {
         if ((size_t)w * pbytes > max_dyn) break;
         int occ = 0;
         PSD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ph.kern, w * 32, (size_t)w * pbytes));
+        if (getenv("PSD_GEN_PROF")) fprintf(stderr, "[psd eig32 occ] order %d w %d -> %d CTAs/SM\n", ph.n, w, occ);
         if (occ * w > best_total || (occ * w == best_total && w > best_w)) {
           best_total = occ * w;
           best_w = w;
         }
       }
       if (best_w < 1) return fail(PSD_ERR_UNSUPPORTED, "packed problem does not fit in shared memory");
+      if (const char* ev = getenv("PSD_PHASE_WPB")) {  // experiment: force warps per CTA, oversubscribed grid
+        const int w = atoi(ev);
+        if (k > 0 && w >= 1 && (size_t)w * pbytes <= max_dyn) {
+          best_w = w;
+          best_total = w * 4;
+        }
+      }
       ph.wpb = best_w;
       ph.smem = (size_t)best_w * pbytes;
       ph.grid = (best_total / best_w) * dev.sm_count;
+      if (getenv("PSD_GEN_PROF"))
+        fprintf(stderr, "[psd eig32 phase %zu] order %d stop %d: %d warps/CTA x %d CTAs/SM, %zu B smem/CTA, %d regs\n", k,
+                ph.n, ph.stop, best_w, best_total / best_w, ph.smem, fa.numRegs);
       phases.push_back(ph);
     }
     if (phases.size() > 9) return fail(PSD_ERR_BAD_ARG, "too many phases");

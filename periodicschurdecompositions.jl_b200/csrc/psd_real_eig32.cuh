@@ -625,7 +625,7 @@ extern __shared__ __align__(16) double psd_smem_eig[];
 // NN, PP > 0 fix the order and period at compile time (packed offsets and strides fold into
 // constants); 0 = taken from the params.
 template <int NN, int PP>
-__global__ void __launch_bounds__(256) rpqr_eig32_kernel_t(EigParams P) {
+__device__ __forceinline__ void rpqr_eig32_body(const EigParams& P) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int n = NN ? NN : P.n, p = PP ? PP : P.p;
   const int psize = pk_problem_size(n, p);
@@ -701,5 +701,16 @@ __global__ void __launch_bounds__(256) rpqr_eig32_kernel_t(EigParams P) {
     __syncwarp();
   }
 }
+
+
+template <int NN, int PP>
+__global__ void __launch_bounds__(256) rpqr_eig32_kernel_t(EigParams P) {
+  rpqr_eig32_body<NN, PP>(P);
+}
+// Register-capped instantiations for the later, small-footprint occupancy phases.  The register
+// file is split over the four SM sub-partitions (16K registers each), so 172 registers per thread
+// allow only 2 warps per sub-partition (8 per SM); <= 168 allow 3 (12 per SM), <= 128 allow 4.
+__global__ void __launch_bounds__(96, 4) rpqr_eig32_kernel_r168(EigParams P) { rpqr_eig32_body<0, 0>(P); }
+__global__ void __launch_bounds__(128, 4) rpqr_eig32_kernel_r128(EigParams P) { rpqr_eig32_body<0, 0>(P); }
 
 }  // namespace psd
