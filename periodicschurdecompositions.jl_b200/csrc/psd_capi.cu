@@ -547,23 +547,17 @@ int run_real_shard(psd_handle_s* h, Device& dev, const RealCall& rc, long long f
   const size_t per = nn * rc.p;  // doubles per problem
   const bool wantZ = rc.wantZ && Z;
   const bool outT = rc.wantT || rc.reduce_only;
-  // chunk: at most ~1 GiB of factors per slot (larger chunks amortise the tail of the persistent
-  // kernels, smaller ones shorten the un-overlapped first copy; 1 GiB measured best for config 2)
-  long long chunk = std::max<long long>(1, (1024LL << 20) / (long long)(per * sizeof(double)));
+  // Chunks grow geometrically (x4) from 1/16 of the full size up to ~2 GiB of factors: the first
+  // host-to-device copy is the only one no kernel overlaps, so it is kept short, while the large
+  // later chunks amortise the tail of the persistent kernels (measured on config 2).
+  long long chunk = std::max<long long>(1, (2048LL << 20) / (long long)(per * sizeof(double)));
   chunk = std::min(chunk, count);
-  if (count > chunk) {
-    // balance chunk sizes
-    long long nchunks = (count + chunk - 1) / chunk;
-    chunk = (count + nchunks - 1) / nchunks;
-  }
   int si = 0;
   int rcode = PSD_OK;
-  // the first chunk is an eighth of the others: its host-to-device copy is the only one that no
-  // kernel overlaps
-  const long long first_chunk = (count > chunk) ? std::max<long long>(1, chunk / 8) : chunk;
-  long long nb = 0;
+  long long nb = 0, next = (count > chunk) ? std::max<long long>(1, chunk / 16) : chunk;
   for (long long off = 0; off < count && rcode == PSD_OK; off += nb, si = (si + 1) % kSlotsPerDevice) {
-    nb = std::min(off == 0 ? first_chunk : chunk, count - off);
+    nb = std::min(next, count - off);
+    next = std::min(chunk, next * 4);
     Slot& s = dev.slots[si];
     if (!s.stream) PSD_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
     // the slot's previous chunk must have fully drained before its buffers are reused
