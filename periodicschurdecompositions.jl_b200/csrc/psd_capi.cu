@@ -41,7 +41,7 @@ int fail(int code, const std::string& msg) {
       return fail(PSD_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));      \
   } while (0)
 
-constexpr int kSlotsPerDevice = 2;
+constexpr int kSlotsPerDevice = 3;
 
 struct Slot {
   cudaStream_t stream = nullptr;
