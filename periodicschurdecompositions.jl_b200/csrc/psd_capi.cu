@@ -509,7 +509,7 @@ int launch_real_large(psd_handle_s* h, Device& dev, Slot& aux, cudaStream_t stre
     P.A = dA; P.Z = wantZ ? dZ : nullptr;
     P.alpha = (psd::cplx*)aux.dX[0]; P.beta = (double*)aux.dX[1]; P.scale = (long long*)aux.dX[2];
     P.info = dInfo;
-    P.use_smem = 0; P.ldh = n; P.debug = 0; P.counter = nullptr;
+    P.use_smem = 0; P.ldh = n; P.debug = 0; P.counter = nullptr; P.blocked_stage1 = 0;
     auto kern = psd::gpschur_team_kernel<double>;
     const size_t smem = (size_t)((psd::cq_small_doubles(n, p) + 1) & ~1LL) * sizeof(double);
     PSD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -693,6 +693,7 @@ int launch_gen_t(psd_handle_s* h, Device& dev, Slot& aux, cudaStream_t stream, c
   P.maxitfac = gc.maxitfac > 0 ? gc.maxitfac : (gc.cplx ? 30 : 120);  // generalized.jl:169, rgeneralized.jl:52
   P.skip_reduce = gc.skip_reduce;
   P.reduce_only = gc.reduce_only;
+  P.blocked_stage1 = 0;
   P.S = aux.dS;
   P.A = (T*)dA; P.Z = wantZ ? (T*)dZ : nullptr;
   P.alpha = (psd::cplx*)dAlpha; P.beta = (T*)dBeta; P.scale = dScale; P.info = dInfo;
@@ -704,6 +705,11 @@ int launch_gen_t(psd_handle_s* h, Device& dev, Slot& aux, cudaStream_t stream, c
   } else {
     if (small > max_dyn) return fail(PSD_ERR_UNSUPPORTED, "n or p too large for the per-CTA state");
     P.use_smem = 0; P.ldh = n; smem = small;
+    const size_t blk = (size_t)psd::blk_work_scalars(n) * sizeof(T);
+    if (!gc.skip_reduce && small + blk <= max_dyn && !getenv("PSD_NO_BLOCKED_STAGE1")) {
+      P.blocked_stage1 = 1;
+      smem = small + blk;
+    }
   }
   PSD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_dyn));
   int occ = 0;

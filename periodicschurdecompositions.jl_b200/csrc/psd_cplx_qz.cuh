@@ -33,6 +33,7 @@ struct GpqzParams {
   long long* scale;         // [batch][n]
   int* info;                // [batch]
   int use_smem, ldh;
+  int blocked_stage1;       // dynamic shared memory holds blk_work_scalars(n) more scalars after the small state
   int debug;                // print a phase breakdown (cycles) for the problems of CTA 0
   unsigned long long* counter;
 };
@@ -1025,6 +1026,7 @@ __global__ void gpschur_kernel(GpqzParams<T> P) {
   cx.stage_in = stage_in;
   cx.wvec = wvec;
   cx.wtid = tid; cx.wnt = nt; cx.lead = true; cx.team = false;
+  cx.blk = P.blocked_stage1 ? mats : nullptr;  // global mode: the matrix area of smem is free
   __shared__ long long s_prof[4];
   cx.prof = P.debug ? s_prof : nullptr;
 
@@ -1148,6 +1150,7 @@ __global__ void gpschur_team_kernel(GpqzParams<T> P, int z_preset) {
   cx.stage = stage; cx.stage_in = stage_in; cx.wvec = wvec; cx.prof = nullptr;
   cx.wtid = blockIdx.x * nt + tid; cx.wnt = gridDim.x * nt;
   cx.lead = blockIdx.x == 0; cx.team = true;
+  cx.blk = nullptr;
   cx.ldh = n; cx.ldz = n;
   for (long long b = 0; b < P.batch; b++) {
     T* Ab = P.A + (size_t)b * p * nn;

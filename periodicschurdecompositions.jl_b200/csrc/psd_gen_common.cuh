@@ -142,6 +142,7 @@ struct GCtx {
   T* stage_in;  // same size: the diagonal blocks of all factors, fetched with ONE parallel load
   long long* prof;  // phase time stamps (debug), or nullptr
   T* wvec;          // n scalars of shared memory: the reflector being applied (Stage 1)
+  T* blk;           // blk_work_scalars(n) scalars of shared memory for the blocked Stage 1, or nullptr
   // Team mode (one large problem on the whole GPU, cooperative launch): every CTA runs the same
   // scalar control flow redundantly on values read from global memory after a grid barrier, the
   // row/column/Z updates are dealt to all threads of the grid (wtid of wnt), single-writer stores
@@ -610,6 +611,282 @@ PSD_DEV void stage1_rq_step(const GCtx<T>& cx, T* Al, T* Am, bool sm1, T* Ql, in
   __syncthreads();
 }
 
+// ------------------------------------------------------------------------------------------
+// Blocked Stage 1 (compact WY), used when the factors live in global memory.
+//
+// The unblocked steps above make two passes over every matrix per reflector; at N = 256..512 with
+// all SMs busy that traffic dominates the whole decomposition (profiles/r1_c5_ncu_full_raw.csv).
+// Here S1_NB reflectors are generated on a panel held in shared memory, their compact-WY form
+// I - V T V^H (dlarft, forward columnwise) is built, and the three big matrices are updated with
+// two passes per PANEL: S1_NB fused multiply-adds per element loaded.
+//
+// The RQ-type factors (S[l] = false) reuse the QR code through the view
+//     B(r, c) = conj(A(n-1-c, n-1-r)):   A = R Q   <=>   B = Qb Rb,   Q = J Qb^H J
+// (J = reversal), so  A_{l-1} Q^H = (A_{l-1} J) Qb J  and  Q A_{l-1} = J Qb^H (J A_{l-1})  are the
+// same right / left block applications on index-reversed views.
+// ------------------------------------------------------------------------------------------
+constexpr int S1_NB = 16;
+
+template <class T>
+struct BlkView {
+  T* p;              // element (0, 0)
+  long long rs, cs;  // element (r, c) at p[r*rs + c*cs]
+  bool cj;           // stored value is the conjugate of the view's value
+};
+template <class T>
+PSD_DEV T bv_get(const BlkView<T>& v, int r, int c) {
+  const T x = v.p[r * v.rs + c * v.cs];
+  return v.cj ? conj_(x) : x;
+}
+template <class T>
+PSD_DEV void bv_set(const BlkView<T>& v, int r, int c, T x) {
+  v.p[r * v.rs + c * v.cs] = v.cj ? conj_(x) : x;
+}
+template <class T>
+PSD_DEV T wsum_t(T d) {
+  if constexpr (sizeof(T) == sizeof(double)) {
+    return warp_sum(d);
+  } else {
+    d.x = warp_sum(d.x);
+    d.y = warp_sum(d.y);
+    return d;
+  }
+}
+
+// shared-memory workspace of the blocked Stage 1: Vs[kb][m] (column q of V at Vs + q*m), Ts, Gs
+template <class T>
+struct BlkWork {
+  T* Vs;
+  T* Ts;  // [S1_NB][S1_NB], T(t,q) at Ts[t + q*S1_NB]
+  T* Gs;  // Gram matrix V^H V, same layout
+  T* taus;
+};
+__host__ __device__ inline long long blk_work_scalars(int n) { return (long long)n * S1_NB + 2 * S1_NB * S1_NB + S1_NB; }
+
+// QR of the panel B[c0:n, c0:c0+kb] (view), reflectors left in W.Vs as an explicit unit lower
+// trapezoid (m x kb), T in W.Ts; the panel of B is overwritten with R (exact zeros below).
+template <class T>
+PSD_DEV void blk_panel_qr(const GCtx<T>& cx, const BlkView<T>& B, int c0, int kb, const BlkWork<T>& W) {
+  const int n = cx.n, tid = cx.tid, nt = cx.nt;
+  const int lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
+  const int m = n - c0;
+  T* Ps = W.Vs;
+  for (int e = tid; e < m * kb; e += nt) Ps[e] = bv_get(B, c0 + e % m, c0 + e / m);
+  __syncthreads();
+  for (int q = 0; q < kb; q++) {
+    const int len = m - q;
+    T* x = Ps + (size_t)q * m + q;
+    double beta;
+    T tau, tv;
+    const bool nontrivial = refl_vec<T, false>(x, 1, len, lane, beta, tau, tv);
+    if (nontrivial) {
+      T* w = cx.wvec;
+      for (int r = tid; r < len; r += nt) w[r] = (r == 0) ? Scalar<T>::one() : tv * x[r];
+      __syncthreads();
+      for (int c = q + 1 + warp; c < kb; c += nw) hh_left_warp<T>(Ps + (size_t)c * m + q, 1, len, w, tau, lane);
+      for (int r = tid; r < len; r += nt) x[r] = (r == 0) ? Scalar<T>::from_real(beta) : w[r];
+      if (tid == 0) W.taus[q] = tau;
+    } else if (tid == 0) {
+      W.taus[q] = Scalar<T>::zero();
+    }
+    __syncthreads();
+  }
+  // R back to the view, then the explicit V (unit diagonal, zeros above)
+  for (int e = tid; e < m * kb; e += nt) {
+    const int r = e % m, q = e / m;
+    bv_set(B, c0 + r, c0 + q, (r <= q) ? Ps[e] : Scalar<T>::zero());
+  }
+  __syncthreads();
+  for (int e = tid; e < kb * kb; e += nt) {
+    const int r = e % kb, q = e / kb;
+    if (r <= q) Ps[(size_t)q * m + r] = (r == q) ? Scalar<T>::one() : Scalar<T>::zero();
+  }
+  __syncthreads();
+  // Gram matrix G(t, q) = V_t^H V_q, t < q (one warp per pair), then T column by column
+  for (int pr = warp; pr < kb * kb; pr += nw) {
+    const int t = pr % kb, q = pr / kb;
+    if (t >= q) continue;
+    T d = Scalar<T>::zero();
+    for (int r = q + lane; r < m; r += 32) d = d + conj_(Ps[(size_t)t * m + r]) * Ps[(size_t)q * m + r];
+    d = wsum_t(d);
+    if (lane == 0) W.Gs[t + q * S1_NB] = d;
+  }
+  __syncthreads();
+  for (int q = 0; q < kb; q++) {
+    if (tid < q) {
+      T acc = Scalar<T>::zero();
+      for (int sidx = tid; sidx < q; sidx++) acc = acc + W.Ts[tid + sidx * S1_NB] * W.Gs[sidx + q * S1_NB];
+      W.Ts[tid + q * S1_NB] = -(W.taus[q] * acc);
+    } else if (tid == q) {
+      W.Ts[q + q * S1_NB] = W.taus[q];
+    }
+    __syncthreads();
+  }
+}
+
+// M <- M (I - V T V^H), M(row, c) at M[row*rs + c*cs], c = 0..m-1; one thread per row.
+// CJ: use conj(V), conj(T) (the operand is stored conjugated).
+template <class T, bool CJ>
+PSD_DEV void blk_apply_right(const GCtx<T>& cx, T* M, long long rs, long long cs, int nrows, int m, int kb,
+                             const BlkWork<T>& W) {
+  const T* Vs = W.Vs;
+  for (int row = cx.tid; row < nrows; row += cx.nt) {
+    T* a = M + row * rs;
+    T acc[S1_NB];
+#pragma unroll
+    for (int q = 0; q < S1_NB; q++) acc[q] = Scalar<T>::zero();
+    for (int c = 0; c < m; c += 4) {
+      T v[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) v[u] = (c + u < m) ? a[(c + u) * cs] : Scalar<T>::zero();
+#pragma unroll
+      for (int u = 0; u < 4; u++)
+        if (c + u < m) {
+#pragma unroll
+          for (int q = 0; q < S1_NB; q++)
+            if (q < kb) {
+              const T vv = Vs[(size_t)q * m + c + u];
+              acc[q] = acc[q] + v[u] * (CJ ? conj_(vv) : vv);
+            }
+        }
+    }
+    T w2[S1_NB];
+#pragma unroll
+    for (int q = 0; q < S1_NB; q++) {
+      T z = Scalar<T>::zero();
+#pragma unroll
+      for (int t = 0; t < S1_NB; t++)
+        if (t <= q && q < kb) {
+          const T tt = W.Ts[t + q * S1_NB];
+          z = z + acc[t] * (CJ ? conj_(tt) : tt);
+        }
+      w2[q] = z;
+    }
+    for (int c = 0; c < m; c += 4) {
+      T v[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) v[u] = (c + u < m) ? a[(c + u) * cs] : Scalar<T>::zero();
+#pragma unroll
+      for (int u = 0; u < 4; u++)
+        if (c + u < m) {
+          T z = v[u];
+#pragma unroll
+          for (int q = 0; q < S1_NB; q++)
+            if (q < kb) {
+              const T vv = Vs[(size_t)q * m + c + u];
+              z = z - w2[q] * (CJ ? vv : conj_(vv));
+            }
+          a[(c + u) * cs] = z;
+        }
+    }
+  }
+}
+
+// M <- (I - V T^H V^H) M, M(r, col) at M[r*rs + col*cs], r = 0..m-1; one warp per column.
+template <class T, bool CJ>
+PSD_DEV void blk_apply_left(const GCtx<T>& cx, T* M, long long rs, long long cs, int ncols, int m, int kb,
+                            const BlkWork<T>& W) {
+  const int lane = cx.tid & 31, warp = cx.tid >> 5, nw = cx.nt >> 5;
+  const T* Vs = W.Vs;
+  for (int col = warp; col < ncols; col += nw) {
+    T* a = M + col * cs;
+    T acc[S1_NB];
+#pragma unroll
+    for (int q = 0; q < S1_NB; q++) acc[q] = Scalar<T>::zero();
+    for (int r = lane; r < m; r += 64) {
+      const T v0 = a[r * rs];
+      const bool h1 = r + 32 < m;
+      const T v1 = h1 ? a[(r + 32) * rs] : Scalar<T>::zero();
+#pragma unroll
+      for (int q = 0; q < S1_NB; q++)
+        if (q < kb) {
+          const T x0 = Vs[(size_t)q * m + r];
+          acc[q] = acc[q] + (CJ ? x0 : conj_(x0)) * v0;
+          if (h1) {
+            const T x1 = Vs[(size_t)q * m + r + 32];
+            acc[q] = acc[q] + (CJ ? x1 : conj_(x1)) * v1;
+          }
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < S1_NB; q++)
+      if (q < kb) acc[q] = wsum_t(acc[q]);
+    T w2[S1_NB];
+#pragma unroll
+    for (int q = 0; q < S1_NB; q++) {
+      T z = Scalar<T>::zero();
+#pragma unroll
+      for (int t = 0; t < S1_NB; t++)
+        if (t <= q && q < kb) {  // (T^H acc)_q = sum_{t <= q} conj(T(t, q)) acc_t
+          const T tt = W.Ts[t + q * S1_NB];
+          z = z + (CJ ? tt : conj_(tt)) * acc[t];
+        }
+      w2[q] = z;
+    }
+    for (int r = lane; r < m; r += 64) {
+      const bool h1 = r + 32 < m;
+      T v0 = a[r * rs];
+      T v1 = h1 ? a[(r + 32) * rs] : Scalar<T>::zero();
+#pragma unroll
+      for (int q = 0; q < S1_NB; q++)
+        if (q < kb) {
+          const T x0 = Vs[(size_t)q * m + r];
+          v0 = v0 - (CJ ? conj_(x0) : x0) * w2[q];
+          if (h1) {
+            const T x1 = Vs[(size_t)q * m + r + 32];
+            v1 = v1 - (CJ ? conj_(x1) : x1) * w2[q];
+          }
+        }
+      a[r * rs] = v0;
+      if (h1) a[(r + 32) * rs] = v1;
+    }
+  }
+}
+
+// Stage 1 for factor l with the blocked scheme (matrices in global memory, leading dimension ld).
+template <class T>
+PSD_DEV void stage1_blocked(const GCtx<T>& cx, int l, const BlkWork<T>& W) {
+  const int n = cx.n, ld = cx.ldh, ldz = cx.ldz;
+  T* Al = cx.Hp(l);
+  T* Am = cx.Hp(l - 1);
+  T* Ql = cx.wantZ ? cx.Zp(l) : nullptr;
+  const bool sl = cx.Sg(l), sm1 = cx.Sg(l - 1);
+  BlkView<T> B;
+  if (sl) {
+    B.p = Al; B.rs = 1; B.cs = ld; B.cj = false;
+  } else {
+    B.p = Al + (n - 1) + (size_t)(n - 1) * ld; B.rs = -(long long)ld; B.cs = -1; B.cj = true;
+  }
+  for (int c0 = 0; c0 < n - 1; c0 += S1_NB) {
+    const int kb = min(S1_NB, n - 1 - c0), m = n - c0, c1 = c0 + kb;
+    blk_panel_qr(cx, B, c0, kb, W);
+    // trailing columns of the factor itself: B[c0:, c1:] <- Qb^H B[c0:, c1:]
+    if (n - c1 > 0) {
+      T* M = B.p + c0 * B.rs + c1 * B.cs;
+      if (B.cj)
+        blk_apply_left<T, true>(cx, M, B.rs, B.cs, n - c1, m, kb, W);
+      else
+        blk_apply_left<T, false>(cx, M, B.rs, B.cs, n - c1, m, kb, W);
+    }
+    if (sl) {
+      // A_{l-1} <- A_{l-1} Qb  or  Qb^H A_{l-1};   Q_l <- Q_l Qb
+      if (sm1)
+        blk_apply_right<T, false>(cx, Am + (size_t)c0 * ld, 1, ld, n, m, kb, W);
+      else
+        blk_apply_left<T, false>(cx, Am + c0, 1, ld, n, m, kb, W);
+      if (Ql) blk_apply_right<T, false>(cx, Ql + (size_t)c0 * ldz, 1, ldz, n, m, kb, W);
+    } else {
+      // Q^H = J Qb J:  A_{l-1} <- (A_{l-1} J) Qb J  or  J Qb^H (J A_{l-1});   Q_l <- (Q_l J) Qb J
+      if (sm1)
+        blk_apply_right<T, false>(cx, Am + (size_t)(n - 1 - c0) * ld, 1, -(long long)ld, n, m, kb, W);
+      else
+        blk_apply_left<T, false>(cx, Am + (n - 1 - c0), -1, ld, n, m, kb, W);
+      if (Ql) blk_apply_right<T, false>(cx, Ql + (size_t)(n - 1 - c0) * ldz, 1, -(long long)ldz, n, m, kb, W);
+    }
+    __syncthreads();
+  }
+}
+
 // _phessenberg!(A, S) (generalized.jl:988-1082) with the Q accumulation fused in.
 template <class T>
 PSD_DEV void gphessenberg_cta(const GCtx<T>& cx) {
@@ -630,7 +907,14 @@ PSD_DEV void gphessenberg_cta(const GCtx<T>& cx) {
     T* Am = cx.Hp(l - 1);
     T* Ql = cx.wantZ ? cx.Zp(l) : nullptr;
     const bool sm1 = cx.Sg(l - 1);
-    if (cx.Sg(l)) {
+    if (cx.blk) {
+      BlkWork<T> W;
+      W.Vs = cx.blk;
+      W.Ts = cx.blk + (size_t)n * S1_NB;
+      W.Gs = W.Ts + S1_NB * S1_NB;
+      W.taus = W.Gs + S1_NB * S1_NB;
+      stage1_blocked(cx, l, W);
+    } else if (cx.Sg(l)) {
       for (int k = 1; k <= n - 1; k++) stage1_qr_step(cx, Al, Am, sm1, Ql, k);
     } else {
       for (int k = n; k >= 2; k--) stage1_rq_step(cx, Al, Am, sm1, Ql, k);
