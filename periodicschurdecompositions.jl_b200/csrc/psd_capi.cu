@@ -510,6 +510,8 @@ int launch_real_large(psd_handle_s* h, Device& dev, Slot& aux, cudaStream_t stre
     P.alpha = (psd::cplx*)aux.dX[0]; P.beta = (double*)aux.dX[1]; P.scale = (long long*)aux.dX[2];
     P.info = dInfo;
     P.use_smem = 0; P.ldh = n; P.debug = 0; P.counter = nullptr; P.blocked_stage1 = 0;
+    P.deep = 0;
+    if (const char* ev = getenv("PSD_DEEP_U")) P.deep = atoi(ev);
     auto kern = psd::gpschur_team_kernel<double>;
     const size_t smem = (size_t)((psd::cq_small_doubles(n, p) + 1) & ~1LL) * sizeof(double);
     PSD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -681,7 +683,11 @@ int launch_gen_t(psd_handle_s* h, Device& dev, Slot& aux, cudaStream_t stream, c
   PSD_CUDA(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev.ordinal));
   int threads = ((2 * n + 31) / 32) * 32;
   threads = std::max(64, std::min(threads, 256));
-  auto kern = psd::gpschur_kernel<T>;
+  // Two instantiations: 255 registers (one 256-thread CTA per SM) and 128 registers (two).  Measured
+  // at C3 / C5 (profiles/r1_gen_variants.txt): the complex path gains 1.5x from the second resident
+  // problem per SM, the real path (longer dependent chains per step, more spills at 128) does not.
+  // (Factors in shared memory: always the 255-register one.)
+  auto kern = psd::gpschur_kernel<T, 256>;
   cudaFuncAttributes fa;
   PSD_CUDA(cudaFuncGetAttributes(&fa, kern));
   const size_t max_dyn = (size_t)optin - fa.sharedSizeBytes;
@@ -702,15 +708,25 @@ int launch_gen_t(psd_handle_s* h, Device& dev, Slot& aux, cudaStream_t stream, c
   size_t smem;
   if (small + mats <= max_dyn) {
     P.use_smem = 1; P.ldh = ldh; smem = small + mats;
+    P.deep = getenv("PSD_DEEP_SMEM") ? 1 : 0;
   } else {
     if (small > max_dyn) return fail(PSD_ERR_UNSUPPORTED, "n or p too large for the per-CTA state");
     P.use_smem = 0; P.ldh = n; smem = small;
+    // table-driven single-pass chases (items in flight per thread), measured as above: a gain for
+    // the complex path, a small loss for the real one
+    P.deep = (sizeof(T) == sizeof(psd::cplx)) ? 2 : 0;
+    if (getenv("PSD_NO_DEEP")) P.deep = 0;
+    if (const char* ev = getenv("PSD_DEEP_U")) P.deep = atoi(ev);
     const size_t blk = (size_t)psd::blk_work_scalars(n) * sizeof(T);
     if (!gc.skip_reduce && small + blk <= max_dyn && !getenv("PSD_NO_BLOCKED_STAGE1")) {
       P.blocked_stage1 = 1;
       smem = small + blk;
     }
   }
+  bool wide = !P.use_smem && sizeof(T) == sizeof(psd::cplx);
+  if (const char* ev = getenv("PSD_GEN_WIDE")) wide = atoi(ev) != 0;
+  if (const char* ev = getenv("PSD_GEN_THREADS")) threads = std::max(64, std::min(atoi(ev), wide ? 512 : 256));
+  if (wide) kern = psd::gpschur_kernel<T, 512>;
   PSD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_dyn));
   int occ = 0;
   PSD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
@@ -743,12 +759,26 @@ int run_gen_shard(psd_handle_s* h, Device& dev, const GenCall& gc, long long fir
   const size_t perB = (size_t)gc.n * gc.n * gc.p * es;  // bytes of factors per problem
   const size_t xB[3] = {(size_t)gc.n * 16, (size_t)gc.n * es, (size_t)gc.n * 8};
   const bool wantZ = gc.wantZ && Z;
+  // One CTA works on one problem (for seconds at the larger orders), so a launch should carry at
+  // least two problems per SM; beyond that, 512 MiB of factors per launch keeps the copies of one
+  // chunk under the kernels of the others.  The cap keeps the slots inside device memory.
+  const bool wantZ0 = gc.wantZ && Z;
   long long chunk = std::max<long long>(1, (512LL << 20) / (long long)perB);
+  chunk = std::max<long long>(chunk, 2LL * dev.sm_count);
+  {
+    size_t free_b = 0, total_b = 0;
+    PSD_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    const size_t per_problem = perB * (wantZ0 ? 2 : 1) + (xB[0] + xB[1] + xB[2]) + 64;
+    const long long cap = (long long)((total_b / 2) / kSlotsPerDevice / per_problem);
+    chunk = std::max<long long>(1, std::min(chunk, cap));
+  }
   chunk = std::min(chunk, count);
   if (count > chunk) {
     long long nchunks = (count + chunk - 1) / chunk;
     chunk = (count + nchunks - 1) / nchunks;
   }
+  // chunks above this size are copied straight from / to pageable memory (no pinned staging copy)
+  const size_t kStageLimit = 1ULL << 30;
   int si = 0;
   for (long long off = 0; off < count; off += chunk, si = (si + 1) % kSlotsPerDevice) {
     const long long nb = std::min(chunk, count - off);
@@ -763,7 +793,8 @@ int run_gen_shard(psd_handle_s* h, Device& dev, const GenCall& gc, long long fir
       if ((e = ensure_dev(s.dX[k], s.capX[k], nb * xB[k]))) return e;
     if ((e = ensure_dev(s.dInfo, s.capInfo, nb * sizeof(int32_t)))) return e;
     char* srcA = A + (size_t)(first + off) * perB;
-    if (pinned) {
+    const bool direct = pinned || bytesA > kStageLimit;
+    if (direct) {
       PSD_CUDA(cudaMemcpyAsync(s.dA, srcA, bytesA, cudaMemcpyHostToDevice, s.stream));
     } else {
       if ((e = ensure_pinned(s.hA, s.hcapA, bytesA))) return e;
@@ -780,7 +811,7 @@ int run_gen_shard(psd_handle_s* h, Device& dev, const GenCall& gc, long long fir
                      ev ? (char*)scale + (size_t)(first + off) * xB[2] : nullptr};
     int32_t* dstInfo = ev ? info + (first + off) : nullptr;
     const size_t bytesInfo = nb * sizeof(int32_t);
-    if (pinned) {
+    if (direct) {
       if (gc.wantT) PSD_CUDA(cudaMemcpyAsync(srcA, s.dA, bytesA, cudaMemcpyDeviceToHost, s.stream));
       if (wantZ) PSD_CUDA(cudaMemcpyAsync(dstZ, s.dZ, bytesA, cudaMemcpyDeviceToHost, s.stream));
       for (int k = 0; k < 3 && ev; k++)

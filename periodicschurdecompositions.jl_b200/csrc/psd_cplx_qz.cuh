@@ -34,6 +34,7 @@ struct GpqzParams {
   int* info;                // [batch]
   int use_smem, ldh;
   int blocked_stage1;       // dynamic shared memory holds blk_work_scalars(n) more scalars after the small state
+  int deep;                 // use the deep (table-driven, single-pass) rotation chases
   int debug;                // print a phase breakdown (cycles) for the problems of CTA 0
   unsigned long long* counter;
 };
@@ -41,8 +42,12 @@ struct GpqzParams {
 // doubles of per-CTA small state: Gc (n+2), Gs 2(n+2), stage (complex: 2(4+3(p-1)); real double
 // chase: 9+6(p-1)), S bytes
 __host__ __device__ inline long long cq_stage_doubles(int p) { return 10LL + 6 * (p > 1 ? p - 1 : 0); }
+// offset of the rotation table of the deep chase variants (12 (p+1) doubles) inside `small`
+__host__ __device__ inline long long cq_rots_offset(int n, int p) {
+  return (5LL * (n + 2) + 2 * cq_stage_doubles(p) + (p + 15) / 8 + 2 + 1) & ~1LL;
+}
 __host__ __device__ inline long long cq_small_doubles(int n, int p) {
-  return 5LL * (n + 2) + 2 * cq_stage_doubles(p) + (p + 15) / 8 + 2;
+  return cq_rots_offset(n, p) + 12LL * (p + 1);
 }
 
 template <class T>
@@ -208,6 +213,77 @@ PSD_DEV void bulk_rot3(int tid, int nt, int total, const Rot2 (&g)[3], Item&& it
   }
 }
 
+// Deep variant of bulk_rot3 (see bulk_rot2_tab): the rotation pair of item w is entry k of a
+// shared-memory table covering all factors of one chase.  item(w, a, st, k).
+template <int U, class Item>
+PSD_DEV void bulk_rot3_tab(int tid, int nt, int total, const Rot2* tab, Item&& item) {
+  for (int w0 = tid; w0 < total; w0 += U * nt) {
+    double* pa[U];
+    int st[U], kk[U];
+    double v0[U], v1[U], v2[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const int w = w0 + u * nt;
+      pa[u] = nullptr;
+      if (w < total) item(w, pa[u], st[u], kk[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++)
+      if (pa[u]) {
+        v0[u] = pa[u][0];
+        v1[u] = pa[u][st[u]];
+        v2[u] = pa[u][2 * st[u]];
+      }
+#pragma unroll
+    for (int u = 0; u < U; u++)
+      if (pa[u]) {
+        const Rot2 gg = tab[kk[u]];
+        rot3(v0[u], v1[u], v2[u], gg);
+        pa[u][0] = v0[u];
+        pa[u][st[u]] = v1[u];
+        pa[u][2 * st[u]] = v2[u];
+      }
+  }
+}
+
+// One link of the double-rotation chain through the 3x3 diagonal block B (upper triangular,
+// B = {b00 b01 b02 b11 b12 b22}) of a triangular factor; gout travels on, B is updated in place.
+PSD_DEV void rot2_chain_step(bool sl, const Rot2& gin, double (&B)[6], Rot2& gout) {
+  double &B00 = B[0], &B01 = B[1], &B02 = B[2], &B11 = B[3], &B12 = B[4], &B22 = B[5];
+  double B10 = 0.0, B21 = 0.0, r;
+  if (sl) {
+    // columns (j+1,j+2) <- G1in; rows (j+1,j+2) re-triangularised by G1out;
+    // columns (j,j+1) <- G2in; rows (j,j+1) re-triangularised by G2out   (:980-991)
+    rrot(B01, B02, gin.c2, gin.s2);
+    rrot(B11, B12, gin.c2, gin.s2);
+    rrot(B21, B22, gin.c2, gin.s2);
+    givens_real(B11, B21, gout.c2, gout.s2, r);
+    B11 = r; B21 = 0.0;
+    rrot(B12, B22, gout.c2, gout.s2);
+    rrot(B00, B01, gin.c1, gin.s1);
+    rrot(B10, B11, gin.c1, gin.s1);
+    givens_real(B00, B10, gout.c1, gout.s1, r);
+    B00 = r; B10 = 0.0;
+    rrot(B01, B11, gout.c1, gout.s1);
+    rrot(B02, B12, gout.c1, gout.s1);
+  } else {
+    // rows (j+1,j+2) <- G1in; columns (j+1,j+2) by G1out (rows <= j+1);
+    // rows (j,j+1) <- G2in; columns (j,j+1) by G2out (rows <= j)           (:993-1004)
+    rrot(B11, B21, gin.c2, gin.s2);
+    rrot(B12, B22, gin.c2, gin.s2);
+    givens_real(B22, -B21, gout.c2, gout.s2, r);
+    B22 = r; B21 = 0.0;
+    rrot(B01, B02, gout.c2, gout.s2);
+    rrot(B11, B12, gout.c2, gout.s2);
+    rrot(B00, B10, gin.c1, gin.s1);
+    rrot(B01, B11, gin.c1, gin.s1);
+    rrot(B02, B12, gin.c1, gin.s1);
+    givens_real(B11, -B10, gout.c1, gout.s1, r);
+    B11 = r; B10 = 0.0;
+    rrot(B00, B01, gout.c1, gout.s1);
+  }
+}
+
 // chase_double: the two rotations G1 = Givens(j+1,j+2), G2 = Givens(j,j+1) act on rows j..j+2
 // of H_1 (columns j..clast), are propagated through factors p..2 (rgeneralized.jl:977-1010) and
 // return to columns j..j+2 of H_1 (rows rfirst..h1r1).  Same organisation as chase_rotation:
@@ -239,6 +315,108 @@ __device__ __noinline__ void chase_double(const GCtx<double>& cx, int j, Rot2 gi
 #pragma unroll
     for (int c = 0; c < 3; c++) X[r][c] = bin[3 * r + c];
   const Rot2 g0 = gin;
+  if (cx.rots) {
+    // Deep variant (see chase_rotation): chain first, then one bulk pass over all factors.
+    Rot2* tab = reinterpret_cast<Rot2*>(cx.rots);
+    const int k1 = 3 * (p - 1);
+    if (tid == 0) {
+      for (int l = p; l >= 2; l--) {
+        const double* bl = bin + 9 + 6 * (l - 2);
+        double Bk[6] = {bl[0], bl[1], bl[2], bl[3], bl[4], bl[5]};
+        Rot2 gout;
+        const bool sl = cx.Sg(l);
+        rot2_chain_step(sl, gin, Bk, gout);
+        const int k = 3 * (l - 2);
+        tab[k] = sl ? gin : gout;      // columns (rows above the block)
+        tab[k + 1] = sl ? gout : gin;  // rows (columns right of the block)
+        tab[k + 2] = gout;             // Z_l
+        double* sg = cx.stage + 9 + 6 * (l - 2);
+#pragma unroll
+        for (int e = 0; e < 6; e++) sg[e] = Bk[e];
+        gin = gout;
+      }
+      tab[k1] = g0;       // rows of H_1 and columns of Z_1
+      tab[k1 + 1] = gin;  // columns of H_1
+#pragma unroll
+      for (int c = 0; c < 3; c++) rot3(X[0][c], X[1][c], X[2][c], g0);
+#pragma unroll
+      for (int r = 0; r < 3; r++) rot3(X[r][0], X[r][1], X[r][2], gin);
+#pragma unroll
+      for (int r = 0; r < 3; r++)
+#pragma unroll
+        for (int c = 0; c < 3; c++) cx.stage[3 * r + c] = X[r][c];
+    }
+    __syncthreads();
+    const int nR = j - rfirst, nL = clast - (j + 2), nZ = cx.wantZ ? n : 0;
+    const int per = nR + nL + nZ, nf = (p - 1) * per;
+    const int nR1 = (h1r1 - rfirst + 1) - 3;
+    const int total = nf + nL + nZ + nR1;
+    const float rper = per > 0 ? 1.0f / (float)per : 0.0f;
+    const int ldz = cx.ldz;
+    auto deep_item = [&](int w, double*& a, int& st, int& k) {
+      if (w < nf) {
+        int f, r;
+        split_index(w, per, rper, f, r);
+        const int l = 2 + f;
+        k = 3 * f;
+        if (r < nR) {
+          a = &PSD_GE(cx.Hp(l), ld, rfirst + r, j);
+          st = ld;
+        } else if (r < nR + nL) {
+          a = &PSD_GE(cx.Hp(l), ld, j, j + 3 + (r - nR));
+          st = 1;
+          k += 1;
+        } else {
+          a = &PSD_GE(cx.Zp(l), ldz, 1 + (r - nR - nL), j);
+          st = ldz;
+          k += 2;
+        }
+      } else {
+        int r = w - nf;
+        if (r < nL) {
+          a = &PSD_GE(H1, ld, j, j + 3 + r);
+          st = 1;
+          k = k1;
+        } else if (r < nL + nZ) {
+          a = &PSD_GE(cx.Zp(1), ldz, 1 + (r - nL), j);
+          st = ldz;
+          k = k1;
+        } else {
+          int row = rfirst + (r - nL - nZ);
+          if (row >= j) row += 3;
+          a = &PSD_GE(H1, ld, row, j);
+          st = ld;
+          k = k1 + 1;
+        }
+      }
+    };
+    if (cx.deep_u == 8)
+      bulk_rot3_tab<6>(cx.wtid, cx.wnt, total, tab, deep_item);
+    else if (cx.deep_u == 2)
+      bulk_rot3_tab<2>(cx.wtid, cx.wnt, total, tab, deep_item);
+    else
+      bulk_rot3_tab<4>(cx.wtid, cx.wnt, total, tab, deep_item);
+    cx.sync();
+    for (int l = 1 + tid; cx.lead && l <= p; l += nt) {
+      if (l == 1) {
+        for (int r = 0; r < 3; r++)
+          for (int c = 0; c < 3; c++) PSD_GE(H1, ld, j + r, j + c) = cx.stage[3 * r + c];
+        if (zcol > 0) {
+          PSD_GE(H1, ld, j, zcol) = r1;
+          PSD_GE(H1, ld, j + 1, zcol) = 0.0;
+          PSD_GE(H1, ld, j + 2, zcol) = 0.0;
+        }
+      } else {
+        double* Hl = cx.Hp(l);
+        const double* sg = cx.stage + 9 + 6 * (l - 2);
+        PSD_GE(Hl, ld, j, j) = sg[0]; PSD_GE(Hl, ld, j, j + 1) = sg[1]; PSD_GE(Hl, ld, j, j + 2) = sg[2];
+        PSD_GE(Hl, ld, j + 1, j) = 0.0; PSD_GE(Hl, ld, j + 1, j + 1) = sg[3]; PSD_GE(Hl, ld, j + 1, j + 2) = sg[4];
+        PSD_GE(Hl, ld, j + 2, j) = 0.0; PSD_GE(Hl, ld, j + 2, j + 1) = 0.0; PSD_GE(Hl, ld, j + 2, j + 2) = sg[5];
+      }
+    }
+    cx.sync();
+    return;
+  }
   {  // left-only columns of H_1 and Z_1
     const int nL = clast - (j + 2);
     const int nZ = cx.wantZ ? n : 0;
@@ -259,41 +437,10 @@ __device__ __noinline__ void chase_double(const GCtx<double>& cx, int j, Rot2 gi
   for (int l = p; l >= 2; l--) {
     double* Hl = cx.Hp(l);
     const double* bl = bin + 9 + 6 * (l - 2);
-    double B00 = bl[0], B01 = bl[1], B02 = bl[2], B11 = bl[3], B12 = bl[4], B22 = bl[5], B10 = 0.0, B21 = 0.0;
+    double Bk[6] = {bl[0], bl[1], bl[2], bl[3], bl[4], bl[5]};
     Rot2 gout;
-    double r;
     const bool sl = cx.Sg(l);
-    if (sl) {
-      // columns (j+1,j+2) <- G1in; rows (j+1,j+2) re-triangularised by G1out;
-      // columns (j,j+1) <- G2in; rows (j,j+1) re-triangularised by G2out   (:980-991)
-      rrot(B01, B02, gin.c2, gin.s2);
-      rrot(B11, B12, gin.c2, gin.s2);
-      rrot(B21, B22, gin.c2, gin.s2);
-      givens_real(B11, B21, gout.c2, gout.s2, r);
-      B11 = r; B21 = 0.0;
-      rrot(B12, B22, gout.c2, gout.s2);
-      rrot(B00, B01, gin.c1, gin.s1);
-      rrot(B10, B11, gin.c1, gin.s1);
-      givens_real(B00, B10, gout.c1, gout.s1, r);
-      B00 = r; B10 = 0.0;
-      rrot(B01, B11, gout.c1, gout.s1);
-      rrot(B02, B12, gout.c1, gout.s1);
-    } else {
-      // rows (j+1,j+2) <- G1in; columns (j+1,j+2) by G1out (rows <= j+1);
-      // rows (j,j+1) <- G2in; columns (j,j+1) by G2out (rows <= j)           (:993-1004)
-      rrot(B11, B21, gin.c2, gin.s2);
-      rrot(B12, B22, gin.c2, gin.s2);
-      givens_real(B22, -B21, gout.c2, gout.s2, r);
-      B22 = r; B21 = 0.0;
-      rrot(B01, B02, gout.c2, gout.s2);
-      rrot(B11, B12, gout.c2, gout.s2);
-      rrot(B00, B10, gin.c1, gin.s1);
-      rrot(B01, B11, gin.c1, gin.s1);
-      rrot(B02, B12, gin.c1, gin.s1);
-      givens_real(B11, -B10, gout.c1, gout.s1, r);
-      B11 = r; B10 = 0.0;
-      rrot(B00, B01, gout.c1, gout.s1);
-    }
+    rot2_chain_step(sl, gin, Bk, gout);
     {
       const Rot2 gR = sl ? gin : gout;  // acts on columns (rows above the block)
       const Rot2 gL = sl ? gout : gin;  // acts on rows (columns right of the block)
@@ -319,7 +466,7 @@ __device__ __noinline__ void chase_double(const GCtx<double>& cx, int j, Rot2 gi
       });
       if (tid == 0) {
         double* sg = cx.stage + 9 + 6 * (l - 2);
-        sg[0] = B00; sg[1] = B01; sg[2] = B02; sg[3] = B11; sg[4] = B12; sg[5] = B22;
+        sg[0] = Bk[0]; sg[1] = Bk[1]; sg[2] = Bk[2]; sg[3] = Bk[3]; sg[4] = Bk[4]; sg[5] = Bk[5];
       }
     }
     gin = gout;
@@ -994,8 +1141,8 @@ PSD_DEV int gpqz_cta(const GCtx<T>& cx, const GqState<T>& st, bool wantT, int ma
 
 extern __shared__ __align__(16) double psd_smem_cq[];
 
-template <class T>
-__global__ void gpschur_kernel(GpqzParams<T> P) {
+template <class T, int MAXT>
+__global__ void __launch_bounds__(MAXT) gpschur_kernel(GpqzParams<T> P) {
   const int n = P.n, p = P.p, tid = threadIdx.x, nt = blockDim.x;
   const size_t nn = (size_t)n * n;
   __shared__ long long s_b;
@@ -1027,6 +1174,8 @@ __global__ void gpschur_kernel(GpqzParams<T> P) {
   cx.wvec = wvec;
   cx.wtid = tid; cx.wnt = nt; cx.lead = true; cx.team = false;
   cx.blk = P.blocked_stage1 ? mats : nullptr;  // global mode: the matrix area of smem is free
+  cx.rots = P.deep ? small + cq_rots_offset(n, p) : nullptr;
+  cx.deep_u = P.deep;
   __shared__ long long s_prof[4];
   cx.prof = P.debug ? s_prof : nullptr;
 
@@ -1151,6 +1300,8 @@ __global__ void gpschur_team_kernel(GpqzParams<T> P, int z_preset) {
   cx.wtid = blockIdx.x * nt + tid; cx.wnt = gridDim.x * nt;
   cx.lead = blockIdx.x == 0; cx.team = true;
   cx.blk = nullptr;
+  cx.rots = P.deep ? small + cq_rots_offset(n, p) : nullptr;
+  cx.deep_u = P.deep;
   cx.ldh = n; cx.ldz = n;
   for (long long b = 0; b < P.batch; b++) {
     T* Ab = P.A + (size_t)b * p * nn;

@@ -143,6 +143,9 @@ struct GCtx {
   long long* prof;  // phase time stamps (debug), or nullptr
   T* wvec;          // n scalars of shared memory: the reflector being applied (Stage 1)
   T* blk;           // blk_work_scalars(n) scalars of shared memory for the blocked Stage 1, or nullptr
+  int deep_u;       // items in flight per thread in the deep variants (0: default)
+  double* rots;     // 12(p+1) doubles of shared memory: rotation table of the deep (latency-hiding)
+                    // chase variants, or nullptr to use the per-factor variants
   // Team mode (one large problem on the whole GPU, cooperative launch): every CTA runs the same
   // scalar control flow redundantly on values read from global memory after a grid barrier, the
   // row/column/Z updates are dealt to all threads of the grid (wtid of wnt), single-writer stores
@@ -220,6 +223,51 @@ PSD_DEV void bulk_rot2(int tid, int nt, int total, Item&& item) {
   }
 }
 
+// Deep variant for factors that live in L2 / HBM: the rotation of item w is looked up in a
+// shared-memory table (rc[k], rs[k]) that covers ALL factors of one chase, so that a single pass
+// with U independent items per thread in flight replaces p dependent passes (one memory round
+// trip each).  item(w, a, off, k): element pair (a[0], a[off]), table entry k.
+template <class T, int U, class Item>
+PSD_DEV void bulk_rot2_tab(int tid, int nt, int total, const double* rc, const T* rs, Item&& item) {
+  for (int w0 = tid; w0 < total; w0 += U * nt) {
+    T* pa[U];
+    int off[U], kk[U];
+    T va[U], vb[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const int w = w0 + u * nt;
+      pa[u] = nullptr;
+      if (w < total) item(w, pa[u], off[u], kk[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++)
+      if (pa[u]) {
+        va[u] = pa[u][0];
+        vb[u] = pa[u][off[u]];
+      }
+#pragma unroll
+    for (int u = 0; u < U; u++)
+      if (pa[u]) {
+        const double c = rc[kk[u]];
+        const T s = rs[kk[u]];
+        pa[u][0] = c * va[u] + s * vb[u];
+        pa[u][off[u]] = c * vb[u] - conj_(s) * va[u];
+      }
+  }
+}
+// w -> (w / per, w % per) with a float reciprocal and a fix-up (w < 2^24)
+PSD_DEV void split_index(int w, int per, float rper, int& q, int& r) {
+  q = (int)((float)w * rper);
+  r = w - q * per;
+  if (r < 0) {
+    q--;
+    r += per;
+  } else if (r >= per) {
+    q++;
+    r -= per;
+  }
+}
+
 // ---- simple CTA-synchronous helpers (used on the rarely taken branches) -------------------
 // lmul!(Givens(i1,i2,c,s), view(M, :, c0:c1)); barrier at the end
 template <class T>
@@ -261,6 +309,48 @@ PSD_DEV double g_opnorm1(const T* M, int ld, int r0, int r1, int c0, int c1, boo
   return m;
 }
 
+// One link of the rotation chain: the incoming rotation (ci, si) meets the 2x2 diagonal block
+// [c00 c01; 0 c11] of a triangular factor (S = true: from the right, S = false: from the left);
+// co, so is the rotation that restores the triangle and travels on, (cR, sR) the one acting on
+// the block's column pair above it, (cL, sL) the one acting on its row pair to the right, m the
+// updated block.
+template <class T>
+struct RotChain {
+  double co, cR, cL;
+  T so, sR, sL, m00, m01, m11;
+};
+template <class T>
+PSD_DEV void rot_chain_step(bool sl, double ci, T si, T c00, T c01, T c11, RotChain<T>& o) {
+  if (sl) {
+    // block * G_in'  then  G_out * block
+    const T n00 = ci * c00 + conj_(si) * c01;
+    const T n01 = ci * c01 - si * c00;
+    const T n10 = conj_(si) * c11;
+    const T n11 = ci * c11;
+    T r;
+    givens_t(n00, n10, o.co, o.so, r);
+    o.m00 = r;
+    o.m01 = o.co * n01 + o.so * n11;
+    o.m11 = o.co * n11 - conj_(o.so) * n01;
+    o.cR = ci; o.sR = si;
+    o.cL = o.co; o.sL = o.so;
+  } else {
+    // G_in * block  then  block * Givens(j+1, j, co, conj(so))'  (rows rfirst..j only)
+    const T n00 = ci * c00;
+    const T n01 = ci * c01 + si * c11;
+    const T n10 = -(conj_(si) * c00);
+    const T n11 = ci * c11 - conj_(si) * c01;
+    T r;
+    givens_t(n11, n10, o.co, o.so, r);
+    o.m01 = o.co * n01 + o.so * n00;
+    o.m00 = o.co * n00 - conj_(o.so) * n01;
+    o.m11 = r;
+    o.cL = ci; o.sL = si;
+    o.so = -o.so;  // equivalent Givens(j, j+1, co, -so)  (generalized.jl:839-840)
+    o.cR = o.co; o.sR = o.so;
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // chase_rotation: apply G1 = Givens(j, j+1, c1, s1) to H_1 from the left (columns h1c0..clast),
 // propagate it through factors p..2 (generalized.jl:823-845 / :1045-1075), apply the rotation
@@ -296,6 +386,112 @@ __device__ __noinline__ void chase_rotation(const GCtx<T>& cx, int j, double c1,
   }
   const T* bin = cx.stage_in;
   const T ha = bin[0], hb = bin[1], hc = bin[2], hd = bin[3];
+  if (cx.rots) {
+    // Deep variant: one thread walks the chain and publishes every rotation, then ONE bulk pass
+    // covers the rows / columns / Z columns of all factors.
+    T* rs = reinterpret_cast<T*>(cx.rots);
+    double* rc = reinterpret_cast<double*>(rs + 3 * p);
+    if (tid == 0) {
+      double ci = c1;
+      T si = s1;
+      for (int l = p; l >= 2; l--) {
+        RotChain<T> o;
+        rot_chain_step<T>(cx.Sg(l), ci, si, bin[4 + 3 * (l - 2)], bin[5 + 3 * (l - 2)], bin[6 + 3 * (l - 2)], o);
+        const int k = 3 * (l - 2);
+        rc[k] = o.cR; rs[k] = conj_(o.sR);
+        rc[k + 1] = o.cL; rs[k + 1] = o.sL;
+        rc[k + 2] = o.co; rs[k + 2] = conj_(o.so);
+        T* st = cx.stage + 4 + 3 * (l - 2);
+        st[0] = o.m00; st[1] = o.m01; st[2] = o.m11;
+        ci = o.co;
+        si = o.so;
+      }
+      const int k = 3 * (p - 1);
+      rc[k] = c1; rs[k] = s1;                // rows (j, j+1) of H_1
+      rc[k + 1] = c1; rs[k + 1] = conj_(s1);  // columns (j, j+1) of Z_1
+      rc[k + 2] = ci; rs[k + 2] = conj_(si);  // columns (j, j+1) of H_1
+      const T a1 = c1 * ha + s1 * hc, b1 = c1 * hb + s1 * hd;
+      const T a2 = c1 * hc - conj_(s1) * ha, b2 = c1 * hd - conj_(s1) * hb;
+      cx.stage[0] = ci * a1 + conj_(si) * b1;
+      cx.stage[1] = ci * b1 - si * a1;
+      cx.stage[2] = ci * a2 + conj_(si) * b2;
+      cx.stage[3] = ci * b2 - si * a2;
+    }
+    __syncthreads();
+    const int nR = j - rfirst, nL = clast - (j + 1), nZ = cx.wantZ ? n : 0;
+    const int per = nR + nL + nZ, nf = (p - 1) * per;
+    const int nL1 = (clast - h1c0 + 1) - 2, nR1 = (h1r1 - rfirst + 1) - 2;
+    const int total = nf + nL1 + nZ + nR1;
+    const float rper = per > 0 ? 1.0f / (float)per : 0.0f;
+    const int ldz = cx.ldz, k1 = 3 * (p - 1);
+    auto deep_item = [&](int w, T*& a, int& off, int& k) {
+      if (w < nf) {
+        int f, r;
+        split_index(w, per, rper, f, r);
+        const int l = 2 + f;
+        k = 3 * f;
+        if (r < nR) {
+          a = &PSD_GE(cx.Hp(l), ld, rfirst + r, j);
+          off = ld;
+        } else if (r < nR + nL) {
+          a = &PSD_GE(cx.Hp(l), ld, j, j + 2 + (r - nR));
+          off = 1;
+          k += 1;
+        } else {
+          a = &PSD_GE(cx.Zp(l), ldz, 1 + (r - nR - nL), j);
+          off = ldz;
+          k += 2;
+        }
+      } else {
+        int r = w - nf;
+        if (r < nL1) {
+          int col = h1c0 + r;
+          if (col >= j) col += 2;
+          a = &PSD_GE(H1, ld, j, col);
+          off = 1;
+          k = k1;
+        } else if (r < nL1 + nZ) {
+          a = &PSD_GE(cx.Zp(1), ldz, 1 + (r - nL1), j);
+          off = ldz;
+          k = k1 + 1;
+        } else {
+          int row = rfirst + (r - nL1 - nZ);
+          if (row >= j) row += 2;
+          a = &PSD_GE(H1, ld, row, j);
+          off = ld;
+          k = k1 + 2;
+        }
+      }
+    };
+    if (cx.deep_u == 8)
+      bulk_rot2_tab<T, 8>(cx.wtid, cx.wnt, total, rc, rs, deep_item);
+    else if (cx.deep_u == 2)
+      bulk_rot2_tab<T, 2>(cx.wtid, cx.wnt, total, rc, rs, deep_item);
+    else
+      bulk_rot2_tab<T, 4>(cx.wtid, cx.wnt, total, rc, rs, deep_item);
+    cx.sync();
+    for (int l = 1 + tid; cx.lead && l <= p; l += nt) {
+      if (l == 1) {
+        PSD_GE(H1, ld, j, j) = cx.stage[0];
+        PSD_GE(H1, ld, j, j + 1) = cx.stage[1];
+        PSD_GE(H1, ld, j + 1, j) = cx.stage[2];
+        PSD_GE(H1, ld, j + 1, j + 1) = cx.stage[3];
+        if (zcol > 0) {
+          PSD_GE(H1, ld, j, zcol) = r1;
+          PSD_GE(H1, ld, j + 1, zcol) = Scalar<T>::zero();
+        }
+      } else {
+        T* Hl = cx.Hp(l);
+        const T* st = cx.stage + 4 + 3 * (l - 2);
+        PSD_GE(Hl, ld, j, j) = st[0];
+        PSD_GE(Hl, ld, j, j + 1) = st[1];
+        PSD_GE(Hl, ld, j + 1, j) = Scalar<T>::zero();
+        PSD_GE(Hl, ld, j + 1, j + 1) = st[2];
+      }
+    }
+    cx.sync();
+    return;
+  }
   double ci = c1;
   T si = s1;
   T b00 = Scalar<T>::zero(), b01 = b00, b11 = b00;
@@ -325,39 +521,10 @@ __device__ __noinline__ void chase_rotation(const GCtx<T>& cx, int j, double c1,
     b00 = bin[4 + 3 * (l - 2)];
     b01 = bin[5 + 3 * (l - 2)];
     b11 = bin[6 + 3 * (l - 2)];
-    const T c00 = b00, c01 = b01, c11 = b11;
-    double co;
-    T so, m00, m01, m11;
-    double cR, cL;  // rotation acting on columns (right-only rows) / on rows (left-only columns)
-    T sR, sL;
-    if (cx.Sg(l)) {
-      // block * G_in'  then  G_out * block
-      const T n00 = ci * c00 + conj_(si) * c01;
-      const T n01 = ci * c01 - si * c00;
-      const T n10 = conj_(si) * c11;
-      const T n11 = ci * c11;
-      T r;
-      givens_t(n00, n10, co, so, r);
-      m00 = r;
-      m01 = co * n01 + so * n11;
-      m11 = co * n11 - conj_(so) * n01;
-      cR = ci; sR = si;
-      cL = co; sL = so;
-    } else {
-      // G_in * block  then  block * Givens(j+1, j, co, conj(so))'  (rows rfirst..j only)
-      const T n00 = ci * c00;
-      const T n01 = ci * c01 + si * c11;
-      const T n10 = -(conj_(si) * c00);
-      const T n11 = ci * c11 - conj_(si) * c01;
-      T r;
-      givens_t(n11, n10, co, so, r);
-      m01 = co * n01 + so * n00;
-      m00 = co * n00 - conj_(so) * n01;
-      m11 = r;
-      cL = ci; sL = si;
-      so = -so;  // equivalent Givens(j, j+1, co, -so)  (generalized.jl:839-840)
-      cR = co; sR = so;
-    }
+    RotChain<T> rc_;
+    rot_chain_step<T>(cx.Sg(l), ci, si, b00, b01, b11, rc_);
+    const double co = rc_.co, cR = rc_.cR, cL = rc_.cL;
+    const T so = rc_.so, sR = rc_.sR, sL = rc_.sL, m00 = rc_.m00, m01 = rc_.m01, m11 = rc_.m11;
     {
       const int nR = j - rfirst;  // rows rfirst..j-1
       const int nL = clast - (j + 1);  // columns j+2..clast
