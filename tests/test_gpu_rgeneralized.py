@@ -125,3 +125,20 @@ def test_real_wrapper(psd):
     assert K.match_eigs(ref, G.values) <= 1e-9 * np.max(np.abs(ref))
     with pytest.raises(ValueError):
         psd.gpschur(mats, [False, True, True], "R")
+
+
+# committed high-precision fixtures (tests/golden/generalized_golden.json), real and complex cases
+from test_oracle_generalized import GGOLD, golden_inputs, golden_tol  # noqa: E402
+
+
+@pytest.mark.parametrize("ci", range(len(GGOLD["cases"])))
+def test_golden_generalized_gpu(psd, ci):
+    case = GGOLD["cases"][ci]
+    A, ref = golden_inputs(case)
+    S = case["S"]
+    T, Z, al, be, sc, info = psd.gpschur_batched(A, S, "L" if case["left"] else "R")
+    assert info[0] == 0
+    lam = _vals(al[0], be[0], sc[0])
+    assert K.match_eigs(ref, lam) <= golden_tol(A, S, ref)
+    K.gpschur_check(A[0], S, T[0], Z[0], al[0], be[0], sc[0], left=case["left"],
+                    real_path=not case["complex"])

@@ -153,3 +153,38 @@ def test_real_larger():
     _check_real(A, [1, 0, 1], OG.rgpschur_batched(A, [1, 0, 1]))
     A = GCs.rand_storage(6, 12, 4, 1, False)
     _check_real(A, [0, 1, 0, 1], OG.rgpschur_batched(A, [0, 1, 0, 1], left=True), True)
+
+
+# ---- committed high-precision fixtures (tests/golden/generalized_golden.json) -----------------
+import json  # noqa: E402
+import os  # noqa: E402
+
+GGOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "generalized_golden.json")))
+
+
+def golden_inputs(case):
+    A = GCs.rand_storage(GGOLD["seed"], case["n"], case["p"], 2, case["complex"])
+    ref = np.array([complex(x, y) for x, y in case["eig"]])
+    return A[case["b"]:case["b"] + 1], ref
+
+
+def golden_tol(A, S, ref):
+    """first-order bound: eps * (product of the factor condition numbers) * |lambda|max, with a
+    floor of 1e-10 relative"""
+    k = 1.0
+    for j in range(A.shape[1]):
+        k *= np.linalg.cond(K.M(A[0, j])) if not S[j] else 1.0
+    return max(1e-10, 1e3 * EPS * k) * np.max(np.abs(ref))
+
+
+@pytest.mark.parametrize("ci", range(len(GGOLD["cases"])))
+def test_golden_generalized_oracle(ci):
+    case = GGOLD["cases"][ci]
+    A, ref = golden_inputs(case)
+    S = case["S"]
+    f = OG.cpschur_batched if case["complex"] else OG.rgpschur_batched
+    T, Z, al, be, sc, info = f(A, S, left=case["left"])
+    assert info[0] == 0
+    with np.errstate(divide="ignore", invalid="ignore", over="ignore"):
+        lam = al[0] / be[0].astype(np.complex128) * np.exp2(sc[0].astype(float))
+    assert K.match_eigs(ref, lam) <= golden_tol(A, S, ref)
