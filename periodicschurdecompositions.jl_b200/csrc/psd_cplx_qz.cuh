@@ -34,6 +34,7 @@ struct GpqzParams {
   int* info;                // [batch]
   int use_smem, ldh;
   int blocked_stage1;       // dynamic shared memory holds blk_work_scalars(n) more scalars after the small state
+  int windowed_stage2;      // dynamic shared memory also covers s2_work_scalars(p) scalars (same area as the blocked Stage 1)
   int deep;                 // use the deep (table-driven, single-pass) rotation chases
   int debug;                // print a phase breakdown (cycles) for the problems of CTA 0
   unsigned long long* counter;
@@ -1139,10 +1140,9 @@ PSD_DEV int gpqz_cta(const GCtx<T>& cx, const GqState<T>& st, bool wantT, int ma
   return 0;
 }
 
-extern __shared__ __align__(16) double psd_smem_cq[];
 
 template <class T, int MAXT>
-__global__ void __launch_bounds__(MAXT) gpschur_kernel(GpqzParams<T> P) {
+__global__ void __launch_bounds__(MAXT, 1) gpschur_kernel(GpqzParams<T> P) {
   const int n = P.n, p = P.p, tid = threadIdx.x, nt = blockDim.x;
   const size_t nn = (size_t)n * n;
   __shared__ long long s_b;
@@ -1176,6 +1176,7 @@ __global__ void __launch_bounds__(MAXT) gpschur_kernel(GpqzParams<T> P) {
   cx.blk = P.blocked_stage1 ? mats : nullptr;  // global mode: the matrix area of smem is free
   cx.rots = P.deep ? small + cq_rots_offset(n, p) : nullptr;
   cx.deep_u = P.deep;
+  cx.s2ws = P.windowed_stage2 ? ((cq_small_doubles(n, p) + 1) & ~1LL) : -1;
   __shared__ long long s_prof[4];
   cx.prof = P.debug ? s_prof : nullptr;
 
@@ -1302,6 +1303,7 @@ __global__ void gpschur_team_kernel(GpqzParams<T> P, int z_preset) {
   cx.blk = nullptr;
   cx.rots = P.deep ? small + cq_rots_offset(n, p) : nullptr;
   cx.deep_u = P.deep;
+  cx.s2ws = -1;
   cx.ldh = n; cx.ldz = n;
   for (long long b = 0; b < P.batch; b++) {
     T* Ab = P.A + (size_t)b * p * nn;

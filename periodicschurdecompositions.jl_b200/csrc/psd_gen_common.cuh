@@ -143,6 +143,8 @@ struct GCtx {
   long long* prof;  // phase time stamps (debug), or nullptr
   T* wvec;          // n scalars of shared memory: the reflector being applied (Stage 1)
   T* blk;           // blk_work_scalars(n) scalars of shared memory for the blocked Stage 1, or nullptr
+  long long s2ws;   // offset (doubles) in dynamic shared memory of the s2_work_scalars(p) workspace of the
+                    // windowed Stage 2, or -1
   int deep_u;       // items in flight per thread in the deep variants (0: default)
   double* rots;     // 12(p+1) doubles of shared memory: rotation table of the deep (latency-hiding)
                     // chase variants, or nullptr to use the per-factor variants
@@ -319,6 +321,36 @@ struct RotChain {
   double co, cR, cL;
   T so, sR, sL, m00, m01, m11;
 };
+// Rotation generation inside the chains.  Real: one reciprocal square root (MUFU seed + two Newton
+// steps, full double precision) instead of a square root and three divisions; same sign convention
+// as givens_real.  Complex: givens_t.
+PSD_DEV double chain_rsqrt(double x) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double hx = 0.5 * x;
+  double e = fma(-hx * y, y, 0.5);
+  y = fma(y, e, y);
+  e = fma(-hx * y, y, 0.5);
+  y = fma(y, e, y);
+  return y;
+}
+PSD_DEV void givens_chain(double f, double g, double& c, double& s, double& r) {
+  const double m = fmax(fabs(f), fabs(g));
+  if (g == 0.0 || f == 0.0 || !(m > 1e-140 && m < 1e140)) {
+    givens_real(f, g, c, s, r);
+    return;
+  }
+  const double t = fma(f, f, g * g);
+  const double y = chain_rsqrt(t);
+  c = f * y;
+  s = g * y;
+  r = t * y;
+  if (fabs(f) > fabs(g) && c < 0.0) {
+    c = -c; s = -s; r = -r;
+  }
+}
+PSD_DEV void givens_chain(cplx f, cplx g, double& c, cplx& s, cplx& r) { givens_t(f, g, c, s, r); }
+
 template <class T>
 PSD_DEV void rot_chain_step(bool sl, double ci, T si, T c00, T c01, T c11, RotChain<T>& o) {
   if (sl) {
@@ -328,7 +360,7 @@ PSD_DEV void rot_chain_step(bool sl, double ci, T si, T c00, T c01, T c11, RotCh
     const T n10 = conj_(si) * c11;
     const T n11 = ci * c11;
     T r;
-    givens_t(n00, n10, o.co, o.so, r);
+    givens_chain(n00, n10, o.co, o.so, r);
     o.m00 = r;
     o.m01 = o.co * n01 + o.so * n11;
     o.m11 = o.co * n11 - conj_(o.so) * n01;
@@ -341,7 +373,7 @@ PSD_DEV void rot_chain_step(bool sl, double ci, T si, T c00, T c01, T c11, RotCh
     const T n10 = -(conj_(si) * c00);
     const T n11 = ci * c11 - conj_(si) * c01;
     T r;
-    givens_t(n11, n10, o.co, o.so, r);
+    givens_chain(n11, n10, o.co, o.so, r);
     o.m01 = o.co * n01 + o.so * n00;
     o.m00 = o.co * n00 - conj_(o.so) * n01;
     o.m11 = r;
@@ -1054,6 +1086,235 @@ PSD_DEV void stage1_blocked(const GCtx<T>& cx, int l, const BlkWork<T>& W) {
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Windowed Stage 2 (factors in global memory).
+//
+// The rotations that zero column jc of H_1 act on the adjacent row pairs (i-1, i), i = n ... jc+2.
+// They are processed S2_K at a time.  Inside one batch everything the rotation chains depend on
+// lives in the (kb+1) x (kb+1) diagonal windows of the triangular factors and in column jc of
+// H_1, so one warp walks the kb chains on copies of those windows in shared memory and records
+// every rotation in a table.  Left and right multiplications commute, so outside the windows a
+// factor only sees a SEQUENCE of column rotations (rows above the window), a sequence of row
+// rotations (columns right of the window), and Z_l a sequence of column rotations: each thread
+// loads the kb+1 adjacent entries of one row / column, applies the whole sequence in registers
+// and stores them back.  Compared with one pass per rotation this halves the traffic, makes the
+// row updates contiguous (kb+1 entries of a column instead of one pair) and needs four barriers
+// per batch instead of three per rotation.  H_1 gets all left rotations first, then all right ones.
+// ------------------------------------------------------------------------------------------
+constexpr int S2_K = 16, S2_W = S2_K + 1;
+__host__ __device__ inline long long s2_work_scalars(int p) {
+  return (long long)(p - 1) * S2_W * S2_W + S2_W + 2LL * S2_K * (3 * (p - 1) + 3) + 8;
+}
+
+// Explicit global-memory accesses (the factor pointers travel through GCtx as generic pointers).
+PSD_DEV double ldg_(const double* p) {
+  double v;
+  asm volatile("ld.global.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  return v;
+}
+PSD_DEV cplx ldg_(const cplx* p) {
+  cplx v;
+  asm volatile("ld.global.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+  return v;
+}
+PSD_DEV void stg_(double* p, double v) { asm volatile("st.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory"); }
+PSD_DEV void stg_(cplx* p, cplx v) {
+  asm volatile("st.global.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(v.x), "d"(v.y) : "memory");
+}
+
+// x[q] <-> ptr[(q - (S2_W - W)) * stride], q = S2_W - W .. S2_W - 1 (W = kb + 1); rotation t acts
+// on the pair (x[S2_W-1-t], x[S2_W-t]) as (a, b) <- (c a + s b, c b - conj(s) a); its entry is at
+// index (t-1)*E of the shared-memory tables rc / rs.  FULL: kb == S2_K, straight-line code.
+template <class T, bool FULL>
+PSD_DEV void s2_apply_seq(T* ptr, long long stride, int kb, const double* rc, const T* rs, int E) {
+  const int sh = FULL ? 0 : S2_W - (kb + 1);
+  T x[S2_W];
+  if (FULL) {
+    double c[S2_K];
+    T sv[S2_K];
+#pragma unroll
+    for (int q = 0; q < S2_W; q++) x[q] = ldg_(ptr + (long long)q * stride);
+#pragma unroll
+    for (int t = 0; t < S2_K; t++) {
+      c[t] = rc[t * E];
+      sv[t] = rs[t * E];
+    }
+#pragma unroll
+    for (int t = 1; t <= S2_K; t++) {
+      const T a = x[S2_W - 1 - t], b = x[S2_W - t];
+      x[S2_W - 1 - t] = c[t - 1] * a + sv[t - 1] * b;
+      x[S2_W - t] = c[t - 1] * b - conj_(sv[t - 1]) * a;
+    }
+#pragma unroll
+    for (int q = 0; q < S2_W; q++) stg_(ptr + (long long)q * stride, x[q]);
+    return;
+  }
+#pragma unroll
+  for (int q = 0; q < S2_W; q++)
+    if (q >= sh) x[q] = ldg_(ptr + (long long)(q - sh) * stride);
+#pragma unroll
+  for (int t = 1; t <= S2_K; t++)
+    if (t <= kb) {
+      const double c = rc[(t - 1) * E];
+      const T sv = rs[(t - 1) * E];
+      const T a = x[S2_W - 1 - t], b = x[S2_W - t];
+      x[S2_W - 1 - t] = c * a + sv * b;
+      x[S2_W - t] = c * b - conj_(sv) * a;
+    }
+#pragma unroll
+  for (int q = 0; q < S2_W; q++)
+    if (q >= sh) stg_(ptr + (long long)(q - sh) * stride, x[q]);
+}
+
+extern __shared__ __align__(16) double psd_smem_cq[];
+
+// ws_off: offset (in doubles) of the workspace inside the kernel's dynamic shared memory; taking
+// the address from the array itself keeps the accesses in the shared state space (LDS / STS).
+template <class T>
+PSD_DEV void stage2_windowed(const GCtx<T>& cx, long long ws_off) {
+  const int n = cx.n, p = cx.p, tid = cx.tid, nt = cx.nt, ld = cx.ldh, ldz = cx.ldz;
+  const int lane = tid & 31, warp = tid >> 5;
+  const int E = 3 * (p - 1) + 3;  // table entries per rotation: (R, L, Z) per factor 2..p, then H1 left, Z1, H1 right
+  T* Dw = reinterpret_cast<T*>(psd_smem_cq + ws_off);  // [(p-1)][S2_W][S2_W], column-major, ld = S2_W
+  T* hcol = Dw + (size_t)(p - 1) * S2_W * S2_W;         // column jc of H_1, rows lo..hi
+  T* rs = hcol + S2_W;                                  // [S2_K][E]
+  double* rc = reinterpret_cast<double*>(rs + (size_t)S2_K * E);
+  T* H1 = cx.Hp(1);
+  const int nZ = cx.wantZ ? n : 0;
+  long long acc0 = 0, acc1 = 0, acc2 = 0, acc3 = 0, tq = 0;  // phase cycles (debug)
+  for (int jc = 1; jc <= n - 2; jc++) {
+    for (int i0 = n; i0 >= jc + 2; i0 -= S2_K) {
+      const int i1 = max(jc + 2, i0 - S2_K + 1);
+      const int kb = i0 - i1 + 1, W = kb + 1, lo = i1 - 1, hi = i0;  // rows / columns lo..hi (1-based)
+      // (1) windows and the generating column into shared memory
+      if (cx.prof) tq = clock64();
+      for (int e = tid; e < (p - 1) * W * W; e += nt) {
+        const int f = e / (W * W), q = e - f * W * W, r = q % W, c = q / W;
+        Dw[(size_t)f * S2_W * S2_W + r + c * S2_W] = ldg_(&PSD_GE(cx.Hp(2 + f), ld, lo + r, lo + c));
+      }
+      for (int e = tid; e < W; e += nt) hcol[e] = ldg_(&PSD_GE(H1, ld, lo + e, jc));
+      __syncthreads();
+      if (cx.prof) { const long long t = clock64(); acc0 += t - tq; tq = t; }
+      // (2) one warp walks the kb rotation chains on the windows
+      if (warp == 0) {
+        for (int t = 1; t <= kb; t++) {
+          const int a = W - 1 - t;  // local index of the upper row / left column of the pair
+          double c1;
+          T s1, r1;
+          givens_chain(hcol[a], hcol[a + 1], c1, s1, r1);
+          __syncwarp();
+          if (lane == 0) {
+            hcol[a] = r1;
+            hcol[a + 1] = Scalar<T>::zero();
+          }
+          double ci = c1;
+          T si = s1;
+          for (int l = p; l >= 2; l--) {
+            T* D = Dw + (size_t)(l - 2) * S2_W * S2_W;
+            RotChain<T> o;
+            rot_chain_step<T>(cx.Sg(l), ci, si, D[a + a * S2_W], D[a + (a + 1) * S2_W], D[a + 1 + (a + 1) * S2_W], o);
+            __syncwarp();
+            if (lane < a) {  // column rotation on the window rows above the block
+              T* pa = D + lane + a * S2_W;
+              const T sv = conj_(o.sR), x = pa[0], y = pa[S2_W];
+              pa[0] = o.cR * x + sv * y;
+              pa[S2_W] = o.cR * y - conj_(sv) * x;
+            } else if (lane >= a + 2 && lane < W) {  // row rotation on the window columns right of it
+              T* pa = D + a + lane * S2_W;
+              const T x = pa[0], y = pa[1];
+              pa[0] = o.cL * x + o.sL * y;
+              pa[1] = o.cL * y - conj_(o.sL) * x;
+            } else if (lane == a) {
+              D[a + a * S2_W] = o.m00;
+              D[a + (a + 1) * S2_W] = o.m01;
+              D[a + 1 + (a + 1) * S2_W] = o.m11;
+              const int k = (t - 1) * E + 3 * (l - 2);
+              rc[k] = o.cR; rs[k] = conj_(o.sR);
+              rc[k + 1] = o.cL; rs[k + 1] = o.sL;
+              rc[k + 2] = o.co; rs[k + 2] = conj_(o.so);
+            }
+            __syncwarp();
+            ci = o.co;
+            si = o.so;
+          }
+          if (lane == 0) {
+            const int k = (t - 1) * E + 3 * (p - 1);
+            rc[k] = c1; rs[k] = s1;                // rows of H_1
+            rc[k + 1] = c1; rs[k + 1] = conj_(s1);  // columns of Z_1
+            rc[k + 2] = ci; rs[k + 2] = conj_(si);  // columns of H_1
+          }
+          __syncwarp();
+        }
+      }
+      __syncthreads();
+      if (cx.prof) { const long long t = clock64(); acc1 += t - tq; tq = t; }
+      // (3) pass A: every strip outside the windows, H_1 from the left, all Z
+      {
+        const int nAb = lo - 1, nRt = n - hi, per = nAb + nRt + nZ, nf = (p - 1) * per;
+        const int nH1 = n - jc, total = nf + nH1 + nZ;
+        const float rper = per > 0 ? 1.0f / (float)per : 0.0f;
+        const int k1 = 3 * (p - 1);
+        for (int w = tid; w < total; w += nt) {
+          T* ptr;
+          long long st;
+          int k;
+          if (w < nf) {
+            int f, r;
+            split_index(w, per, rper, f, r);
+            const int l = 2 + f;
+            k = 3 * f;
+            if (r < nAb) {
+              ptr = &PSD_GE(cx.Hp(l), ld, 1 + r, lo);
+              st = ld;
+            } else if (r < nAb + nRt) {
+              ptr = &PSD_GE(cx.Hp(l), ld, lo, hi + 1 + (r - nAb));
+              st = 1;
+              k += 1;
+            } else {
+              ptr = &PSD_GE(cx.Zp(l), ldz, 1 + (r - nAb - nRt), lo);
+              st = ldz;
+              k += 2;
+            }
+          } else {
+            const int r = w - nf;
+            if (r < nH1) {
+              ptr = &PSD_GE(H1, ld, lo, jc + 1 + r);
+              st = 1;
+              k = k1;
+            } else {
+              ptr = &PSD_GE(cx.Zp(1), ldz, 1 + (r - nH1), lo);
+              st = ldz;
+              k = k1 + 1;
+            }
+          }
+          if (kb == S2_K)
+            s2_apply_seq<T, true>(ptr, st, kb, rc + k, rs + k, E);
+          else
+            s2_apply_seq<T, false>(ptr, st, kb, rc + k, rs + k, E);
+        }
+      }
+      __syncthreads();
+      if (cx.prof) { const long long t = clock64(); acc2 += t - tq; tq = t; }
+      // (4) pass B: H_1 from the right; windows and the generating column back to global memory
+      for (int r = tid; r < n; r += nt) {
+        if (kb == S2_K)
+          s2_apply_seq<T, true>(&PSD_GE(H1, ld, 1 + r, lo), ld, kb, rc + 3 * (p - 1) + 2, rs + 3 * (p - 1) + 2, E);
+        else
+          s2_apply_seq<T, false>(&PSD_GE(H1, ld, 1 + r, lo), ld, kb, rc + 3 * (p - 1) + 2, rs + 3 * (p - 1) + 2, E);
+      }
+      for (int e = tid; e < (p - 1) * W * W; e += nt) {
+        const int f = e / (W * W), q = e - f * W * W, r = q % W, c = q / W;
+        if (r <= c) stg_(&PSD_GE(cx.Hp(2 + f), ld, lo + r, lo + c), Dw[(size_t)f * S2_W * S2_W + r + c * S2_W]);
+      }
+      for (int e = tid; e < W; e += nt) stg_(&PSD_GE(H1, ld, lo + e, jc), hcol[e]);
+      __syncthreads();
+      if (cx.prof) acc3 += clock64() - tq;
+    }
+  }
+  if (cx.prof && tid == 0 && blockIdx.x == 0)
+    printf("[psd stage2 windowed] load %lld  window %lld  passA %lld  passB+store %lld cycles\n", acc0, acc1, acc2, acc3);
+}
+
 // _phessenberg!(A, S) (generalized.jl:988-1082) with the Q accumulation fused in.
 template <class T>
 PSD_DEV void gphessenberg_cta(const GCtx<T>& cx) {
@@ -1089,6 +1350,10 @@ PSD_DEV void gphessenberg_cta(const GCtx<T>& cx) {
   }
   if (cx.prof && tid == 0) cx.prof[0] = clock64();
   // Stage 2 (:1034-1079): rotation (i-1, i) zeroing A_1[i, jc], chased through all factors
+  if (cx.s2ws >= 0) {
+    stage2_windowed<T>(cx, cx.s2ws);
+    return;
+  }
   T* A1 = cx.Hp(1);
   for (int jc = 1; jc <= n - 2; jc++) {
     for (int i = n; i >= jc + 2; i--) {
