@@ -509,7 +509,7 @@ int launch_real_large(psd_handle_s* h, Device& dev, Slot& aux, cudaStream_t stre
     P.A = dA; P.Z = wantZ ? dZ : nullptr;
     P.alpha = (psd::cplx*)aux.dX[0]; P.beta = (double*)aux.dX[1]; P.scale = (long long*)aux.dX[2];
     P.info = dInfo;
-    P.use_smem = 0; P.ldh = n; P.debug = 0; P.counter = nullptr; P.blocked_stage1 = 0; P.windowed_stage2 = 0;
+    P.use_smem = 0; P.ldh = n; P.debug = 0; P.counter = nullptr; P.blocked_stage1 = 0; P.windowed_stage2 = 0; P.windowed_qz = 0;
     P.deep = 4;  // team mode: < 1 element pair per thread and factor, one pass instead of p + 1 (N = 1024: 7.1 s -> 5.3 s)
     if (const char* ev = getenv("PSD_DEEP_U")) P.deep = atoi(ev);
     auto kern = psd::gpschur_team_kernel<double>;
@@ -701,6 +701,7 @@ int launch_gen_t(psd_handle_s* h, Device& dev, Slot& aux, cudaStream_t stream, c
   P.reduce_only = gc.reduce_only;
   P.blocked_stage1 = 0;
   P.windowed_stage2 = 0;
+  P.windowed_qz = 0;
   P.S = aux.dS;
   P.A = (T*)dA; P.Z = wantZ ? (T*)dZ : nullptr;
   P.alpha = (psd::cplx*)dAlpha; P.beta = (T*)dBeta; P.scale = dScale; P.info = dInfo;
@@ -722,6 +723,11 @@ int launch_gen_t(psd_handle_s* h, Device& dev, Slot& aux, cudaStream_t stream, c
     if (!gc.skip_reduce && small + blk <= max_dyn && !getenv("PSD_NO_BLOCKED_STAGE1")) {
       P.blocked_stage1 = 1;
       smem = small + blk;
+    }
+    const size_t qzw = (size_t)psd::qzw_work_doubles(p) * sizeof(double);
+    if (sizeof(T) == sizeof(double) && !gc.reduce_only && small + qzw <= max_dyn && !getenv("PSD_NO_WINDOWED_QZ")) {
+      P.windowed_qz = 1;
+      smem = std::max(smem, small + qzw);
     }
     const size_t s2w = (size_t)psd::s2_work_scalars(p) * sizeof(T);
     if (!gc.skip_reduce && small + s2w <= max_dyn && !getenv("PSD_NO_WINDOWED_STAGE2")) {

@@ -34,6 +34,7 @@ struct GpqzParams {
   int* info;                // [batch]
   int use_smem, ldh;
   int blocked_stage1;       // dynamic shared memory holds blk_work_scalars(n) more scalars after the small state
+  int windowed_qz;          // dynamic shared memory also covers qzw_work_doubles(p) doubles (real path, same area)
   int windowed_stage2;      // dynamic shared memory also covers s2_work_scalars(p) scalars (same area as the blocked Stage 1)
   int deep;                 // use the deep (table-driven, single-pass) rotation chases
   int debug;                // print a phase breakdown (cycles) for the problems of CTA 0
@@ -630,6 +631,177 @@ PSD_DEV bool rq_block2x2(const GCtx<double>& cx, int j, int ifirstm, int ilastm,
   return true;
 }
 
+// ------------------------------------------------------------------------------------------
+// Windowed double-shift sweep (factors in global memory), the QZ counterpart of stage2_windowed.
+//
+// S3_K consecutive bulge steps j = j0 .. j0+kb-1 only read and write, as far as the rotation
+// chains are concerned, the diagonal windows [j0-1, j0+kb+2]^2 of H_1 and of the triangular
+// factors.  One warp runs the kb steps on copies of the windows in shared memory (bulge column,
+// 3x3 blocks, in-window row / column updates) and tabulates every rotation pair; afterwards each
+// thread takes one row above the windows, one column right of them or one row of a Z_l, loads its
+// <= S3_W entries, applies the whole sequence of 3-element rotations in registers and stores them.
+// Local index q <-> global index j0 - 1 + q; step s acts on q = s+1, s+2, s+3.
+// ------------------------------------------------------------------------------------------
+constexpr int S3_K = 12, S3_W = S3_K + 4;
+__host__ __device__ inline long long qzw_work_doubles(int p) {
+  return (long long)p * S3_W * S3_W + 4LL * S3_K * (3 * (p - 1) + 2) + 8;
+}
+
+template <bool FULL>
+PSD_DEV void s3_apply_seq(double* ptr, long long stride, int qmin, int qmax, int kb, const Rot2* tab, int E) {
+  double x[S3_W];
+  if (FULL) {
+#pragma unroll
+    for (int q = 0; q < S3_W; q++) x[q] = ldg_(ptr + (long long)q * stride);
+#pragma unroll
+    for (int sx = 0; sx < S3_K; sx++) {
+      const Rot2 g = tab[sx * E];
+      rot3(x[sx + 1], x[sx + 2], x[sx + 3], g);
+    }
+#pragma unroll
+    for (int q = 0; q < S3_W; q++) stg_(ptr + (long long)q * stride, x[q]);
+    return;
+  }
+#pragma unroll
+  for (int q = 0; q < S3_W; q++)
+    if (q >= qmin && q <= qmax) x[q] = ldg_(ptr + (long long)q * stride);
+#pragma unroll
+  for (int sx = 0; sx < S3_K; sx++)
+    if (sx < kb) {
+      const Rot2 g = tab[sx * E];
+      rot3(x[sx + 1], x[sx + 2], x[sx + 3], g);
+    }
+#pragma unroll
+  for (int q = 0; q < S3_W; q++)
+    if (q >= qmin && q <= qmax) stg_(ptr + (long long)q * stride, x[q]);
+}
+
+// Steps j = ifirst .. ilast-2 of one sweep; g = the two starting rotations.  The trailing single
+// rotation is left to the caller.
+PSD_DEV void sweep_windowed(const GCtx<double>& cx, int ifirst, int ilast, int ifirstm, int ilastm, Rot2 g,
+                            long long ws_off) {
+  const int n = cx.n, p = cx.p, tid = cx.tid, nt = cx.nt, ld = cx.ldh, ldz = cx.ldz;
+  const int lane = tid & 31, warp = tid >> 5;
+  const int E = 3 * (p - 1) + 2;
+  constexpr int WW = S3_W * S3_W;
+  double* Xw = psd_smem_cq + ws_off;  // window of H_1, column-major, ld = S3_W
+  double* Dw = Xw + WW;               // windows of factors 2..p
+  Rot2* tab = reinterpret_cast<Rot2*>(Dw + (size_t)(p - 1) * WW);
+  double* H1 = cx.Hp(1);
+  const int nZ = cx.wantZ ? n : 0;
+  for (int j0 = ifirst; j0 <= ilast - 2; j0 += S3_K) {
+    const int j1 = min(ilast - 2, j0 + S3_K - 1), kb = j1 - j0 + 1;
+    const int base = j0 - 1;  // global index of local q = 0
+    const int qmin = (base >= ifirstm) ? 0 : 1;
+    const int qmax = min(j1 + 3, ilast) - base;
+    // (1) windows into shared memory (entries outside [qmin, qmax] are never touched)
+    for (int e = tid; e < p * WW; e += nt) {
+      const int f = e / WW, q = e - f * WW, r = q % S3_W, c = q / S3_W;
+      if (r >= qmin && r <= qmax && c >= qmin && c <= qmax)
+        (f == 0 ? Xw : Dw + (size_t)(f - 1) * WW)[r + c * S3_W] = ldg_(&PSD_GE(cx.Hp(1 + f), ld, base + r, base + c));
+    }
+    __syncthreads();
+    // (2) one warp runs the kb bulge steps on the windows
+    if (warp == 0) {
+      for (int sx = 0; sx < kb; sx++) {
+        const int j = j0 + sx, a = sx + 1;
+        if (j > ifirst) {
+          double r2, r1;
+          givens_chain(Xw[a + 1 + (a - 1) * S3_W], Xw[a + 2 + (a - 1) * S3_W], g.c2, g.s2, r2);
+          givens_chain(Xw[a + (a - 1) * S3_W], r2, g.c1, g.s1, r1);
+          __syncwarp();
+          if (lane == 0) {
+            Xw[a + (a - 1) * S3_W] = r1;
+            Xw[a + 1 + (a - 1) * S3_W] = 0.0;
+            Xw[a + 2 + (a - 1) * S3_W] = 0.0;
+          }
+        }
+        // rows a..a+2 of the H_1 window, columns a..qmax
+        if (lane >= a && lane <= qmax) {
+          double* c0 = Xw + a + lane * S3_W;
+          rot3(c0[0], c0[1], c0[2], g);
+        }
+        if (lane == 0) tab[sx * E + 3 * (p - 1)] = g;
+        Rot2 gin = g;
+        for (int l = p; l >= 2; l--) {
+          double* D = Dw + (size_t)(l - 2) * WW;
+          double Bk[6] = {D[a + a * S3_W], D[a + (a + 1) * S3_W], D[a + (a + 2) * S3_W],
+                          D[a + 1 + (a + 1) * S3_W], D[a + 1 + (a + 2) * S3_W], D[a + 2 + (a + 2) * S3_W]};
+          Rot2 gout;
+          const bool sl = cx.Sg(l);
+          rot2_chain_step(sl, gin, Bk, gout);
+          __syncwarp();
+          const Rot2 gR = sl ? gin : gout, gL = sl ? gout : gin;
+          if (lane >= qmin && lane < a) {  // rows above the block: columns a..a+2
+            double* r0 = D + lane + a * S3_W;
+            rot3(r0[0], r0[S3_W], r0[2 * S3_W], gR);
+          } else if (lane >= a + 3 && lane <= qmax) {  // columns right of the block: rows a..a+2
+            double* c0 = D + a + lane * S3_W;
+            rot3(c0[0], c0[1], c0[2], gL);
+          } else if (lane == a) {
+            D[a + a * S3_W] = Bk[0]; D[a + (a + 1) * S3_W] = Bk[1]; D[a + (a + 2) * S3_W] = Bk[2];
+            D[a + 1 + (a + 1) * S3_W] = Bk[3]; D[a + 1 + (a + 2) * S3_W] = Bk[4];
+            D[a + 2 + (a + 2) * S3_W] = Bk[5];
+            const int k = sx * E + 3 * (l - 2);
+            tab[k] = gR;
+            tab[k + 1] = gL;
+            tab[k + 2] = gout;
+          }
+          __syncwarp();
+          gin = gout;
+        }
+        __syncwarp();
+        // columns a..a+2 of the H_1 window, rows qmin..min(a+3, qmax)
+        if (lane >= qmin && lane <= min(a + 3, qmax)) {
+          double* r0 = Xw + lane + a * S3_W;
+          rot3(r0[0], r0[S3_W], r0[2 * S3_W], gin);
+        }
+        if (lane == 0) tab[sx * E + 3 * (p - 1) + 1] = gin;
+        __syncwarp();
+      }
+    }
+    __syncthreads();
+    // (3) the strips outside the windows and all Z
+    {
+      const int lo = base + qmin, hi = base + qmax;
+      const int nAb = lo - ifirstm, nRt = ilastm - hi, per = nAb + nRt + nZ, total = p * per;
+      const float rper = per > 0 ? 1.0f / (float)per : 0.0f;
+      const bool full = (qmin == 0 && qmax == S3_W - 1 && kb == S3_K);
+      for (int w = tid; w < total; w += nt) {
+        int f, r;
+        split_index(w, per, rper, f, r);  // f = 0: H_1 / Z_1, f >= 1: factor 1 + f
+        double* ptr;
+        long long st;
+        int k;
+        if (r < nAb) {  // row above the window, window columns: column rotations
+          ptr = &PSD_GE(cx.Hp(1 + f), ld, ifirstm + r, base);
+          st = ld;
+          k = (f == 0) ? 3 * (p - 1) + 1 : 3 * (f - 1);
+        } else if (r < nAb + nRt) {  // column right of the window, window rows: row rotations
+          ptr = &PSD_GE(cx.Hp(1 + f), ld, base, hi + 1 + (r - nAb));
+          st = 1;
+          k = (f == 0) ? 3 * (p - 1) : 3 * (f - 1) + 1;
+        } else {
+          ptr = &PSD_GE(cx.Zp(1 + f), ldz, 1 + (r - nAb - nRt), base);
+          st = ldz;
+          k = (f == 0) ? 3 * (p - 1) : 3 * (f - 1) + 2;
+        }
+        if (full)
+          s3_apply_seq<true>(ptr, st, qmin, qmax, kb, tab + k, E);
+        else
+          s3_apply_seq<false>(ptr, st, qmin, qmax, kb, tab + k, E);
+      }
+    }
+    // (4) windows back to global memory (disjoint from the strips)
+    for (int e = tid; e < p * WW; e += nt) {
+      const int f = e / WW, q = e - f * WW, r = q % S3_W, c = q / S3_W;
+      if (r >= qmin && r <= qmax && c >= qmin && c <= qmax && (f == 0 || r <= c))
+        stg_(&PSD_GE(cx.Hp(1 + f), ld, base + r, base + c), (f == 0 ? Xw : Dw + (size_t)(f - 1) * WW)[r + c * S3_W]);
+    }
+    __syncthreads();
+  }
+}
+
 // One double-shift sweep on the active block ifirst..ilast (order >= 3).
 PSD_DEV void rq_double_shift_sweep(const GCtx<double>& cx, int ifirst, int ilast, int ifirstm, int ilastm,
                                    int iiter, int& nexc) {
@@ -705,6 +877,9 @@ PSD_DEV void rq_double_shift_sweep(const GCtx<double>& cx, int ifirst, int ilast
   double r2, r1;
   givens_real(v1, v2, g.c2, g.s2, r2);
   givens_real(v0, r2, g.c1, g.s1, r1);
+  if (cx.qzws >= 0 && ilast - ifirst - 1 >= 4) {
+    sweep_windowed(cx, ifirst, ilast, ifirstm, ilastm, g, cx.qzws);
+  } else
   for (int j = ifirst; j <= ilast - 2; j++) {
     int zcol = 0;
     if (j > ifirst) {
@@ -1177,6 +1352,7 @@ __global__ void __launch_bounds__(MAXT, 1) gpschur_kernel(GpqzParams<T> P) {
   cx.rots = P.deep ? small + cq_rots_offset(n, p) : nullptr;
   cx.deep_u = P.deep;
   cx.s2ws = P.windowed_stage2 ? ((cq_small_doubles(n, p) + 1) & ~1LL) : -1;
+  cx.qzws = P.windowed_qz ? ((cq_small_doubles(n, p) + 1) & ~1LL) : -1;
   __shared__ long long s_prof[4];
   cx.prof = P.debug ? s_prof : nullptr;
 
@@ -1304,6 +1480,7 @@ __global__ void gpschur_team_kernel(GpqzParams<T> P, int z_preset) {
   cx.rots = P.deep ? small + cq_rots_offset(n, p) : nullptr;
   cx.deep_u = P.deep;
   cx.s2ws = -1;
+  cx.qzws = -1;
   cx.ldh = n; cx.ldz = n;
   for (long long b = 0; b < P.batch; b++) {
     T* Ab = P.A + (size_t)b * p * nn;

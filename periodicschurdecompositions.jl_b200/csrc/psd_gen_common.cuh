@@ -145,6 +145,7 @@ struct GCtx {
   T* blk;           // blk_work_scalars(n) scalars of shared memory for the blocked Stage 1, or nullptr
   long long s2ws;   // offset (doubles) in dynamic shared memory of the s2_work_scalars(p) workspace of the
                     // windowed Stage 2, or -1
+  long long qzws;   // same for the windowed double-shift sweep (qzw_work_doubles(p) doubles), or -1
   int deep_u;       // items in flight per thread in the deep variants (0: default)
   double* rots;     // 12(p+1) doubles of shared memory: rotation table of the deep (latency-hiding)
                     // chase variants, or nullptr to use the per-factor variants
