@@ -724,8 +724,9 @@ int launch_gen_t(psd_handle_s* h, Device& dev, Slot& aux, cudaStream_t stream, c
       P.blocked_stage1 = 1;
       smem = small + blk;
     }
-    const size_t qzw = (size_t)psd::qzw_work_doubles(p) * sizeof(double);
-    if (sizeof(T) == sizeof(double) && !gc.reduce_only && small + qzw <= max_dyn && !getenv("PSD_NO_WINDOWED_QZ")) {
+    const size_t qzw = sizeof(T) == sizeof(double) ? (size_t)psd::qzw_work_doubles(p) * sizeof(double)
+                                                   : (size_t)psd::s4_work_scalars<T>(p) * sizeof(T);
+    if (!gc.reduce_only && small + qzw <= max_dyn && !getenv("PSD_NO_WINDOWED_QZ")) {
       P.windowed_qz = 1;
       smem = std::max(smem, small + qzw);
     }

@@ -898,6 +898,189 @@ PSD_DEV void rq_double_shift_sweep(const GCtx<double>& cx, int ifirst, int ilast
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Windowed single-shift sweep (complex path, factors in global memory): same organisation as
+// sweep_windowed with one rotation per step.  Local index q <-> global index j0 - 1 + q; step s
+// acts on q = s+1, s+2.  Rotations are tabulated in the bulk convention
+// (a, b) <- (c a + s b, c b - conj(s) a).
+// ------------------------------------------------------------------------------------------
+template <class T>
+struct S4 {
+  static constexpr int K = (sizeof(T) == sizeof(double)) ? 13 : 9;
+  static constexpr int W = K + 3;
+};
+template <class T>
+__host__ __device__ inline long long s4_work_scalars(int p) {
+  return (long long)p * S4<T>::W * S4<T>::W + 2LL * S4<T>::K * (3 * (p - 1) + 3) + 8;
+}
+
+template <class T, bool FULL>
+PSD_DEV void s4_apply_seq(T* ptr, long long stride, int qmin, int qmax, int kb, const double* rc, const T* rs, int E) {
+  constexpr int K = S4<T>::K, W = S4<T>::W;
+  T x[W];
+  if (FULL) {
+#pragma unroll
+    for (int q = 0; q < W; q++) x[q] = ldg_(ptr + (long long)q * stride);
+#pragma unroll
+    for (int sx = 0; sx < K; sx++) {
+      const double c = rc[sx * E];
+      const T sv = rs[sx * E];
+      const T a = x[sx + 1], b = x[sx + 2];
+      x[sx + 1] = c * a + sv * b;
+      x[sx + 2] = c * b - conj_(sv) * a;
+    }
+#pragma unroll
+    for (int q = 0; q < W; q++) stg_(ptr + (long long)q * stride, x[q]);
+    return;
+  }
+#pragma unroll
+  for (int q = 0; q < W; q++)
+    if (q >= qmin && q <= qmax) x[q] = ldg_(ptr + (long long)q * stride);
+#pragma unroll
+  for (int sx = 0; sx < K; sx++)
+    if (sx < kb) {
+      const double c = rc[sx * E];
+      const T sv = rs[sx * E];
+      const T a = x[sx + 1], b = x[sx + 2];
+      x[sx + 1] = c * a + sv * b;
+      x[sx + 2] = c * b - conj_(sv) * a;
+    }
+#pragma unroll
+  for (int q = 0; q < W; q++)
+    if (q >= qmin && q <= qmax) stg_(ptr + (long long)q * stride, x[q]);
+}
+
+// Steps j = ifirst .. ilast-1 of one single-shift sweep; (c, s) = the starting rotation.
+template <class T>
+PSD_DEV void sweep1_windowed(const GCtx<T>& cx, int ifirst, int ilast, int ifirstm, int ilastm, double c0, T s0,
+                             long long ws_off) {
+  constexpr int K = S4<T>::K, W = S4<T>::W, WW = W * W;
+  const int n = cx.n, p = cx.p, tid = cx.tid, nt = cx.nt, ld = cx.ldh, ldz = cx.ldz;
+  const int lane = tid & 31, warp = tid >> 5;
+  const int E = 3 * (p - 1) + 3;
+  T* Xw = reinterpret_cast<T*>(psd_smem_cq + ws_off);  // window of H_1, column-major, ld = W
+  T* Dw = Xw + WW;                                      // windows of factors 2..p
+  T* rs = Dw + (size_t)(p - 1) * WW;
+  double* rc = reinterpret_cast<double*>(rs + (size_t)K * E);
+  T* H1 = cx.Hp(1);
+  const int nZ = cx.wantZ ? n : 0;
+  for (int j0 = ifirst; j0 <= ilast - 1; j0 += K) {
+    const int j1 = min(ilast - 1, j0 + K - 1), kb = j1 - j0 + 1;
+    const int base = j0 - 1;
+    const int qmin = (base >= ifirstm) ? 0 : 1;
+    const int qmax = min(j1 + 2, ilast) - base;
+    for (int e = tid; e < p * WW; e += nt) {
+      const int f = e / WW, q = e - f * WW, r = q % W, c = q / W;
+      if (r >= qmin && r <= qmax && c >= qmin && c <= qmax)
+        (f == 0 ? Xw : Dw + (size_t)(f - 1) * WW)[r + c * W] = ldg_(&PSD_GE(cx.Hp(1 + f), ld, base + r, base + c));
+    }
+    __syncthreads();
+    if (warp == 0) {
+      for (int sx = 0; sx < kb; sx++) {
+        const int j = j0 + sx, a = sx + 1;
+        double c1 = c0;
+        T s1 = s0;
+        if (j > ifirst) {
+          T r1;
+          givens_chain(Xw[a + (a - 1) * W], Xw[a + 1 + (a - 1) * W], c1, s1, r1);
+          __syncwarp();
+          if (lane == 0) {
+            Xw[a + (a - 1) * W] = r1;
+            Xw[a + 1 + (a - 1) * W] = Scalar<T>::zero();
+          }
+        }
+        if (lane >= a && lane <= qmax) {  // rows a, a+1 of the H_1 window
+          T* pa = Xw + a + lane * W;
+          const T x = pa[0], y = pa[1];
+          pa[0] = c1 * x + s1 * y;
+          pa[1] = c1 * y - conj_(s1) * x;
+        }
+        double ci = c1;
+        T si = s1;
+        for (int l = p; l >= 2; l--) {
+          T* D = Dw + (size_t)(l - 2) * WW;
+          RotChain<T> o;
+          rot_chain_step<T>(cx.Sg(l), ci, si, D[a + a * W], D[a + (a + 1) * W], D[a + 1 + (a + 1) * W], o);
+          __syncwarp();
+          if (lane >= qmin && lane < a) {
+            T* pa = D + lane + a * W;
+            const T sv = conj_(o.sR), x = pa[0], y = pa[W];
+            pa[0] = o.cR * x + sv * y;
+            pa[W] = o.cR * y - conj_(sv) * x;
+          } else if (lane >= a + 2 && lane <= qmax) {
+            T* pa = D + a + lane * W;
+            const T x = pa[0], y = pa[1];
+            pa[0] = o.cL * x + o.sL * y;
+            pa[1] = o.cL * y - conj_(o.sL) * x;
+          } else if (lane == a) {
+            D[a + a * W] = o.m00;
+            D[a + (a + 1) * W] = o.m01;
+            D[a + 1 + (a + 1) * W] = o.m11;
+            const int k = sx * E + 3 * (l - 2);
+            rc[k] = o.cR; rs[k] = conj_(o.sR);
+            rc[k + 1] = o.cL; rs[k + 1] = o.sL;
+            rc[k + 2] = o.co; rs[k + 2] = conj_(o.so);
+          }
+          __syncwarp();
+          ci = o.co;
+          si = o.so;
+        }
+        __syncwarp();
+        if (lane >= qmin && lane <= min(a + 2, qmax)) {  // columns a, a+1 of the H_1 window
+          T* pa = Xw + lane + a * W;
+          const T sv = conj_(si), x = pa[0], y = pa[W];
+          pa[0] = ci * x + sv * y;
+          pa[W] = ci * y - conj_(sv) * x;
+        }
+        if (lane == 0) {
+          const int k = sx * E + 3 * (p - 1);
+          rc[k] = c1; rs[k] = s1;                // rows of H_1
+          rc[k + 1] = c1; rs[k + 1] = conj_(s1);  // columns of Z_1
+          rc[k + 2] = ci; rs[k + 2] = conj_(si);  // columns of H_1
+        }
+        __syncwarp();
+      }
+    }
+    __syncthreads();
+    {
+      const int lo = base + qmin, hi = base + qmax;
+      const int nAb = lo - ifirstm, nRt = ilastm - hi, per = nAb + nRt + nZ, total = p * per;
+      const float rper = per > 0 ? 1.0f / (float)per : 0.0f;
+      const bool full = (qmin == 0 && qmax == W - 1 && kb == K);
+      for (int w = tid; w < total; w += nt) {
+        int f, r;
+        split_index(w, per, rper, f, r);  // f = 0: H_1 / Z_1, f >= 1: factor 1 + f
+        T* ptr;
+        long long st;
+        int k;
+        if (r < nAb) {
+          ptr = &PSD_GE(cx.Hp(1 + f), ld, ifirstm + r, base);
+          st = ld;
+          k = (f == 0) ? 3 * (p - 1) + 2 : 3 * (f - 1);
+        } else if (r < nAb + nRt) {
+          ptr = &PSD_GE(cx.Hp(1 + f), ld, base, hi + 1 + (r - nAb));
+          st = 1;
+          k = (f == 0) ? 3 * (p - 1) : 3 * (f - 1) + 1;
+        } else {
+          ptr = &PSD_GE(cx.Zp(1 + f), ldz, 1 + (r - nAb - nRt), base);
+          st = ldz;
+          k = (f == 0) ? 3 * (p - 1) + 1 : 3 * (f - 1) + 2;
+        }
+        if (full)
+          s4_apply_seq<T, true>(ptr, st, qmin, qmax, kb, rc + k, rs + k, E);
+        else
+          s4_apply_seq<T, false>(ptr, st, qmin, qmax, kb, rc + k, rs + k, E);
+      }
+    }
+    for (int e = tid; e < p * WW; e += nt) {
+      const int f = e / WW, q = e - f * WW, r = q % W, c = q / W;
+      if (r >= qmin && r <= qmax && c >= qmin && c <= qmax && (f == 0 || r <= c))
+        stg_(&PSD_GE(cx.Hp(1 + f), ld, base + r, base + c), (f == 0 ? Xw : Dw + (size_t)(f - 1) * WW)[r + c * W]);
+    }
+    __syncthreads();
+  }
+}
+
 // Single-shift sweep of the complex periodic QZ iteration (generalized.jl:770-854).
 PSD_DEV void cq_single_shift_sweep(const GCtx<cplx>& cx, int ifirst, int ilast, int ifirstm, int ilastm,
                                    int iiter, int& nexc) {
@@ -930,6 +1113,10 @@ PSD_DEV void cq_single_shift_sweep(const GCtx<cplx>& cx, int ifirst, int ilast, 
         const cplx f = c * PSD_GE(H1, ld, ifirst, ifirst) - PSD_GE(H1, ld, ilast, ilast) * conj_(s);
         const cplx g = c * PSD_GE(H1, ld, ifirst + 1, ifirst);
         givens_t(f, g, c, s, r);
+      }
+      if (cx.qzws >= 0 && ilast - ifirst >= 4) {
+        sweep1_windowed<cplx>(cx, ifirst, ilast, ifirstm, ilastm, c, s, cx.qzws);
+        return;
       }
       for (int j = ifirst; j <= ilast - 1; j++) {
         int zcol = 0;
