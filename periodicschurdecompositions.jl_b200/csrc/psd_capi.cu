@@ -513,7 +513,11 @@ int launch_real_large(psd_handle_s* h, Device& dev, Slot& aux, cudaStream_t stre
     P.deep = 4;  // team mode: < 1 element pair per thread and factor, one pass instead of p + 1 (N = 1024: 7.1 s -> 5.3 s)
     if (const char* ev = getenv("PSD_DEEP_U")) P.deep = atoi(ev);
     auto kern = psd::gpschur_team_kernel<double>;
-    const size_t smem = (size_t)((psd::cq_small_doubles(n, p) + 1) & ~1LL) * sizeof(double);
+    size_t smem = (size_t)((psd::cq_small_doubles(n, p) + 1) & ~1LL) * sizeof(double);
+    if (!getenv("PSD_NO_WINDOWED_QZ")) {
+      P.windowed_qz = 1;  // batches of 12 bulge steps between grid barriers instead of two barriers per step
+      smem += (size_t)psd::qzw_work_doubles(p) * sizeof(double);
+    }
     PSD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
     PSD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, smem));

@@ -767,7 +767,7 @@ PSD_DEV void sweep_windowed(const GCtx<double>& cx, int ifirst, int ilast, int i
       const int nAb = lo - ifirstm, nRt = ilastm - hi, per = nAb + nRt + nZ, total = p * per;
       const float rper = per > 0 ? 1.0f / (float)per : 0.0f;
       const bool full = (qmin == 0 && qmax == S3_W - 1 && kb == S3_K);
-      for (int w = tid; w < total; w += nt) {
+      for (int w = cx.wtid; w < total; w += cx.wnt) {
         int f, r;
         split_index(w, per, rper, f, r);  // f = 0: H_1 / Z_1, f >= 1: factor 1 + f
         double* ptr;
@@ -792,13 +792,16 @@ PSD_DEV void sweep_windowed(const GCtx<double>& cx, int ifirst, int ilast, int i
           s3_apply_seq<false>(ptr, st, qmin, qmax, kb, tab + k, E);
       }
     }
-    // (4) windows back to global memory (disjoint from the strips)
-    for (int e = tid; e < p * WW; e += nt) {
+    // (4) windows back to global memory.  Team mode: every CTA holds the same windows; the leader
+    // writes them once all CTAs have finished reading the old ones (barrier), and the next batch
+    // may only load after that (second barrier).
+    if (cx.team) cx.sync();
+    for (int e = tid; cx.lead && e < p * WW; e += nt) {
       const int f = e / WW, q = e - f * WW, r = q % S3_W, c = q / S3_W;
       if (r >= qmin && r <= qmax && c >= qmin && c <= qmax && (f == 0 || r <= c))
         stg_(&PSD_GE(cx.Hp(1 + f), ld, base + r, base + c), (f == 0 ? Xw : Dw + (size_t)(f - 1) * WW)[r + c * S3_W]);
     }
-    __syncthreads();
+    cx.sync();
   }
 }
 
@@ -1667,7 +1670,7 @@ __global__ void gpschur_team_kernel(GpqzParams<T> P, int z_preset) {
   cx.rots = P.deep ? small + cq_rots_offset(n, p) : nullptr;
   cx.deep_u = P.deep;
   cx.s2ws = -1;
-  cx.qzws = -1;
+  cx.qzws = P.windowed_qz ? ((cq_small_doubles(n, p) + 1) & ~1LL) : -1;
   cx.ldh = n; cx.ldz = n;
   for (long long b = 0; b < P.batch; b++) {
     T* Ab = P.A + (size_t)b * p * nn;
