@@ -687,9 +687,9 @@ int launch_gen_t(psd_handle_s* h, Device& dev, Slot& aux, cudaStream_t stream, c
   PSD_CUDA(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev.ordinal));
   int threads = ((2 * n + 31) / 32) * 32;
   threads = std::max(64, std::min(threads, 256));
-  // Two instantiations: 255 registers (one 256-thread CTA per SM) and 128 registers (two).  Measured
-  // at C3 / C5 (profiles/r1_gen_variants.txt): the complex path gains 1.5x from the second resident
-  // problem per SM, the real path (longer dependent chains per step, more spills at 128) does not.
+  // Two instantiations: 255 registers (one 256-thread CTA per SM) and 128 registers (two).  With the
+  // factors in global memory the second resident problem pays: while one CTA walks its rotation
+  // chains (one warp busy) the other streams its strips (profiles/r1_gen_variants.txt).
   // (Factors in shared memory: always the 255-register one.)
   auto kern = psd::gpschur_kernel<T, 256>;
   cudaFuncAttributes fa;
@@ -740,7 +740,7 @@ int launch_gen_t(psd_handle_s* h, Device& dev, Slot& aux, cudaStream_t stream, c
       smem = std::max(smem, small + s2w);
     }
   }
-  bool wide = !P.use_smem && sizeof(T) == sizeof(psd::cplx);
+  bool wide = !P.use_smem;
   if (const char* ev = getenv("PSD_GEN_WIDE")) wide = atoi(ev) != 0;
   if (const char* ev = getenv("PSD_GEN_THREADS")) threads = std::max(64, std::min(atoi(ev), wide ? 512 : 256));
   if (wide) kern = psd::gpschur_kernel<T, 512>;

@@ -259,12 +259,12 @@ PSD_DEV void rot2_chain_step(bool sl, const Rot2& gin, double (&B)[6], Rot2& gou
     rrot(B01, B02, gin.c2, gin.s2);
     rrot(B11, B12, gin.c2, gin.s2);
     rrot(B21, B22, gin.c2, gin.s2);
-    givens_real(B11, B21, gout.c2, gout.s2, r);
+    givens_chain(B11, B21, gout.c2, gout.s2, r);
     B11 = r; B21 = 0.0;
     rrot(B12, B22, gout.c2, gout.s2);
     rrot(B00, B01, gin.c1, gin.s1);
     rrot(B10, B11, gin.c1, gin.s1);
-    givens_real(B00, B10, gout.c1, gout.s1, r);
+    givens_chain(B00, B10, gout.c1, gout.s1, r);
     B00 = r; B10 = 0.0;
     rrot(B01, B11, gout.c1, gout.s1);
     rrot(B02, B12, gout.c1, gout.s1);
@@ -273,14 +273,14 @@ PSD_DEV void rot2_chain_step(bool sl, const Rot2& gin, double (&B)[6], Rot2& gou
     // rows (j,j+1) <- G2in; columns (j,j+1) by G2out (rows <= j)           (:993-1004)
     rrot(B11, B21, gin.c2, gin.s2);
     rrot(B12, B22, gin.c2, gin.s2);
-    givens_real(B22, -B21, gout.c2, gout.s2, r);
+    givens_chain(B22, -B21, gout.c2, gout.s2, r);
     B22 = r; B21 = 0.0;
     rrot(B01, B02, gout.c2, gout.s2);
     rrot(B11, B12, gout.c2, gout.s2);
     rrot(B00, B10, gin.c1, gin.s1);
     rrot(B01, B11, gin.c1, gin.s1);
     rrot(B02, B12, gin.c1, gin.s1);
-    givens_real(B11, -B10, gout.c1, gout.s1, r);
+    givens_chain(B11, -B10, gout.c1, gout.s1, r);
     B11 = r; B10 = 0.0;
     rrot(B00, B01, gout.c1, gout.s1);
   }
