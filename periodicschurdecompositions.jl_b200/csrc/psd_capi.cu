@@ -781,7 +781,8 @@ int run_gen_shard(psd_handle_s* h, Device& dev, const GenCall& gc, long long fir
   // chunk under the kernels of the others.  The cap keeps the slots inside device memory.
   const bool wantZ0 = gc.wantZ && Z;
   long long chunk = std::max<long long>(1, (512LL << 20) / (long long)perB);
-  chunk = std::max<long long>(chunk, 2LL * dev.sm_count);
+  const long long wave = 2LL * dev.sm_count;  // resident problems per launch in global-memory mode
+  chunk = (chunk + wave - 1) / wave * wave;   // whole waves: no half-empty tail inside a launch
   {
     size_t free_b = 0, total_b = 0;
     PSD_CUDA(cudaMemGetInfo(&free_b, &total_b));
@@ -790,10 +791,6 @@ int run_gen_shard(psd_handle_s* h, Device& dev, const GenCall& gc, long long fir
     chunk = std::max<long long>(1, std::min(chunk, cap));
   }
   chunk = std::min(chunk, count);
-  if (count > chunk) {
-    long long nchunks = (count + chunk - 1) / chunk;
-    chunk = (count + nchunks - 1) / nchunks;
-  }
   // chunks above this size are copied straight from / to pageable memory (no pinned staging copy)
   const size_t kStageLimit = 1ULL << 30;
   int si = 0;
