@@ -516,7 +516,7 @@ int launch_real_large(psd_handle_s* h, Device& dev, Slot& aux, cudaStream_t stre
     size_t smem = (size_t)((psd::cq_small_doubles(n, p) + 1) & ~1LL) * sizeof(double);
     if (!getenv("PSD_NO_WINDOWED_QZ")) {
       P.windowed_qz = 1;  // batches of 12 bulge steps between grid barriers instead of two barriers per step
-      smem += (size_t)psd::qzw_work_doubles(p) * sizeof(double);
+      smem += (size_t)psd::qzw_work_doubles(p, psd::S3_K_TEAM) * sizeof(double);
     }
     PSD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
@@ -728,7 +728,7 @@ int launch_gen_t(psd_handle_s* h, Device& dev, Slot& aux, cudaStream_t stream, c
       P.blocked_stage1 = 1;
       smem = small + blk;
     }
-    const size_t qzw = sizeof(T) == sizeof(double) ? (size_t)psd::qzw_work_doubles(p) * sizeof(double)
+    const size_t qzw = sizeof(T) == sizeof(double) ? (size_t)psd::qzw_work_doubles(p, psd::S3_K_CTA) * sizeof(double)
                                                    : (size_t)psd::s4_work_scalars<T>(p) * sizeof(T);
     if (!gc.reduce_only && small + qzw <= max_dyn && !getenv("PSD_NO_WINDOWED_QZ")) {
       P.windowed_qz = 1;

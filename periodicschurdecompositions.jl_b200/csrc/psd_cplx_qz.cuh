@@ -642,13 +642,16 @@ PSD_DEV bool rq_block2x2(const GCtx<double>& cx, int j, int ifirstm, int ilastm,
 // <= S3_W entries, applies the whole sequence of 3-element rotations in registers and stores them.
 // Local index q <-> global index j0 - 1 + q; step s acts on q = s+1, s+2, s+3.
 // ------------------------------------------------------------------------------------------
-constexpr int S3_K = 12, S3_W = S3_K + 4;
-__host__ __device__ inline long long qzw_work_doubles(int p) {
-  return (long long)p * S3_W * S3_W + 4LL * S3_K * (3 * (p - 1) + 2) + 8;
+// S3_K = 12 steps per batch with one CTA per problem (two problems per SM share the shared
+// memory); team mode uses the same (28 was measured: no gain, the serial chain dominates).
+constexpr int S3_K_CTA = 12, S3_K_TEAM = 12;
+__host__ __device__ inline long long qzw_work_doubles(int p, int K) {
+  return (long long)p * (K + 4) * (K + 4) + 4LL * K * (3 * (p - 1) + 2) + 8;
 }
 
-template <bool FULL>
+template <int S3_K, bool FULL>
 PSD_DEV void s3_apply_seq(double* ptr, long long stride, int qmin, int qmax, int kb, const Rot2* tab, int E) {
+  constexpr int S3_W = S3_K + 4;
   double x[S3_W];
   if (FULL) {
 #pragma unroll
@@ -678,12 +681,13 @@ PSD_DEV void s3_apply_seq(double* ptr, long long stride, int qmin, int qmax, int
 
 // Steps j = ifirst .. ilast-2 of one sweep; g = the two starting rotations.  The trailing single
 // rotation is left to the caller.
+template <int S3_K>
 PSD_DEV void sweep_windowed(const GCtx<double>& cx, int ifirst, int ilast, int ifirstm, int ilastm, Rot2 g,
                             long long ws_off) {
   const int n = cx.n, p = cx.p, tid = cx.tid, nt = cx.nt, ld = cx.ldh, ldz = cx.ldz;
   const int lane = tid & 31, warp = tid >> 5;
   const int E = 3 * (p - 1) + 2;
-  constexpr int WW = S3_W * S3_W;
+  constexpr int S3_W = S3_K + 4, WW = S3_W * S3_W;
   double* Xw = psd_smem_cq + ws_off;  // window of H_1, column-major, ld = S3_W
   double* Dw = Xw + WW;               // windows of factors 2..p
   Rot2* tab = reinterpret_cast<Rot2*>(Dw + (size_t)(p - 1) * WW);
@@ -787,9 +791,9 @@ PSD_DEV void sweep_windowed(const GCtx<double>& cx, int ifirst, int ilast, int i
           k = (f == 0) ? 3 * (p - 1) : 3 * (f - 1) + 2;
         }
         if (full)
-          s3_apply_seq<true>(ptr, st, qmin, qmax, kb, tab + k, E);
+          s3_apply_seq<S3_K, true>(ptr, st, qmin, qmax, kb, tab + k, E);
         else
-          s3_apply_seq<false>(ptr, st, qmin, qmax, kb, tab + k, E);
+          s3_apply_seq<S3_K, false>(ptr, st, qmin, qmax, kb, tab + k, E);
       }
     }
     // (4) windows back to global memory.  Team mode: every CTA holds the same windows; the leader
@@ -881,7 +885,10 @@ PSD_DEV void rq_double_shift_sweep(const GCtx<double>& cx, int ifirst, int ilast
   givens_real(v1, v2, g.c2, g.s2, r2);
   givens_real(v0, r2, g.c1, g.s1, r1);
   if (cx.qzws >= 0 && ilast - ifirst - 1 >= 4) {
-    sweep_windowed(cx, ifirst, ilast, ifirstm, ilastm, g, cx.qzws);
+    if (cx.team)
+      sweep_windowed<S3_K_TEAM>(cx, ifirst, ilast, ifirstm, ilastm, g, cx.qzws);
+    else
+      sweep_windowed<S3_K_CTA>(cx, ifirst, ilast, ifirstm, ilastm, g, cx.qzws);
   } else
   for (int j = ifirst; j <= ilast - 2; j++) {
     int zcol = 0;

@@ -12,6 +12,6 @@ def run(A,S,lr):
     kt=h.kernel_times()
     return round(kt['iterate_ms']/1e3,3), round(t1,3), int((out[5]!=0).sum())
 A5=psd_rng.gen_uniform(1234,512,10,296)
-for env,B in (({},148),({'PSD_GEN_WIDE':'1'},296),({},256),({'PSD_GEN_WIDE':'1'},256)):
+for env,B in (({},256),):
     os.environ.pop('PSD_GEN_WIDE',None); os.environ.update(env)
     r=run(A5[:B],S,"L"); print(env,'C5',B,r,'problems/s %.2f'%(B/r[0]),flush=True)
