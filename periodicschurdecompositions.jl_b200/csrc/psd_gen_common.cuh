@@ -260,6 +260,11 @@ PSD_DEV void bulk_rot2_tab(int tid, int nt, int total, const double* rc, const T
 }
 // w -> (w / per, w % per) with a float reciprocal and a fix-up (w < 2^24)
 PSD_DEV void split_index(int w, int per, float rper, int& q, int& r) {
+  if (w >= (1 << 24)) {  // beyond the exact range of the float estimate
+    q = w / per;
+    r = w - q * per;
+    return;
+  }
   q = (int)((float)w * rper);
   r = w - q * per;
   if (r < 0) {

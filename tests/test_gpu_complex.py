@@ -159,3 +159,22 @@ def test_generalized_hessenberg(psd, cplx, n, p):
     assert Q2 is None and np.allclose(H2, H, atol=1e-13)
     with pytest.raises(ValueError):
         psd.gphessenberg_batched(A, [False] + S[1:])
+
+
+# Windowed Stage 2 / windowed sweeps (factors in global memory) at the small periods, both
+# orientations, with and without T / Z: sizes chosen so that the factors do not fit in shared memory.
+@pytest.mark.parametrize("p,S,left", [(1, [1], False), (2, [1, 0], False), (2, [0, 1], True), (3, [1, 1, 1], True)])
+def test_windowed_small_periods_complex(psd, p, S, left):
+    n = 150
+    A = GCs.rand_storage(4242 + p, n, p, 2, True)
+    T, Z, al, be, sc, info = psd.gpschur_batched(A, S, "L" if left else "R")
+    assert (info == 0).all()
+    for b in range(2):
+        r = K.gpschur_check(A[b], S, T[b], Z[b], al[b], be[b], sc[b], left=left)
+        ref = K.gproduct_eigvals(A[b], S, left)
+        assert K.match_eigs(ref, r["values"]) <= 1e-8 * np.max(np.abs(ref))
+    # eigenvalues only: updates restricted to the active window
+    _, _, al2, be2, sc2, info2 = psd.gpschur_batched(A, S, "L" if left else "R", wantT=False, wantZ=False)
+    assert (info2 == 0).all()
+    worst, scale = K.match_eigs_finite(_vals(al[0], be[0], sc[0]), _vals(al2[0], be2[0], sc2[0]))
+    assert worst <= 1e-8 * scale

@@ -142,3 +142,21 @@ def test_golden_generalized_gpu(psd, ci):
     assert K.match_eigs(ref, lam) <= golden_tol(A, S, ref)
     K.gpschur_check(A[0], S, T[0], Z[0], al[0], be[0], sc[0], left=case["left"],
                     real_path=not case["complex"])
+
+
+# Windowed Stage 2 / windowed double-shift sweeps at the small periods (factors in global memory)
+@pytest.mark.parametrize("p,S,left", [(1, [1], False), (2, [1, 0], False), (2, [0, 1], True), (3, [1, 1, 1], True)])
+def test_windowed_small_periods_real(psd, p, S, left):
+    n = 200
+    A = GCs.rand_storage(4343 + p, n, p, 2, False)
+    T, Z, al, be, sc, info = psd.gpschur_batched(A, S, "L" if left else "R")
+    assert (info == 0).all()
+    for b in range(2):
+        r = K.gpschur_check(A[b], S, T[b], Z[b], al[b], be[b], sc[b], left=left, real_path=True)
+        _pairs_ok(r["values"])
+        ref = K.gproduct_eigvals(A[b], S, left)
+        assert K.match_eigs(ref, r["values"]) <= 1e-7 * np.max(np.abs(ref))
+    _, _, al2, be2, sc2, info2 = psd.gpschur_batched(A, S, "L" if left else "R", wantT=False, wantZ=False)
+    assert (info2 == 0).all()
+    worst, scale = K.match_eigs_finite(_vals(al[0], be[0], sc[0]), _vals(al2[0], be2[0], sc2[0]))
+    assert worst <= 1e-7 * scale
