@@ -1201,21 +1201,46 @@ PSD_DEV void stage2_windowed(const GCtx<T>& cx, long long ws_off) {
       for (int e = tid; e < W; e += nt) hcol[e] = ldg_(&PSD_GE(H1, ld, lo + e, jc));
       __syncthreads();
       if (cx.prof) { const long long t = clock64(); acc0 += t - tq; tq = t; }
-      // (2) one warp walks the kb rotation chains on the windows
-      if (warp == 0) {
-        for (int t = 1; t <= kb; t++) {
-          const int a = W - 1 - t;  // local index of the upper row / left column of the pair
-          double c1;
-          T s1, r1;
-          givens_chain(hcol[a], hcol[a + 1], c1, s1, r1);
-          __syncwarp();
-          if (lane == 0) {
-            hcol[a] = r1;
-            hcol[a + 1] = Scalar<T>::zero();
-          }
-          double ci = c1;
-          T si = s1;
-          for (int l = p; l >= 2; l--) {
+      // (2) the kb rotation chains on the windows, as a wavefront: cell (t, f) = rotation t at
+      // chain position f (f = 0: generation from column jc of H_1; f >= 1: factor l = p + 1 - f)
+      // needs (t, f-1) for its incoming rotation and (t-1, f) for the state of its window, so all
+      // cells of an anti-diagonal t + f = d are independent: one warp per chain position, a CTA
+      // barrier per anti-diagonal, kb + p - 1 of them instead of kb * p serial cells.
+      {
+        const int nw = nt >> 5, k1 = 3 * (p - 1);
+        for (int d = 1; d <= kb + p - 1; d++) {
+          for (int f = warp; f < p; f += nw) {
+            const int t = d - f;
+            if (t < 1 || t > kb) continue;
+            const int a = W - 1 - t;  // local index of the upper row / left column of the pair
+            if (f == 0) {
+              double c1;
+              T s1, r1;
+              givens_chain(hcol[a], hcol[a + 1], c1, s1, r1);
+              __syncwarp();
+              if (lane == 0) {
+                hcol[a] = r1;
+                hcol[a + 1] = Scalar<T>::zero();
+                const int k = (t - 1) * E + k1;
+                rc[k] = c1; rs[k] = s1;                // rows of H_1
+                rc[k + 1] = c1; rs[k + 1] = conj_(s1);  // columns of Z_1
+                if (p == 1) {
+                  rc[k + 2] = c1; rs[k + 2] = conj_(s1);  // columns of H_1
+                }
+              }
+              __syncwarp();
+              continue;
+            }
+            const int l = p + 1 - f;
+            double ci;
+            T si;
+            if (f == 1) {
+              ci = rc[(t - 1) * E + k1];
+              si = rs[(t - 1) * E + k1];
+            } else {
+              ci = rc[(t - 1) * E + 3 * (l + 1 - 2) + 2];
+              si = conj_(rs[(t - 1) * E + 3 * (l + 1 - 2) + 2]);
+            }
             T* D = Dw + (size_t)(l - 2) * S2_W * S2_W;
             RotChain<T> o;
             rot_chain_step<T>(cx.Sg(l), ci, si, D[a + a * S2_W], D[a + (a + 1) * S2_W], D[a + 1 + (a + 1) * S2_W], o);
@@ -1238,18 +1263,14 @@ PSD_DEV void stage2_windowed(const GCtx<T>& cx, long long ws_off) {
               rc[k] = o.cR; rs[k] = conj_(o.sR);
               rc[k + 1] = o.cL; rs[k + 1] = o.sL;
               rc[k + 2] = o.co; rs[k + 2] = conj_(o.so);
+              if (l == 2) {
+                rc[(t - 1) * E + k1 + 2] = o.co;
+                rs[(t - 1) * E + k1 + 2] = conj_(o.so);  // columns of H_1
+              }
             }
             __syncwarp();
-            ci = o.co;
-            si = o.so;
           }
-          if (lane == 0) {
-            const int k = (t - 1) * E + 3 * (p - 1);
-            rc[k] = c1; rs[k] = s1;                // rows of H_1
-            rc[k + 1] = c1; rs[k + 1] = conj_(s1);  // columns of Z_1
-            rc[k + 2] = ci; rs[k + 2] = conj_(si);  // columns of H_1
-          }
-          __syncwarp();
+          __syncthreads();
         }
       }
       __syncthreads();
