@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """Full real pschur! (reduction + periodic QR iteration, T and Z) on one larger problem:
-blocked reduction on the whole GPU, then the one-CTA periodic QR iteration (the multishift /
-windowed iteration that would make N = 4096 practical is not built yet)."""
+blocked reduction on the whole GPU, then the team-mode iteration (windowed double-shift sweeps on
+all SMs; small-bulge multishift with aggressive early deflation is not built, see DESIGN.md
+section 9)."""
 import argparse, json, os, sys, time
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
