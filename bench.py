@@ -292,7 +292,7 @@ def run_ours(args):
                      "kernel_ms": k_ms,
                      "problems_per_launch": units_per_launch,
                      "kernel_share_of_step": kt["iterate_ms"] / (kt["iterate_ms"] + kt["reduce_ms"]),
-                     "reduce_kernel": "psd::rphess_warp32_kernel_t<32,8>",
+                     "reduce_kernel": "psd::rphess_pair32_kernel_t<32,8>",
                      "reduce_kernel_ms": kt["reduce_ms"] / max(1, kt["reduce_launches"]),
                      "step_ms_device": step_ms,
                      "fp64_gflops_standard_count": FLOPS_PER_PROBLEM * B / (step_ms * 1e-3) / 1e9,

@@ -338,9 +338,13 @@ int launch_real_eig32(psd_handle_s* h, Device& dev, Slot& aux, cudaStream_t stre
       R.A = dA + (size_t)off * p * nn;
       R.packed_out = aux.dPacked;
       R.counter = aux.dCounter;
-      void (*hk)(psd::Hess32Params) = (n == 32 && p == 8 && !getenv("PSD_NO_SPECIAL"))
-                                          ? psd::rphess_warp32_kernel_t<32, 8>
-                                          : psd::rphess_warp32_kernel_t<0, 0>;
+      // p >= 2: two warps per problem (left / right half of every reflector step on two schedulers)
+      const bool pair = p >= 2 && !getenv("PSD_NO_HESS_PAIR");
+      const bool special = n == 32 && p == 8 && !getenv("PSD_NO_SPECIAL");
+      void (*hk)(psd::Hess32Params) =
+          pair ? (special ? psd::rphess_pair32_kernel_t<32, 8> : psd::rphess_pair32_kernel_t<0, 0>)
+               : (special ? psd::rphess_warp32_kernel_t<32, 8> : psd::rphess_warp32_kernel_t<0, 0>);
+      const int wpp = pair ? 2 : 1;  // warps per problem
       cudaFuncAttributes fh;
       PSD_CUDA(cudaFuncGetAttributes(&fh, hk));
       const size_t max_dyn1 = (size_t)optin - fh.sharedSizeBytes;
@@ -351,13 +355,13 @@ int launch_real_eig32(psd_handle_s* h, Device& dev, Slot& aux, cudaStream_t stre
       PSD_CUDA(cudaFuncSetAttribute(hk, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)max_dyn1));
       int occ1 = 0;
-      PSD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ1, hk, wpb1 * 32, smem1));
+      PSD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ1, hk, wpb1 * wpp * 32, smem1));
       if (occ1 < 1) return fail(PSD_ERR_UNSUPPORTED, "reduction kernel does not fit on an SM");
       const long long ctas1 = (nb + wpb1 - 1) / wpb1;
       const int grid1 = (int)std::max(1LL, std::min((long long)occ1 * dev.sm_count, ctas1));
       {
         ScopedKernelTimer tm(h, dev, stream, 0);
-        hk<<<grid1, wpb1 * 32, smem1, stream>>>(R);
+        hk<<<grid1, wpb1 * wpp * 32, smem1, stream>>>(R);
       }
       PSD_CUDA(cudaGetLastError());
     }
