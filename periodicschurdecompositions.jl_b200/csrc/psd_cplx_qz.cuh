@@ -916,6 +916,7 @@ PSD_DEV void rq_double_shift_sweep(const GCtx<double>& cx, int ifirst, int ilast
 // ------------------------------------------------------------------------------------------
 template <class T>
 struct S4 {
+  // complex, C3 (128 registers per thread): K = 7 / 9 / 13 -> 1249 / 1263 / 1147 problems/s
   static constexpr int K = (sizeof(T) == sizeof(double)) ? 13 : 9;
   static constexpr int W = K + 3;
 };
