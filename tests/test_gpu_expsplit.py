@@ -1,0 +1,107 @@
+"""GPU parity on the reference's one golden family: expsplit(p, T) (Kressner 2001;
+/root/reference test/testfuncs.jl:412-421, asserted at test/runtests.jl:68-87) for
+T in {Float64, ComplexF64}, p in {5, 20}, :R and :L, with Schur vectors and eigenvalues only.
+
+This is the case that separates a periodic algorithm from "form the product": the product has
+eigenvalues down to ~ -6.5e-57 (p = 20), which are lost completely when the product is formed.
+Gates: the reference's own (within 1e-3 of the asymptotic values, pschur_check with tol=128)
+AND the relative accuracy of EVERY eigenvalue against the 200-digit values stored in
+tests/golden/real_golden.json (<= 1e-10 relative, the bar the CPU oracle is held to in
+tests/test_oracle_real.py)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import psd_checks as K
+
+pytestmark = pytest.mark.gpu
+EPS = np.finfo(np.float64).eps
+GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "real_golden.json")))
+
+
+def _c(v):
+    return np.array([complex(a, b if abs(b) > 1e-30 * abs(complex(a, b)) else 0.0) for a, b in v])
+
+
+def _storage(es, left, dtype):
+    p = es["p"]
+    A1 = np.array(es["A1"], dtype=dtype)
+    Aj = np.diag(es["Aj_diag"]).astype(dtype)
+    mats = [A1] + [Aj.copy() for _ in range(p - 1)]
+    if left:
+        mats[0], mats[-1] = mats[-1], mats[0]  # test/runtests.jl:80
+    return np.stack([m.T for m in mats])[None].copy()
+
+
+def _gates(es, lam, rel=1e-10):
+    # the reference's assertion (test/runtests.jl:74-78)
+    for lr, li in es["lambda_reference_asymptotic"]:
+        lj = complex(lr, li)
+        d = np.abs(lam - lj)
+        k = int(np.argmin(d))
+        assert d[k] < 1e-3 * abs(lj) or max(abs(lj), abs(lam[k])) < EPS ** 2, (lj, lam)
+    # relative accuracy of every eigenvalue, including the ~1e-57 one
+    for g in _c(es["lambda_mp"]):
+        d = np.abs(lam - g)
+        k = int(np.argmin(d))
+        assert d[k] <= rel * abs(g) or max(abs(g), abs(lam[k])) < EPS ** 2, (g, lam)
+
+
+@pytest.mark.parametrize("es", GOLD["expsplit"], ids=lambda e: f"p{e['p']}")
+@pytest.mark.parametrize("left", [False, True], ids=["R", "L"])
+def test_expsplit_real_with_vectors(psd, es, left):
+    A = _storage(es, left, np.float64)
+    T, Z, lam, info = psd.pschur_batched(A, "L" if left else "R")
+    assert info[0] == 0
+    K.pschur_check(A[0], T[0], Z[0], lam[0], left=left, tol=128, check_lambda=False)
+    _gates(es, lam[0])
+
+
+@pytest.mark.parametrize("es", GOLD["expsplit"], ids=lambda e: f"p{e['p']}")
+@pytest.mark.parametrize("left", [False, True], ids=["R", "L"])
+def test_expsplit_real_eigenvalues_only(psd, es, left):
+    """N = 6, p >= 3: this is the one-warp-per-problem packed kernel (rpqr_eig32) with its
+    un-normalised reflectors and power-of-two renormalisation."""
+    A = _storage(es, left, np.float64)
+    # a small batch of identical problems: every warp slot of a CTA must give the same answer
+    Ab = np.repeat(A, 5, axis=0)
+    _, _, lam, info = psd.pschur_batched(Ab, "L" if left else "R", wantT=False, wantZ=False)
+    assert (info == 0).all()
+    for b in range(5):
+        _gates(es, lam[b])
+    _, _, lam1, info1 = psd.pschur_batched(A, "L" if left else "R", wantT=True, wantZ=False)
+    assert info1[0] == 0
+    _gates(es, lam1[0])
+
+
+@pytest.mark.parametrize("es", GOLD["expsplit"], ids=lambda e: f"p{e['p']}")
+@pytest.mark.parametrize("left", [False, True], ids=["R", "L"])
+def test_expsplit_complex(psd, es, left):
+    """expsplit(p, ComplexF64) through the complex standard method (S = trues), as
+    test/runtests.jl:68-87 does for T = ComplexF64."""
+    p = es["p"]
+    A = _storage(es, left, np.complex128)
+    S = [True] * p
+    T, Z, al, be, sc, info = psd.gpschur_batched(A, S, "L" if left else "R")
+    assert info[0] == 0
+    r = K.gpschur_check(A[0], S, T[0], Z[0], al[0], be[0], sc[0], left=left, tol=128)
+    _gates(es, r["values"])
+    # eigenvalues only
+    _, _, al0, be0, sc0, info0 = psd.gpschur_batched(A, S, "L" if left else "R", wantT=False, wantZ=False)
+    assert info0[0] == 0
+    _gates(es, psd.gvalues(al0[0], be0[0], sc0[0]))
+
+
+@pytest.mark.parametrize("es", GOLD["expsplit"], ids=lambda e: f"p{e['p']}")
+def test_expsplit_real_generalized_alltrue(psd, es):
+    """the same family through the real periodic QZ (S = trues): its 2x2 handling works on
+    explicitly formed scaled products, so the small eigenvalues are the ones at risk"""
+    p = es["p"]
+    A = _storage(es, False, np.float64)
+    S = [True] * p
+    T, Z, al, be, sc, info = psd.gpschur_batched(A, S, "R")
+    assert info[0] == 0
+    r = K.gpschur_check(A[0], S, T[0], Z[0], al[0], be[0], sc[0], tol=128, real_path=True)
+    _gates(es, r["values"])

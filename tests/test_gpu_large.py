@@ -68,3 +68,40 @@ def test_large_fast_paths_and_batch(psd, oracle):
         assert K.match_eigs(ref, lam[b]) <= 1e-8 * scale
         refl = np.linalg.eigvals(K.M(A[b, 1]) @ K.M(A[b, 0]))
         assert K.match_eigs(refl, lam1[b]) <= 1e-8 * scale
+
+
+def test_large_pschur_n1024_reference_tolerance(psd, oracle):
+    """N = 1024, p = 4 with Schur vectors, held to the reference's own pschur_check threshold
+    (tol = 32 eps ||A||_1, test/testfuncs.jl:119) - no loosened tolerance - plus the trace identity
+    and eigenvalues against LAPACK on the explicitly formed product."""
+    n, p = 1024, 4
+    A = oracle.gen_real(2024, n, p, 1)
+    T, Z, lam, info = psd.pschur_batched(A, "R")
+    assert info[0] == 0
+    out = K.pschur_check(A[0], T[0], Z[0], lam[0], tol=32, check_lambda=False)
+    print("N=1024 p=4: residual %.1f eps*|A|_1, orthogonality %.2f N eps" % (out["residual_eps_a1"], out["orth_epsn"]))
+    P = np.linalg.multi_dot([K.M(A[0, j]) for j in range(p)])
+    tr = np.trace(P)
+    assert abs(lam[0].sum() - tr) <= 1e-9 * abs(tr)
+    ref = np.linalg.eigvals(P)
+    # the dominant (Perron) eigenvalue is well conditioned: relative 1e-10
+    assert abs(np.max(np.abs(ref)) - np.max(np.abs(lam[0]))) <= 1e-10 * np.max(np.abs(ref))
+
+
+@pytest.mark.parametrize("scale", [1e-160, 1e160])
+def test_large_badly_scaled(psd, oracle, scale):
+    """N = 256 with entries whose squares are not representable: the blocked reduction must keep
+    the overflow / underflow safety of the reference's reflector (householder.jl:5-24, 80-100)."""
+    n, p = 256, 2
+    A = oracle.gen_real(555, n, p, 1)
+    As = A.copy()
+    As[:, 0] *= scale          # one factor tiny / huge, the other O(1): the product stays representable
+    T, Z, lam, info = psd.pschur_batched(As, "R")
+    assert info[0] == 0 and np.isfinite(T).all() and np.isfinite(Z).all()
+    K.pschur_check(As[0], T[0], Z[0], lam[0], tol=32, check_lambda=False)
+    T1, Z1, lam1, info1 = psd.pschur_batched(A, "R")
+    s1 = np.max(np.abs(lam1[0]))
+    assert K.match_eigs(lam1[0], lam[0] / scale) <= 1e-8 * s1
+    H, Q = psd.phessenberg_batched(As)
+    assert np.isfinite(H).all()
+    _check_hess(As[0], H[0], Q[0])
