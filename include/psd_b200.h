@@ -237,6 +237,17 @@ int psd_last_stats(psd_handle_t handle, int64_t stats[8]);
 int psd_set_profiling(psd_handle_t handle, int on);
 int psd_kernel_times(psd_handle_t handle, double ms[8]);
 
+/* Counters of the most recent large-N (N >= 192) iteration on this handle: the small-bulge
+ * multishift periodic QR sweeps that replace the single double-shift bulge of
+ * PeriodicSchurDecompositions.jl:806-886 (mirrors the reference's niter report, :458-459, 1077).
+ * out[0] = status (0 finished, 1 fell back to the single-bulge team kernel), out[1] = sweeps,
+ * out[2] = rounds (chase + update launches), out[3] = window-rounds, out[4] = shift pairs used,
+ * out[5] = exceptional-shift sweeps, out[6] = diagonal blocks finished by the small kernel,
+ * out[7] = kernel launches, out[8] = flops of the FP64 tensor-core window updates;
+ * with profiling on additionally device milliseconds: out[9] = bulge chase, out[10] = tensor-core
+ * updates, out[11] = shift computation, out[12] = deflation scans, out[13] = final blocks. */
+int psd_large_stats(psd_handle_t handle, double out[16]);
+
 #ifdef __cplusplus
 }
 #endif

@@ -31,6 +31,7 @@ EXPORTED_SYMBOLS = [
     "psd_last_stats",
     "psd_set_profiling",
     "psd_kernel_times",
+    "psd_large_stats",
     "psd_fill_uniform_host",
     "psd_fill_uniform_dev",
 ]
@@ -90,6 +91,7 @@ def lib():
         L.psd_last_stats.argtypes = [vp, C.POINTER(C.c_int64)]
         L.psd_set_profiling.argtypes = [vp, C.c_int]
         L.psd_kernel_times.argtypes = [vp, C.POINTER(C.c_double)]
+        L.psd_large_stats.argtypes = [vp, C.POINTER(C.c_double)]
         L.psd_fill_uniform_host.argtypes = [C.c_uint64, C.c_int, C.c_int, C.c_int64, C.c_int64,
                                             C.c_int, vp]
         L.psd_fill_uniform_dev.argtypes = [vp, C.c_uint64, C.c_int, C.c_int, C.c_int64,

@@ -23,11 +23,23 @@
 #include "psd_rowhess.cuh"
 #include "psd_dgemm.cuh"
 #include "psd_large_hess.cuh"
+#include "psd_ms.h"
 #include "psd_rng.cuh"
 
 namespace {
 
 thread_local std::string g_err;
+
+// Experiment switches (PSD_* environment variables) exist only in builds made with
+// -DPSD_DEBUG_ENV; the product library never reads the environment.
+inline const char* dbg_env(const char* name) {
+#ifdef PSD_DEBUG_ENV
+  return getenv(name);
+#else
+  (void)name;
+  return nullptr;
+#endif
+}
 
 int fail(int code, const std::string& msg) {
   g_err = msg;
@@ -71,6 +83,8 @@ struct Slot {
   size_t hcapX[3] = {0, 0, 0};
   unsigned char* dS = nullptr;
   size_t capS = 0;
+  psd::ms::Workspace* ms = nullptr;  // large-N multishift iteration (psd_ms.cu)
+  long long* dProf = nullptr;        // PSD_PANEL_PROF cycle counters (debug builds)
 };
 
 struct Device {
@@ -78,6 +92,7 @@ struct Device {
   int sm_count = 0;
   Slot slots[kSlotsPerDevice];
   Slot user;  // counter/scratch for *_dev entry points running on caller streams
+  cudaEvent_t userDone = nullptr;  // last *_dev call on this device (they share `user`)
 };
 
 }  // namespace
@@ -96,6 +111,7 @@ struct psd_handle_s {
   std::vector<KernelTimer> timers;  // pending event pairs (resolved by psd_kernel_times)
   double gemm_flops = 0.0;          // FP64 GEMM flops issued by the large-N reduction since then
   double extra_launches = 0.0;      // kernel launches covered by a timer that brackets several
+  psd::ms::Result ms_last;          // counters of the most recent large-N iteration
   std::mutex tmu;
 };
 
@@ -225,7 +241,7 @@ int launch_real_eig32(psd_handle_s* h, Device& dev, Slot& aux, cudaStream_t stre
   const size_t nn = (size_t)n * n;
   const size_t psize = (size_t)psd::pk_problem_size(n, p);
   long long chunk_max = kEigChunk;
-  if (const char* ev = getenv("PSD_EIG_CHUNK")) chunk_max = std::max(1LL, atoll(ev));
+  if (const char* ev = dbg_env("PSD_EIG_CHUNK")) chunk_max = std::max(1LL, atoll(ev));
   const long long chunk = std::min(batch, chunk_max);
   int e = ensure_dev(aux.dPacked, aux.capPacked, (size_t)chunk * psd::pk_problem_stride(n, p) * sizeof(double));
   if (e) return e;
@@ -242,10 +258,10 @@ int launch_real_eig32(psd_handle_s* h, Device& dev, Slot& aux, cudaStream_t stre
   std::vector<Phase> phases;
   {
     std::vector<int> orders{n};
-    if (n >= 24 && !getenv("PSD_NO_PHASES"))
+    if (n >= 24 && !dbg_env("PSD_NO_PHASES"))
       for (int k = 1; k <= 5; k++) orders.push_back(n - k * (n / 8));  // n = 32: 28, 24, 20, 16, 12
-    bool special = (n == 32 && p == 8 && !getenv("PSD_NO_SPECIAL"));
-    if (const char* ev = getenv("PSD_PHASES")) {  // experiment: comma-separated decreasing orders after n
+    bool special = (n == 32 && p == 8 && !dbg_env("PSD_NO_SPECIAL"));
+    if (const char* ev = dbg_env("PSD_PHASES")) {  // experiment: comma-separated decreasing orders after n
       orders.assign(1, n);
       special = false;
       for (const char* c = ev; *c;) {
@@ -263,7 +279,7 @@ int launch_real_eig32(psd_handle_s* h, Device& dev, Slot& aux, cudaStream_t stre
       if (special && k == 0) ph.kern = psd::rpqr_eig32_kernel_t<32, 8>;
       int wmax = 8;
       if (k > 0) {
-        const char* lr = getenv("PSD_LOWREG");
+        const char* lr = dbg_env("PSD_LOWREG");
         const int mode = lr ? atoi(lr) : 168;
         if (mode == 168) { ph.kern = psd::rpqr_eig32_kernel_r168; wmax = 3; }
         if (mode == 128) { ph.kern = psd::rpqr_eig32_kernel_r128; wmax = 4; }
@@ -282,14 +298,14 @@ int launch_real_eig32(psd_handle_s* h, Device& dev, Slot& aux, cudaStream_t stre
         if ((size_t)w * pbytes > max_dyn) break;
         int occ = 0;
         PSD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ph.kern, w * 32, (size_t)w * pbytes));
-        if (getenv("PSD_GEN_PROF")) fprintf(stderr, "[psd eig32 occ] order %d w %d -> %d CTAs/SM\n", ph.n, w, occ);
+        if (dbg_env("PSD_GEN_PROF")) fprintf(stderr, "[psd eig32 occ] order %d w %d -> %d CTAs/SM\n", ph.n, w, occ);
         if (occ * w > best_total || (occ * w == best_total && w > best_w)) {
           best_total = occ * w;
           best_w = w;
         }
       }
       if (best_w < 1) return fail(PSD_ERR_UNSUPPORTED, "packed problem does not fit in shared memory");
-      if (const char* ev = getenv("PSD_PHASE_WPB")) {  // experiment: force warps per CTA, oversubscribed grid
+      if (const char* ev = dbg_env("PSD_PHASE_WPB")) {  // experiment: force warps per CTA, oversubscribed grid
         const int w = atoi(ev);
         if (k > 0 && w >= 1 && (size_t)w * pbytes <= max_dyn) {
           best_w = w;
@@ -299,7 +315,7 @@ int launch_real_eig32(psd_handle_s* h, Device& dev, Slot& aux, cudaStream_t stre
       ph.wpb = best_w;
       ph.smem = (size_t)best_w * pbytes;
       ph.grid = (best_total / best_w) * dev.sm_count;
-      if (getenv("PSD_GEN_PROF"))
+      if (dbg_env("PSD_GEN_PROF"))
         fprintf(stderr, "[psd eig32 phase %zu] order %d stop %d: %d warps/CTA x %d CTAs/SM, %zu B smem/CTA, %d regs\n", k,
                 ph.n, ph.stop, best_w, best_total / best_w, ph.smem, fa.numRegs);
       phases.push_back(ph);
@@ -339,8 +355,8 @@ int launch_real_eig32(psd_handle_s* h, Device& dev, Slot& aux, cudaStream_t stre
       R.packed_out = aux.dPacked;
       R.counter = aux.dCounter;
       // p >= 2: two warps per problem (left / right half of every reflector step on two schedulers)
-      const bool pair = p >= 2 && !getenv("PSD_NO_HESS_PAIR");
-      const bool special = n == 32 && p == 8 && !getenv("PSD_NO_SPECIAL");
+      const bool pair = p >= 2 && !dbg_env("PSD_NO_HESS_PAIR");
+      const bool special = n == 32 && p == 8 && !dbg_env("PSD_NO_SPECIAL");
       void (*hk)(psd::Hess32Params) =
           pair ? (special ? psd::rphess_pair32_kernel_t<32, 8> : psd::rphess_pair32_kernel_t<0, 0>)
                : (special ? psd::rphess_warp32_kernel_t<32, 8> : psd::rphess_warp32_kernel_t<0, 0>);
@@ -379,14 +395,17 @@ int launch_real_eig32(psd_handle_s* h, Device& dev, Slot& aux, cudaStream_t stre
         Q.info = dInfo + off;
         Q.iters = nullptr;
         Q.counter = aux.dPhaseCtr + k;
-        Q.force_safe = getenv("PSD_EIG32_SAFE") ? 1 : 0;
+        Q.force_safe = dbg_env("PSD_EIG32_SAFE") ? 1 : 0;
         const long long ctas = (nb + ph.wpb - 1) / ph.wpb;
         const int grid2 = (int)std::max(1LL, std::min((long long)ph.grid, ctas));
         ph.kern<<<grid2, ph.wpb * 32, ph.smem, stream>>>(Q);
       }
     }
     PSD_CUDA(cudaGetLastError());
-    h->extra_launches += (double)(phases.size() - 1);
+    {
+      std::lock_guard<std::mutex> lk(h->tmu);
+      h->extra_launches += (double)(phases.size() - 1);
+    }
     __atomic_fetch_add(&h->stats[0], (int64_t)2, __ATOMIC_RELAXED);
   }
   __atomic_fetch_add(&h->stats[1], (int64_t)batch, __ATOMIC_RELAXED);
@@ -398,6 +417,7 @@ int launch_real_eig32(psd_handle_s* h, Device& dev, Slot& aux, cudaStream_t stre
 // a time), then the periodic QR iteration on the reduced factors with Z preset to the Q_j.
 int launch_real_large(psd_handle_s* h, Device& dev, Slot& aux, cudaStream_t stream, const RealCall& rc,
                       long long batch, double* dA, double* dZ, double* dEig, int32_t* dInfo);
+bool large_feasible(const Device& dev, int n, int p);
 
 // Enqueue the real kernel for `batch` device-resident problems on `stream`.
 int launch_real(psd_handle_s* h, Device& dev, Slot& aux, cudaStream_t stream, const RealCall& rc,
@@ -405,9 +425,9 @@ int launch_real(psd_handle_s* h, Device& dev, Slot& aux, cudaStream_t stream, co
   if (batch == 0) return PSD_OK;
   RealLaunchPlan pl;
   const bool wantZ = rc.wantZ && dZ;
-  if (rc.n >= kLargeN && rc.p <= psd::LH_MAXP && !rc.skip_reduce && !getenv("PSD_DISABLE_LARGE"))
+  if (rc.n >= kLargeN && !rc.skip_reduce && !dbg_env("PSD_DISABLE_LARGE") && large_feasible(dev, rc.n, rc.p))
     return launch_real_large(h, dev, aux, stream, rc, batch, dA, dZ, dEig, dInfo);
-  if (!rc.wantT && !wantZ && !rc.reduce_only && rc.n <= 32 && rc.p >= 3 && !getenv("PSD_DISABLE_EIG32"))
+  if (!rc.wantT && !wantZ && !rc.reduce_only && rc.n <= 32 && rc.p >= 3 && !dbg_env("PSD_DISABLE_EIG32"))
     return launch_real_eig32(h, dev, aux, stream, rc, batch, dA, dEig, dInfo);
   int e = plan_real(dev, rc.n, rc.p, batch, wantZ, pl);
   if (e) return e;
@@ -441,6 +461,79 @@ int launch_real(psd_handle_s* h, Device& dev, Slot& aux, cudaStream_t stream, co
 }
 
 
+// Feasibility of the blocked large-N reduction on this device (slab scheme of the panel kernel,
+// its shared memory, one resident CTA per SM); otherwise the generic CTA kernel takes the problem.
+bool large_feasible(const Device& dev, int n, int p) {
+  if (p > psd::LH_MAXP) return false;
+  const int nb = psd::lh_panel_width(p);
+  int R = (n + dev.sm_count - 1) / dev.sm_count;
+  R = (R + 3) & ~3;
+  if (R > psd::LH_RMAX) return false;
+  int optin = 0;
+  if (cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev.ordinal) != cudaSuccess) return false;
+  const size_t smem = ((size_t)p * nb * nb + n) * sizeof(double);
+  cudaFuncAttributes fa;
+  if (cudaFuncGetAttributes(&fa, psd::rphess_panel_kernel) != cudaSuccess) return false;
+  if (smem + fa.sharedSizeBytes > (size_t)optin) return false;
+  if (cudaFuncSetAttribute(psd::rphess_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  int occ = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, psd::rphess_panel_kernel, psd::LH_THREADS, smem) != cudaSuccess || occ < 1) {
+    cudaGetLastError();
+    return false;
+  }
+  return true;
+}
+
+// Team-mode iteration (one double-shift bulge at a time on the whole GPU): the fallback of the
+// large-N path when the multishift iteration does not apply (p > 12) or reports no convergence.
+int launch_team_iteration(psd_handle_s* h, Device& dev, Slot& aux, cudaStream_t stream, const RealCall& rc,
+                          long long batch, double* dA, double* dZ, double* dEig, int32_t* dInfo) {
+  const int n = rc.n, p = rc.p;
+  const bool wantZ = rc.wantZ && dZ;
+  int e;
+  const size_t cnt = (size_t)batch * n;
+  if ((e = ensure_dev(aux.dX[0], aux.capX[0], cnt * 16))) return e;
+  if ((e = ensure_dev(aux.dX[1], aux.capX[1], cnt * 8))) return e;
+  if ((e = ensure_dev(aux.dX[2], aux.capX[2], cnt * 8))) return e;
+  psd::GpqzParams<double> P;
+  P.n = n; P.p = p; P.batch = batch; P.left = rc.left; P.wantT = rc.wantT; P.wantZ = wantZ ? 1 : 0;
+  P.maxitfac = 4 * (rc.maxitfac > 0 ? rc.maxitfac : 30);  // QZ loop counts deflation steps too (rgeneralized.jl:52)
+  P.skip_reduce = 1; P.reduce_only = 0;
+  P.S = nullptr;
+  P.A = dA; P.Z = wantZ ? dZ : nullptr;
+  P.alpha = (psd::cplx*)aux.dX[0]; P.beta = (double*)aux.dX[1]; P.scale = (long long*)aux.dX[2];
+  P.info = dInfo;
+  P.use_smem = 0; P.ldh = n; P.debug = 0; P.counter = nullptr; P.blocked_stage1 = 0; P.windowed_stage2 = 0; P.windowed_qz = 0;
+  P.deep = 4;  // team mode: < 1 element pair per thread and factor, one pass instead of p + 1 (N = 1024: 7.1 s -> 5.3 s)
+  if (const char* ev = dbg_env("PSD_DEEP_U")) P.deep = atoi(ev);
+  auto kern = psd::gpschur_team_kernel<double>;
+  size_t smem = (size_t)((psd::cq_small_doubles(n, p) + 1) & ~1LL) * sizeof(double);
+  if (!dbg_env("PSD_NO_WINDOWED_QZ")) {
+    P.windowed_qz = 1;  // batches of 12 bulge steps between grid barriers instead of two barriers per step
+    smem += (size_t)psd::qzw_work_doubles(p, psd::S3_K_TEAM) * sizeof(double);
+  }
+  PSD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int occ = 0;
+  PSD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, smem));
+  if (occ < 1) return fail(PSD_ERR_UNSUPPORTED, "team kernel does not fit on an SM");
+  int zp = 1;
+  void* args[] = {&P, &zp};
+  int ctas = dev.sm_count;
+  if (const char* ev = dbg_env("PSD_TEAM_CTAS")) ctas = std::max(1, std::min(atoi(ev), dev.sm_count * occ));
+  {
+    ScopedKernelTimer tm(h, dev, stream, 1);
+    PSD_CUDA(cudaLaunchCooperativeKernel((void*)kern, dim3(ctas), dim3(256), args, smem, stream));
+  }
+  psd::gvalues_kernel<<<std::min<long long>(1024, (long long)(cnt + 255) / 256), 256, 0, stream>>>(
+      (const psd::cplx*)aux.dX[0], (const double*)aux.dX[1], (const long long*)aux.dX[2], dEig, (long long)cnt);
+  PSD_CUDA(cudaGetLastError());
+  __atomic_fetch_add(&h->stats[0], (int64_t)2, __ATOMIC_RELAXED);
+  return PSD_OK;
+}
+
 int launch_real_large(psd_handle_s* h, Device& dev, Slot& aux, cudaStream_t stream, const RealCall& rc,
                       long long batch, double* dA, double* dZ, double* dEig, int32_t* dInfo) {
   const int n = rc.n, p = rc.p;
@@ -450,6 +543,13 @@ int launch_real_large(psd_handle_s* h, Device& dev, Slot& aux, cudaStream_t stre
                      (psd::lh_work_doubles(n, p) + (size_t)psd::rp_small_doubles(n, p) * 2) * sizeof(double));
   if (e) return e;
   double* work = aux.dScratch + (size_t)psd::rp_small_doubles(n, p) * 2;  // QR scratch lives in front
+  if (!aux.ms) aux.ms = psd::ms::ws_create();
+  // Exact power-of-two normalisation of every factor (undone on T and the eigenvalues at the end):
+  // the blocked reduction forms sums of squares and the iteration products of entries, which the
+  // reference protects with scaled sums (householder.jl:5-24, 80-100).
+  const bool scaled = p <= psd::ms::kMaxPeriod && !dbg_env("PSD_NO_PRESCALE");
+  const bool use_ms = psd::ms::supported(n, p) && !rc.reduce_only && !dbg_env("PSD_DISABLE_MS");
+  bool team_needed = false;
   for (long long b = 0; b < batch; b++) {
     double* Ab = dA + (size_t)b * p * nn;
     double* Zb = wantZ ? dZ + (size_t)b * p * nn : nullptr;
@@ -460,6 +560,7 @@ int launch_real_large(psd_handle_s* h, Device& dev, Slot& aux, cudaStream_t stre
       const int s = (rc.left && j > 1) ? (p + 2 - j) : j;
       Qp[j - 1] = Zb ? Zb + (size_t)(s - 1) * nn : nullptr;
     }
+    if (scaled) PSD_CUDA(psd::ms::prescale(stream, aux.ms, n, p, Ap));
     double fl = 0.0;
     std::vector<ScopedKernelTimer*> open(4, nullptr);
     auto mark = [&](int kind, int phase) {
@@ -471,12 +572,10 @@ int launch_real_large(psd_handle_s* h, Device& dev, Slot& aux, cudaStream_t stre
       }
     };
     long long* dprof = nullptr;
-    if (getenv("PSD_PANEL_PROF")) {
-      if (!aux.dCounter) PSD_CUDA(cudaMalloc((void**)&aux.dCounter, 2 * sizeof(unsigned long long)));
-      static long long* s_prof = nullptr;
-      if (!s_prof) PSD_CUDA(cudaMalloc((void**)&s_prof, 8 * sizeof(long long)));
-      PSD_CUDA(cudaMemsetAsync(s_prof, 0, 8 * sizeof(long long), stream));
-      dprof = s_prof;
+    if (dbg_env("PSD_PANEL_PROF")) {
+      if (!aux.dProf) PSD_CUDA(cudaMalloc((void**)&aux.dProf, 8 * sizeof(long long)));
+      PSD_CUDA(cudaMemsetAsync(aux.dProf, 0, 8 * sizeof(long long), stream));
+      dprof = aux.dProf;
     }
     cudaError_t ce = psd::rphess_large(stream, dev.sm_count, n, p, Ap, Zb ? Qp : nullptr, work, &fl, mark, dprof);
     if (dprof) {
@@ -488,71 +587,80 @@ int launch_real_large(psd_handle_s* h, Device& dev, Slot& aux, cudaStream_t stre
     }
     for (auto* t : open) delete t;
     if (ce != cudaSuccess) return fail(PSD_ERR_CUDA, std::string("large-N reduction: ") + cudaGetErrorString(ce));
-    h->gemm_flops += fl;
-    __atomic_fetch_add(&h->stats[0], (int64_t)((n + 63) / 64) * (1 + 7 * p), __ATOMIC_RELAXED);
-  }
-  if (rc.reduce_only) {
-    __atomic_fetch_add(&h->stats[2], (int64_t)batch, __ATOMIC_RELAXED);
-    return PSD_OK;
-  }
-  // Periodic QR iteration on the Hessenberg-triangular factors, Z preset to Q.  For large N a
-  // single CTA per problem is hopeless (~N^2.8); the generalized double-shift kernel with S = trues
-  // runs instead as a cooperative team on the whole GPU, one problem at a time.  Its 2x2 blocks
-  // are left unstandardised (as the reference's real generalized path does, rgeneralized.jl:748-790);
-  // consumers only test T1[j+1,j] != 0 (rordschur.jl:56).
-  if (!getenv("PSD_DISABLE_TEAM")) {
-    const size_t cnt = (size_t)batch * n;
-    if ((e = ensure_dev(aux.dX[0], aux.capX[0], cnt * 16))) return e;
-    if ((e = ensure_dev(aux.dX[1], aux.capX[1], cnt * 8))) return e;
-    if ((e = ensure_dev(aux.dX[2], aux.capX[2], cnt * 8))) return e;
-    psd::GpqzParams<double> P;
-    P.n = n; P.p = p; P.batch = batch; P.left = rc.left; P.wantT = rc.wantT; P.wantZ = wantZ ? 1 : 0;
-    P.maxitfac = 4 * (rc.maxitfac > 0 ? rc.maxitfac : 30);  // QZ loop counts deflation steps too (rgeneralized.jl:52)
-    P.skip_reduce = 1; P.reduce_only = 0;
-    P.S = nullptr;
-    P.A = dA; P.Z = wantZ ? dZ : nullptr;
-    P.alpha = (psd::cplx*)aux.dX[0]; P.beta = (double*)aux.dX[1]; P.scale = (long long*)aux.dX[2];
-    P.info = dInfo;
-    P.use_smem = 0; P.ldh = n; P.debug = 0; P.counter = nullptr; P.blocked_stage1 = 0; P.windowed_stage2 = 0; P.windowed_qz = 0;
-    P.deep = 4;  // team mode: < 1 element pair per thread and factor, one pass instead of p + 1 (N = 1024: 7.1 s -> 5.3 s)
-    if (const char* ev = getenv("PSD_DEEP_U")) P.deep = atoi(ev);
-    auto kern = psd::gpschur_team_kernel<double>;
-    size_t smem = (size_t)((psd::cq_small_doubles(n, p) + 1) & ~1LL) * sizeof(double);
-    if (!getenv("PSD_NO_WINDOWED_QZ")) {
-      P.windowed_qz = 1;  // batches of 12 bulge steps between grid barriers instead of two barriers per step
-      smem += (size_t)psd::qzw_work_doubles(p, psd::S3_K_TEAM) * sizeof(double);
-    }
-    PSD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int occ = 0;
-    PSD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, smem));
-    if (occ < 1) return fail(PSD_ERR_UNSUPPORTED, "team kernel does not fit on an SM");
-    int zp = 1;
-    void* args[] = {&P, &zp};
-    int ctas = dev.sm_count;
-    if (const char* ev = getenv("PSD_TEAM_CTAS")) ctas = std::max(1, std::min(atoi(ev), dev.sm_count * occ));
     {
-      ScopedKernelTimer tm(h, dev, stream, 1);
-      PSD_CUDA(cudaLaunchCooperativeKernel((void*)kern, dim3(ctas), dim3(256), args, smem, stream));
+      std::lock_guard<std::mutex> lk(h->tmu);
+      h->gemm_flops += fl;
     }
-    psd::gvalues_kernel<<<std::min<long long>(1024, (long long)(cnt + 255) / 256), 256, 0, stream>>>(
-        (const psd::cplx*)aux.dX[0], (const double*)aux.dX[1], (const long long*)aux.dX[2], dEig, (long long)cnt);
-    PSD_CUDA(cudaGetLastError());
-    __atomic_fetch_add(&h->stats[0], (int64_t)2, __ATOMIC_RELAXED);
-    __atomic_fetch_add(&h->stats[2], (int64_t)batch, __ATOMIC_RELAXED);
-    return PSD_OK;
+    __atomic_fetch_add(&h->stats[0], (int64_t)((n + 63) / 64) * (1 + 7 * p), __ATOMIC_RELAXED);
+    if (rc.reduce_only) {
+      if (scaled) PSD_CUDA(psd::ms::postscale(stream, aux.ms, n, p, Ap, 1, nullptr));
+      continue;
+    }
+    if (use_ms) {
+      // Small-bulge multishift sweeps in diagonal windows + tensor-core updates (psd_ms.cu).
+      PSD_CUDA(cudaMemsetAsync(dInfo + b, 0, sizeof(int32_t), stream));
+      psd::ms::Result res;
+      {
+        ScopedKernelTimer tm(h, dev, stream, 1);
+        ce = psd::ms::iterate(stream, dev.sm_count, aux.ms, n, p, Ap, Zb ? Qp : nullptr, rc.wantT, wantZ ? 1 : 0,
+                              rc.maxitfac, dEig + (size_t)b * 2 * n, dInfo + b, h->profiling ? 1 : 0, &res);
+      }
+      if (ce != cudaSuccess) return fail(PSD_ERR_CUDA, std::string("large-N iteration: ") + cudaGetErrorString(ce));
+      {
+        std::lock_guard<std::mutex> lk(h->tmu);
+        h->ms_last = res;
+      }
+      __atomic_fetch_add(&h->stats[0], (int64_t)res.launches, __ATOMIC_RELAXED);
+      if (res.status == 0) {
+        if (scaled) PSD_CUDA(psd::ms::postscale(stream, aux.ms, n, p, Ap, rc.wantT, dEig + (size_t)b * 2 * n));
+        continue;
+      }
+      // no convergence: the factors are still Hessenberg-triangular with Z accumulated, let the
+      // single-bulge team kernel finish this problem
+    }
+    if (batch == 1) {
+      team_needed = true;
+    } else {
+      RealCall r1 = rc;
+      if ((e = launch_team_iteration(h, dev, aux, stream, r1, 1, Ab, Zb, dEig + (size_t)b * 2 * n, dInfo + b))) return e;
+      if (scaled) PSD_CUDA(psd::ms::postscale(stream, aux.ms, n, p, Ap, rc.wantT, dEig + (size_t)b * 2 * n));
+    }
   }
-  RealCall rq = rc;
-  rq.skip_reduce = 1;
-  rq.z_preset = 1;
-  return launch_real(h, dev, aux, stream, rq, batch, dA, dZ, dEig, dInfo);
+  if (team_needed) {
+    if ((e = launch_team_iteration(h, dev, aux, stream, rc, 1, dA, dZ, dEig, dInfo))) return e;
+    if (scaled) {
+      double* Ap[psd::LH_MAXP];
+      for (int j = 1; j <= p; j++) Ap[j - 1] = dA + (size_t)((rc.left ? (p + 1 - j) : j) - 1) * nn;
+      PSD_CUDA(psd::ms::postscale(stream, aux.ms, n, p, Ap, rc.wantT, dEig));
+    }
+  }
+  __atomic_fetch_add(&h->stats[2], (int64_t)batch, __ATOMIC_RELAXED);
+  return PSD_OK;
 }
+
+// On an error inside a shard loop: wait for every slot stream of the device (copies into the
+// caller's buffers may still be in flight) before the call returns.
+int drain_slots(Device& dev, int code) {
+  const std::string keep = g_err;
+  for (int k = 0; k < kSlotsPerDevice; k++)
+    if (dev.slots[k].stream) cudaStreamSynchronize(dev.slots[k].stream);
+  cudaGetLastError();
+  g_err = keep;
+  return code;
+}
+#define PSD_SHARD_CUDA(call)                                                                        \
+  do {                                                                                              \
+    cudaError_t e__ = (call);                                                                       \
+    if (e__ != cudaSuccess)                                                                         \
+      return drain_slots(dev, fail(PSD_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__))); \
+  } while (0)
 
 // One device's share of a host-buffer batched call.
 int run_real_shard(psd_handle_s* h, Device& dev, const RealCall& rc, long long first, long long count,
                    double* A, double* Z, double* eig, int32_t* info, bool pinned,
                    int64_t* bytes_h2d, int64_t* bytes_d2h) {
   if (count <= 0) return PSD_OK;
-  PSD_CUDA(cudaSetDevice(dev.ordinal));
+  PSD_SHARD_CUDA(cudaSetDevice(dev.ordinal));
   const size_t nn = (size_t)rc.n * rc.n;
   const size_t per = nn * rc.p;  // doubles per problem
   const bool wantZ = rc.wantZ && Z;
@@ -561,6 +669,7 @@ int run_real_shard(psd_handle_s* h, Device& dev, const RealCall& rc, long long f
   // host-to-device copy is the only one no kernel overlaps, so it is kept short, while the large
   // later chunks amortise the tail of the persistent kernels (measured on config 2).
   long long chunk = std::max<long long>(1, (2048LL << 20) / (long long)(per * sizeof(double)));
+  if (!pinned) chunk = std::max<long long>(1, std::min<long long>(chunk, (512LL << 20) / (long long)(per * sizeof(double))));
   chunk = std::min(chunk, count);
   int si = 0;
   int rcode = PSD_OK;
@@ -569,26 +678,26 @@ int run_real_shard(psd_handle_s* h, Device& dev, const RealCall& rc, long long f
     nb = std::min(next, count - off);
     next = std::min(chunk, next * 4);
     Slot& s = dev.slots[si];
-    if (!s.stream) PSD_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+    if (!s.stream) PSD_SHARD_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
     // the slot's previous chunk must have fully drained before its buffers are reused
-    PSD_CUDA(cudaStreamSynchronize(s.stream));
+    PSD_SHARD_CUDA(cudaStreamSynchronize(s.stream));
     int e;
-    if ((e = ensure_dev(s.dA, s.capA, nb * per * sizeof(double)))) return e;
-    if (wantZ && (e = ensure_dev(s.dZ, s.capZ, nb * per * sizeof(double)))) return e;
-    if ((e = ensure_dev(s.dEig, s.capEig, nb * 2 * rc.n * sizeof(double)))) return e;
-    if ((e = ensure_dev(s.dInfo, s.capInfo, nb * sizeof(int32_t)))) return e;
+    if ((e = ensure_dev(s.dA, s.capA, nb * per * sizeof(double)))) return drain_slots(dev, e);
+    if (wantZ && (e = ensure_dev(s.dZ, s.capZ, nb * per * sizeof(double)))) return drain_slots(dev, e);
+    if ((e = ensure_dev(s.dEig, s.capEig, nb * 2 * rc.n * sizeof(double)))) return drain_slots(dev, e);
+    if ((e = ensure_dev(s.dInfo, s.capInfo, nb * sizeof(int32_t)))) return drain_slots(dev, e);
     double* srcA = A + (size_t)(first + off) * per;
     const size_t bytesA = nb * per * sizeof(double);
     if (pinned) {
-      PSD_CUDA(cudaMemcpyAsync(s.dA, srcA, bytesA, cudaMemcpyHostToDevice, s.stream));
+      PSD_SHARD_CUDA(cudaMemcpyAsync(s.dA, srcA, bytesA, cudaMemcpyHostToDevice, s.stream));
     } else {
-      if ((e = ensure_pinned(s.hA, s.hcapA, bytesA))) return e;
+      if ((e = ensure_pinned(s.hA, s.hcapA, bytesA))) return drain_slots(dev, e);
       std::memcpy(s.hA, srcA, bytesA);
-      PSD_CUDA(cudaMemcpyAsync(s.dA, s.hA, bytesA, cudaMemcpyHostToDevice, s.stream));
+      PSD_SHARD_CUDA(cudaMemcpyAsync(s.dA, s.hA, bytesA, cudaMemcpyHostToDevice, s.stream));
     }
     *bytes_h2d += (int64_t)bytesA;
     e = launch_real(h, dev, s, s.stream, rc, nb, s.dA, wantZ ? s.dZ : nullptr, s.dEig, s.dInfo);
-    if (e) return e;
+    if (e) return drain_slots(dev, e);
     // results
     double* dstEig = eig ? eig + (size_t)(first + off) * 2 * rc.n : nullptr;
     int32_t* dstInfo = info ? info + (first + off) : nullptr;
@@ -596,21 +705,21 @@ int run_real_shard(psd_handle_s* h, Device& dev, const RealCall& rc, long long f
     const size_t bytesEig = nb * 2 * rc.n * sizeof(double);
     const size_t bytesInfo = nb * sizeof(int32_t);
     if (pinned) {
-      if (outT) PSD_CUDA(cudaMemcpyAsync(srcA, s.dA, bytesA, cudaMemcpyDeviceToHost, s.stream));
-      if (wantZ) PSD_CUDA(cudaMemcpyAsync(dstZ, s.dZ, bytesA, cudaMemcpyDeviceToHost, s.stream));
-      if (dstEig) PSD_CUDA(cudaMemcpyAsync(dstEig, s.dEig, bytesEig, cudaMemcpyDeviceToHost, s.stream));
-      if (dstInfo) PSD_CUDA(cudaMemcpyAsync(dstInfo, s.dInfo, bytesInfo, cudaMemcpyDeviceToHost, s.stream));
+      if (outT) PSD_SHARD_CUDA(cudaMemcpyAsync(srcA, s.dA, bytesA, cudaMemcpyDeviceToHost, s.stream));
+      if (wantZ) PSD_SHARD_CUDA(cudaMemcpyAsync(dstZ, s.dZ, bytesA, cudaMemcpyDeviceToHost, s.stream));
+      if (dstEig) PSD_SHARD_CUDA(cudaMemcpyAsync(dstEig, s.dEig, bytesEig, cudaMemcpyDeviceToHost, s.stream));
+      if (dstInfo) PSD_SHARD_CUDA(cudaMemcpyAsync(dstInfo, s.dInfo, bytesInfo, cudaMemcpyDeviceToHost, s.stream));
     } else {
-      if (wantZ && (e = ensure_pinned(s.hZ, s.hcapZ, bytesA))) return e;
-      if ((e = ensure_pinned(s.hEig, s.hcapEig, bytesEig))) return e;
-      if ((e = ensure_pinned(s.hInfo, s.hcapInfo, bytesInfo))) return e;
-      if (outT) PSD_CUDA(cudaMemcpyAsync(s.hA, s.dA, bytesA, cudaMemcpyDeviceToHost, s.stream));
-      if (wantZ) PSD_CUDA(cudaMemcpyAsync(s.hZ, s.dZ, bytesA, cudaMemcpyDeviceToHost, s.stream));
-      PSD_CUDA(cudaMemcpyAsync(s.hEig, s.dEig, bytesEig, cudaMemcpyDeviceToHost, s.stream));
-      PSD_CUDA(cudaMemcpyAsync(s.hInfo, s.dInfo, bytesInfo, cudaMemcpyDeviceToHost, s.stream));
+      if (wantZ && (e = ensure_pinned(s.hZ, s.hcapZ, bytesA))) return drain_slots(dev, e);
+      if ((e = ensure_pinned(s.hEig, s.hcapEig, bytesEig))) return drain_slots(dev, e);
+      if ((e = ensure_pinned(s.hInfo, s.hcapInfo, bytesInfo))) return drain_slots(dev, e);
+      if (outT) PSD_SHARD_CUDA(cudaMemcpyAsync(s.hA, s.dA, bytesA, cudaMemcpyDeviceToHost, s.stream));
+      if (wantZ) PSD_SHARD_CUDA(cudaMemcpyAsync(s.hZ, s.dZ, bytesA, cudaMemcpyDeviceToHost, s.stream));
+      PSD_SHARD_CUDA(cudaMemcpyAsync(s.hEig, s.dEig, bytesEig, cudaMemcpyDeviceToHost, s.stream));
+      PSD_SHARD_CUDA(cudaMemcpyAsync(s.hInfo, s.dInfo, bytesInfo, cudaMemcpyDeviceToHost, s.stream));
       // pageable destination: drain this slot now and copy out (the other slot keeps the
       // GPU busy meanwhile)
-      PSD_CUDA(cudaStreamSynchronize(s.stream));
+      PSD_SHARD_CUDA(cudaStreamSynchronize(s.stream));
       if (outT) std::memcpy(srcA, s.hA, bytesA);
       if (wantZ) std::memcpy(dstZ, s.hZ, bytesA);
       if (dstEig) std::memcpy(dstEig, s.hEig, bytesEig);
@@ -619,7 +728,7 @@ int run_real_shard(psd_handle_s* h, Device& dev, const RealCall& rc, long long f
     *bytes_d2h += (int64_t)((outT ? bytesA : 0) + (wantZ ? bytesA : 0) + bytesEig + bytesInfo);
   }
   for (int k = 0; k < kSlotsPerDevice; k++)
-    if (dev.slots[k].stream) PSD_CUDA(cudaStreamSynchronize(dev.slots[k].stream));
+    if (dev.slots[k].stream) PSD_SHARD_CUDA(cudaStreamSynchronize(dev.slots[k].stream));
   return rcode;
 }
 
@@ -714,39 +823,39 @@ int launch_gen_t(psd_handle_s* h, Device& dev, Slot& aux, cudaStream_t stream, c
   P.A = (T*)dA; P.Z = wantZ ? (T*)dZ : nullptr;
   P.alpha = (psd::cplx*)dAlpha; P.beta = (T*)dBeta; P.scale = dScale; P.info = dInfo;
   P.counter = aux.dCounter;
-  P.debug = getenv("PSD_GEN_PROF") ? 1 : 0;
+  P.debug = dbg_env("PSD_GEN_PROF") ? 1 : 0;
   size_t smem;
   if (small + mats <= max_dyn) {
     P.use_smem = 1; P.ldh = ldh; smem = small + mats;
-    P.deep = getenv("PSD_DEEP_SMEM") ? 1 : 0;
+    P.deep = dbg_env("PSD_DEEP_SMEM") ? 1 : 0;
   } else {
     if (small > max_dyn) return fail(PSD_ERR_UNSUPPORTED, "n or p too large for the per-CTA state");
     P.use_smem = 0; P.ldh = n; smem = small;
     // table-driven single-pass chases (items in flight per thread), measured as above: a gain for
     // the complex path, a small loss for the real one
     P.deep = (sizeof(T) == sizeof(psd::cplx)) ? 2 : 0;
-    if (getenv("PSD_NO_DEEP")) P.deep = 0;
-    if (const char* ev = getenv("PSD_DEEP_U")) P.deep = atoi(ev);
+    if (dbg_env("PSD_NO_DEEP")) P.deep = 0;
+    if (const char* ev = dbg_env("PSD_DEEP_U")) P.deep = atoi(ev);
     const size_t blk = (size_t)psd::blk_work_scalars(n) * sizeof(T);
-    if (!gc.skip_reduce && small + blk <= max_dyn && !getenv("PSD_NO_BLOCKED_STAGE1")) {
+    if (!gc.skip_reduce && small + blk <= max_dyn && !dbg_env("PSD_NO_BLOCKED_STAGE1")) {
       P.blocked_stage1 = 1;
       smem = small + blk;
     }
     const size_t qzw = sizeof(T) == sizeof(double) ? (size_t)psd::qzw_work_doubles(p, psd::S3_K_CTA) * sizeof(double)
                                                    : (size_t)psd::s4_work_scalars<T>(p) * sizeof(T);
-    if (!gc.reduce_only && small + qzw <= max_dyn && !getenv("PSD_NO_WINDOWED_QZ")) {
+    if (!gc.reduce_only && small + qzw <= max_dyn && !dbg_env("PSD_NO_WINDOWED_QZ")) {
       P.windowed_qz = 1;
       smem = std::max(smem, small + qzw);
     }
     const size_t s2w = (size_t)psd::s2_work_scalars(p) * sizeof(T);
-    if (!gc.skip_reduce && small + s2w <= max_dyn && !getenv("PSD_NO_WINDOWED_STAGE2")) {
+    if (!gc.skip_reduce && small + s2w <= max_dyn && !dbg_env("PSD_NO_WINDOWED_STAGE2")) {
       P.windowed_stage2 = 1;
       smem = std::max(smem, small + s2w);
     }
   }
   bool wide = !P.use_smem;
-  if (const char* ev = getenv("PSD_GEN_WIDE")) wide = atoi(ev) != 0;
-  if (const char* ev = getenv("PSD_GEN_THREADS")) threads = std::max(64, std::min(atoi(ev), wide ? 512 : 256));
+  if (const char* ev = dbg_env("PSD_GEN_WIDE")) wide = atoi(ev) != 0;
+  if (const char* ev = dbg_env("PSD_GEN_THREADS")) threads = std::max(64, std::min(atoi(ev), wide ? 512 : 256));
   if (wide) kern = psd::gpschur_kernel<T, 512>;
   PSD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_dyn));
   int occ = 0;
@@ -775,7 +884,7 @@ int run_gen_shard(psd_handle_s* h, Device& dev, const GenCall& gc, long long fir
                   char* Z, char* alpha, char* beta, int64_t* scale, int32_t* info, bool pinned,
                   int64_t* bytes_h2d, int64_t* bytes_d2h) {
   if (count <= 0) return PSD_OK;
-  PSD_CUDA(cudaSetDevice(dev.ordinal));
+  PSD_SHARD_CUDA(cudaSetDevice(dev.ordinal));
   const size_t es = gen_elem(gc);
   const size_t perB = (size_t)gc.n * gc.n * gc.p * es;  // bytes of factors per problem
   const size_t xB[3] = {(size_t)gc.n * 16, (size_t)gc.n * es, (size_t)gc.n * 8};
@@ -789,7 +898,7 @@ int run_gen_shard(psd_handle_s* h, Device& dev, const GenCall& gc, long long fir
   chunk = (chunk + wave - 1) / wave * wave;   // whole waves: no half-empty tail inside a launch
   {
     size_t free_b = 0, total_b = 0;
-    PSD_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    PSD_SHARD_CUDA(cudaMemGetInfo(&free_b, &total_b));
     const size_t per_problem = perB * (wantZ0 ? 2 : 1) + (xB[0] + xB[1] + xB[2]) + 64;
     const long long cap = (long long)((total_b / 2) / kSlotsPerDevice / per_problem);
     chunk = std::max<long long>(1, std::min(chunk, cap));
@@ -801,28 +910,28 @@ int run_gen_shard(psd_handle_s* h, Device& dev, const GenCall& gc, long long fir
   for (long long off = 0; off < count; off += chunk, si = (si + 1) % kSlotsPerDevice) {
     const long long nb = std::min(chunk, count - off);
     Slot& s = dev.slots[si];
-    if (!s.stream) PSD_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
-    PSD_CUDA(cudaStreamSynchronize(s.stream));
+    if (!s.stream) PSD_SHARD_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+    PSD_SHARD_CUDA(cudaStreamSynchronize(s.stream));
     int e;
     const size_t bytesA = nb * perB;
-    if ((e = ensure_dev(s.dA, s.capA, bytesA))) return e;
-    if (wantZ && (e = ensure_dev(s.dZ, s.capZ, bytesA))) return e;
+    if ((e = ensure_dev(s.dA, s.capA, bytesA))) return drain_slots(dev, e);
+    if (wantZ && (e = ensure_dev(s.dZ, s.capZ, bytesA))) return drain_slots(dev, e);
     for (int k = 0; k < 3; k++)
-      if ((e = ensure_dev(s.dX[k], s.capX[k], nb * xB[k]))) return e;
-    if ((e = ensure_dev(s.dInfo, s.capInfo, nb * sizeof(int32_t)))) return e;
+      if ((e = ensure_dev(s.dX[k], s.capX[k], nb * xB[k]))) return drain_slots(dev, e);
+    if ((e = ensure_dev(s.dInfo, s.capInfo, nb * sizeof(int32_t)))) return drain_slots(dev, e);
     char* srcA = A + (size_t)(first + off) * perB;
     const bool direct = pinned || bytesA > kStageLimit;
     if (direct) {
-      PSD_CUDA(cudaMemcpyAsync(s.dA, srcA, bytesA, cudaMemcpyHostToDevice, s.stream));
+      PSD_SHARD_CUDA(cudaMemcpyAsync(s.dA, srcA, bytesA, cudaMemcpyHostToDevice, s.stream));
     } else {
-      if ((e = ensure_pinned(s.hA, s.hcapA, bytesA))) return e;
+      if ((e = ensure_pinned(s.hA, s.hcapA, bytesA))) return drain_slots(dev, e);
       std::memcpy(s.hA, srcA, bytesA);
-      PSD_CUDA(cudaMemcpyAsync(s.dA, s.hA, bytesA, cudaMemcpyHostToDevice, s.stream));
+      PSD_SHARD_CUDA(cudaMemcpyAsync(s.dA, s.hA, bytesA, cudaMemcpyHostToDevice, s.stream));
     }
     *bytes_h2d += (int64_t)bytesA;
     e = launch_gen(h, dev, s, s.stream, gc, nb, s.dA, wantZ ? s.dZ : nullptr, s.dX[0], s.dX[1],
                    (long long*)s.dX[2], s.dInfo);
-    if (e) return e;
+    if (e) return drain_slots(dev, e);
     char* dstZ = wantZ ? Z + (size_t)(first + off) * perB : nullptr;
     const bool ev = !gc.reduce_only;
     char* dstX[3] = {ev ? alpha + (size_t)(first + off) * xB[0] : nullptr, ev ? beta + (size_t)(first + off) * xB[1] : nullptr,
@@ -830,22 +939,22 @@ int run_gen_shard(psd_handle_s* h, Device& dev, const GenCall& gc, long long fir
     int32_t* dstInfo = ev ? info + (first + off) : nullptr;
     const size_t bytesInfo = nb * sizeof(int32_t);
     if (direct) {
-      if (gc.wantT) PSD_CUDA(cudaMemcpyAsync(srcA, s.dA, bytesA, cudaMemcpyDeviceToHost, s.stream));
-      if (wantZ) PSD_CUDA(cudaMemcpyAsync(dstZ, s.dZ, bytesA, cudaMemcpyDeviceToHost, s.stream));
+      if (gc.wantT) PSD_SHARD_CUDA(cudaMemcpyAsync(srcA, s.dA, bytesA, cudaMemcpyDeviceToHost, s.stream));
+      if (wantZ) PSD_SHARD_CUDA(cudaMemcpyAsync(dstZ, s.dZ, bytesA, cudaMemcpyDeviceToHost, s.stream));
       for (int k = 0; k < 3 && ev; k++)
-        PSD_CUDA(cudaMemcpyAsync(dstX[k], s.dX[k], nb * xB[k], cudaMemcpyDeviceToHost, s.stream));
-      if (ev) PSD_CUDA(cudaMemcpyAsync(dstInfo, s.dInfo, bytesInfo, cudaMemcpyDeviceToHost, s.stream));
+        PSD_SHARD_CUDA(cudaMemcpyAsync(dstX[k], s.dX[k], nb * xB[k], cudaMemcpyDeviceToHost, s.stream));
+      if (ev) PSD_SHARD_CUDA(cudaMemcpyAsync(dstInfo, s.dInfo, bytesInfo, cudaMemcpyDeviceToHost, s.stream));
     } else {
-      if (wantZ && (e = ensure_pinned(s.hZ, s.hcapZ, bytesA))) return e;
+      if (wantZ && (e = ensure_pinned(s.hZ, s.hcapZ, bytesA))) return drain_slots(dev, e);
       for (int k = 0; k < 3; k++)
-        if ((e = ensure_pinned(s.hX[k], s.hcapX[k], nb * xB[k]))) return e;
-      if ((e = ensure_pinned(s.hInfo, s.hcapInfo, bytesInfo))) return e;
-      if (gc.wantT) PSD_CUDA(cudaMemcpyAsync(s.hA, s.dA, bytesA, cudaMemcpyDeviceToHost, s.stream));
-      if (wantZ) PSD_CUDA(cudaMemcpyAsync(s.hZ, s.dZ, bytesA, cudaMemcpyDeviceToHost, s.stream));
+        if ((e = ensure_pinned(s.hX[k], s.hcapX[k], nb * xB[k]))) return drain_slots(dev, e);
+      if ((e = ensure_pinned(s.hInfo, s.hcapInfo, bytesInfo))) return drain_slots(dev, e);
+      if (gc.wantT) PSD_SHARD_CUDA(cudaMemcpyAsync(s.hA, s.dA, bytesA, cudaMemcpyDeviceToHost, s.stream));
+      if (wantZ) PSD_SHARD_CUDA(cudaMemcpyAsync(s.hZ, s.dZ, bytesA, cudaMemcpyDeviceToHost, s.stream));
       for (int k = 0; k < 3; k++)
-        PSD_CUDA(cudaMemcpyAsync(s.hX[k], s.dX[k], nb * xB[k], cudaMemcpyDeviceToHost, s.stream));
-      PSD_CUDA(cudaMemcpyAsync(s.hInfo, s.dInfo, bytesInfo, cudaMemcpyDeviceToHost, s.stream));
-      PSD_CUDA(cudaStreamSynchronize(s.stream));
+        PSD_SHARD_CUDA(cudaMemcpyAsync(s.hX[k], s.dX[k], nb * xB[k], cudaMemcpyDeviceToHost, s.stream));
+      PSD_SHARD_CUDA(cudaMemcpyAsync(s.hInfo, s.dInfo, bytesInfo, cudaMemcpyDeviceToHost, s.stream));
+      PSD_SHARD_CUDA(cudaStreamSynchronize(s.stream));
       if (gc.wantT) std::memcpy(srcA, s.hA, bytesA);
       if (wantZ) std::memcpy(dstZ, s.hZ, bytesA);
       for (int k = 0; k < 3 && ev; k++) std::memcpy(dstX[k], s.hX[k], nb * xB[k]);
@@ -854,7 +963,7 @@ int run_gen_shard(psd_handle_s* h, Device& dev, const GenCall& gc, long long fir
     *bytes_d2h += (int64_t)((gc.wantT ? bytesA : 0) + (wantZ ? bytesA : 0) + nb * (xB[0] + xB[1] + xB[2]) + bytesInfo);
   }
   for (int k = 0; k < kSlotsPerDevice; k++)
-    if (dev.slots[k].stream) PSD_CUDA(cudaStreamSynchronize(dev.slots[k].stream));
+    if (dev.slots[k].stream) PSD_SHARD_CUDA(cudaStreamSynchronize(dev.slots[k].stream));
   return PSD_OK;
 }
 
@@ -970,6 +1079,8 @@ int psd_destroy(psd_handle_t h) {
       cudaFree(s.dCounter); cudaFree(s.dScratch); cudaFree(s.dPacked); cudaFree(s.dS);
       for (int k = 0; k < 8; k++) cudaFree(s.dPk[k]);
       cudaFree(s.dPhaseCtr);
+      cudaFree(s.dProf);
+      psd::ms::ws_destroy(s.ms);
       for (int k = 0; k < 3; k++) {
         cudaFree(s.dX[k]);
         cudaFreeHost(s.hX[k]);
@@ -978,6 +1089,7 @@ int psd_destroy(psd_handle_t h) {
     };
     for (auto& s : d.slots) freeSlot(s);
     freeSlot(d.user);
+    if (d.userDone) cudaEventDestroy(d.userDone);
   }
   cudaGetLastError();
   delete h;
@@ -1021,8 +1133,14 @@ int psd_rpschur_batched_dev(psd_handle_t h, int dev_index, void* stream, int n, 
     if (!dev.user.stream) PSD_CUDA(cudaStreamCreateWithFlags(&dev.user.stream, cudaStreamNonBlocking));
     st = dev.user.stream;
   }
+  // Every *_dev call on this device uses the same scratch set (work counters, packed buffers):
+  // a call waits for the previous one, whatever stream that was enqueued on.
+  if (!dev.userDone) PSD_CUDA(cudaEventCreateWithFlags(&dev.userDone, cudaEventDisableTiming));
+  else PSD_CUDA(cudaStreamWaitEvent(st, dev.userDone, 0));
   RealCall rc{n, p, orientation, wantT != 0, wantZ != 0, maxitfac, 0, 0};
-  return launch_real(h, dev, dev.user, st, rc, batch, dA, dZ, deig, dinfo);
+  const int rcode = launch_real(h, dev, dev.user, st, rc, batch, dA, dZ, deig, dinfo);
+  PSD_CUDA(cudaEventRecord(dev.userDone, st));
+  return rcode;
 }
 
 int psd_cpschur_batched(psd_handle_t h, int n, int p, int64_t batch, int orientation, const uint8_t* S, int wantT,
@@ -1246,6 +1364,18 @@ int psd_kernel_times(psd_handle_t h, double ms[8]) {
     }
   }
   h->timers.clear();
+  return PSD_OK;
+}
+
+int psd_large_stats(psd_handle_t h, double out[16]) {
+  if (!h || !out) return fail(PSD_ERR_BAD_ARG, "null argument");
+  std::lock_guard<std::mutex> lk(h->tmu);
+  const psd::ms::Result& r = h->ms_last;
+  for (int i = 0; i < 16; i++) out[i] = 0.0;
+  out[0] = r.status; out[1] = r.sweeps; out[2] = (double)r.rounds; out[3] = (double)r.windows;
+  out[4] = (double)r.shift_pairs; out[5] = r.exceptional; out[6] = r.final_blocks; out[7] = (double)r.launches;
+  out[8] = r.apply_flops; out[9] = r.ms_chase; out[10] = r.ms_apply; out[11] = r.ms_shifts; out[12] = r.ms_scan;
+  out[13] = r.ms_final;
   return PSD_OK;
 }
 

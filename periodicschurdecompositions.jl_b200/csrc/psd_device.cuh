@@ -26,7 +26,7 @@ namespace psd {
 PSD_DEV double pow2_rescale(double m) {
   int e;
   (void)frexp(m, &e);  // m = f * 2^e, f in [0.5,1)
-  return scalbn(1.0, -e);
+  return scalbn(1.0, (-e > 1000) ? 1000 : -e);  // 2^-e itself overflows for subnormal m
 }
 
 // Reflector for a 2- or 3-vector held in registers.  On return x0 = beta, (v1,v2) the

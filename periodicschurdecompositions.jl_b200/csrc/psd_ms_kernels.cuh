@@ -1,0 +1,489 @@
+// CUDA kernels of the large-N multishift periodic QR iteration (see psd_ms_core.cuh for the
+// algorithm and psd_ms.cu for the host driver):
+//   ms_chase_kernel      one CTA per diagonal window: stage the p windows in shared memory, chase
+//                        the packet of bulges, accumulate U_j, write windows and U_j back
+//   ms_apply_kernel      in-place tile updates  X <- U' X  /  X <- X U  on the FP64 tensor cores
+//                        (DMMA m8n8k4) for the off-window parts of H_j and for Z_j
+//   ms_scan_kernel       deflation scan of the subdiagonal of H_1, active block
+//   ms_shifts_kernel     eigenvalues of the trailing window (periodic_qr_cta, eigenvalues only)
+//   ms_blocklist_kernel / ms_blocks_kernel   final stage: every remaining diagonal block of order
+//                        <= W is brought to (standardised) periodic Schur form by one CTA each
+//   ms_maxabs / ms_scale  exact power-of-two normalisation of the factors (overflow safety)
+#pragma once
+#include <cuda_runtime.h>
+
+#include "psd_ms_core.cuh"
+#include "psd_real_qr.cuh"
+
+namespace psd {
+namespace ms {
+
+extern __shared__ __align__(16) double ms_smem[];
+
+// FP64 tensor-core instruction (SASS DMMA): D(8x8) += A(8x4) * B(4x8); per lane a = A[lane/4][lane%4],
+// b = B[lane%4][lane/4], d0/d1 = D[lane/4][2*(lane%4) + 0/1].
+__device__ __forceinline__ void ms_dmma(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(d0), "+d"(d1)
+               : "d"(a), "d"(b));
+}
+
+// ------------------------------------------------------------------------------------------
+// Workspace layout (device): U_j of the window / block that starts at row s lives at
+//   U + (j-1) * n * W + s * W,  column-major with leading dimension = order of the window.
+// Windows that exist at the same time are disjoint in index space, so these never overlap.
+// ------------------------------------------------------------------------------------------
+struct ChaseParams {
+  int n, p;
+  Geom g;
+  double* H[MS_MAXP];  // internal factor j at H[j-1], column-major, ld = n
+  double* U;
+  const double* shifts;
+  const WinDesc* wins;
+};
+
+struct DevExec {
+  static constexpr int LANES = 32;
+  BState st;
+  int b, role, lane;
+  template <class F>
+  __device__ __forceinline__ void each(F&& f) { f(b, role, lane, st); }
+  __device__ __forceinline__ void barrier() { __syncthreads(); }
+};
+
+__global__ void __launch_bounds__(64 * MS_MAXNB, 1) ms_chase_kernel(ChaseParams P) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const WinDesc d = P.wins[blockIdx.x];
+  const int W = P.g.W, LD = P.g.LD, p = P.p, n = P.n;
+  Ctx c;
+  c.p = p; c.W = W; c.LD = LD;
+  c.Hw = ms_smem;
+  c.Uw = ms_smem + (size_t)p * W * LD;
+  c.shifts = P.shifts;
+  c.d = d;
+  const int wl = d.wl, s = d.s;
+  for (int j = 1; j <= p; j++) {
+    const double* src = P.H[j - 1] + s + (size_t)s * n;
+    double* dst = c.H(j);
+    double* u = c.U(j);
+    for (int e = tid; e < wl * wl; e += nt) {
+      const int r = e % wl, cc = e / wl;
+      dst[r + (size_t)cc * LD] = src[r + (size_t)cc * n];
+      u[r + (size_t)cc * LD] = (r == cc) ? 1.0 : 0.0;
+    }
+  }
+  __syncthreads();
+  DevExec ex;
+  ex.b = tid >> 6;
+  ex.role = (tid >> 5) & 1;
+  ex.lane = tid & 31;
+  ex.st.active = 0;
+  ex.st.defer_j = 0;
+  chase_window(c, ex);
+  __syncthreads();
+  for (int j = 1; j <= p; j++) {
+    double* dst = P.H[j - 1] + s + (size_t)s * n;
+    const double* src = c.H(j);
+    const double* u = c.U(j);
+    double* ud = P.U + (size_t)(j - 1) * n * W + (size_t)s * W;
+    for (int e = tid; e < wl * wl; e += nt) {
+      const int r = e % wl, cc = e / wl;
+      dst[r + (size_t)cc * n] = src[r + (size_t)cc * LD];
+      ud[e] = u[r + (size_t)cc * LD];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// In-place application of the window factors on the FP64 tensor cores.
+//   phase 0: left   H_j[s:s+wl, c_lo:c_hi)  <- U_j' * (same)       tiles of 64 columns
+//            and    Z_j[:, s:s+wl)          <- (same) * U_j          tiles of 64 rows
+//   phase 1: right  H_jm[r_lo:s, s:s+wl)    <- (same) * U_j,  jm = j-1 (cyclic)
+// A CTA reads its whole tile and U_j into shared memory before it writes anything, and tiles of
+// one launch are disjoint, so the update is in place without workspace.  (The two phases touch
+// the same off-diagonal blocks from different sides, hence two launches.)
+// 8 warps as 2 x 4, warp tile 32 x 16 = 4 x 2 DMMA m8n8k4 tiles; operands are kept in their
+// natural column-major layout with leading dimension 68 (= 4 mod 16): both fragment patterns
+// (8 rows x 4 k and 4 k x 8 columns per half-warp) are then bank-conflict free.
+// ------------------------------------------------------------------------------------------
+constexpr int AP_T = 64;    // tile extent along the long dimension
+constexpr int AP_LD = 68;
+constexpr int AP_SMEM = 2 * 64 * AP_LD * 8;
+
+struct ApplyParams {
+  int n, p, W, wantT, wantZ, phase, nwin;
+  double* H[MS_MAXP];
+  double* Z[MS_MAXP];
+  const double* U;
+  const WinDesc* wins;
+};
+
+__global__ void __launch_bounds__(256) ms_apply_kernel(ApplyParams P) {
+  double* Us = ms_smem;               // U(k, c) at Us[c * AP_LD + k]
+  double* Xs = ms_smem + 64 * AP_LD;  // X(r, c) at Xs[c * AP_LD + r]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n = P.n, p = P.p;
+  // item -> (window, factor, kind)
+  const int kinds = (P.phase == 0) ? 2 : 1;
+  int it = blockIdx.y;
+  const int w = it / (p * kinds);
+  it -= w * p * kinds;
+  const int j = it / kinds + 1;
+  const int kind = (P.phase == 0) ? (it % kinds == 0 ? 0 : 2) : 1;  // 0 left, 1 right, 2 Z
+  const WinDesc d = P.wins[w];
+  const int s = d.s, wl = d.wl;
+  double* X;
+  int lo, hi;  // extent of the long dimension
+  if (kind == 0) {
+    X = P.H[j - 1];
+    lo = s + wl;
+    hi = P.wantT ? n : d.ihi + 1;
+  } else if (kind == 1) {
+    X = P.H[(j == 1) ? p - 1 : j - 2];
+    lo = P.wantT ? 0 : d.ilo;
+    hi = s;
+  } else {
+    if (!P.wantZ) return;
+    X = P.Z[j - 1];
+    lo = 0;
+    hi = n;
+  }
+  const int t0 = lo + blockIdx.x * AP_T;
+  if (t0 >= hi) return;
+  const int tl = min(AP_T, hi - t0);
+  const double* Ug = P.U + (size_t)(j - 1) * n * P.W + (size_t)s * P.W;
+  // ---- stage U (wl x wl, zero padded to 64 x 64) and the tile ----
+  for (int e = tid; e < 64 * 64; e += 256) {
+    const int r = e & 63, cc = e >> 6;
+    Us[cc * AP_LD + r] = (r < wl && cc < wl) ? Ug[r + (size_t)cc * wl] : 0.0;
+  }
+  if (kind == 0) {
+    // tile: rows s .. s+wl-1 (r), columns t0 .. t0+tl-1 (cc)
+    for (int e = tid; e < 64 * 64; e += 256) {
+      const int r = e & 63, cc = e >> 6;
+      Xs[cc * AP_LD + r] = (r < wl && cc < tl) ? X[(s + r) + (size_t)(t0 + cc) * n] : 0.0;
+    }
+  } else {
+    // tile: rows t0 .. t0+tl-1 (r), columns s .. s+wl-1 (cc)
+    for (int e = tid; e < 64 * 64; e += 256) {
+      const int r = e & 63, cc = e >> 6;
+      Xs[cc * AP_LD + r] = (r < tl && cc < wl) ? X[(t0 + r) + (size_t)(s + cc) * n] : 0.0;
+    }
+  }
+  __syncthreads();
+  // ---- C = U' X (kind 0)  or  C = X U (kinds 1, 2), 64 x 64 x 64 ----
+  const int wm = warp & 1, wn = warp >> 1;
+  const int gq = lane >> 2, tq = lane & 3;
+  double acc[4][2][2];
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int q = 0; q < 2; q++) acc[i][q][0] = acc[i][q][1] = 0.0;
+  const int kmax = (wl + 3) & ~3;
+  if (kind == 0) {
+    // A(m, k) = U(k, m) = Us[m * LD + k];  B(k, nn) = X(k, nn) = Xs[nn * LD + k]
+    for (int k0 = 0; k0 < kmax; k0 += 4) {
+      double a[4], b[2];
+#pragma unroll
+      for (int i = 0; i < 4; i++) a[i] = Us[(wm * 32 + i * 8 + gq) * AP_LD + k0 + tq];
+#pragma unroll
+      for (int q = 0; q < 2; q++) b[q] = Xs[(wn * 16 + q * 8 + gq) * AP_LD + k0 + tq];
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int q = 0; q < 2; q++) ms_dmma(acc[i][q][0], acc[i][q][1], a[i], b[q]);
+    }
+  } else {
+    // A(m, k) = X(m, k) = Xs[k * LD + m];  B(k, nn) = U(k, nn) = Us[nn * LD + k]
+    for (int k0 = 0; k0 < kmax; k0 += 4) {
+      double a[4], b[2];
+#pragma unroll
+      for (int i = 0; i < 4; i++) a[i] = Xs[(k0 + tq) * AP_LD + wm * 32 + i * 8 + gq];
+#pragma unroll
+      for (int q = 0; q < 2; q++) b[q] = Us[(wn * 16 + q * 8 + gq) * AP_LD + k0 + tq];
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int q = 0; q < 2; q++) ms_dmma(acc[i][q][0], acc[i][q][1], a[i], b[q]);
+    }
+  }
+  __syncthreads();  // every warp has finished reading Xs
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int q = 0; q < 2; q++)
+#pragma unroll
+      for (int e = 0; e < 2; e++) {
+        const int m = wm * 32 + i * 8 + gq;
+        const int nn = wn * 16 + q * 8 + 2 * tq + e;
+        Xs[nn * AP_LD + m] = acc[i][q][e];
+      }
+  __syncthreads();
+  if (kind == 0) {
+    for (int e = tid; e < 64 * 64; e += 256) {
+      const int r = e & 63, cc = e >> 6;
+      if (r < wl && cc < tl) X[(s + r) + (size_t)(t0 + cc) * n] = Xs[cc * AP_LD + r];
+    }
+  } else {
+    for (int e = tid; e < 64 * 64; e += 256) {
+      const int r = e & 63, cc = e >> 6;
+      if (r < tl && cc < wl) X[(t0 + r) + (size_t)(s + cc) * n] = Xs[cc * AP_LD + r];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Deflation scan + active block.  ctl (device ints): [0] ilo, [1] ihi, [2] done,
+// [3] number of subdiagonal entries set to zero by this scan.
+// Criterion: |h(k,k-1)| <= max(smlnum, ulp (|h(k-1,k-1)| + |h(k,k)|)) on H_1 (the "Test 1" of the
+// periodic QZ drivers, rgeneralized.jl:1086-1112), which perturbs H_1 by at most 2 ulp ||H_1||.
+// The active block is the lowest unreduced diagonal block of order > nmin.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) ms_scan_kernel(double* H1, int n, int nmin, int* ctl) {
+  __shared__ int s_ihi, s_ilo, s_cnt;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  if (tid == 0) { s_ihi = -1; s_ilo = 0; s_cnt = 0; }
+  __syncthreads();
+  const double smlnum = DBL_MIN * ((double)n / DBL_EPSILON);
+  int cnt = 0;
+  for (int k = 1 + tid; k < n; k += nt) {
+    double* e = H1 + k + (size_t)(k - 1) * n;
+    const double sub = *e;
+    if (sub != 0.0 && ms_negligible(sub, H1[(k - 1) + (size_t)(k - 1) * n], H1[k + (size_t)k * n], smlnum)) {
+      *e = 0.0;
+      cnt++;
+    }
+  }
+  if (cnt) atomicAdd(&s_cnt, cnt);
+  __syncthreads();
+  // block ends: k = n-1 or H1[k+1, k] == 0; a block is "large" when no boundary lies within nmin
+  for (int k = tid; k < n; k += nt) {
+    const bool end = (k == n - 1) || (H1[(k + 1) + (size_t)k * n] == 0.0);
+    if (!end) continue;
+    int len = 1;
+    int r = k;
+    while (r > 0 && len <= nmin && H1[r + (size_t)(r - 1) * n] != 0.0) { r--; len++; }
+    if (len > nmin) atomicMax(&s_ihi, k);
+  }
+  __syncthreads();
+  const int ihi = s_ihi;
+  if (ihi >= 0) {
+    for (int k = 1 + tid; k <= ihi; k += nt)
+      if (H1[k + (size_t)(k - 1) * n] == 0.0) atomicMax(&s_ilo, k);
+    __syncthreads();
+  }
+  if (tid == 0) {
+    ctl[0] = (ihi >= 0) ? s_ilo : 0;
+    ctl[1] = ihi;
+    ctl[2] = (ihi < 0) ? 1 : 0;
+    ctl[3] = s_cnt;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Shifts: eigenvalues of the trailing nsw x nsw block of the active block, computed by the
+// reference algorithm itself (periodic_qr_cta, eigenvalues only) on a copy in shared memory.
+// Output: pairs[q] = (re1, im1, re2, im2); ctl[4] = number of pairs.
+// `perturb` != 0 spreads the shifts deterministically (exceptional shifts after stagnation).
+// ------------------------------------------------------------------------------------------
+struct ShiftParams {
+  int n, p, lo, m;  // window rows/cols lo .. lo+m-1
+  double* H[MS_MAXP];
+  double* pairs;
+  int* ctl;
+  double perturb;
+};
+
+__global__ void __launch_bounds__(256) ms_shifts_kernel(ShiftParams P) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int m = P.m, p = P.p, n = P.n;
+  const int ld = (m % 2 == 0) ? m + 1 : m;
+  double* small = ms_smem;
+  double* mats = ms_smem + ((rp_small_doubles(m, p) + 1) & ~1LL);
+  RCtx c;
+  c.n = m; c.p = p; c.tid = tid; c.nt = nt;
+  c.hdiag = small;
+  c.hsub = c.hdiag + (m + 2);
+  c.hsup = c.hsub + (m + 2);
+  c.t0 = c.hsup + (m + 2);
+  c.t1 = c.t0 + (m + 2);
+  c.t2 = c.t1 + (m + 2);
+  c.lre = c.t2 + (m + 2);
+  c.lim = c.lre + (m + 2);
+  c.hnorms = c.lim + (m + 2);
+  c.ldh = ld; c.ldz = ld;
+  c.H = mats; c.hs = (long long)ld * m;
+  c.Z = nullptr; c.zs = 0;
+  c.zmap_left = false;
+  for (int j = 1; j <= p; j++) {
+    const double* src = P.H[j - 1] + P.lo + (size_t)P.lo * n;
+    double* dst = c.Hp(j);
+    const int keep = (j == 1) ? 1 : 0;
+    for (int e = tid; e < m * m; e += nt) {
+      const int r = e % m, cc = e / m;
+      dst[r + (size_t)cc * ld] = (r > cc + keep) ? 0.0 : src[r + (size_t)cc * n];
+    }
+  }
+  __syncthreads();
+  int niter = 0;
+  const int info = periodic_qr_cta(c, false, false, 30, &niter);
+  __syncthreads();
+  if (tid == 0) P.ctl[4] = pair_shifts(c.lre + 1, c.lim + 1, info, m, P.perturb, P.pairs);
+}
+
+// ------------------------------------------------------------------------------------------
+// Final stage.  ms_blocklist_kernel: diagonal blocks of H_1 (maximal runs of non-zero
+// subdiagonal entries).  1 x 1 blocks get their eigenvalue at once; blocks of order >= 2 are
+// listed as WinDesc {s, wl} (ctl[5] = count) for ms_blocks_kernel and the apply kernel.
+// ------------------------------------------------------------------------------------------
+struct BlockParams {
+  int n, p, W, wantT, wantZ, maxitfac;
+  double* H[MS_MAXP];
+  double* U;
+  double* eig;  // [n][2]
+  int* info;    // one int (this problem), atomicMax of the failing level
+  WinDesc* list;
+  int* ctl;
+};
+
+__global__ void __launch_bounds__(1024) ms_blocklist_kernel(BlockParams P) {
+  const int n = P.n, p = P.p;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const double* H1 = P.H[0];
+  __shared__ int s_cnt;
+  if (tid == 0) s_cnt = 0;
+  __syncthreads();
+  for (int k = tid; k < n; k += nt) {
+    const bool start = (k == 0) || (H1[k + (size_t)(k - 1) * n] == 0.0);
+    if (!start) continue;
+    int e = k;
+    while (e + 1 < n && H1[(e + 1) + (size_t)e * n] != 0.0) e++;
+    const int m = e - k + 1;
+    if (m == 1) {
+      double l = 1.0;
+      for (int j = 0; j < p; j++) l *= P.H[j][k + (size_t)k * n];
+      P.eig[2 * k] = l;
+      P.eig[2 * k + 1] = 0.0;
+    } else {
+      const int slot = atomicAdd(&s_cnt, 1);
+      WinDesc d;
+      d.s = k; d.wl = m; d.kbase = 0; d.nbul = 0; d.T = 0; d.ilo = k; d.ihi = e; d.pair0 = 0; d.npairs = 1; d.intro = 0;
+      P.list[slot] = d;
+    }
+  }
+  __syncthreads();
+  if (tid == 0) P.ctl[5] = s_cnt;
+}
+
+// One CTA per listed block (grid-stride): stage the block of every factor (and an identity for
+// the local Schur vectors) in shared memory, run the reference iteration with its 2 x 2
+// standardisation (periodic_qr_cta), write the block and V_j (as U_j of this "window") back.
+__global__ void __launch_bounds__(256) ms_blocks_kernel(BlockParams P, int nblocks) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int p = P.p, n = P.n;
+  for (int bi = blockIdx.x; bi < nblocks; bi += gridDim.x) {
+    const WinDesc d = P.list[bi];
+    const int m = d.wl, s = d.s;
+    const int ld = (m % 2 == 0) ? m + 1 : m;
+    double* small = ms_smem;
+    double* mats = ms_smem + ((rp_small_doubles(m, p) + 1) & ~1LL);
+    const bool vec = P.wantT || P.wantZ;
+    RCtx c;
+    c.n = m; c.p = p; c.tid = tid; c.nt = nt;
+    c.hdiag = small;
+    c.hsub = c.hdiag + (m + 2);
+    c.hsup = c.hsub + (m + 2);
+    c.t0 = c.hsup + (m + 2);
+    c.t1 = c.t0 + (m + 2);
+    c.t2 = c.t1 + (m + 2);
+    c.lre = c.t2 + (m + 2);
+    c.lim = c.lre + (m + 2);
+    c.hnorms = c.lim + (m + 2);
+    c.ldh = ld; c.ldz = ld;
+    c.H = mats; c.hs = (long long)ld * m;
+    c.Z = mats + (size_t)p * ld * m; c.zs = (long long)ld * m;
+    c.zmap_left = false;
+    for (int j = 1; j <= p; j++) {
+      const double* src = P.H[j - 1] + s + (size_t)s * n;
+      double* dst = c.Hp(j);
+      double* z = c.Zp(j);
+      const int keep = (j == 1) ? 1 : 0;
+      for (int e = tid; e < m * m; e += nt) {
+        const int r = e % m, cc = e / m;
+        dst[r + (size_t)cc * ld] = (r > cc + keep) ? 0.0 : src[r + (size_t)cc * n];
+        if (vec) z[r + (size_t)cc * ld] = (r == cc) ? 1.0 : 0.0;
+      }
+    }
+    __syncthreads();
+    int niter = 0;
+    const int info = periodic_qr_cta(c, vec, vec, P.maxitfac, &niter);
+    __syncthreads();
+    for (int k = tid; k < m; k += nt) {
+      P.eig[2 * (s + k)] = c.lre[k + 1];
+      P.eig[2 * (s + k) + 1] = c.lim[k + 1];
+    }
+    if (tid == 0 && info != 0) atomicMax(P.info, s + info);
+    if (vec) {
+      for (int j = 1; j <= p; j++) {
+        double* dst = P.H[j - 1] + s + (size_t)s * n;
+        const double* src = c.Hp(j);
+        const double* z = c.Zp(j);
+        double* ud = P.U + (size_t)(j - 1) * n * P.W + (size_t)s * P.W;
+        for (int e = tid; e < m * m; e += nt) {
+          const int r = e % m, cc = e / m;
+          dst[r + (size_t)cc * n] = src[r + (size_t)cc * ld];
+          ud[e] = z[r + (size_t)cc * ld];
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Power-of-two normalisation of the factors (the large-N path forms sums of squares and
+// products of entries; the reference protects these with scaled sums, householder.jl:5-24,
+// 80-100).  sc[j] = 2^-e_j with max |A_j| * sc[j] in [0.5, 1); sc[p + j] = 2^e_j; expo[0] = sum e_j.
+// ------------------------------------------------------------------------------------------
+__global__ void ms_maxabs_kernel(const double* A, long long count, unsigned long long* out) {
+  double m = 0.0;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < count; e += (long long)gridDim.x * blockDim.x) {
+    const double v = fabs(A[e]);
+    if (v == v) m = fmax(m, v);
+  }
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0 && m > 0.0) atomicMax(out, (unsigned long long)__double_as_longlong(m));
+}
+
+__global__ void ms_scales_kernel(const unsigned long long* mx, int p, double* sc, int* expo) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    int tot = 0;
+    for (int j = 0; j < p; j++) {
+      const double m = __longlong_as_double((long long)mx[j]);
+      int e = 0;
+      if (m > 0.0 && m < 1.7e308) (void)frexp(m, &e);
+      if (e < -1000) e = -1000;  // subnormal maxima: 2^-e itself would overflow
+      sc[j] = scalbn(1.0, -e);
+      sc[p + j] = scalbn(1.0, e);
+      tot += e;
+    }
+    expo[0] = tot;
+  }
+}
+
+__global__ void ms_scale_kernel(double* A, long long count, const double* sc) {
+  const double s = *sc;
+  if (s == 1.0) return;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < count; e += (long long)gridDim.x * blockDim.x)
+    A[e] *= s;
+}
+
+__global__ void ms_scale_eig_kernel(double* eig, int n, const int* expo) {
+  const int e = expo[0];
+  if (e == 0) return;
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < 2 * n; k += gridDim.x * blockDim.x)
+    eig[k] = scalbn(eig[k], e);
+}
+
+}  // namespace ms
+}  // namespace psd

@@ -196,7 +196,7 @@ __global__ void __launch_bounds__(256) rphess_warp32_kernel_t(Hess32Params P) {
         int e;
         (void)frexp(m, &e);
         if (e != 0) {
-          const double sc = scalbn(1.0, -e);
+          const double sc = scalbn(1.0, (-e > 1000) ? 1000 : -e);
           if (lane < n)
             for (int c = 0; c < n; c++) dst[c * ld + lane] *= sc;
           escale += e;
@@ -365,7 +365,7 @@ __global__ void __launch_bounds__(512) rphess_pair32_kernel_t(Hess32Params P) {
         int e;
         (void)frexp(m, &e);
         if (e != 0) {
-          const double sc = scalbn(1.0, -e);
+          const double sc = scalbn(1.0, (-e > 1000) ? 1000 : -e);
           if (lane < n)
             for (int c = 0; c < n; c++) dst[c * ld + lane] *= sc;
           escale += e;

@@ -125,6 +125,14 @@ class Handle:
                 "iterate_launches": int(ms[3]), "large_panel_ms": ms[4], "large_gemm_ms": ms[5],
                 "large_gemm_flops": ms[6], "extra_launches": int(ms[7])}
 
+    def large_stats(self):
+        """Counters of the most recent large-N multishift iteration (psd_large_stats)."""
+        o = (C.c_double * 16)()
+        check(lib().psd_large_stats(self._h, o))
+        names = ["status", "sweeps", "rounds", "windows", "shift_pairs", "exceptional", "final_blocks",
+                 "launches", "apply_flops", "chase_ms", "apply_ms", "shifts_ms", "scan_ms", "final_ms"]
+        return {k: (o[i] if k.endswith(("_ms", "_flops")) else int(o[i])) for i, k in enumerate(names)}
+
     def close(self):
         if self._h:
             lib().psd_destroy(self._h)

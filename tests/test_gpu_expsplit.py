@@ -61,16 +61,27 @@ def test_expsplit_real_with_vectors(psd, es, left):
 
 @pytest.mark.parametrize("es", GOLD["expsplit"], ids=lambda e: f"p{e['p']}")
 @pytest.mark.parametrize("left", [False, True], ids=["R", "L"])
-def test_expsplit_real_eigenvalues_only(psd, es, left):
+def test_expsplit_real_eigenvalues_only(psd, oracle, es, left):
     """N = 6, p >= 3: this is the one-warp-per-problem packed kernel (rpqr_eig32) with its
-    un-normalised reflectors and power-of-two renormalisation."""
+    un-normalised reflectors and power-of-two renormalisation.  With wantT = false the reference
+    algorithm takes a deflated eigenvalue from the product band without the refinement passes of
+    the wantT branch (PeriodicSchurDecompositions.jl:905-912 vs :913-1030): the CPU restatement
+    gives 2.4e-10 relative for the -6.5e-12 eigenvalue at p = 5 (1.5e-14 with wantT), so the gate
+    against the 200-digit values is 1e-9 here, and the GPU is additionally held to the oracle's
+    own values to 1e-10 relative per eigenvalue."""
     A = _storage(es, left, np.float64)
+    _, _, lo, io, _ = oracle.rpschur_batched(A, left=left, wantT=False, wantZ=False)
+    assert io[0] == 0
     # a small batch of identical problems: every warp slot of a CTA must give the same answer
     Ab = np.repeat(A, 5, axis=0)
     _, _, lam, info = psd.pschur_batched(Ab, "L" if left else "R", wantT=False, wantZ=False)
     assert (info == 0).all()
     for b in range(5):
-        _gates(es, lam[b])
+        _gates(es, lam[b], rel=1e-9)
+        for g in lo[0]:
+            d = np.abs(lam[b] - g)
+            k = int(np.argmin(d))
+            assert d[k] <= 1e-10 * abs(g) or max(abs(g), abs(lam[b][k])) < EPS ** 2, (g, lam[b])
     _, _, lam1, info1 = psd.pschur_batched(A, "L" if left else "R", wantT=True, wantZ=False)
     assert info1[0] == 0
     _gates(es, lam1[0])
