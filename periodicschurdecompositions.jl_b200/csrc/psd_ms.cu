@@ -14,26 +14,45 @@
 namespace psd {
 namespace ms {
 
+constexpr int kPlanRing = 8;     // rounds whose window lists may be in flight (> lag + 1)
+constexpr int kScanRing = 16;    // scan results in flight
+constexpr int kShiftSlots = 4;   // shift sets in flight (one side stream each)
+constexpr int kMaxWin = MS_MAXCHAINS;
+
 struct Workspace {
   double* dU = nullptr;  size_t capU = 0;        // [p][n * W]
-  double* dPairs = nullptr; size_t capPairs = 0; // shift pairs
-  WinDesc* dPlan = nullptr; size_t capPlan = 0;  // windows of the current sweep (or final block list)
-  int* dCtl = nullptr;                           // control block (16 ints)
+  double* dPairs = nullptr;                      // [kShiftSlots][66][4] shift pairs
+  double* dSnap = nullptr; size_t capSnap = 0;   // [kShiftSlots][p * 64 * 64] trailing-block snapshots
+  WinDesc* dPlan = nullptr;                      // [kPlanRing][kMaxWin]
+  WinDesc* dList = nullptr; size_t capList = 0;  // final block list
+  int* dCtl = nullptr;                           // [kScanRing][8] scan results, [.. + kShiftSlots] pair counts, misc
   double* dSc = nullptr;                         // [2 * MS_MAXP] scales
   unsigned long long* dMax = nullptr;            // [MS_MAXP]
   int* hCtl = nullptr;                           // pinned mirror of dCtl
-  WinDesc* hPlan = nullptr; size_t hcapPlan = 0; // pinned staging of the plan
-  cudaEvent_t evCopy = nullptr;
+  WinDesc* hPlan = nullptr;                      // pinned [kPlanRing][kMaxWin]
+  cudaEvent_t evScan[kScanRing] = {nullptr};
+  cudaEvent_t evPlan[kPlanRing] = {nullptr};     // the copy of a plan slot has been consumed
+  cudaEvent_t evSnap[kShiftSlots] = {nullptr}, evShift[kShiftSlots] = {nullptr};
+  cudaStream_t side[kShiftSlots] = {nullptr};
 };
+constexpr int kCtlInts = kScanRing * 8 + kShiftSlots + 16;
+constexpr int kCtlPairs = kScanRing * 8;          // pair counts
+constexpr int kCtlMisc = kScanRing * 8 + kShiftSlots;  // [0] expo of the scaling, [1] number of final blocks
 
 Workspace* ws_create() { return new Workspace(); }
 
 void ws_destroy(Workspace* ws) {
   if (!ws) return;
-  cudaFree(ws->dU); cudaFree(ws->dPairs); cudaFree(ws->dPlan); cudaFree(ws->dCtl); cudaFree(ws->dSc);
-  cudaFree(ws->dMax);
+  cudaFree(ws->dU); cudaFree(ws->dPairs); cudaFree(ws->dSnap); cudaFree(ws->dPlan); cudaFree(ws->dList);
+  cudaFree(ws->dCtl); cudaFree(ws->dSc); cudaFree(ws->dMax);
   cudaFreeHost(ws->hCtl); cudaFreeHost(ws->hPlan);
-  if (ws->evCopy) cudaEventDestroy(ws->evCopy);
+  for (auto& e : ws->evScan) if (e) cudaEventDestroy(e);
+  for (auto& e : ws->evPlan) if (e) cudaEventDestroy(e);
+  for (int k = 0; k < kShiftSlots; k++) {
+    if (ws->evSnap[k]) cudaEventDestroy(ws->evSnap[k]);
+    if (ws->evShift[k]) cudaEventDestroy(ws->evShift[k]);
+    if (ws->side[k]) cudaStreamDestroy(ws->side[k]);
+  }
   delete ws;
 }
 
@@ -61,11 +80,20 @@ cudaError_t grow(T*& ptr, size_t& cap, size_t bytes) {
 }
 
 cudaError_t ws_basic(Workspace* ws) {
-  if (!ws->dCtl) MS_CHECK(cudaMalloc((void**)&ws->dCtl, 16 * sizeof(int)));
+  if (!ws->dCtl) MS_CHECK(cudaMalloc((void**)&ws->dCtl, kCtlInts * sizeof(int)));
   if (!ws->dSc) MS_CHECK(cudaMalloc((void**)&ws->dSc, 2 * MS_MAXP * sizeof(double)));
   if (!ws->dMax) MS_CHECK(cudaMalloc((void**)&ws->dMax, MS_MAXP * sizeof(unsigned long long)));
-  if (!ws->hCtl) MS_CHECK(cudaHostAlloc((void**)&ws->hCtl, 16 * sizeof(int), cudaHostAllocDefault));
-  if (!ws->evCopy) MS_CHECK(cudaEventCreateWithFlags(&ws->evCopy, cudaEventDisableTiming));
+  if (!ws->hCtl) MS_CHECK(cudaHostAlloc((void**)&ws->hCtl, kCtlInts * sizeof(int), cudaHostAllocDefault));
+  if (!ws->dPairs) MS_CHECK(cudaMalloc((void**)&ws->dPairs, (size_t)kShiftSlots * 66 * 4 * sizeof(double)));
+  if (!ws->dPlan) MS_CHECK(cudaMalloc((void**)&ws->dPlan, (size_t)kPlanRing * kMaxWin * sizeof(WinDesc)));
+  if (!ws->hPlan) MS_CHECK(cudaHostAlloc((void**)&ws->hPlan, (size_t)kPlanRing * kMaxWin * sizeof(WinDesc), cudaHostAllocDefault));
+  for (auto& e : ws->evScan) if (!e) MS_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  for (auto& e : ws->evPlan) if (!e) MS_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  for (int k = 0; k < kShiftSlots; k++) {
+    if (!ws->evSnap[k]) MS_CHECK(cudaEventCreateWithFlags(&ws->evSnap[k], cudaEventDisableTiming));
+    if (!ws->evShift[k]) MS_CHECK(cudaEventCreateWithFlags(&ws->evShift[k], cudaEventDisableTiming));
+    if (!ws->side[k]) MS_CHECK(cudaStreamCreateWithFlags(&ws->side[k], cudaStreamNonBlocking));
+  }
   return cudaSuccess;
 }
 
@@ -115,59 +143,78 @@ struct CudaBackend {
   size_t chase_smem, shift_smem, block_smem;
   cudaError_t err = cudaSuccess;
   long long launches = 0;
-  Timer tm;
+  long long nscan = 0, nplan = 0;
+  bool slot_used[kShiftSlots] = {false};
+  Timer tm, tm_side[kShiftSlots];
 
   bool ok() const { return err == cudaSuccess; }
   void note(cudaError_t e) {
     if (err == cudaSuccess && e != cudaSuccess) err = e;
   }
+  int shift_slots() const { return kShiftSlots; }
+  int max_windows() const { return kMaxWin; }
+  int pair_offset(int slot) const { return slot * 66; }
 
-  void scan(int nmin, int& ilo, int& ihi, int& done, int& nzero) {
-    if (!ok()) { done = 1; return; }
+  // Scan of the subdiagonal after a round (wins = that round's windows, already on the device in
+  // the plan slot used last); the result lands in a pinned ring slot.
+  const WinDesc* last_plan = nullptr;
+  int scan_async(const WinDesc* /*host copy, unused here*/, int cnt, int nmin) {
+    const int slot = (int)(nscan % kScanRing);
+    nscan++;
+    if (!ok()) return slot;
     tm.begin(3);
-    ms_scan_kernel<<<1, 1024, 0, st>>>(H[0], n, nmin, ws->dCtl);
+    ms_scan_kernel<<<1, 1024, 0, st>>>(H[0], n, nmin, ws->dCtl + slot * 8, last_plan, last_plan ? cnt : 0, g.W, g.D);
     tm.end();
     launches++;
     note(cudaGetLastError());
-    note(cudaMemcpyAsync(ws->hCtl, ws->dCtl, 8 * sizeof(int), cudaMemcpyDeviceToHost, st));
-    note(cudaStreamSynchronize(st));
-    if (!ok()) { done = 1; return; }
-    ilo = ws->hCtl[0]; ihi = ws->hCtl[1]; done = ws->hCtl[2]; nzero = ws->hCtl[3];
+    note(cudaMemcpyAsync(ws->hCtl + slot * 8, ws->dCtl + slot * 8, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    note(cudaEventRecord(ws->evScan[slot], st));
+    return slot;
+  }
+  void scan_wait(int slot, ScanInfo& info) {
+    if (!ok()) { info.done = 1; return; }
+    note(cudaEventSynchronize(ws->evScan[slot]));
+    if (!ok()) { info.done = 1; return; }
+    const int* c = ws->hCtl + slot * 8;
+    info.ilo = c[0]; info.ihi = c[1]; info.done = c[2]; info.nzero = c[3];
   }
 
-  int shifts(int lo, int m, double perturb) {
-    if (!ok()) return 0;
+  // Shift set: snapshot of the trailing block on the main stream, eigenvalues on a side stream.
+  int shifts_request(int slot, int lo, int m, double perturb) {
+    if (!ok()) return slot;
+    // the slot's previous computation must have finished before its snapshot is overwritten
+    if (slot_used[slot]) note(cudaStreamWaitEvent(st, ws->evShift[slot], 0));
+    slot_used[slot] = true;
+    double* snap = ws->dSnap + (size_t)slot * p * 64 * 64;
+    SnapParams S;
+    S.n = n; S.p = p; S.lo = lo; S.m = m; S.snap = snap;
+    for (int j = 0; j < p; j++) S.H[j] = H[j];
+    ms_snapshot_kernel<<<std::min(64, (p * m * m + 255) / 256), 256, 0, st>>>(S);
+    note(cudaGetLastError());
+    note(cudaEventRecord(ws->evSnap[slot], st));
+    cudaStream_t ss = ws->side[slot];
+    note(cudaStreamWaitEvent(ss, ws->evSnap[slot], 0));
     ShiftParams P;
-    P.n = n; P.p = p; P.lo = lo; P.m = m;
-    for (int j = 0; j < p; j++) P.H[j] = H[j];
-    P.pairs = ws->dPairs; P.ctl = ws->dCtl; P.perturb = perturb;
-    tm.begin(2);
-    ms_shifts_kernel<<<1, 256, shift_smem, st>>>(P);
-    tm.end();
-    launches++;
+    P.p = p; P.m = m; P.snap = snap;
+    P.pairs = ws->dPairs + (size_t)pair_offset(slot) * 4;
+    P.count = ws->dCtl + kCtlPairs + slot;
+    P.perturb = perturb;
+    tm_side[slot].begin(2);
+    ms_shifts_kernel<<<1, 256, shift_smem, ss>>>(P);
+    tm_side[slot].end();
+    launches += 2;
     note(cudaGetLastError());
-    note(cudaMemcpyAsync(ws->hCtl, ws->dCtl, 8 * sizeof(int), cudaMemcpyDeviceToHost, st));
-    note(cudaStreamSynchronize(st));
-    if (!ok()) return 0;
-    return ws->hCtl[4];
+    note(cudaMemcpyAsync(ws->hCtl + kCtlPairs + slot, ws->dCtl + kCtlPairs + slot, sizeof(int), cudaMemcpyDeviceToHost, ss));
+    note(cudaEventRecord(ws->evShift[slot], ss));
+    return slot;
   }
-
-  void upload_plan(const std::vector<WinDesc>& plan) {
-    if (!ok() || plan.empty()) return;
-    const size_t bytes = plan.size() * sizeof(WinDesc);
-    // the previous sweep's copy has long completed (scan/shifts synchronised the stream)
-    if (bytes > ws->hcapPlan) {
-      if (ws->hPlan) cudaFreeHost(ws->hPlan);
-      ws->hPlan = nullptr;
-      ws->hcapPlan = 0;
-      note(cudaHostAlloc((void**)&ws->hPlan, bytes * 2, cudaHostAllocDefault));
-      if (!ok()) return;
-      ws->hcapPlan = bytes * 2;
-    }
-    note(grow(ws->dPlan, ws->capPlan, bytes));
-    if (!ok()) return;
-    std::copy(plan.begin(), plan.end(), ws->hPlan);
-    note(cudaMemcpyAsync(ws->dPlan, ws->hPlan, bytes, cudaMemcpyHostToDevice, st));
+  int shifts_wait(int slot) {
+    if (!ok()) return 0;
+    note(cudaEventSynchronize(ws->evShift[slot]));
+    if (!ok()) return 0;
+    // the chase kernels of the main stream read this set's pairs from now on
+    note(cudaStreamWaitEvent(st, ws->evShift[slot], 0));
+    return ws->hCtl[kCtlPairs + slot];
   }
 
   void apply(const WinDesc* wins, int cnt) {
@@ -176,47 +223,63 @@ struct CudaBackend {
     for (int j = 0; j < p; j++) { A.H[j] = H[j]; A.Z[j] = Z[j]; }
     A.U = ws->dU; A.wins = wins;
     const int tiles = (n + AP_T - 1) / AP_T;
+    // consecutive tiles per CTA (U_j staged once): as many as still leave a few waves of CTAs
+    int tpb = 1;
+    while (tpb < 8 && (long long)(tiles / (2 * tpb)) * cnt * p * 2 >= 6LL * sm_count) tpb *= 2;
+    A.tpb = tpb;
+    const int chunks = (tiles + tpb - 1) / tpb;
     tm.begin(1);
     A.phase = 0;
-    ms_apply_kernel<<<dim3(tiles, cnt * p * 2), 256, AP_SMEM, st>>>(A);
+    ms_apply_kernel<<<dim3(chunks, cnt * p * 2), 256, AP_SMEM, st>>>(A);
     A.phase = 1;
-    ms_apply_kernel<<<dim3(tiles, cnt * p), 256, AP_SMEM, st>>>(A);
+    ms_apply_kernel<<<dim3(chunks, cnt * p), 256, AP_SMEM, st>>>(A);
     tm.end();
     launches += 2;
     note(cudaGetLastError());
   }
 
-  void round(int off, int cnt) {
+  void round(const std::vector<WinDesc>& wins) {
     if (!ok()) return;
+    const int cnt = (int)std::min<size_t>(wins.size(), kMaxWin);
+    const int slot = (int)(nplan % kPlanRing);
+    // the pinned slot may be rewritten once the copy of its previous use has executed
+    if (nplan >= kPlanRing) note(cudaEventSynchronize(ws->evPlan[slot]));
+    nplan++;
+    WinDesc* hp = ws->hPlan + (size_t)slot * kMaxWin;
+    WinDesc* dp = ws->dPlan + (size_t)slot * kMaxWin;
+    std::copy(wins.begin(), wins.begin() + cnt, hp);
+    note(cudaMemcpyAsync(dp, hp, (size_t)cnt * sizeof(WinDesc), cudaMemcpyHostToDevice, st));
+    note(cudaEventRecord(ws->evPlan[slot], st));
     ChaseParams C;
     C.n = n; C.p = p; C.g = g;
     for (int j = 0; j < p; j++) C.H[j] = H[j];
-    C.U = ws->dU; C.shifts = ws->dPairs; C.wins = ws->dPlan + off;
+    C.U = ws->dU; C.shifts = ws->dPairs; C.wins = dp;
     tm.begin(0);
     ms_chase_kernel<<<cnt, 64 * g.NB, chase_smem, st>>>(C);
     tm.end();
     launches++;
     note(cudaGetLastError());
-    apply(ws->dPlan + off, cnt);
+    apply(dp, cnt);
+    last_plan = dp;
   }
 
   void finish(int& nblocks) {
     nblocks = 0;
     if (!ok()) return;
-    note(grow(ws->dPlan, ws->capPlan, (size_t)(n / 2 + 1) * sizeof(WinDesc)));
+    note(grow(ws->dList, ws->capList, (size_t)(n / 2 + 1) * sizeof(WinDesc)));
     if (!ok()) return;
     BlockParams B;
     B.n = n; B.p = p; B.W = g.W; B.wantT = wantT; B.wantZ = wantZ; B.maxitfac = maxitfac;
     for (int j = 0; j < p; j++) B.H[j] = H[j];
-    B.U = ws->dU; B.eig = dEig; B.info = dInfo; B.list = ws->dPlan; B.ctl = ws->dCtl;
+    B.U = ws->dU; B.eig = dEig; B.info = dInfo; B.list = ws->dList; B.ctl = ws->dCtl + kCtlMisc - 4;
     tm.begin(4);
     ms_blocklist_kernel<<<1, 1024, 0, st>>>(B);
     launches++;
     note(cudaGetLastError());
-    note(cudaMemcpyAsync(ws->hCtl, ws->dCtl, 8 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    note(cudaMemcpyAsync(ws->hCtl + kCtlMisc + 1, ws->dCtl + kCtlMisc + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
     note(cudaStreamSynchronize(st));
     if (!ok()) return;
-    nblocks = ws->hCtl[5];
+    nblocks = ws->hCtl[kCtlMisc + 1];
     if (nblocks > 0) {
       ms_blocks_kernel<<<std::min(nblocks, sm_count), 256, block_smem, st>>>(B, nblocks);
       launches++;
@@ -226,7 +289,7 @@ struct CudaBackend {
     if (nblocks > 0 && (wantT || wantZ)) {
       // grid.y is limited to 65535: apply in slices of blocks
       const int per = std::max(1, 60000 / (2 * p));
-      for (int o = 0; o < nblocks; o += per) apply(ws->dPlan + o, std::min(per, nblocks - o));
+      for (int o = 0; o < nblocks; o += per) apply(ws->dList + o, std::min(per, nblocks - o));
     }
   }
 };
@@ -239,7 +302,7 @@ cudaError_t prescale(cudaStream_t st, Workspace* ws, int n, int p, double* const
   MS_CHECK(cudaMemsetAsync(ws->dMax, 0, MS_MAXP * sizeof(unsigned long long), st));
   const long long cnt = (long long)n * n;
   for (int j = 0; j < p; j++) ms_maxabs_kernel<<<296, 256, 0, st>>>(A[j], cnt, ws->dMax + j);
-  ms_scales_kernel<<<1, 32, 0, st>>>(ws->dMax, p, ws->dSc, ws->dCtl + 8);
+  ms_scales_kernel<<<1, 32, 0, st>>>(ws->dMax, p, ws->dSc, ws->dCtl + kCtlMisc);
   for (int j = 0; j < p; j++) ms_scale_kernel<<<592, 256, 0, st>>>(A[j], cnt, ws->dSc + j);
   return cudaGetLastError();
 }
@@ -249,7 +312,7 @@ cudaError_t postscale(cudaStream_t st, Workspace* ws, int n, int p, double* cons
   const long long cnt = (long long)n * n;
   if (wantT)
     for (int j = 0; j < p; j++) ms_scale_kernel<<<592, 256, 0, st>>>(A[j], cnt, ws->dSc + p + j);
-  if (dEig) ms_scale_eig_kernel<<<32, 256, 0, st>>>(dEig, n, ws->dCtl + 8);
+  if (dEig) ms_scale_eig_kernel<<<32, 256, 0, st>>>(dEig, n, ws->dCtl + kCtlMisc);
   return cudaGetLastError();
 }
 
@@ -278,8 +341,11 @@ cudaError_t iterate(cudaStream_t st, int sm_count, Workspace* ws, int n, int p, 
   while (nsw > 16 && ((size_t)((rp_small_doubles(nsw, p) + 1) & ~1LL) + (size_t)p * (nsw + 1) * nsw) * 8 > 200 * 1024) nsw -= 8;
   cfg.nsw = nsw;
   if (const char* ev = getenv("PSD_MS_REP")) cfg.rep_max = std::max(1, atoi(ev));
+  if (const char* ev = getenv("PSD_MS_AHEAD")) cfg.sets_ahead = std::max(1, atoi(ev));
+  if (const char* ev = getenv("PSD_MS_LAG")) cfg.lag = std::max(1, std::min(kPlanRing - 2, atoi(ev)));
   if (const char* ev = getenv("PSD_MS_NSW")) cfg.nsw = std::max(2, std::min(nsw, atoi(ev)));
-  MS_CHECK(grow(ws->dPairs, ws->capPairs, (size_t)(cfg.nsw + 2) * 4 * sizeof(double)));
+  MS_CHECK(grow(ws->dSnap, ws->capSnap, (size_t)kShiftSlots * p * 64 * 64 * sizeof(double)));
+  for (int k = 0; k < kShiftSlots; k++) { be.tm_side[k].on = profile != 0; be.tm_side[k].st = ws->side[k]; }
   be.chase_smem = (size_t)2 * p * g.W * g.LD * sizeof(double);
   be.shift_smem = ((size_t)((rp_small_doubles(cfg.nsw, p) + 1) & ~1LL) + (size_t)p * (cfg.nsw + 1) * cfg.nsw) * 8;
   be.block_smem = ((size_t)((rp_small_doubles(g.W, p) + 1) & ~1LL) + (size_t)2 * p * (g.W + 1) * g.W) * 8;
@@ -289,6 +355,9 @@ cudaError_t iterate(cudaStream_t st, int sm_count, Workspace* ws, int n, int p, 
   MS_CHECK(cudaFuncSetAttribute(ms_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AP_SMEM));
   DriverStats ds;
   const int status = drive(be, cfg, ds);
+  // side streams: nothing of this call may still be running when the caller reuses the buffers
+  for (int k = 0; k < kShiftSlots; k++)
+    if (be.slot_used[k]) cudaStreamSynchronize(ws->side[k]);
   if (!be.ok()) return be.err;
   if (res) {
     res->status = status;
@@ -298,6 +367,7 @@ cudaError_t iterate(cudaStream_t st, int sm_count, Workspace* ws, int n, int p, 
     if (profile) {
       double ms[5] = {0, 0, 0, 0, 0};
       be.tm.collect(ms);
+      for (int k = 0; k < kShiftSlots; k++) be.tm_side[k].collect(ms);
       res->ms_chase = ms[0]; res->ms_apply = ms[1]; res->ms_shifts = ms[2]; res->ms_scan = ms[3]; res->ms_final = ms[4];
     }
   }

@@ -75,7 +75,8 @@ struct WinDesc {
   int T;       // lockstep steps of this round
   int ilo, ihi;
   int pair0;   // index of the shift pair of bulge 0 (bulge i uses (pair0 + i) mod npairs)
-  int npairs;  // distinct shift pairs of this sweep
+  int npairs;  // distinct shift pairs of the set
+  int pair_off;  // first pair of the set in the pair buffer
   int intro;   // 1: bulges are introduced in this window (positions start at ilo - 1)
 };
 
@@ -84,6 +85,7 @@ struct Ctx {
   double* Hw;  // [p][W * LD]  staged windows, (r, c) at r + c * LD
   double* Uw;  // [p][W * LD]  accumulated U_j
   const double* shifts;  // [npairs][4] = (re1, im1, re2, im2)
+  int* bihi;   // [nbul] end of the block each bulge really works in (clamp_block_end)
   WinDesc d;
   PSD_HD double* H(int j) const { return Hw + (size_t)(j - 1) * W * LD; }
   PSD_HD double* U(int j) const { return Uw + (size_t)(j - 1) * W * LD; }
@@ -97,6 +99,7 @@ struct BState {
   int k;       // window-relative position (column the bulge hangs from; -1 at introduction)
   int r;       // first row/column the reflectors act on (k + 1)
   int nr;      // 3, or 2 at the bottom of the active block
+  int ihi;     // end of the block this bulge works in
   // reflectors generated in the last gen phase: first (order nr) at r, second (order 2) at r + 1
   double v1, v2, tau1, u1, tau2;
   int have2;
@@ -107,24 +110,47 @@ struct BState {
 
 // dlarfg for 2 or 3 entries held in registers (householder.jl:66-108); exact power-of-two
 // prescale instead of the reference's sfmin loop.  x0 <- beta, (v1, v2) <- essential part.
+// Division-free formulation (the reflector generation of all bulges runs redundantly in every
+// warp, so it sits on the FP64 pipe): with r = 1/sqrt(a^2 + |y|^2), norm = 1/r,
+//   beta = -sign(a) norm,  tau = (beta - a)/beta = 1 + |a| r,  1/(a - beta) = sign(a)/(|a| + norm).
+PSD_HD double ms_rsqrt(double x) {
+#if defined(__CUDA_ARCH__)
+  return rsqrt(x);
+#else
+  return 1.0 / sqrt(x);
+#endif
+}
+PSD_HD double ms_rcp(double x) {
+#if defined(__CUDA_ARCH__)
+  return __drcp_rn(x);
+#else
+  return 1.0 / x;
+#endif
+}
+
 PSD_HD double refl3(int nr, double& x0, double& v1, double& v2) {
   if (nr < 3) v2 = 0.0;
   const double amax = fmax(fabs(v1), fabs(v2));
   if (amax == 0.0) return 0.0;
   const double m = fmax(amax, fabs(x0));
-  double s = 1.0;
+  double s = 1.0, is = 1.0;
   if (m < 1e-140 || m > 1e140) {
     int e;
     (void)frexp(m, &e);
-    s = ldexp(1.0, (-e > 1000) ? 1000 : -e);  // 2^-e overflows for subnormal m
+    const int ee = (-e > 1000) ? 1000 : -e;  // 2^-e overflows for subnormal m
+    s = ldexp(1.0, ee);
+    is = ldexp(1.0, -ee);
   }
   const double al = x0 * s, y1 = v1 * s, y2 = v2 * s;
-  const double beta = -copysign(sqrt(fma(al, al, y1 * y1 + y2 * y2)), al);
-  const double tau = (beta - al) / beta;
-  const double t = 1.0 / (al - beta);
+  const double ss = fma(al, al, fma(y1, y1, y2 * y2));
+  const double r = ms_rsqrt(ss);
+  const double nrm = ss * r;
+  const double aa = fabs(al);
+  const double tau = fma(aa, r, 1.0);
+  const double t = copysign(ms_rcp(aa + nrm), al);
   v1 = y1 * t;
   v2 = y2 * t;
-  x0 = beta / s;
+  x0 = -copysign(nrm, al) * is;
   return tau;
 }
 
@@ -147,7 +173,7 @@ PSD_HD void start_vector(const Ctx& c, int o, int pair, double& x0, double& w1, 
   // P[:, 0] = H1[:, 0] t00 ; P[:, 1] = H1[:, 0] t01 + H1[:, 1] t11
   const double p00 = h00 * t00, p10 = h10 * t00;
   const double p01 = h00 * t01 + h01 * t11, p11 = h10 * t01 + h11 * t11, p21 = h21 * t11;
-  const double* sh = c.shifts + 4 * (size_t)pair;
+  const double* sh = c.shifts + 4 * ((size_t)c.d.pair_off + pair);
   const double tr = sh[0] + sh[2];                    // s1 + s2 (real for a conjugate or real pair)
   const double det = sh[0] * sh[2] - sh[1] * sh[3];  // s1 s2
   double s = fabs(p00) + fabs(p10) + fabs(p01) + fabs(p11) + fabs(p21) + fabs(tr);
@@ -162,16 +188,44 @@ PSD_HD void start_vector(const Ctx& c, int o, int pair, double& x0, double& w1, 
   }
 }
 
+// A packet is planned from block bounds that are a few rounds old.  Deflations made since then
+// show up as exact zeros on the subdiagonal of H_1 (only the scan writes them, and it leaves the
+// rows of every chain in flight alone): bulge b stops at the first such zero below its own reach
+// (rows up to k_b + 3), wherever the bulges ahead of it are - the ones that have already left at
+// that zero are carried along as no-ops (their generating vectors are exactly (x, 0, 0)).
+// Returns the end of the block bulge b really works in.
+PSD_HD int clamp_block_end(const Ctx& c, int b) {
+  const WinDesc& d = c.d;
+  int z = d.intro ? d.ilo : d.kbase - 3 * b + 3;
+  if (z < d.s) z = d.s;
+  const double* H1 = c.H(1);
+  for (; z + 1 < d.s + d.wl && z < d.ihi; z++)
+    if (H1[(z + 1 - d.s) + (size_t)(z - d.s) * c.LD] == 0.0) return z;
+  return d.ihi;
+}
+
+// Rows whose subdiagonal entries the scan after a round must not touch: the chain of the packet
+// as it sits after the round (first, last), or false when the packet has left (last window).
+PSD_HD bool chain_after_round(const WinDesc& d, int W, int D, int& first, int& last) {
+  if (d.s + W >= d.ihi + 1) return false;
+  const int top = d.intro ? d.ilo + D : d.s + D;
+  first = top - 1;
+  last = top + 3 * d.nbul + 1;
+  return true;
+}
+
 // Time-dependent part of the state of bulge b at lockstep time t.
 PSD_HD void bulge_setup(const Ctx& c, BState& st, int b, int t) {
   const WinDesc& d = c.d;
   const int posg = d.kbase - 3 * b + t;
   st.b = b;
-  st.active = (b < d.nbul) && (posg >= d.ilo - 1) && (posg <= d.ihi - 2) && (d.intro || posg >= d.s);
+  const int ihi = (b < d.nbul) ? c.bihi[b] : d.ihi;
+  st.ihi = ihi;
+  st.active = (b < d.nbul) && (posg >= d.ilo - 1) && (posg <= ihi - 2) && (d.intro || posg >= d.s);
   st.intro = st.active && (posg == d.ilo - 1);
   st.k = posg - d.s;
   st.r = st.k + 1;
-  const int rem = d.ihi - posg;  // rows below the hanging column inside the active block
+  const int rem = ihi - posg;  // rows below the hanging column inside the active block
   st.nr = rem >= 3 ? 3 : rem;
   st.defer_j = 0;
   st.have2 = 0;
@@ -287,7 +341,7 @@ PSD_HD void phase_right(const Ctx& c, BState& st, int j, int jn, int role, int l
   int nrow;
   if (role == 0) {
     M = c.H(j);
-    const int ihl = c.d.ihi - c.d.s;
+    const int ihl = st.ihi - c.d.s;
     nrow = (j == 1) ? ((r + nr < ihl ? r + nr : ihl) + 1) : (r + nr);
   } else {
     M = c.U(jn);
@@ -399,55 +453,6 @@ PSD_HD int pair_shifts(const double* lre, const double* lim, int info, int m, do
     q[0] = pend; q[1] = 0.0; q[2] = pend; q[3] = 0.0;
   }
   return np;
-}
-
-// ---------------------------------------------------------------------------------------------
-// Host-side schedule of one sweep: which windows exist in which round.
-// Packet q (bulges pair0 = q * NB ..) is introduced in round 2 q at the top of the active block
-// and then hops down by D rows per round; windows of different packets never overlap.
-// ---------------------------------------------------------------------------------------------
-struct SweepPlan {
-  int rounds;
-};
-
-// Has packet q finished before round rd (its previous window was a last window)?
-inline bool packet_done(const Geom& g, int ilo, int ihi, int q, int rd) {
-  const int h = rd - 2 * q;
-  if (h <= 0) return false;
-  // window of hop h-1
-  const int sprev = (h - 1 == 0) ? ilo : ilo + g.D + (h - 2) * g.D;
-  return sprev + g.W >= ihi + 1;
-}
-
-// Window of packet q in round rd, or false when the packet is not in flight.
-inline bool packet_window(const Geom& g, int ilo, int ihi, int npairs, int q, int rd, WinDesc& w) {
-  const int h = rd - 2 * q;
-  if (h < 0) return false;
-  const int nb = (npairs - q * g.NB < g.NB) ? npairs - q * g.NB : g.NB;
-  if (nb <= 0) return false;
-  w.ilo = ilo; w.ihi = ihi; w.pair0 = q * g.NB; w.nbul = nb; w.npairs = npairs;
-  const int top_after_intro = ilo + g.D;  // sitting position of the last bulge after the introduction round
-  if (h >= 1 && packet_done(g, ilo, ihi, q, rd)) return false;
-  if (h == 0) {
-    w.intro = 1;
-    w.s = ilo;
-    w.kbase = ilo - 1;
-    w.T = g.D + 1 + 3 * (nb - 1);
-  } else {
-    w.intro = 0;
-    w.s = top_after_intro + (h - 1) * g.D;
-    w.kbase = w.s + 3 * (nb - 1);
-    w.T = g.D;
-    if (w.s > ihi - 2) return false;  // the whole packet has left the block
-  }
-  w.wl = (w.s + g.W <= ihi + 1) ? g.W : ihi + 1 - w.s;
-  if (w.s + g.W >= ihi + 1) {
-    // last window of this packet: chase every bulge off the bottom
-    const int last_base = w.kbase - 3 * (nb - 1);
-    w.T = (ihi - 2) - last_base + 1;
-    if (w.T < 1) w.T = 1;
-  }
-  return true;
 }
 
 }  // namespace ms

@@ -1,22 +1,30 @@
-// Host driver of the large-N multishift periodic QR iteration (pure C++, no CUDA): the sweep
-// loop, the shift strategy and the window schedule.  It talks to a backend - the CUDA kernels
+// Host driver of the large-N multishift periodic QR iteration (pure C++, no CUDA): the packet
+// pipeline, the shift strategy and the window schedule.  It talks to a backend - the CUDA kernels
 // (psd_ms.cu) in the product, the CPU emulation of the same kernels in tests/ms_emul/ - so the
 // control logic that decides convergence is tested on the CPU as well.
 //
-// Loop (replaces the outer iteration of pschur!(H1, Hs), PeriodicSchurDecompositions.jl:442-1060,
-// for N >= 192):
-//   scan      negligible subdiagonal entries of H_1 are set to zero; the lowest unreduced diagonal
-//             block of order > W becomes the active block [ilo, ihi]
-//   shifts    eigenvalues of the trailing ns x ns block of the active block (reference algorithm on
-//             one CTA, eigenvalues only)
-//   sweep     packets of NB bulges each are introduced at ilo every second round and chased to the
-//             bottom, D rows per round, every packet inside its own diagonal window; every round
-//             ends with the tensor-core updates of the off-window parts of H_j and of Z_j
-//   finish    all remaining blocks (order <= W) are reduced independently by one CTA each
+// Replaces the outer iteration of pschur!(H1, Hs) (PeriodicSchurDecompositions.jl:442-1060) for
+// N >= 192.  Organisation: a continuous pipeline of bulge packets.
+//   round      every packet in flight moves down by D rows inside its own diagonal window (chase
+//              kernel, one CTA per window), then the off-window parts of H_j and Z_j are updated
+//              on the tensor cores, then the subdiagonal of H_1 is scanned for negligible entries
+//   injection  every second round (as soon as the top window of the active block is free) a new
+//              packet of NB bulges is introduced at the top of the active block, so up to
+//              N / W packets are in flight and the pipeline never drains between "sweeps"
+//   shifts     eigenvalues of the trailing ns x ns block of the active block, computed by the
+//              reference algorithm on one CTA on a side stream from a snapshot of that block;
+//              several requests are in flight, a set is used `sets_ahead` requests after it was
+//              asked for (stale shifts cost no convergence in practice: scripts/ms_proto.py)
+//   control    the host plans round r from the scan made after round r - lag (a fixed lag, so the
+//              schedule is a deterministic function of the data while the device queue stays
+//              full); a packet learns about deflations that happened since it was planned from
+//              the exact zeros of its own window (clamp_block_end)
+//   finish     all remaining blocks (order <= W) are reduced independently by one CTA each
 #pragma once
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
+#include <deque>
 #include <vector>
 
 #include "psd_ms_core.cuh"
@@ -25,10 +33,10 @@ namespace psd {
 namespace ms {
 
 struct DriverStats {
-  int sweeps = 0;
+  int sweeps = 0;            // shift sets used
   long long rounds = 0;
   long long windows = 0;     // window-rounds (chase CTAs launched)
-  long long shift_pairs = 0;
+  long long shift_pairs = 0; // bulges introduced
   int exceptional = 0;
   int final_blocks = 0;
   double apply_flops = 0.0;  // 2 * wl^2 * (extent) summed over the tensor-core updates
@@ -37,9 +45,31 @@ struct DriverStats {
 struct DriverConfig {
   int n = 0, p = 0;
   int wantT = 1, wantZ = 1;
-  int nsw = 64;      // order of the shift window (<= 64, limited by shared memory for large p)
-  int rep_max = 2;   // each shift pair is used up to this many times per sweep
-  int max_sweeps = 0;  // 0: 40 + 30 n / nsw
+  int nsw = 64;         // order of the shift window (<= 64, limited by shared memory for large p)
+  int rep_max = 1;      // each shift pair of a set is used this many times
+  int sets_ahead = 4;   // shift requests in flight
+  int lag = 3;          // rounds between a scan and the plan that uses it
+  long long max_rounds = 0;  // 0: 64 + 40 n / D
+};
+
+struct ScanInfo {
+  int ilo = 0, ihi = -1, done = 0, nzero = 0;
+};
+
+struct Packet {
+  int s;      // first row of the next window
+  int hops;   // rounds done
+  int nbul, pair0, npairs, pair_off;
+  int ilo, ihi;  // active block when the packet was introduced
+  int fin_s;     // position at which the packet was first seen in finished territory (-1: not yet)
+};
+
+struct ShiftSet {
+  int ticket = -1;
+  int slot = 0;
+  int ilo = 0, ihi = -1;  // block it was requested for
+  int npairs = -1;        // known once waited for
+  int next_pair = 0, quota = 0;
 };
 
 // status: 0 = reduced to blocks of order <= W and finished; 1 = no convergence (the factors are
@@ -47,78 +77,162 @@ struct DriverConfig {
 template <class Backend>
 int drive(Backend& be, const DriverConfig& cfg, DriverStats& st) {
   const Geom g = geom_for(cfg.p);
-  const int n = cfg.n;
-  const int max_sweeps = cfg.max_sweeps > 0 ? cfg.max_sweeps : 40 + 30 * n / std::max(2, cfg.nsw);
-  int last_ilo = -1, last_ihi = -1, stagnant = 0;
-  std::vector<WinDesc> plan;
-  std::vector<int> round_off;
-  for (;;) {
-    int ilo = 0, ihi = -1, done = 0, nzero = 0;
-    be.scan(g.W, ilo, ihi, done, nzero);
-    if (done) break;
-    if (st.sweeps >= max_sweeps) return 1;
-    if (ilo == last_ilo && ihi == last_ihi && nzero == 0) stagnant++; else stagnant = 0;
-    last_ilo = ilo; last_ihi = ihi;
-    const int m = ihi - ilo + 1;
+  const int n = cfg.n, W = g.W, D = g.D;
+  const long long max_rounds = cfg.max_rounds > 0 ? cfg.max_rounds : 256 + 100LL * n / D;
+  const int lag = std::max(1, cfg.lag);
+  const int ahead = std::max(1, std::min(cfg.sets_ahead, be.shift_slots()));
+  const bool trace = getenv("PSD_MS_TRACE") != nullptr;
+
+  ScanInfo info;
+  be.scan_wait(be.scan_async(nullptr, 0, W), info);
+  std::deque<int> scan_tickets;   // scans made after the rounds enqueued so far
+  std::deque<ShiftSet> sets;      // front = in use, others requested
+  std::vector<Packet> pk;
+  std::vector<WinDesc> wins;
+  int next_slot = 0;
+  int idle_sets = 0;              // shift sets used up since the last deflation
+  long long last_progress_round = 0;
+  int last_ihi = info.ihi, last_ilo = info.ilo;
+
+  auto request_set = [&](double perturb) {
+    const int m = info.ihi - info.ilo + 1;
     int ns = std::min(cfg.nsw, 2 * (m / 3));
     ns = std::max(2, ns & ~1);
-    double perturb = 0.0;
-    if (stagnant >= 4 && stagnant % 4 == 0) {
-      perturb = 0.5;  // exceptional shifts: spread the stale set
-      st.exceptional++;
+    ShiftSet s;
+    s.slot = next_slot;
+    next_slot = (next_slot + 1) % be.shift_slots();
+    s.ilo = info.ilo; s.ihi = info.ihi;
+    s.ticket = be.shifts_request(s.slot, info.ihi - ns + 1, ns, perturb);
+    sets.push_back(s);
+  };
+
+  for (long long r = 0;; r++) {
+    // ---- block information: the scan made `lag` rounds ago ----
+    while ((int)scan_tickets.size() > lag - 1) {
+      be.scan_wait(scan_tickets.front(), info);
+      scan_tickets.pop_front();
+      if (info.nzero > 0 || info.ihi != last_ihi || info.ilo != last_ilo) {
+        idle_sets = 0;
+        last_progress_round = r;
+      }
+      last_ihi = info.ihi; last_ilo = info.ilo;
     }
-    if (stagnant >= 40) return 1;
-    const int npairs = be.shifts(ihi - ns + 1, ns, perturb);
-    if (getenv("PSD_MS_TRACE"))
-      fprintf(stderr, "[psd ms] sweep %d: block [%d, %d] zeroed %d stagnant %d ns %d -> %d pairs\n", st.sweeps, ilo, ihi,
-              nzero, stagnant, ns, npairs);
-    if (npairs <= 0) return 1;
-    // how often each pair is used: enough packets to keep the diagonal busy, at most rep_max
-    const int npk1 = (npairs + g.NB - 1) / g.NB;
-    int rep = std::max(1, std::min(cfg.rep_max, (m / g.W) / std::max(1, 2 * npk1)));
-    const int total_pairs = npairs * rep;
-    const int npk = (total_pairs + g.NB - 1) / g.NB;
-    plan.clear();
-    round_off.clear();
-    for (int rd = 0;; rd++) {
-      const size_t before = plan.size();
-      for (int q = 0; q < npk; q++) {
-        WinDesc w;
-        if (packet_window(g, ilo, ihi, total_pairs, q, rd, w)) {
-          w.npairs = npairs;
-          plan.push_back(w);
+    if (!be.ok()) return 1;
+    // ---- retire packets that have left the matrix or travel through finished territory ----
+    {
+      size_t k = 0;
+      for (size_t i = 0; i < pk.size(); i++) {
+        // (a) the previous window reached the bottom of the block the packet was planned for
+        // (every bulge chased off), or (b) the packet has travelled 2 W rows through finished
+        // territory (blocks of order <= W below the active block) since it was first seen there:
+        // each of its bulges has met an exact zero of the subdiagonal within W + 3 NB rows and has
+        // been chased off at it (clamp_block_end)
+        Packet& q = pk[i];
+        const int limit = info.done ? -1 : info.ihi;
+        if (q.fin_s < 0 && q.s > limit) q.fin_s = q.s;
+        const bool gone = (q.hops > 0 && q.s - D + W >= q.ihi + 1) || (q.fin_s >= 0 && q.s >= q.fin_s + 2 * W);
+        if (!gone) pk[k++] = q;
+      }
+      pk.resize(k);
+    }
+    if (info.done && pk.empty() && scan_tickets.empty()) break;
+    if (info.done && pk.empty()) {
+      // drain the scans still in flight (they cannot undo `done`: zeros are only ever added)
+      ScanInfo tmp;
+      while (!scan_tickets.empty()) { be.scan_wait(scan_tickets.front(), tmp); scan_tickets.pop_front(); }
+      break;
+    }
+    const int pass_sets = std::max(1, (info.done ? 1 : (info.ihi - info.ilo + 1) / W) / std::max(1, cfg.nsw / (2 * g.NB)));
+    if (r > max_rounds || idle_sets > 60 + 40 * pass_sets) return 1;
+    // ---- shift sets: drop sets asked for a block that is finished, keep `ahead` requests going ----
+    if (!info.done) {
+      while (!sets.empty() && sets.front().ilo > info.ihi) sets.pop_front();
+      double perturb = 0.0;
+      const int ex_every = 6 + 4 * pass_sets;  // sets without any deflation before the shifts are spread
+      if (idle_sets >= ex_every && idle_sets % ex_every == 0) perturb = 0.5;  // exceptional shifts
+      while ((int)sets.size() < ahead) {
+        request_set(perturb);
+        if (perturb != 0.0) st.exceptional++;
+        perturb = 0.0;
+      }
+    }
+    // ---- introduce a packet when the top window of the active block is free ----
+    if (!info.done) {
+      bool top_free = true;
+      for (const Packet& q : pk)
+        if (q.s < info.ilo + W && q.s + W > info.ilo) top_free = false;
+      if (top_free && (int)pk.size() < be.max_windows()) {
+        ShiftSet& s = sets.front();
+        if (s.npairs < 0) {
+          s.npairs = be.shifts_wait(s.ticket);
+          const int npk1 = std::max(1, (s.npairs + g.NB - 1) / g.NB);
+          s.quota = s.npairs * std::max(1, cfg.rep_max);
+          (void)npk1;
+          st.sweeps++;
+          if (trace)
+            fprintf(stderr, "[psd ms] round %lld: set %d for block [%d, %d] -> %d pairs; active [%d, %d], %zu packets in flight\n",
+                    r, st.sweeps, s.ilo, s.ihi, s.npairs, info.ilo, info.ihi, pk.size());
+        }
+        if (s.npairs <= 0) {
+          // the shift computation found nothing usable: try the next set, give up after a few
+          sets.pop_front();
+          idle_sets += 6;
+        } else {
+          Packet q;
+          q.nbul = std::min(g.NB, s.quota - s.next_pair);
+          q.pair0 = s.next_pair % s.npairs;
+          q.npairs = s.npairs;
+          q.pair_off = be.pair_offset(s.slot);
+          q.ilo = info.ilo; q.ihi = info.ihi;
+          q.s = info.ilo; q.hops = 0; q.fin_s = -1;
+          s.next_pair += q.nbul;
+          st.shift_pairs += q.nbul;
+          pk.push_back(q);
+          if (s.next_pair >= s.quota) {
+            sets.pop_front();
+            idle_sets++;
+          }
         }
       }
-      if (plan.size() == before) {
-        if (rd >= 2 * (npk - 1)) break;  // every packet has been introduced and has left
-        round_off.push_back((int)before);  // an empty round between introductions
-        continue;
-      }
-      round_off.push_back((int)before);
     }
-    round_off.push_back((int)plan.size());
-    be.upload_plan(plan);
-    for (size_t rd = 0; rd + 1 < round_off.size(); rd++) {
-      const int off = round_off[rd], cnt = round_off[rd + 1] - off;
-      if (cnt == 0) continue;
-      be.round(off, cnt);
+    // ---- this round's windows ----
+    wins.clear();
+    for (Packet& q : pk) {
+      WinDesc w;
+      w.ilo = q.ilo; w.ihi = q.ihi; w.nbul = q.nbul; w.pair0 = q.pair0; w.npairs = q.npairs; w.pair_off = q.pair_off;
+      if (q.hops == 0) {
+        w.intro = 1; w.s = q.ilo; w.kbase = q.ilo - 1; w.T = D + 1 + 3 * (q.nbul - 1);
+      } else {
+        w.intro = 0; w.s = q.s; w.kbase = q.s + 3 * (q.nbul - 1); w.T = D;
+      }
+      w.wl = (w.s + W <= q.ihi + 1) ? W : q.ihi + 1 - w.s;
+      if (w.s + W >= q.ihi + 1) {
+        // last window of this packet: chase every bulge off the bottom
+        const int last_base = w.kbase - 3 * (q.nbul - 1);
+        w.T = std::max(1, (q.ihi - 2) - last_base + 1);
+      }
+      wins.push_back(w);
+      q.s = (q.hops == 0) ? q.ilo + D : q.s + D;
+      q.hops++;
+    }
+    if (!wins.empty()) {
+      be.round(wins);
       st.rounds++;
-      st.windows += cnt;
-      for (int i = 0; i < cnt; i++) {
-        const WinDesc& w = plan[off + i];
+      st.windows += (long long)wins.size();
+      for (const WinDesc& w : wins) {
         const double left = (cfg.wantT ? n : w.ihi + 1) - (w.s + w.wl);
         const double right = w.s - (cfg.wantT ? 0 : w.ilo);
         const double z = cfg.wantZ ? n : 0;
         st.apply_flops += 2.0 * w.wl * w.wl * (left + right + z) * cfg.p;
       }
     }
-    st.sweeps++;
-    st.shift_pairs += total_pairs;
+    scan_tickets.push_back(be.scan_async(wins.data(), (int)wins.size(), W));
+    (void)last_progress_round;
   }
   int nblocks = 0;
   be.finish(nblocks);
   st.final_blocks = nblocks;
-  return 0;
+  return be.ok() ? 0 : 1;
 }
 
 }  // namespace ms

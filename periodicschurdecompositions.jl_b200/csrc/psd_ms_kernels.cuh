@@ -73,6 +73,11 @@ __global__ void __launch_bounds__(64 * MS_MAXNB, 1) ms_chase_kernel(ChaseParams 
     }
   }
   __syncthreads();
+  // deflations made since this window was planned (exact zeros on the subdiagonal of H_1)
+  __shared__ int s_bihi[MS_MAXNB];
+  c.bihi = s_bihi;
+  if (tid < d.nbul) s_bihi[tid] = clamp_block_end(c, tid);
+  __syncthreads();
   DevExec ex;
   ex.b = tid >> 6;
   ex.role = (tid >> 5) & 1;
@@ -112,6 +117,7 @@ constexpr int AP_SMEM = 2 * 64 * AP_LD * 8;
 
 struct ApplyParams {
   int n, p, W, wantT, wantZ, phase, nwin;
+  int tpb;  // tiles per CTA (consecutive tiles of one item: U_j is staged once)
   double* H[MS_MAXP];
   double* Z[MS_MAXP];
   const double* U;
@@ -148,87 +154,106 @@ __global__ void __launch_bounds__(256) ms_apply_kernel(ApplyParams P) {
     lo = 0;
     hi = n;
   }
-  const int t0 = lo + blockIdx.x * AP_T;
-  if (t0 >= hi) return;
-  const int tl = min(AP_T, hi - t0);
+  const int tfirst = blockIdx.x * P.tpb;
+  if (lo + tfirst * AP_T >= hi) return;
   const double* Ug = P.U + (size_t)(j - 1) * n * P.W + (size_t)s * P.W;
-  // ---- stage U (wl x wl, zero padded to 64 x 64) and the tile ----
+  // ---- stage U (wl x wl, zero padded to 64 x 64) ----
   for (int e = tid; e < 64 * 64; e += 256) {
     const int r = e & 63, cc = e >> 6;
     Us[cc * AP_LD + r] = (r < wl && cc < wl) ? Ug[r + (size_t)cc * wl] : 0.0;
   }
-  if (kind == 0) {
-    // tile: rows s .. s+wl-1 (r), columns t0 .. t0+tl-1 (cc)
-    for (int e = tid; e < 64 * 64; e += 256) {
-      const int r = e & 63, cc = e >> 6;
-      Xs[cc * AP_LD + r] = (r < wl && cc < tl) ? X[(s + r) + (size_t)(t0 + cc) * n] : 0.0;
-    }
-  } else {
-    // tile: rows t0 .. t0+tl-1 (r), columns s .. s+wl-1 (cc)
-    for (int e = tid; e < 64 * 64; e += 256) {
-      const int r = e & 63, cc = e >> 6;
-      Xs[cc * AP_LD + r] = (r < tl && cc < wl) ? X[(t0 + r) + (size_t)(s + cc) * n] : 0.0;
-    }
-  }
-  __syncthreads();
-  // ---- C = U' X (kind 0)  or  C = X U (kinds 1, 2), 64 x 64 x 64 ----
+  // element (r, cc) of the 64 x 64 staging tile <-> global address, by kind:
+  //   left:      rows s .. s+wl-1 (r), columns t0 .. t0+tl-1 (cc)
+  //   right / Z: rows t0 .. t0+tl-1 (r), columns s .. s+wl-1 (cc)
   const int wm = warp & 1, wn = warp >> 1;
   const int gq = lane >> 2, tq = lane & 3;
-  double acc[4][2][2];
-#pragma unroll
-  for (int i = 0; i < 4; i++)
-#pragma unroll
-    for (int q = 0; q < 2; q++) acc[i][q][0] = acc[i][q][1] = 0.0;
   const int kmax = (wl + 3) & ~3;
-  if (kind == 0) {
-    // A(m, k) = U(k, m) = Us[m * LD + k];  B(k, nn) = X(k, nn) = Xs[nn * LD + k]
-    for (int k0 = 0; k0 < kmax; k0 += 4) {
-      double a[4], b[2];
+  double pre[16];
+  auto fetch = [&](int t0, int tl) {
 #pragma unroll
-      for (int i = 0; i < 4; i++) a[i] = Us[(wm * 32 + i * 8 + gq) * AP_LD + k0 + tq];
-#pragma unroll
-      for (int q = 0; q < 2; q++) b[q] = Xs[(wn * 16 + q * 8 + gq) * AP_LD + k0 + tq];
-#pragma unroll
-      for (int i = 0; i < 4; i++)
-#pragma unroll
-        for (int q = 0; q < 2; q++) ms_dmma(acc[i][q][0], acc[i][q][1], a[i], b[q]);
+    for (int i = 0; i < 16; i++) {
+      const int e = tid + 256 * i;
+      const int r = e & 63, cc = e >> 6;
+      if (kind == 0)
+        pre[i] = (r < wl && cc < tl) ? X[(s + r) + (size_t)(t0 + cc) * n] : 0.0;
+      else
+        pre[i] = (r < tl && cc < wl) ? X[(t0 + r) + (size_t)(s + cc) * n] : 0.0;
     }
-  } else {
-    // A(m, k) = X(m, k) = Xs[k * LD + m];  B(k, nn) = U(k, nn) = Us[nn * LD + k]
-    for (int k0 = 0; k0 < kmax; k0 += 4) {
-      double a[4], b[2];
+  };
+  int t0 = lo + tfirst * AP_T;
+  int tl = min(AP_T, hi - t0);
+  fetch(t0, tl);
+  for (int tt = 0; tt < P.tpb; tt++) {
+    __syncthreads();  // Us staged (first pass) / the previous tile has been written out of Xs
 #pragma unroll
-      for (int i = 0; i < 4; i++) a[i] = Xs[(k0 + tq) * AP_LD + wm * 32 + i * 8 + gq];
-#pragma unroll
-      for (int q = 0; q < 2; q++) b[q] = Us[(wn * 16 + q * 8 + gq) * AP_LD + k0 + tq];
-#pragma unroll
-      for (int i = 0; i < 4; i++)
-#pragma unroll
-        for (int q = 0; q < 2; q++) ms_dmma(acc[i][q][0], acc[i][q][1], a[i], b[q]);
+    for (int i = 0; i < 16; i++) {
+      const int e = tid + 256 * i;
+      Xs[(e >> 6) * AP_LD + (e & 63)] = pre[i];
     }
-  }
-  __syncthreads();  // every warp has finished reading Xs
+    __syncthreads();
+    const int t0n = t0 + AP_T;
+    const bool more = (tt + 1 < P.tpb) && (t0n < hi);
+    const int tln = more ? min(AP_T, hi - t0n) : 0;
+    if (more) fetch(t0n, tln);  // in flight during the multiplication
+    // ---- C = U' X (left)  or  C = X U (right, Z): 64 x 64 x wl ----
+    double acc[4][2][2];
 #pragma unroll
-  for (int i = 0; i < 4; i++)
+    for (int i = 0; i < 4; i++)
 #pragma unroll
-    for (int q = 0; q < 2; q++)
+      for (int q = 0; q < 2; q++) acc[i][q][0] = acc[i][q][1] = 0.0;
+    if (kind == 0) {
+      // A(m, k) = U(k, m) = Us[m * LD + k];  B(k, nn) = X(k, nn) = Xs[nn * LD + k]
+      for (int k0 = 0; k0 < kmax; k0 += 4) {
+        double a[4], b[2];
 #pragma unroll
-      for (int e = 0; e < 2; e++) {
-        const int m = wm * 32 + i * 8 + gq;
-        const int nn = wn * 16 + q * 8 + 2 * tq + e;
-        Xs[nn * AP_LD + m] = acc[i][q][e];
+        for (int i = 0; i < 4; i++) a[i] = Us[(wm * 32 + i * 8 + gq) * AP_LD + k0 + tq];
+#pragma unroll
+        for (int q = 0; q < 2; q++) b[q] = Xs[(wn * 16 + q * 8 + gq) * AP_LD + k0 + tq];
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+          for (int q = 0; q < 2; q++) ms_dmma(acc[i][q][0], acc[i][q][1], a[i], b[q]);
       }
-  __syncthreads();
-  if (kind == 0) {
-    for (int e = tid; e < 64 * 64; e += 256) {
-      const int r = e & 63, cc = e >> 6;
-      if (r < wl && cc < tl) X[(s + r) + (size_t)(t0 + cc) * n] = Xs[cc * AP_LD + r];
+    } else {
+      // A(m, k) = X(m, k) = Xs[k * LD + m];  B(k, nn) = U(k, nn) = Us[nn * LD + k]
+      for (int k0 = 0; k0 < kmax; k0 += 4) {
+        double a[4], b[2];
+#pragma unroll
+        for (int i = 0; i < 4; i++) a[i] = Xs[(k0 + tq) * AP_LD + wm * 32 + i * 8 + gq];
+#pragma unroll
+        for (int q = 0; q < 2; q++) b[q] = Us[(wn * 16 + q * 8 + gq) * AP_LD + k0 + tq];
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+          for (int q = 0; q < 2; q++) ms_dmma(acc[i][q][0], acc[i][q][1], a[i], b[q]);
+      }
     }
-  } else {
-    for (int e = tid; e < 64 * 64; e += 256) {
-      const int r = e & 63, cc = e >> 6;
-      if (r < tl && cc < wl) X[(t0 + r) + (size_t)(s + cc) * n] = Xs[cc * AP_LD + r];
+    __syncthreads();  // every warp has finished reading Xs
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+      for (int q = 0; q < 2; q++)
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+          const int m = wm * 32 + i * 8 + gq;
+          const int nn = wn * 16 + q * 8 + 2 * tq + e;
+          Xs[nn * AP_LD + m] = acc[i][q][e];
+        }
+    __syncthreads();
+    if (kind == 0) {
+      for (int e = tid; e < 64 * 64; e += 256) {
+        const int r = e & 63, cc = e >> 6;
+        if (r < wl && cc < tl) X[(s + r) + (size_t)(t0 + cc) * n] = Xs[cc * AP_LD + r];
+      }
+    } else {
+      for (int e = tid; e < 64 * 64; e += 256) {
+        const int r = e & 63, cc = e >> 6;
+        if (r < tl && cc < wl) X[(t0 + r) + (size_t)(s + cc) * n] = Xs[cc * AP_LD + r];
+      }
     }
+    if (!more) break;
+    t0 = t0n;
+    tl = tln;
   }
 }
 
@@ -239,14 +264,30 @@ __global__ void __launch_bounds__(256) ms_apply_kernel(ApplyParams P) {
 // periodic QZ drivers, rgeneralized.jl:1086-1112), which perturbs H_1 by at most 2 ulp ||H_1||.
 // The active block is the lowest unreduced diagonal block of order > nmin.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) ms_scan_kernel(double* H1, int n, int nmin, int* ctl) {
+// The rows of the bulge chains that sit in the matrix after the round (wins[0..nwin), see
+// chain_after_round) are left alone: subdiagonal entries there are part of the bulges.
+constexpr int MS_MAXCHAINS = 160;
+
+__global__ void __launch_bounds__(1024) ms_scan_kernel(double* H1, int n, int nmin, int* ctl, const WinDesc* wins,
+                                                       int nwin, int W, int D) {
   __shared__ int s_ihi, s_ilo, s_cnt;
+  __shared__ int s_first[MS_MAXCHAINS], s_last[MS_MAXCHAINS];
   const int tid = threadIdx.x, nt = blockDim.x;
   if (tid == 0) { s_ihi = -1; s_ilo = 0; s_cnt = 0; }
+  if (nwin > MS_MAXCHAINS) nwin = MS_MAXCHAINS;  // (the host never plans more)
+  for (int w = tid; w < nwin; w += nt) {
+    int a = 1, b = 0;
+    if (!chain_after_round(wins[w], W, D, a, b)) { a = 1; b = 0; }
+    s_first[w] = a; s_last[w] = b;
+  }
   __syncthreads();
   const double smlnum = DBL_MIN * ((double)n / DBL_EPSILON);
   int cnt = 0;
   for (int k = 1 + tid; k < n; k += nt) {
+    // entry H1[k, k-1]: "z" = k - 1 in the notation of clamp_block_end
+    bool skip = false;
+    for (int w = 0; w < nwin; w++) skip |= (k - 1 >= s_first[w] && k - 1 <= s_last[w]);
+    if (skip) continue;
     double* e = H1 + k + (size_t)(k - 1) * n;
     const double sub = *e;
     if (sub != 0.0 && ms_negligible(sub, H1[(k - 1) + (size_t)(k - 1) * n], H1[k + (size_t)k * n], smlnum)) {
@@ -287,16 +328,34 @@ __global__ void __launch_bounds__(1024) ms_scan_kernel(double* H1, int n, int nm
 // `perturb` != 0 spreads the shifts deterministically (exceptional shifts after stagnation).
 // ------------------------------------------------------------------------------------------
 struct ShiftParams {
-  int n, p, lo, m;  // window rows/cols lo .. lo+m-1
-  double* H[MS_MAXP];
-  double* pairs;
-  int* ctl;
+  int p, m;            // the snapshot holds the m x m trailing blocks, [p][m * m] column-major
+  const double* snap;
+  double* pairs;       // this set's pair buffer
+  int* count;          // number of pairs
   double perturb;
 };
 
+// Copy of the trailing blocks (rows / columns lo .. lo+m-1 of every factor) taken on the main
+// stream, so that the shift computation on a side stream sees one consistent state.
+struct SnapParams {
+  int n, p, lo, m;
+  const double* H[MS_MAXP];
+  double* snap;
+};
+
+__global__ void ms_snapshot_kernel(SnapParams P) {
+  const int m = P.m, total = P.p * m * m;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+    const int j = e / (m * m), rem = e - j * m * m;
+    const int r = rem % m, cc = rem / m;
+    const int keep = (j == 0) ? 1 : 0;
+    P.snap[e] = (r > cc + keep) ? 0.0 : P.H[j][(P.lo + r) + (size_t)(P.lo + cc) * P.n];
+  }
+}
+
 __global__ void __launch_bounds__(256) ms_shifts_kernel(ShiftParams P) {
   const int tid = threadIdx.x, nt = blockDim.x;
-  const int m = P.m, p = P.p, n = P.n;
+  const int m = P.m, p = P.p;
   const int ld = (m % 2 == 0) ? m + 1 : m;
   double* small = ms_smem;
   double* mats = ms_smem + ((rp_small_doubles(m, p) + 1) & ~1LL);
@@ -316,19 +375,18 @@ __global__ void __launch_bounds__(256) ms_shifts_kernel(ShiftParams P) {
   c.Z = nullptr; c.zs = 0;
   c.zmap_left = false;
   for (int j = 1; j <= p; j++) {
-    const double* src = P.H[j - 1] + P.lo + (size_t)P.lo * n;
+    const double* src = P.snap + (size_t)(j - 1) * m * m;
     double* dst = c.Hp(j);
-    const int keep = (j == 1) ? 1 : 0;
     for (int e = tid; e < m * m; e += nt) {
       const int r = e % m, cc = e / m;
-      dst[r + (size_t)cc * ld] = (r > cc + keep) ? 0.0 : src[r + (size_t)cc * n];
+      dst[r + (size_t)cc * ld] = src[e];
     }
   }
   __syncthreads();
   int niter = 0;
   const int info = periodic_qr_cta(c, false, false, 30, &niter);
   __syncthreads();
-  if (tid == 0) P.ctl[4] = pair_shifts(c.lre + 1, c.lim + 1, info, m, P.perturb, P.pairs);
+  if (tid == 0) *P.count = pair_shifts(c.lre + 1, c.lim + 1, info, m, P.perturb, P.pairs);
 }
 
 // ------------------------------------------------------------------------------------------

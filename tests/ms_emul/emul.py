@@ -44,9 +44,9 @@ def run(H, Z, wantT=True, wantZ=True, nsw=0, rep_max=0):
     Zo = np.ascontiguousarray(Z).copy() if Z is not None else None
     eig = np.zeros((n, 2))
     info = C.c_int(0)
-    stats = (C.c_longlong * 8)()
+    stats = (C.c_longlong * 9)()
     dp = C.POINTER(C.c_double)
     lib().ms_emul_run(n, p, T.ctypes.data_as(dp), Zo.ctypes.data_as(dp) if Zo is not None else None,
                       int(wantT), int(wantZ), nsw, rep_max, eig.ctypes.data_as(dp), C.byref(info), stats)
-    names = ["sweeps", "rounds", "windows", "shift_pairs", "exceptional", "final_blocks", "bulge_steps", "status"]
+    names = ["sweeps", "rounds", "windows", "shift_pairs", "exceptional", "final_blocks", "bulge_steps", "status", "bulges_left_behind"]
     return T, Zo, eig[:, 0] + 1j * eig[:, 1], info.value, dict(zip(names, list(stats)))

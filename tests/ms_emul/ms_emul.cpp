@@ -55,17 +55,34 @@ struct EmuBackend {
 
   double& h(int j, int r, int c) { return H[j][r + (size_t)c * n]; }
 
-  void scan(int nmin, int& ilo, int& ihi, int& done, int& nzero) {
+  bool ok() const { return true; }
+  int shift_slots() const { return 4; }
+  int max_windows() const { return 160; }
+  int pair_offset(int slot) const { return slot * 66; }
+  std::vector<ScanInfo> scan_ring = std::vector<ScanInfo>(16);
+  long long nscan = 0;
+
+  int scan_async(const WinDesc* wins, int cnt, int nmin) {
+    const int slot = (int)(nscan++ % 16);
+    ScanInfo& out = scan_ring[slot];
     const double smlnum = DBL_MIN * ((double)n / DBL_EPSILON);
-    nzero = 0;
+    out.nzero = 0;
+    std::vector<int> first, last;
+    for (int w = 0; w < cnt; w++) {
+      int a, b;
+      if (chain_after_round(wins[w], g.W, g.D, a, b)) { first.push_back(a); last.push_back(b); }
+    }
     for (int k = 1; k < n; k++) {
+      bool skip = false;
+      for (size_t w = 0; w < first.size(); w++) skip |= (k - 1 >= first[w] && k - 1 <= last[w]);
+      if (skip) continue;
       const double sub = h(0, k, k - 1);
       if (sub != 0.0 && ms_negligible(sub, h(0, k - 1, k - 1), h(0, k, k), smlnum)) {
         h(0, k, k - 1) = 0.0;
-        nzero++;
+        out.nzero++;
       }
     }
-    ihi = -1;
+    int ihi = -1;
     for (int k = n - 1; k >= 0; k--) {
       const bool end = (k == n - 1) || h(0, k + 1, k) == 0.0;
       if (!end) continue;
@@ -73,14 +90,18 @@ struct EmuBackend {
       while (r > 0 && len <= nmin && h(0, r, r - 1) != 0.0) { r--; len++; }
       if (len > nmin) { ihi = k; break; }
     }
-    ilo = 0;
+    int ilo = 0;
     if (ihi >= 0)
       for (int k = 1; k <= ihi; k++)
         if (h(0, k, k - 1) == 0.0) ilo = k;
-    done = ihi < 0;
+    out.ilo = ilo; out.ihi = ihi; out.done = ihi < 0;
+    return slot;
   }
+  void scan_wait(int slot, ScanInfo& info) { info = scan_ring[slot]; }
 
-  int shifts(int lo, int m, double perturb) {
+  int slot_pairs[4] = {0, 0, 0, 0};
+  int shifts_wait(int slot) { return slot_pairs[slot]; }
+  int shifts_request(int slot, int lo, int m, double perturb) {
     std::vector<double> buf((size_t)p * m * m);
     std::vector<psdo::Mat> Hm(p), Zm(p);
     for (int j = 0; j < p; j++) {
@@ -91,15 +112,12 @@ struct EmuBackend {
     }
     std::vector<double> lre(m), lim(m);
     const int inf = psdo::real_periodic_qr(m, p, Hm, Zm, false, false, 30, lre.data(), lim.data());
-    pairs.assign((size_t)(m + 2) * 4, 0.0);
-    if (getenv("MS_EMUL_VERBOSE")) fprintf(stderr, "[emul] shifts lo %d m %d info %d\n", lo, m, inf);
-    const int np_ = pair_shifts(lre.data(), lim.data(), inf, m, perturb, pairs.data());
-    if (getenv("MS_EMUL_VERBOSE"))
-      for (int q = 0; q < np_; q++) fprintf(stderr, "[emul] pair %d: %g %g %g %g\n", q, pairs[4*q], pairs[4*q+1], pairs[4*q+2], pairs[4*q+3]);
-    return np_;
+    if (pairs.empty()) pairs.assign((size_t)4 * 66 * 4, 0.0);
+    if (getenv("MS_EMUL_VERBOSE")) fprintf(stderr, "[emul] shifts slot %d lo %d m %d info %d\n", slot, lo, m, inf);
+    slot_pairs[slot] = pair_shifts(lre.data(), lim.data(), inf, m, perturb, pairs.data() + (size_t)pair_offset(slot) * 4);
+    return slot;
   }
 
-  void upload_plan(const std::vector<WinDesc>& pl) { plan = pl; }
 
   double* Uptr(int j, int s) { return U.data() + (size_t)j * n * g.W + (size_t)s * g.W; }
 
@@ -153,9 +171,11 @@ struct EmuBackend {
 
   long long max_rounds = -1, nrounds = 0;
   bool skip_apply = false;
-  void round(int off, int cnt) {
+  void round(const std::vector<WinDesc>& wins_) {
     if (max_rounds >= 0 && nrounds >= max_rounds) return;
     nrounds++;
+    plan = wins_;
+    const int off = 0, cnt = (int)plan.size();
     const int W = g.W, LD = g.LD;
     std::vector<double> Hw((size_t)p * W * LD), Uw((size_t)p * W * LD);
     for (int w = 0; w < cnt; w++) {
@@ -171,6 +191,9 @@ struct EmuBackend {
             c.H(j + 1)[r + (size_t)cc * LD] = h(j, d.s + r, d.s + cc);
             c.U(j + 1)[r + (size_t)cc * LD] = (r == cc) ? 1.0 : 0.0;
           }
+      int bihi[MS_MAXNB];
+      c.bihi = bihi;
+      for (int b = 0; b < d.nbul; b++) bihi[b] = clamp_block_end(c, b);
       HostExec ex;
       ex.nb = g.NB;
       for (int b = 0; b < g.NB; b++)
@@ -198,8 +221,12 @@ struct EmuBackend {
     apply(plan.data() + off, cnt);
   }
 
+  double junk = 0.0;  // largest entry below the Hessenberg / triangular structure when the pipeline ends
   void finish(int& nblocks) {
     nblocks = 0;
+    for (int j = 0; j < p; j++)
+      for (int c = 0; c < n; c++)
+        for (int r = c + (j == 0 ? 2 : 1); r < n; r++) junk = std::max(junk, std::fabs(h(j, r, c)));
     if (max_rounds >= 0) return;
     std::vector<WinDesc> list;
     for (int k = 0; k < n;) {
@@ -260,7 +287,7 @@ struct EmuBackend {
 extern "C" {
 
 // H: [p][n*n] column-major Hessenberg-triangular factors (rightwards order), Z: [p][n*n] preset
-// Schur vectors or NULL.  stats[8]: sweeps, rounds, windows, shift pairs, exceptional, final
+// Schur vectors or NULL.  stats[9] (last: 1 if a bulge was left behind when the pipeline ended): sweeps, rounds, windows, shift pairs, exceptional, final
 // blocks, bulge steps, status.  Returns the status of the driver (0 = finished).
 int ms_emul_run(int n, int p, double* Hbuf, double* Zbuf, int wantT, int wantZ, int nsw, int rep_max,
                 double* eig, int* info, long long* stats) {
@@ -279,14 +306,17 @@ int ms_emul_run(int n, int p, double* Hbuf, double* Zbuf, int wantT, int wantZ, 
   if (rep_max > 0) cfg.rep_max = rep_max;
   if (const char* ev = getenv("MS_EMUL_MAXROUNDS")) {
     be.max_rounds = atoll(ev);
-    cfg.max_sweeps = 1;
+    cfg.max_rounds = be.max_rounds + 4;
   }
+  if (const char* ev = getenv("MS_EMUL_LAG")) cfg.lag = atoi(ev);
+  if (const char* ev = getenv("MS_EMUL_AHEAD")) cfg.sets_ahead = atoi(ev);
   DriverStats ds;
   const int status = drive(be, cfg, ds);
   *info = be.info;
   if (stats) {
     stats[0] = ds.sweeps; stats[1] = ds.rounds; stats[2] = ds.windows; stats[3] = ds.shift_pairs;
     stats[4] = ds.exceptional; stats[5] = ds.final_blocks; stats[6] = be.chase_steps; stats[7] = status;
+    stats[8] = (be.junk != 0.0) ? 1 : 0;
   }
   return status;
 }
