@@ -136,7 +136,7 @@ def run_reference(args):
         t += dt
     rate = sample * args.steps / t
     line = {
-        "impl": "reference", "metric": "pschur!/sec batched (p=8,N=32)", "value": rate,
+        "impl": "reference", "metric": "pschur!/sec batched (p=8,N=32); large-N FP64 % peak in large_n", "value": rate,
         "unit": "problems/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -150,6 +150,107 @@ def run_reference(args):
     }
     print(json.dumps(line))
     return 0
+
+
+LARGE_N, LARGE_P = 4096, 4   # BASELINE configs[3]
+
+
+def cublas_dgemm_tflops(torch, dev, m=8192, reps=5):
+    """FP64 tensor-core denominator: cuBLAS DGEMM m^3, best of `reps`,
+    measured in this very run."""
+    x = torch.randn(m, m, dtype=torch.float64, device=dev)
+    y = torch.randn(m, m, dtype=torch.float64, device=dev)
+    torch.matmul(x, y)
+    best = 1e30
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); torch.matmul(x, y); e1.record(); torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    del x, y
+    torch.cuda.empty_cache()
+    return 2.0 * m ** 3 / (best * 1e-3) / 1e12
+
+
+def large_n_block(torch, psd_b200, L, h, dev, n=LARGE_N, p=LARGE_P):
+    """Second half of BASELINE's metric ("large-N FP64 % peak"): one full real pschur! with T and
+    Z at p = 4, N = 4096 on device-resident buffers through psd_rpschur_batched_dev; standard flop
+    count against the cuBLAS DGEMM rate of the same run; the FP64 tensor-core (DMMA) window
+    updates of the iteration and the GEMM updates of the reduction against it separately;
+    residual and orthogonality checked on the device."""
+    peak = cublas_dgemm_tflops(torch, dev)
+    nn = n * n
+    A0 = torch.empty((1, p, n, n), dtype=torch.float64, device=dev)
+    st = torch.cuda.Stream(device=dev)  # a real stream handle (NULL would select the library's own)
+    psd_b200.capi.check(L.psd_fill_uniform_dev(C.c_void_p(st.cuda_stream), SEED, n, p, 1, 0, 0, C.c_void_p(A0.data_ptr())))
+    T = torch.empty_like(A0)
+    Z = torch.empty_like(A0)
+    E = torch.empty((1, n, 2), dtype=torch.float64, device=dev)
+    I = torch.empty(1, dtype=torch.int32, device=dev)
+
+    torch.cuda.synchronize()
+
+    def run():
+        T.copy_(A0)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(st)
+        psd_b200.capi.check(L.psd_rpschur_batched_dev(h.ptr, 0, C.c_void_p(st.cuda_stream), n, p, 1, 0, 1, 1, 30,
+                                                      C.c_void_p(T.data_ptr()), C.c_void_p(Z.data_ptr()),
+                                                      C.c_void_p(E.data_ptr()), C.c_void_p(I.data_ptr())))
+        e1.record(st)
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) * 1e-3
+
+    h.set_profiling(False)
+    run()                     # warm-up (workspaces, module load)
+    secs = min(run(), run())  # timed without per-launch events
+    h.set_profiling(True); h.kernel_times()
+    run()                     # one more pass with CUDA events around every launch, for the split
+    kt = h.kernel_times()
+    ls = h.large_stats()
+    h.set_profiling(False)
+    # residual / orthogonality on the device (storage is column-major: tensor [c][r] = M^T)
+    eps = 2.220446049250313e-16
+    res = orth = 0.0
+    for j in range(p):
+        Aj, Tj, Zj, Zn = A0[0, j].T, T[0, j].T, Z[0, j].T, Z[0, (j + 1) % p].T
+        res = max(res, float(torch.linalg.norm(Aj - Zj @ Tj @ Zn.T) / torch.linalg.norm(Aj)))
+        orth = max(orth, float(torch.linalg.norm(Zj @ Zj.T - torch.eye(n, dtype=torch.float64, device=dev))))
+    low = max(float(torch.tril(T[0, j].T, -2 if j == 0 else -1).abs().max()) for j in range(p))
+    flops = 25.0 * p * n ** 3
+    upd_tf = ls["apply_flops"] / max(1e-9, ls["apply_ms"] * 1e-3) / 1e12
+    red_tf = kt["large_gemm_flops"] / max(1e-9, kt["large_gemm_ms"] * 1e-3) / 1e12
+    return {
+        "workload": f"real pschur! p={p} N={n} :R with T and Z, single problem (BASELINE configs[3])",
+        "seconds": secs, "info": int(I.item()),
+        "standard_flops": flops, "tflops_standard_count": flops / secs / 1e12,
+        "dgemm_cublas_tflops_same_run": peak, "frac_of_dgemm": flops / secs / 1e12 / peak,
+        "reduction_ms": kt["large_panel_ms"] + kt["large_gemm_ms"], "iteration_ms": kt["iterate_ms"],
+        "iteration": {k: ls[k] for k in ("status", "sweeps", "rounds", "windows", "shift_pairs", "final_blocks",
+                                         "chase_ms", "apply_ms", "scan_ms", "final_ms")},
+        "dmma_window_updates": {"flops": ls["apply_flops"], "ms": ls["apply_ms"], "tflops": upd_tf,
+                                "frac_of_dgemm": upd_tf / peak, "kernel": "psd::ms::ms_apply_kernel"},
+        "dmma_reduction_updates": {"flops": kt["large_gemm_flops"], "ms": kt["large_gemm_ms"], "tflops": red_tf,
+                                   "frac_of_dgemm": red_tf / peak, "kernel": "psd::dgemm_dmma_kernel"},
+        "residual_over_n_eps": res / (n * eps), "orthogonality_over_n_eps": orth / (n * eps),
+        "largest_entry_below_structure": low,
+        "gates": "BASELINE: residual <= 10 N eps, ||Z'Z - I|| <= 10 N eps, exact quasi-triangular structure",
+    }
+
+
+def cpu_large_baseline(n_small=384, p=LARGE_P):
+    """CPU restatement of the reference on the same kind of problem at a small order, with the
+    N^3-extrapolated figure for N = 4096 (the reference's unblocked BLAS-1/2 algorithm needs hours
+    there; a single problem does not thread).  SURVEY.md section 8(d)."""
+    from oracle import oracle as O
+    A = O.gen_real(SEED, n_small, p, 1)
+    t0 = time.perf_counter()
+    _, _, _, info, _ = O.rpschur_batched(A, nthreads=1)
+    dt = time.perf_counter() - t0
+    return {"seconds_measured": dt, "n_measured": n_small, "cores": 1, "kind": "port",
+            "seconds_extrapolated_n4096": dt * (LARGE_N / n_small) ** 3,
+            "sample": f"one p={p} N={n_small} problem with T and Z on one core (C++ restatement of the reference, "
+                      f"Julia unavailable); N=4096 figure = measured x (4096/{n_small})^3, an extrapolation"}
 
 
 def run_ours(args):
@@ -272,7 +373,7 @@ def run_ours(args):
         except Exception:
             traffic = None
     line = {
-        "metric": "pschur!/sec batched (p=8,N=32)", "value": value, "unit": "problems/s",
+        "metric": "pschur!/sec batched (p=8,N=32); large-N FP64 % peak in large_n", "value": value, "unit": "problems/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
@@ -300,6 +401,16 @@ def run_ours(args):
         "clocks": clocks,
         "unconverged": fails,
     }
+    if world == 1 and not args.no_large:
+        try:
+            del dA, dE, dI
+            torch.cuda.empty_cache()
+            line["large_n"] = large_n_block(torch, psd_b200, L, h, dev)
+            line["large_n"]["cpu_baseline"] = cpu_large_baseline()
+            line["large_n"]["speedup_vs_cpu_extrapolated"] = (
+                line["large_n"]["cpu_baseline"]["seconds_extrapolated_n4096"] / line["large_n"]["seconds"])
+        except Exception as ex:  # the headline line must still be printed
+            line["large_n"] = {"error": repr(ex)}
     if world == 1:
         # bounded CPU sample: ~10-20 s on the box's host cores
         probe, cores, _ = cpu_reference_rate(max(64, 32 * host_cores()))
@@ -329,6 +440,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=100000, help="problems per GPU per step")
+    ap.add_argument("--no-large", dest="no_large", action="store_true",
+                    help="skip the large-N (p=4, N=4096) block of the N=1 line")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -1376,6 +1376,8 @@ int psd_large_stats(psd_handle_t h, double out[16]) {
   out[4] = (double)r.shift_pairs; out[5] = r.exceptional; out[6] = r.final_blocks; out[7] = (double)r.launches;
   out[8] = r.apply_flops; out[9] = r.ms_chase; out[10] = r.ms_apply; out[11] = r.ms_shifts; out[12] = r.ms_scan;
   out[13] = r.ms_final;
+  out[14] = r.ms_rounds;
+  out[15] = r.host_seconds;
   return PSD_OK;
 }
 

@@ -4,6 +4,7 @@
 // libpsd_b200.so; called from launch_real_large in psd_capi.cu.
 #include "psd_ms.h"
 
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
@@ -16,7 +17,7 @@ namespace ms {
 
 constexpr int kPlanRing = 8;     // rounds whose window lists may be in flight (> lag + 1)
 constexpr int kScanRing = 16;    // scan results in flight
-constexpr int kShiftSlots = 4;   // shift sets in flight (one side stream each)
+constexpr int kShiftSlots = 8;   // shift sets in flight (one side stream each)
 constexpr int kMaxWin = MS_MAXCHAINS;
 
 struct Workspace {
@@ -29,15 +30,19 @@ struct Workspace {
   double* dSc = nullptr;                         // [2 * MS_MAXP] scales
   unsigned long long* dMax = nullptr;            // [MS_MAXP]
   int* hCtl = nullptr;                           // pinned mirror of dCtl
-  WinDesc* hPlan = nullptr;                      // pinned [kPlanRing][kMaxWin]
-  cudaEvent_t evScan[kScanRing] = {nullptr};
-  cudaEvent_t evPlan[kPlanRing] = {nullptr};     // the copy of a plan slot has been consumed
+  // Mapped pinned host memory, read / written by the kernels directly (no copy-engine operation
+  // between the kernels of a round): window lists of the rounds in flight, scan results.
+  WinDesc* hPlan = nullptr;                      // [kPlanRing][kMaxWin]
+  int* hScan = nullptr;                          // [kScanRing][8]: ilo, ihi, done, nzero
+  cudaEvent_t evScan[kScanRing] = {nullptr};     // scan kernel done (main stream)
+  cudaEvent_t evPub[kScanRing] = {nullptr};      // its result has reached the host (publish stream)
+  cudaStream_t pub = nullptr;                    // carries the device -> host copies of the scan results
   cudaEvent_t evSnap[kShiftSlots] = {nullptr}, evShift[kShiftSlots] = {nullptr};
   cudaStream_t side[kShiftSlots] = {nullptr};
 };
-constexpr int kCtlInts = kScanRing * 8 + kShiftSlots + 16;
-constexpr int kCtlPairs = kScanRing * 8;          // pair counts
-constexpr int kCtlMisc = kScanRing * 8 + kShiftSlots;  // [0] expo of the scaling, [1] number of final blocks
+constexpr int kCtlInts = kScanRing * 8 + kShiftSlots + 1 + 16;
+constexpr int kCtlPairs = kScanRing * 8;          // shift supply state: newest set, pair counts
+constexpr int kCtlMisc = kScanRing * 8 + kShiftSlots + 1;  // [0] expo of the scaling, [1] number of final blocks
 
 Workspace* ws_create() { return new Workspace(); }
 
@@ -45,9 +50,10 @@ void ws_destroy(Workspace* ws) {
   if (!ws) return;
   cudaFree(ws->dU); cudaFree(ws->dPairs); cudaFree(ws->dSnap); cudaFree(ws->dPlan); cudaFree(ws->dList);
   cudaFree(ws->dCtl); cudaFree(ws->dSc); cudaFree(ws->dMax);
-  cudaFreeHost(ws->hCtl); cudaFreeHost(ws->hPlan);
+  cudaFreeHost(ws->hCtl); cudaFreeHost(ws->hPlan); cudaFreeHost(ws->hScan);
   for (auto& e : ws->evScan) if (e) cudaEventDestroy(e);
-  for (auto& e : ws->evPlan) if (e) cudaEventDestroy(e);
+  for (auto& e : ws->evPub) if (e) cudaEventDestroy(e);
+  if (ws->pub) cudaStreamDestroy(ws->pub);
   for (int k = 0; k < kShiftSlots; k++) {
     if (ws->evSnap[k]) cudaEventDestroy(ws->evSnap[k]);
     if (ws->evShift[k]) cudaEventDestroy(ws->evShift[k]);
@@ -86,9 +92,12 @@ cudaError_t ws_basic(Workspace* ws) {
   if (!ws->hCtl) MS_CHECK(cudaHostAlloc((void**)&ws->hCtl, kCtlInts * sizeof(int), cudaHostAllocDefault));
   if (!ws->dPairs) MS_CHECK(cudaMalloc((void**)&ws->dPairs, (size_t)kShiftSlots * 66 * 4 * sizeof(double)));
   if (!ws->dPlan) MS_CHECK(cudaMalloc((void**)&ws->dPlan, (size_t)kPlanRing * kMaxWin * sizeof(WinDesc)));
-  if (!ws->hPlan) MS_CHECK(cudaHostAlloc((void**)&ws->hPlan, (size_t)kPlanRing * kMaxWin * sizeof(WinDesc), cudaHostAllocDefault));
+  if (!ws->hPlan)
+    MS_CHECK(cudaHostAlloc((void**)&ws->hPlan, (size_t)kPlanRing * kMaxWin * sizeof(WinDesc), cudaHostAllocMapped | cudaHostAllocPortable));
+  if (!ws->hScan) MS_CHECK(cudaHostAlloc((void**)&ws->hScan, (size_t)kScanRing * 8 * sizeof(int), cudaHostAllocDefault));
   for (auto& e : ws->evScan) if (!e) MS_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-  for (auto& e : ws->evPlan) if (!e) MS_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  for (auto& e : ws->evPub) if (!e) MS_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  if (!ws->pub) MS_CHECK(cudaStreamCreateWithFlags(&ws->pub, cudaStreamNonBlocking));
   for (int k = 0; k < kShiftSlots; k++) {
     if (!ws->evSnap[k]) MS_CHECK(cudaEventCreateWithFlags(&ws->evSnap[k], cudaEventDisableTiming));
     if (!ws->evShift[k]) MS_CHECK(cudaEventCreateWithFlags(&ws->evShift[k], cudaEventDisableTiming));
@@ -102,8 +111,8 @@ struct Timer {  // optional per-launch timing (profile mode only)
   cudaStream_t st;
   std::vector<cudaEvent_t> ev;
   std::vector<int> kind;
-  void begin(int k) {
-    if (!on) return;
+  int begin(int k) {
+    if (!on) return -1;
     cudaEvent_t a, b;
     cudaEventCreate(&a);
     cudaEventCreate(&b);
@@ -111,10 +120,26 @@ struct Timer {  // optional per-launch timing (profile mode only)
     ev.push_back(a);
     ev.push_back(b);
     kind.push_back(k);
+    return (int)kind.size() - 1;
   }
-  void end() {
+  void end(int id = -2) {
     if (!on) return;
-    cudaEventRecord(ev.back(), st);
+    if (id == -2) id = (int)kind.size() - 1;
+    if (id >= 0) cudaEventRecord(ev[2 * id + 1], st);
+  }
+  // gaps[a * 6 + b]: device time between the end of a kernel of kind a and the start of the next
+  // timed kernel (kind b) on the stream
+  void collect_gaps(double* gaps) {
+    int prev = -1;
+    for (size_t i = 0; i < kind.size(); i++) {
+      if (kind[i] == 5) continue;
+      if (prev >= 0) {
+        float f = 0.f;
+        cudaEventSynchronize(ev[2 * i]);
+        if (cudaEventElapsedTime(&f, ev[2 * prev + 1], ev[2 * i]) == cudaSuccess) gaps[kind[prev] * 6 + kind[i]] += f;
+      }
+      prev = (int)i;
+    }
   }
   void collect(double* ms) {
     for (size_t i = 0; i < kind.size(); i++) {
@@ -144,8 +169,18 @@ struct CudaBackend {
   cudaError_t err = cudaSuccess;
   long long launches = 0;
   long long nscan = 0, nplan = 0;
+  int scan_seq[kScanRing] = {0};
+  long long* dProf = nullptr;
+  int round_timer = -1;
   bool slot_used[kShiftSlots] = {false};
   Timer tm, tm_side[kShiftSlots];
+  double wait_scan = 0.0, wait_shift = 0.0, wait_plan = 0.0;  // host seconds blocked on the device
+  struct Stopwatch {
+    double& acc;
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    explicit Stopwatch(double& a) : acc(a) {}
+    ~Stopwatch() { acc += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); }
+  };
 
   bool ok() const { return err == cudaSuccess; }
   void note(cudaError_t e) {
@@ -158,30 +193,50 @@ struct CudaBackend {
   // Scan of the subdiagonal after a round (wins = that round's windows, already on the device in
   // the plan slot used last); the result lands in a pinned ring slot.
   const WinDesc* last_plan = nullptr;
+  // The scan kernel leaves its result in device memory; a side stream copies it to the host, so
+  // that no operation of the main stream ever waits for a write to host memory (measured: a kernel
+  // that writes its result to mapped host memory delays its successor by ~100 us).
   int scan_async(const WinDesc* /*host copy, unused here*/, int cnt, int nmin) {
     const int slot = (int)(nscan % kScanRing);
     nscan++;
     if (!ok()) return slot;
     tm.begin(3);
-    ms_scan_kernel<<<1, 1024, 0, st>>>(H[0], n, nmin, ws->dCtl + slot * 8, last_plan, last_plan ? cnt : 0, g.W, g.D);
+    ms_scan_kernel<<<1, 1024, (size_t)2 * n + 16, st>>>(H[0], n, nmin, ws->dCtl + slot * 8, 0, last_plan,
+                                                          last_plan ? cnt : 0, g.W, g.D, dProf);
     tm.end();
+    if (round_timer >= 0) tm.end(round_timer);
+    round_timer = -1;
     launches++;
     note(cudaGetLastError());
-    note(cudaMemcpyAsync(ws->hCtl + slot * 8, ws->dCtl + slot * 8, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
     note(cudaEventRecord(ws->evScan[slot], st));
+    note(cudaStreamWaitEvent(ws->pub, ws->evScan[slot], 0));
+    note(cudaMemcpyAsync(ws->hScan + slot * 8, ws->dCtl + slot * 8, 4 * sizeof(int), cudaMemcpyDeviceToHost, ws->pub));
+    note(cudaEventRecord(ws->evPub[slot], ws->pub));
     return slot;
   }
   void scan_wait(int slot, ScanInfo& info) {
     if (!ok()) { info.done = 1; return; }
-    note(cudaEventSynchronize(ws->evScan[slot]));
+    {
+      Stopwatch sw(wait_scan);
+      for (;;) {
+        const cudaError_t q = cudaEventQuery(ws->evPub[slot]);
+        if (q == cudaSuccess) break;
+        if (q != cudaErrorNotReady) { note(q); break; }
+#if defined(__x86_64__)
+        __builtin_ia32_pause();
+#endif
+      }
+    }
     if (!ok()) { info.done = 1; return; }
-    const int* c = ws->hCtl + slot * 8;
+    const int* c = ws->hScan + slot * 8;
     info.ilo = c[0]; info.ihi = c[1]; info.done = c[2]; info.nzero = c[3];
   }
 
-  // Shift set: snapshot of the trailing block on the main stream, eigenvalues on a side stream.
-  int shifts_request(int slot, int lo, int m, double perturb) {
-    if (!ok()) return slot;
+  // Shift set: snapshot of the trailing block on the main stream, eigenvalues on a side stream;
+  // the kernel publishes the set as "newest" when it is complete.  fence: the main stream waits.
+  int shift_seq = 0;
+  void shifts_request(int slot, int lo, int m, double perturb, bool fence) {
+    if (!ok()) return;
     // the slot's previous computation must have finished before its snapshot is overwritten
     if (slot_used[slot]) note(cudaStreamWaitEvent(st, ws->evShift[slot], 0));
     slot_used[slot] = true;
@@ -197,24 +252,16 @@ struct CudaBackend {
     ShiftParams P;
     P.p = p; P.m = m; P.snap = snap;
     P.pairs = ws->dPairs + (size_t)pair_offset(slot) * 4;
-    P.count = ws->dCtl + kCtlPairs + slot;
+    P.state = ws->dCtl + kCtlPairs;
+    P.slot = slot; P.seq = ++shift_seq;
     P.perturb = perturb;
     tm_side[slot].begin(2);
     ms_shifts_kernel<<<1, 256, shift_smem, ss>>>(P);
     tm_side[slot].end();
     launches += 2;
     note(cudaGetLastError());
-    note(cudaMemcpyAsync(ws->hCtl + kCtlPairs + slot, ws->dCtl + kCtlPairs + slot, sizeof(int), cudaMemcpyDeviceToHost, ss));
     note(cudaEventRecord(ws->evShift[slot], ss));
-    return slot;
-  }
-  int shifts_wait(int slot) {
-    if (!ok()) return 0;
-    note(cudaEventSynchronize(ws->evShift[slot]));
-    if (!ok()) return 0;
-    // the chase kernels of the main stream read this set's pairs from now on
-    note(cudaStreamWaitEvent(st, ws->evShift[slot], 0));
-    return ws->hCtl[kCtlPairs + slot];
+    if (fence) note(cudaStreamWaitEvent(st, ws->evShift[slot], 0));
   }
 
   void apply(const WinDesc* wins, int cnt) {
@@ -241,19 +288,27 @@ struct CudaBackend {
   void round(const std::vector<WinDesc>& wins) {
     if (!ok()) return;
     const int cnt = (int)std::min<size_t>(wins.size(), kMaxWin);
+    // The host runs at most `lag` (< kPlanRing - 1) rounds ahead of the scans it has seen, and a
+    // scan is enqueued behind the chase kernel that read the slot, so the slot is free again.
     const int slot = (int)(nplan % kPlanRing);
-    // the pinned slot may be rewritten once the copy of its previous use has executed
-    if (nplan >= kPlanRing) note(cudaEventSynchronize(ws->evPlan[slot]));
     nplan++;
     WinDesc* hp = ws->hPlan + (size_t)slot * kMaxWin;
     WinDesc* dp = ws->dPlan + (size_t)slot * kMaxWin;
     std::copy(wins.begin(), wins.begin() + cnt, hp);
-    note(cudaMemcpyAsync(dp, hp, (size_t)cnt * sizeof(WinDesc), cudaMemcpyHostToDevice, st));
-    note(cudaEventRecord(ws->evPlan[slot], st));
+    __sync_synchronize();
+    WinDesc* hp_dev = nullptr;
+    note(cudaHostGetDevicePointer((void**)&hp_dev, hp, 0));
+    if (!ok()) return;
     ChaseParams C;
     C.n = n; C.p = p; C.g = g;
     for (int j = 0; j < p; j++) C.H[j] = H[j];
-    C.U = ws->dU; C.shifts = ws->dPairs; C.wins = dp;
+    C.U = ws->dU; C.shifts = ws->dPairs; C.shift_state = ws->dCtl + kCtlPairs; C.wins = hp_dev; C.wins_dev = dp; C.prof = dProf;
+    if (dProf && getenv("PSD_MS_STAMP")) {
+      const int mode = atoi(getenv("PSD_MS_STAMP"));
+      if (mode == 1) ms_stamp_kernel<<<1, 32, 0, st>>>(dProf, 8);
+      if (mode == 2) ms_stamp_kernel<<<cnt, 512, chase_smem, st>>>(dProf, 8);
+    }
+    round_timer = tm.begin(5);
     tm.begin(0);
     ms_chase_kernel<<<cnt, 64 * g.NB, chase_smem, st>>>(C);
     tm.end();
@@ -342,39 +397,81 @@ cudaError_t iterate(cudaStream_t st, int sm_count, Workspace* ws, int n, int p, 
   cfg.nsw = nsw;
   if (const char* ev = getenv("PSD_MS_REP")) cfg.rep_max = std::max(1, atoi(ev));
   if (const char* ev = getenv("PSD_MS_AHEAD")) cfg.sets_ahead = std::max(1, atoi(ev));
+  if (const char* ev = getenv("PSD_MS_SCAN_EVERY")) cfg.scan_every = std::max(1, atoi(ev));
   if (const char* ev = getenv("PSD_MS_LAG")) cfg.lag = std::max(1, std::min(kPlanRing - 2, atoi(ev)));
   if (const char* ev = getenv("PSD_MS_NSW")) cfg.nsw = std::max(2, std::min(nsw, atoi(ev)));
   MS_CHECK(grow(ws->dSnap, ws->capSnap, (size_t)kShiftSlots * p * 64 * 64 * sizeof(double)));
   for (int k = 0; k < kShiftSlots; k++) { be.tm_side[k].on = profile != 0; be.tm_side[k].st = ws->side[k]; }
-  be.chase_smem = (size_t)2 * p * g.W * g.LD * sizeof(double);
+  be.chase_smem = ((size_t)2 * p * g.W * g.LD + (size_t)MS_MAXNB * MS_MAXP * MB_STRIDE) * sizeof(double);
   be.shift_smem = ((size_t)((rp_small_doubles(cfg.nsw, p) + 1) & ~1LL) + (size_t)p * (cfg.nsw + 1) * cfg.nsw) * 8;
   be.block_smem = ((size_t)((rp_small_doubles(g.W, p) + 1) & ~1LL) + (size_t)2 * p * (g.W + 1) * g.W) * 8;
   MS_CHECK(cudaFuncSetAttribute(ms_chase_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)be.chase_smem));
   MS_CHECK(cudaFuncSetAttribute(ms_shifts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)be.shift_smem));
   MS_CHECK(cudaFuncSetAttribute(ms_blocks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)be.block_smem));
   MS_CHECK(cudaFuncSetAttribute(ms_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AP_SMEM));
+  MS_CHECK(cudaFuncSetAttribute(ms_stamp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)be.chase_smem));
+  // every kernel of a round asks for the same (largest) shared-memory carve-out, so that the SMs
+  // are not reconfigured between the kernels of the pipeline
+  if (getenv("PSD_MS_SCAN_CARVEOUT")) {
+    MS_CHECK(cudaFuncSetAttribute(ms_scan_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+    MS_CHECK(cudaFuncSetAttribute(ms_snapshot_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+  }
+  if (!getenv("PSD_MS_NO_CARVEOUT")) {
+
+    MS_CHECK(cudaFuncSetAttribute(ms_apply_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+    MS_CHECK(cudaFuncSetAttribute(ms_chase_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+    MS_CHECK(cudaFuncSetAttribute(ms_shifts_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+  }
+  MS_CHECK(cudaMemsetAsync(ws->dCtl + kCtlPairs, 0, (kShiftSlots + 1) * sizeof(int), st));
+  long long* dprof = nullptr;
+  if (getenv("PSD_MS_CHASE_PROF")) {
+    cudaMalloc((void**)&dprof, 16 * sizeof(long long));
+    cudaMemsetAsync(dprof, 0, 16 * sizeof(long long), st);
+    be.dProf = dprof;
+  }
   DriverStats ds;
+  const auto t_drive0 = std::chrono::steady_clock::now();
   const int status = drive(be, cfg, ds);
+  const double t_drive = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_drive0).count();
   // side streams: nothing of this call may still be running when the caller reuses the buffers
   for (int k = 0; k < kShiftSlots; k++)
     if (be.slot_used[k]) cudaStreamSynchronize(ws->side[k]);
+  cudaStreamSynchronize(ws->pub);
   if (!be.ok()) return be.err;
   if (res) {
     res->status = status;
     res->sweeps = ds.sweeps; res->rounds = ds.rounds; res->windows = ds.windows;
     res->shift_pairs = ds.shift_pairs; res->exceptional = ds.exceptional;
     res->final_blocks = ds.final_blocks; res->launches = be.launches; res->apply_flops = ds.apply_flops;
+    res->host_seconds = t_drive;
     if (profile) {
-      double ms[5] = {0, 0, 0, 0, 0};
+      double ms[6] = {0, 0, 0, 0, 0, 0};
+      if (getenv("PSD_MS_VERBOSE")) {
+        double gaps[36] = {0};
+        cudaStreamSynchronize(st);
+        be.tm.collect_gaps(gaps);
+        fprintf(stderr, "[psd ms gaps, ms] scan->chase %.1f | chase->apply %.1f | apply->scan %.1f | scan->scan %.1f | apply->chase %.1f | other %.1f\n",
+                gaps[3 * 6 + 0], gaps[0 * 6 + 1], gaps[1 * 6 + 3], gaps[3 * 6 + 3], gaps[1 * 6 + 0],
+                gaps[4 * 6 + 1] + gaps[1 * 6 + 4] + gaps[3 * 6 + 4] + gaps[3 * 6 + 1] + gaps[1 * 6 + 1]);
+      }
       be.tm.collect(ms);
       for (int k = 0; k < kShiftSlots; k++) be.tm_side[k].collect(ms);
       res->ms_chase = ms[0]; res->ms_apply = ms[1]; res->ms_shifts = ms[2]; res->ms_scan = ms[3]; res->ms_final = ms[4];
+      res->ms_rounds = ms[5];
     }
   }
+  if (dprof) {
+    long long hp[16];
+    cudaMemcpy(hp, dprof, sizeof(hp), cudaMemcpyDeviceToHost);
+    cudaFree(dprof);
+    const double k = hp[6] ? 1.0 / hp[6] : 0.0;
+    fprintf(stderr, "[psd ms chase, CTA 0 of %lld launches, cycles per launch] chain %.0f | columns %.0f | rows %.0f | write-back %.0f | whole CTA %.0f | steps %.1f | scan end -> chase start %.1f us (globaltimer) | -> stamp kernel %.1f us\n",
+            hp[6], hp[0] * k, hp[1] * k, hp[2] * k, hp[3] * k, hp[4] * k, hp[5] * k, hp[7] * k * 1e-3, hp[8] * k * 1e-3);
+  }
   if (getenv("PSD_MS_VERBOSE"))
-    fprintf(stderr, "[psd ms] n %d p %d W %d NB %d nsw %d: status %d, %d sweeps, %lld rounds, %lld windows, %lld pairs, %d exceptional, %d final blocks, %.3f TFLOP applied\n",
+    fprintf(stderr, "[psd ms] n %d p %d W %d NB %d nsw %d: status %d, %d sets, %lld rounds, %lld windows, %lld pairs, %d exceptional, %d final blocks, %.3f TFLOP applied; host %.3f s (blocked: scans %.3f, shifts %.3f, plan ring %.3f)\n",
             n, p, g.W, g.NB, cfg.nsw, status, ds.sweeps, ds.rounds, ds.windows, ds.shift_pairs, ds.exceptional,
-            ds.final_blocks, ds.apply_flops * 1e-12);
+            ds.final_blocks, ds.apply_flops * 1e-12, t_drive, be.wait_scan, be.wait_shift, be.wait_plan);
   return cudaSuccess;
 }
 

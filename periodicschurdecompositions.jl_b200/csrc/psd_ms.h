@@ -23,6 +23,8 @@ struct Result {
   double apply_flops = 0.0;  // flops of the tensor-core window updates
   // device milliseconds by kind (only with profile != 0): chase, apply, shifts, scan, final
   double ms_chase = 0.0, ms_apply = 0.0, ms_shifts = 0.0, ms_scan = 0.0, ms_final = 0.0;
+  double host_seconds = 0.0;  // wall time of the pipeline (host clock, excludes the collection of profile events)
+  double ms_rounds = 0.0;  // sum over the rounds of (first kernel start .. scan kernel end)
 };
 
 // largest period / smallest order this path takes

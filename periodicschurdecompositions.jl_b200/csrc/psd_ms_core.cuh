@@ -17,12 +17,19 @@
 // applied to the rows of H_1 and the columns of H_p; then for j = p..2 a 3- and a 2-reflector that
 // restore the triangular form of H_j, pushed into the columns of H_{j-1}.
 //
-// Parallel organisation inside a window: every bulge of the packet owns two warps.  All bulges
-// advance in lockstep; a step is 2p barrier-separated phases (generate + row update of H_j /
-// column update of H_{j-1} and U_j), in each of which different bulges touch disjoint rows
-// (row phases) or disjoint columns (column phases), so there are no races and the result does not
-// depend on the thread schedule.  Reflectors are computed redundantly by every lane from
-// broadcast shared-memory reads (no shuffles, no mailbox).
+// Parallel organisation inside a window: every bulge of the packet owns two warps, and all
+// bulges advance in lockstep.  A step has three barrier-separated phases instead of the 2p + 1 a
+// literal transcription needs:
+//   C  chain: the 2p - 1 reflectors of the step depend only on the hanging column of H_1 and on
+//      the 3 x 3 diagonal blocks of H_p .. H_2, so one warp per bulge evaluates the whole chain
+//      H_1 -> H_p -> ... -> H_2 in registers and posts the reflectors in a shared-memory mailbox;
+//   R  every column update of the step (H_j by the reflectors of its right neighbour, U_j);
+//   L  every row update of the step, and the exact structural entries (beta, 0) of the columns
+//      the reflectors were generated from.
+// Within R different bulges touch disjoint columns, within L disjoint rows, and a row update
+// commutes with the column updates of the other bulges, so there are no races and the result does
+// not depend on the thread schedule.  (The one place where the order matters - the hanging column
+// of H_1, whose entries below the subdiagonal are annihilated, not rotated - is written in C.)
 #pragma once
 #include <cfloat>
 #include <cmath>
@@ -86,12 +93,13 @@ struct Ctx {
   double* Uw;  // [p][W * LD]  accumulated U_j
   const double* shifts;  // [npairs][4] = (re1, im1, re2, im2)
   int* bihi;   // [nbul] end of the block each bulge really works in (clamp_block_end)
+  double* mbox;  // [MS_MAXNB][MS_MAXP][8] reflectors of the current step (see mb())
   WinDesc d;
   PSD_HD double* H(int j) const { return Hw + (size_t)(j - 1) * W * LD; }
   PSD_HD double* U(int j) const { return Uw + (size_t)(j - 1) * W * LD; }
 };
 
-// Per (bulge, role) state carried through the phases of one step.
+// Per (bulge, role) state of the current step.
 struct BState {
   int b;       // bulge index inside the packet
   int active;  // bulge takes a step at this time
@@ -100,29 +108,45 @@ struct BState {
   int r;       // first row/column the reflectors act on (k + 1)
   int nr;      // 3, or 2 at the bottom of the active block
   int ihi;     // end of the block this bulge works in
-  // reflectors generated in the last gen phase: first (order nr) at r, second (order 2) at r + 1
-  double v1, v2, tau1, u1, tau2;
-  int have2;
-  // structural entries of the generating columns, written at the start of the next phase
-  double beta1, a0n, beta2;
-  int defer_j;  // factor whose columns get them (0 = none)
 };
+
+// Mailbox entry of (bulge b, factor j): the reflectors generated on H_j in this step,
+//   [0] v1 [1] v2 [2] tau1   first reflector (order nr) on rows/columns r ..
+//   [3] u1 [4] tau2          second reflector (order 2) on r+1, r+2 (tau2 = 0: none)
+//   [5] beta1 [6] a0n [7] beta2   structural entries of the generating columns
+constexpr int MB_STRIDE = 8;
+PSD_HD double* mb(const Ctx& c, int b, int j) { return c.mbox + ((size_t)b * MS_MAXP + (j - 1)) * MB_STRIDE; }
 
 // dlarfg for 2 or 3 entries held in registers (householder.jl:66-108); exact power-of-two
 // prescale instead of the reference's sfmin loop.  x0 <- beta, (v1, v2) <- essential part.
 // Division-free formulation (the reflector generation of all bulges runs redundantly in every
 // warp, so it sits on the FP64 pipe): with r = 1/sqrt(a^2 + |y|^2), norm = 1/r,
 //   beta = -sign(a) norm,  tau = (beta - a)/beta = 1 + |a| r,  1/(a - beta) = sign(a)/(|a| + norm).
+// On the device: MUFU seeds (about 20 bits) and two Newton steps, no special-case code (the
+// arguments are sums of squares / sums of magnitudes prescaled into the safe range).
 PSD_HD double ms_rsqrt(double x) {
 #if defined(__CUDA_ARCH__)
-  return rsqrt(x);
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double hx = 0.5 * x;
+  double e = fma(-hx * y, y, 0.5);
+  y = fma(y, e, y);
+  e = fma(-hx * y, y, 0.5);
+  y = fma(y, e, y);
+  return y;
 #else
   return 1.0 / sqrt(x);
 #endif
 }
 PSD_HD double ms_rcp(double x) {
 #if defined(__CUDA_ARCH__)
-  return __drcp_rn(x);
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double e = fma(-x, y, 1.0);
+  y = fma(y, e, y);
+  e = fma(-x, y, 1.0);
+  y = fma(y, e, y);
+  return y;
 #else
   return 1.0 / x;
 #endif
@@ -173,9 +197,12 @@ PSD_HD void start_vector(const Ctx& c, int o, int pair, double& x0, double& w1, 
   // P[:, 0] = H1[:, 0] t00 ; P[:, 1] = H1[:, 0] t01 + H1[:, 1] t11
   const double p00 = h00 * t00, p10 = h10 * t00;
   const double p01 = h00 * t01 + h01 * t11, p11 = h10 * t01 + h11 * t11, p21 = h21 * t11;
-  const double* sh = c.shifts + 4 * ((size_t)c.d.pair_off + pair);
-  const double tr = sh[0] + sh[2];                    // s1 + s2 (real for a conjugate or real pair)
-  const double det = sh[0] * sh[2] - sh[1] * sh[3];  // s1 s2
+  double tr = 0.0, det = 0.0;  // no shift set yet: a plain (unshifted) double step
+  if (pair >= 0) {
+    const double* sh = c.shifts + 4 * ((size_t)c.d.pair_off + pair);
+    tr = sh[0] + sh[2];                    // s1 + s2 (real for a conjugate or real pair)
+    det = sh[0] * sh[2] - sh[1] * sh[3];  // s1 s2
+  }
   double s = fabs(p00) + fabs(p10) + fabs(p01) + fabs(p11) + fabs(p21) + fabs(tr);
   if (s == 0.0) s = 1.0;
   const double is = 1.0 / s;
@@ -227,141 +254,201 @@ PSD_HD void bulge_setup(const Ctx& c, BState& st, int b, int t) {
   st.r = st.k + 1;
   const int rem = ihi - posg;  // rows below the hanging column inside the active block
   st.nr = rem >= 3 ? 3 : rem;
-  st.defer_j = 0;
-  st.have2 = 0;
 }
 
-// Row phase of factor j: generate the reflector(s) of every active bulge and apply them to the
-// rows r .. r+nr-1 of H_j inside the window.  role 0 / 1 split the columns.  LANES = 32 on the
-// device (lane = threadIdx & 31), 1 in the host emulation.
-// part: 1 = generate only, 2 = row update only (after a barrier), 3 = both.
+// One row (a0, a1, a2) times the reflector pair from the right / one column from the left (the
+// arithmetic is the same): first reflector (v1, v2, t1) on all three, second (u1, t2) on the last two.
+PSD_HD void refl_pair_apply(double& a0, double& a1, double& a2, double v1, double v2, double t1, double u1,
+                            double t2) {
+  const double s1 = t1 * (a0 + v1 * a1 + v2 * a2);
+  a0 -= s1; a1 -= s1 * v1; a2 -= s1 * v2;
+  const double s2 = t2 * (a1 + u1 * a2);
+  a1 -= s2; a2 -= s2 * u1;
+}
+
+// Phase C: the reflector chain of the step, in registers (role 0; every lane computes the same
+// values, lane 0 posts them).  Writes the structural entries of the hanging column of H_1.
 template <int LANES>
-PSD_HD void phase_gen_left(const Ctx& c, BState& st, int j, int role, int lane, int part = 3) {
-  if (!st.active) return;
-  const int LD = c.LD, wl = c.d.wl, r = st.r, nr = st.nr;
-  double* Hj = c.H(j);
-  int cfirst;  // first column updated by the row operation
-  if (part == 2) {
-    cfirst = (j == 1) ? r : (st.have2 ? r + 2 : r + 1);
-  } else
-  if (j == 1) {
-    double x0, w1, w2;
-    if (st.intro) {
-      start_vector(c, r, (c.d.pair0 + st.b) % c.d.npairs, x0, w1, w2);
-    } else {
-      const double* x = Hj + r + (size_t)st.k * LD;
-      x0 = x[0]; w1 = x[1]; w2 = (nr == 3) ? x[2] : 0.0;
-    }
-    st.tau1 = refl3(nr, x0, w1, w2);
-    st.v1 = w1; st.v2 = w2;
-    st.beta1 = x0;
-    st.have2 = 0;
-    st.defer_j = st.intro ? 0 : 1;
-    cfirst = r;
+PSD_HD void phase_chain(const Ctx& c, BState& st, int role, int lane) {
+  if (!st.active || role != 0) return;
+  const int LD = c.LD, r = st.r, nr = st.nr, p = c.p;
+  double x0, w1, w2;
+  double* H1 = c.H(1);
+  if (st.intro) {
+    start_vector(c, r, c.d.npairs > 0 ? (c.d.pair0 + st.b) % c.d.npairs : -1, x0, w1, w2);
   } else {
-    const double* x = Hj + r + (size_t)r * LD;
-    double x0 = x[0], w1 = x[1], w2 = (nr == 3) ? x[2] : 0.0;
-    st.tau1 = refl3(nr, x0, w1, w2);
-    st.v1 = w1; st.v2 = w2;
-    st.beta1 = x0;
-    st.defer_j = j;
+    const double* x = H1 + r + (size_t)st.k * LD;
+    x0 = x[0]; w1 = x[1]; w2 = (nr == 3) ? x[2] : 0.0;
+  }
+  double pt1 = refl3(nr, x0, w1, w2);
+  double pv1 = w1, pv2 = w2, pu1 = 0.0, pt2 = 0.0;
+  PSD_MS_WARPSYNC();  // every lane has read the hanging column before lane 0 overwrites it
+  if (lane == 0) {
+    double* m = mb(c, st.b, 1);
+    m[0] = pv1; m[1] = pv2; m[2] = pt1; m[3] = 0.0; m[4] = 0.0; m[5] = x0;
+    if (!st.intro) {
+      double* x = H1 + r + (size_t)st.k * LD;
+      x[0] = x0; x[1] = 0.0;
+      if (nr == 3) x[2] = 0.0;
+    }
+  }
+  for (int j = p; j >= 2; j--) {
+    // C = B Q_prev for the upper triangular diagonal block B of H_j (columns 0, 1 are enough)
+    const double* B = c.H(j) + r + (size_t)r * LD;
+    double c00 = B[0], c01 = B[LD], c02 = 0.0;
+    double c10 = 0.0, c11 = B[1 + LD], c12 = 0.0;
+    double c20 = 0.0, c21 = 0.0, c22 = 0.0;
     if (nr == 3) {
-      // column r+1 after the first reflector, then the 2-reflector that clears H_j[r+2, r+1]
-      const double* y = Hj + r + (size_t)(r + 1) * LD;
-      double a0 = y[0], a1 = y[1], a2 = y[2];
-      const double s1 = st.tau1 * (a0 + st.v1 * a1 + st.v2 * a2);
-      a0 -= s1; a1 -= s1 * st.v1; a2 -= s1 * st.v2;
+      c02 = B[2 * LD]; c12 = B[1 + 2 * LD]; c22 = B[2 + 2 * LD];
+    }
+    refl_pair_apply(c00, c01, c02, pv1, pv2, pt1, pu1, pt2);
+    refl_pair_apply(c10, c11, c12, pv1, pv2, pt1, pu1, pt2);
+    refl_pair_apply(c20, c21, c22, pv1, pv2, pt1, pu1, pt2);
+    // QR of C: 3-reflector from column 0, then the 2-reflector from rows 1, 2 of column 1
+    double y0 = c00, y1 = c10, y2 = c20;
+    const double t1 = refl3(nr, y0, y1, y2);
+    double a0 = c01, a1 = c11, a2 = c21;
+    const double s1 = t1 * (a0 + y1 * a1 + y2 * a2);
+    a0 -= s1; a1 -= s1 * y1; a2 -= s1 * y2;
+    double t2 = 0.0, u1 = 0.0;
+    if (nr == 3) {
       double dum = 0.0;
-      st.tau2 = refl3(2, a1, a2, dum);
-      st.u1 = a2;
-      st.a0n = a0;
-      st.beta2 = a1;
-      st.have2 = 1;
-      cfirst = r + 2;
-    } else {
-      st.have2 = 0;
-      cfirst = r + 1;
+      t2 = refl3(2, a1, a2, dum);
+      u1 = a2;
     }
-  }
-  if (part == 1) return;
-  PSD_MS_WARPSYNC();  // every lane has read the generating entries before any lane writes
-  // the two roles split the columns
-  int c0 = cfirst, c1 = wl;
-  {
-    const int mid = cfirst + (wl - cfirst + 1) / 2;
-    if (role == 0) c1 = mid; else c0 = mid;
-  }
-  const double v1 = st.v1, v2 = st.v2, t1 = st.tau1, u1 = st.u1, t2 = st.tau2;
-  const bool two = st.have2 != 0;
-  for (int cc = c0 + lane; cc < c1; cc += LANES) {
-    double* a = Hj + r + (size_t)cc * LD;
-    double a0 = a[0], a1 = a[1], a2 = (nr == 3) ? a[2] : 0.0;
-    const double s1 = t1 * (a0 + v1 * a1 + v2 * a2);
-    a0 -= s1; a1 -= s1 * v1; a2 -= s1 * v2;
-    if (two) {
-      const double s2 = t2 * (a1 + u1 * a2);
-      a1 -= s2; a2 -= s2 * u1;
+    if (lane == 0) {
+      double* m = mb(c, st.b, j);
+      m[0] = y1; m[1] = y2; m[2] = t1; m[3] = u1; m[4] = t2; m[5] = y0; m[6] = a0; m[7] = a1;
     }
-    a[0] = a0; a[1] = a1;
-    if (nr == 3) a[2] = a2;
+    pv1 = y1; pv2 = y2; pt1 = t1; pu1 = u1; pt2 = t2;
   }
 }
 
-// Structural entries of the generating columns (beta, exact zeros) of the factor the reflectors
-// were generated on; stored by one lane in the phase after the generation.
-PSD_HD void flush_deferred(const Ctx& c, BState& st, int role, int lane) {
-  if (!st.active || role != 0 || lane != 0 || st.defer_j == 0) return;
-  const int LD = c.LD, r = st.r, nr = st.nr;
-  double* G = c.H(st.defer_j);
-  if (st.defer_j == 1) {
-    double* x = G + r + (size_t)st.k * LD;
-    x[0] = st.beta1; x[1] = 0.0;
-    if (nr == 3) x[2] = 0.0;
-  } else {
-    double* x = G + r + (size_t)r * LD;
-    x[0] = st.beta1; x[1] = 0.0;
-    if (nr == 3) {
-      x[2] = 0.0;
-      double* y = G + r + (size_t)(r + 1) * LD;
-      y[0] = st.a0n; y[1] = st.beta2; y[2] = 0.0;
-    }
-  }
-  st.defer_j = 0;
-}
-
-// Column phase: the reflectors generated on factor jn (the phase before) are applied to the
-// columns r .. r+nr-1 of H_j (role 0, rows 0 .. rlast) and of U_jn (role 1, all rows); role 0
-// first stores the structural entries of the generating columns of H_jn.
+// Phase R: every column update of the step.  H_j gets the reflectors generated on its right
+// neighbour jn (role 0, rows 0 .. last row of the block / of the new bulge), U_jn the same
+// reflectors (role 1, all rows).  The phase is latency bound (a few hundred elements per warp), so
+// the strips of two factors and both 32-row passes of a strip are loaded before anything is
+// computed or stored: 12 independent loads in flight per lane.
 template <int LANES>
-PSD_HD void phase_right(const Ctx& c, BState& st, int j, int jn, int role, int lane) {
+PSD_HD void phase_rights(const Ctx& c, BState& st, int role, int lane) {
   if (!st.active) return;
-  const int LD = c.LD, r = st.r, nr = st.nr;
-  flush_deferred(c, st, role, lane);
-  double* M;
-  int nrow;
-  if (role == 0) {
-    M = c.H(j);
-    const int ihl = st.ihi - c.d.s;
-    nrow = (j == 1) ? ((r + nr < ihl ? r + nr : ihl) + 1) : (r + nr);
-  } else {
-    M = c.U(jn);
-    nrow = c.d.wl;
-  }
-  const double v1 = st.v1, v2 = st.v2, t1 = st.tau1, u1 = st.u1, t2 = st.tau2;
-  const bool two = st.have2 != 0;
-  double* col = M + (size_t)r * LD;
-  for (int rr = lane; rr < nrow; rr += LANES) {
-    double a0 = col[rr], a1 = col[rr + LD], a2 = (nr == 3) ? col[rr + 2 * LD] : 0.0;
-    const double s1 = t1 * (a0 + v1 * a1 + v2 * a2);
-    a0 -= s1; a1 -= s1 * v1; a2 -= s1 * v2;
-    if (two) {
-      const double s2 = t2 * (a1 + u1 * a2);
-      a1 -= s2; a2 -= s2 * u1;
+  const int LD = c.LD, r = st.r, nr = st.nr, p = c.p;
+  const int ihl = st.ihi - c.d.s;
+  constexpr int NP = (LANES == 32) ? 2 : 1;  // passes handled per trip (W <= 64 = 2 x 32 lanes)
+  for (int j0 = 1; j0 <= p; j0 += 2) {
+    double* col[2];
+    int nrow[2];
+    double v1[2], v2[2], t1[2], u1[2], t2[2];
+#pragma unroll
+    for (int q = 0; q < 2; q++) {
+      const int j = j0 + q;
+      if (j > p) { nrow[q] = 0; col[q] = c.Hw; v1[q] = v2[q] = t1[q] = u1[q] = t2[q] = 0.0; continue; }
+      const int jn = (j == p) ? 1 : j + 1;
+      const double* m = mb(c, st.b, jn);
+      v1[q] = m[0]; v2[q] = m[1]; t1[q] = m[2]; u1[q] = m[3]; t2[q] = m[4];
+      if (role == 0) {
+        col[q] = c.H(j) + (size_t)r * LD;
+        nrow[q] = (j == 1) ? ((r + nr < ihl ? r + nr : ihl) + 1) : (r + nr);
+      } else {
+        col[q] = c.U(jn) + (size_t)r * LD;
+        nrow[q] = c.d.wl;
+      }
     }
-    col[rr] = a0; col[rr + LD] = a1;
-    if (nr == 3) col[rr + 2 * LD] = a2;
+    const int nmax = nrow[0] > nrow[1] ? nrow[0] : nrow[1];
+    for (int rb = 0; rb < nmax; rb += NP * LANES) {
+      double a[2][NP][3];
+      bool on[2][NP];
+#pragma unroll
+      for (int q = 0; q < 2; q++)
+#pragma unroll
+        for (int h = 0; h < NP; h++) {
+          const int rr = rb + h * LANES + lane;
+          on[q][h] = rr < nrow[q];
+          const int ri = on[q][h] ? rr : 0;
+          a[q][h][0] = col[q][ri];
+          a[q][h][1] = col[q][ri + LD];
+          a[q][h][2] = (nr == 3) ? col[q][ri + 2 * LD] : 0.0;
+        }
+#pragma unroll
+      for (int q = 0; q < 2; q++)
+#pragma unroll
+        for (int h = 0; h < NP; h++) refl_pair_apply(a[q][h][0], a[q][h][1], a[q][h][2], v1[q], v2[q], t1[q], u1[q], t2[q]);
+#pragma unroll
+      for (int q = 0; q < 2; q++)
+#pragma unroll
+        for (int h = 0; h < NP; h++) {
+          if (!on[q][h]) continue;
+          const int rr = rb + h * LANES + lane;
+          col[q][rr] = a[q][h][0];
+          col[q][rr + LD] = a[q][h][1];
+          if (nr == 3) col[q][rr + 2 * LD] = a[q][h][2];
+        }
+    }
   }
-  st.defer_j = 0;
+}
+
+// Phase L: every row update of the step (the two roles split the columns), and the exact
+// structural entries of the generating columns of H_2 .. H_p.  Two factors per trip (independent
+// loads first), as in phase R.
+template <int LANES>
+PSD_HD void phase_lefts(const Ctx& c, BState& st, int role, int lane) {
+  if (!st.active) return;
+  const int LD = c.LD, wl = c.d.wl, r = st.r, nr = st.nr, p = c.p;
+  for (int j0 = 1; j0 <= p; j0 += 2) {
+    double* row[2];
+    int c0[2], c1[2];
+    double v1[2], v2[2], t1[2], u1[2], t2[2];
+#pragma unroll
+    for (int q = 0; q < 2; q++) {
+      const int j = j0 + q;
+      if (j > p) { c0[q] = c1[q] = 0; row[q] = c.Hw; v1[q] = v2[q] = t1[q] = u1[q] = t2[q] = 0.0; continue; }
+      const double* m = mb(c, st.b, j);
+      v1[q] = m[0]; v2[q] = m[1]; t1[q] = m[2]; u1[q] = m[3]; t2[q] = m[4];
+      double* Hj = c.H(j);
+      int cfirst = r;
+      if (j > 1) {
+        cfirst = (nr == 3) ? r + 2 : r + 1;
+        if (role == 0 && lane == 0) {
+          double* x = Hj + r + (size_t)r * LD;
+          x[0] = m[5]; x[1] = 0.0;
+          if (nr == 3) {
+            x[2] = 0.0;
+            double* y = x + LD;
+            y[0] = m[6]; y[1] = m[7]; y[2] = 0.0;
+          }
+        }
+      }
+      const int mid = cfirst + (wl - cfirst + 1) / 2;
+      c0[q] = (role == 0) ? cfirst : mid;
+      c1[q] = (role == 0) ? mid : wl;
+      row[q] = Hj + r;
+    }
+    const int w0 = c1[0] - c0[0], w1 = c1[1] - c0[1];
+    const int wmax = w0 > w1 ? w0 : w1;
+    for (int cb = 0; cb < wmax; cb += LANES) {
+      double a[2][3];
+      bool on[2];
+#pragma unroll
+      for (int q = 0; q < 2; q++) {
+        const int cc = c0[q] + cb + lane;
+        on[q] = cc < c1[q];
+        const double* e = row[q] + (size_t)(on[q] ? cc : c0[q]) * LD;
+        a[q][0] = e[0];
+        a[q][1] = e[1];
+        a[q][2] = (nr == 3) ? e[2] : 0.0;
+      }
+#pragma unroll
+      for (int q = 0; q < 2; q++) refl_pair_apply(a[q][0], a[q][1], a[q][2], v1[q], v2[q], t1[q], u1[q], t2[q]);
+#pragma unroll
+      for (int q = 0; q < 2; q++) {
+        if (!on[q]) continue;
+        double* e = row[q] + (size_t)(c0[q] + cb + lane) * LD;
+        e[0] = a[q][0];
+        e[1] = a[q][1];
+        if (nr == 3) e[2] = a[q][2];
+      }
+    }
+  }
 }
 
 // The whole in-window chase.  `ex.each(f)` runs f(b, role, lane, st) for the caller's own
@@ -369,44 +456,21 @@ PSD_HD void phase_right(const Ctx& c, BState& st, int j, int jn, int role, int l
 // `ex.barrier()` separates the phases.
 template <class Exec>
 PSD_HD void chase_window(const Ctx& c, Exec& ex) {
-  const int p = c.p;
   const WinDesc& d = c.d;
   constexpr int L = Exec::LANES;
   for (int t = 0; t < d.T; t++) {
-    if (d.intro) {
-      // a bulge that is being introduced reads the leading 3 x 3 blocks, which its own row update
-      // changes: generate first, update after a barrier
-      ex.each([&](int b, int role, int lane, BState& st) {
-        bulge_setup(c, st, b, t);
-        phase_gen_left<L>(c, st, 1, role, lane, 1);
-      });
-      ex.barrier();
-      ex.each([&](int b, int role, int lane, BState& st) { phase_gen_left<L>(c, st, 1, role, lane, 2); });
-    } else {
-      ex.each([&](int b, int role, int lane, BState& st) {
-        bulge_setup(c, st, b, t);
-        phase_gen_left<L>(c, st, 1, role, lane);
-      });
-    }
+    ex.each([&](int b, int role, int lane, BState& st) {
+      bulge_setup(c, st, b, t);
+      phase_chain<L>(c, st, role, lane);
+    });
     ex.barrier();
-    for (int j = p; j >= 2; j--) {
-      const int jn = (j == p) ? 1 : j + 1;
-      ex.each([&](int b, int role, int lane, BState& st) { phase_right<L>(c, st, j, jn, role, lane); });
-      ex.barrier();
-      ex.each([&](int b, int role, int lane, BState& st) { phase_gen_left<L>(c, st, j, role, lane); });
-      ex.barrier();
-    }
-    if (p == 1) {
-      // H_1 is both the generating and the target factor: its structural entries must be in
-      // place before the column phase of the neighbouring bulges reads them
-      ex.each([&](int b, int role, int lane, BState& st) { flush_deferred(c, st, role, lane); });
-      ex.barrier();
-    }
-    {
-      const int jn = (p == 1) ? 1 : 2;
-      ex.each([&](int b, int role, int lane, BState& st) { phase_right<L>(c, st, 1, jn, role, lane); });
-      ex.barrier();
-    }
+    ex.tick(1);
+    ex.each([&](int b, int role, int lane, BState& st) { phase_rights<L>(c, st, role, lane); });
+    ex.barrier();
+    ex.tick(2);
+    ex.each([&](int b, int role, int lane, BState& st) { phase_lefts<L>(c, st, role, lane); });
+    ex.barrier();
+    ex.tick(3);
   }
 }
 

@@ -13,8 +13,10 @@
 //              N / W packets are in flight and the pipeline never drains between "sweeps"
 //   shifts     eigenvalues of the trailing ns x ns block of the active block, computed by the
 //              reference algorithm on one CTA on a side stream from a snapshot of that block;
-//              several requests are in flight, a set is used `sets_ahead` requests after it was
-//              asked for (stale shifts cost no convergence in practice: scripts/ms_proto.py)
+//              the supply is free running: a new set is requested every few packets, and a packet
+//              takes the newest complete set when it is introduced (chosen on the device), so
+//              neither the host nor the main stream ever waits for a shift computation (stale
+//              shifts cost little convergence: scripts/ms_proto.py)
 //   control    the host plans round r from the scan made after round r - lag (a fixed lag, so the
 //              schedule is a deterministic function of the data while the device queue stays
 //              full); a packet learns about deflations that happened since it was planned from
@@ -46,9 +48,11 @@ struct DriverConfig {
   int n = 0, p = 0;
   int wantT = 1, wantZ = 1;
   int nsw = 64;         // order of the shift window (<= 64, limited by shared memory for large p)
-  int rep_max = 1;      // each shift pair of a set is used this many times
-  int sets_ahead = 4;   // shift requests in flight
+  int rep_max = 2;      // a new shift set is requested after (pairs of a set) x rep_max bulges
+  int sets_ahead = 6;   // (unused by the free-running shift supply; kept for the emulation switches)
   int lag = 3;          // rounds between a scan and the plan that uses it
+  int shift_blocks = 1; // consecutive shift sets come from this many different trailing diagonal blocks
+  int scan_every = 1;   // the subdiagonal is scanned after every scan_every-th round
   long long max_rounds = 0;  // 0: 64 + 40 n / D
 };
 
@@ -64,14 +68,6 @@ struct Packet {
   int fin_s;     // position at which the packet was first seen in finished territory (-1: not yet)
 };
 
-struct ShiftSet {
-  int ticket = -1;
-  int slot = 0;
-  int ilo = 0, ihi = -1;  // block it was requested for
-  int npairs = -1;        // known once waited for
-  int next_pair = 0, quota = 0;
-};
-
 // status: 0 = reduced to blocks of order <= W and finished; 1 = no convergence (the factors are
 // still a valid Hessenberg-triangular form with Z accumulated; the caller may fall back).
 template <class Backend>
@@ -80,30 +76,46 @@ int drive(Backend& be, const DriverConfig& cfg, DriverStats& st) {
   const int n = cfg.n, W = g.W, D = g.D;
   const long long max_rounds = cfg.max_rounds > 0 ? cfg.max_rounds : 256 + 100LL * n / D;
   const int lag = std::max(1, cfg.lag);
-  const int ahead = std::max(1, std::min(cfg.sets_ahead, be.shift_slots()));
   const bool trace = getenv("PSD_MS_TRACE") != nullptr;
 
   ScanInfo info;
   be.scan_wait(be.scan_async(nullptr, 0, W), info);
   std::deque<int> scan_tickets;   // scans made after the rounds enqueued so far
-  std::deque<ShiftSet> sets;      // front = in use, others requested
   std::vector<Packet> pk;
   std::vector<WinDesc> wins;
   int next_slot = 0;
-  int idle_sets = 0;              // shift sets used up since the last deflation
-  long long last_progress_round = 0;
+  int idle_sets = 0;              // shift sets requested since the last deflation
   int last_ihi = info.ihi, last_ilo = info.ilo;
+  int req_ilo = -1, req_ihi = -1; // block the newest shift set was requested for
+  int since_request = 0;          // bulges introduced since then
+  int quota = 2 * g.NB;           // ... after which the next set is requested
+  long long pair_counter = 0;     // running index of the next shift pair (taken modulo the set size on the device)
 
-  auto request_set = [&](double perturb) {
+  // Shift supply: free running.  A request snapshots the trailing block of the active block on
+  // the main stream and computes its eigenvalues on a side stream; a packet that is introduced
+  // takes the newest set that is complete at that moment (decided on the device), so the host never
+  // waits for a shift computation.  `fence` makes the main stream wait for this request (first
+  // set; first set of a new active block).
+  auto request_set = [&](double perturb, bool fence) {
     const int m = info.ihi - info.ilo + 1;
     int ns = std::min(cfg.nsw, 2 * (m / 3));
     ns = std::max(2, ns & ~1);
-    ShiftSet s;
-    s.slot = next_slot;
+    // Many packets are in flight at once; shifts that all approximate the same few eigenvalues
+    // would be wasted, so consecutive sets are the Ritz values of consecutive diagonal blocks of
+    // the trailing part of the active block (block 0 = the trailing block itself).
+    int blk = 0;
+    if (cfg.shift_blocks > 1 && !fence) blk = (int)(st.sweeps % cfg.shift_blocks);
+    while (blk > 0 && info.ihi - (blk + 1) * ns + 1 < info.ilo) blk--;
+    be.shifts_request(next_slot, info.ihi - (blk + 1) * ns + 1, ns, perturb, fence);
     next_slot = (next_slot + 1) % be.shift_slots();
-    s.ilo = info.ilo; s.ihi = info.ihi;
-    s.ticket = be.shifts_request(s.slot, info.ihi - ns + 1, ns, perturb);
-    sets.push_back(s);
+    req_ilo = info.ilo; req_ihi = info.ihi;
+    since_request = 0;
+    quota = std::max(g.NB, (ns / 2) * std::max(1, cfg.rep_max));
+    st.sweeps++;
+    idle_sets++;
+    if (trace)
+      fprintf(stderr, "[psd ms] shift set %d for block [%d, %d] (%d x %d)%s, %zu packets in flight\n", st.sweeps, info.ilo,
+              info.ihi, ns, ns, fence ? " fenced" : "", pk.size());
   };
 
   for (long long r = 0;; r++) {
@@ -111,10 +123,7 @@ int drive(Backend& be, const DriverConfig& cfg, DriverStats& st) {
     while ((int)scan_tickets.size() > lag - 1) {
       be.scan_wait(scan_tickets.front(), info);
       scan_tickets.pop_front();
-      if (info.nzero > 0 || info.ihi != last_ihi || info.ilo != last_ilo) {
-        idle_sets = 0;
-        last_progress_round = r;
-      }
+      if (info.nzero > 0 || info.ihi != last_ihi || info.ilo != last_ilo) idle_sets = 0;
       last_ihi = info.ihi; last_ilo = info.ilo;
     }
     if (!be.ok()) return 1;
@@ -135,7 +144,6 @@ int drive(Backend& be, const DriverConfig& cfg, DriverStats& st) {
       }
       pk.resize(k);
     }
-    if (info.done && pk.empty() && scan_tickets.empty()) break;
     if (info.done && pk.empty()) {
       // drain the scans still in flight (they cannot undo `done`: zeros are only ever added)
       ScanInfo tmp;
@@ -144,16 +152,15 @@ int drive(Backend& be, const DriverConfig& cfg, DriverStats& st) {
     }
     const int pass_sets = std::max(1, (info.done ? 1 : (info.ihi - info.ilo + 1) / W) / std::max(1, cfg.nsw / (2 * g.NB)));
     if (r > max_rounds || idle_sets > 60 + 40 * pass_sets) return 1;
-    // ---- shift sets: drop sets asked for a block that is finished, keep `ahead` requests going ----
+    // ---- shift sets ----
     if (!info.done) {
-      while (!sets.empty() && sets.front().ilo > info.ihi) sets.pop_front();
-      double perturb = 0.0;
       const int ex_every = 6 + 4 * pass_sets;  // sets without any deflation before the shifts are spread
+      double perturb = 0.0;
       if (idle_sets >= ex_every && idle_sets % ex_every == 0) perturb = 0.5;  // exceptional shifts
-      while ((int)sets.size() < ahead) {
-        request_set(perturb);
+      const bool other_block = (req_ihi < 0) || (info.ihi < req_ilo);
+      if (other_block || since_request >= quota) {
+        request_set(perturb, other_block);
         if (perturb != 0.0) st.exceptional++;
-        perturb = 0.0;
       }
     }
     // ---- introduce a packet when the top window of the active block is free ----
@@ -162,37 +169,17 @@ int drive(Backend& be, const DriverConfig& cfg, DriverStats& st) {
       for (const Packet& q : pk)
         if (q.s < info.ilo + W && q.s + W > info.ilo) top_free = false;
       if (top_free && (int)pk.size() < be.max_windows()) {
-        ShiftSet& s = sets.front();
-        if (s.npairs < 0) {
-          s.npairs = be.shifts_wait(s.ticket);
-          const int npk1 = std::max(1, (s.npairs + g.NB - 1) / g.NB);
-          s.quota = s.npairs * std::max(1, cfg.rep_max);
-          (void)npk1;
-          st.sweeps++;
-          if (trace)
-            fprintf(stderr, "[psd ms] round %lld: set %d for block [%d, %d] -> %d pairs; active [%d, %d], %zu packets in flight\n",
-                    r, st.sweeps, s.ilo, s.ihi, s.npairs, info.ilo, info.ihi, pk.size());
-        }
-        if (s.npairs <= 0) {
-          // the shift computation found nothing usable: try the next set, give up after a few
-          sets.pop_front();
-          idle_sets += 6;
-        } else {
-          Packet q;
-          q.nbul = std::min(g.NB, s.quota - s.next_pair);
-          q.pair0 = s.next_pair % s.npairs;
-          q.npairs = s.npairs;
-          q.pair_off = be.pair_offset(s.slot);
-          q.ilo = info.ilo; q.ihi = info.ihi;
-          q.s = info.ilo; q.hops = 0; q.fin_s = -1;
-          s.next_pair += q.nbul;
-          st.shift_pairs += q.nbul;
-          pk.push_back(q);
-          if (s.next_pair >= s.quota) {
-            sets.pop_front();
-            idle_sets++;
-          }
-        }
+        Packet q;
+        q.nbul = g.NB;
+        q.pair0 = (int)(pair_counter % 1000000);
+        q.npairs = 0;   // the set (and its size) is chosen on the device when the window runs
+        q.pair_off = 0;
+        q.ilo = info.ilo; q.ihi = info.ihi;
+        q.s = info.ilo; q.hops = 0; q.fin_s = -1;
+        pair_counter += q.nbul;
+        since_request += q.nbul;
+        st.shift_pairs += q.nbul;
+        pk.push_back(q);
       }
     }
     // ---- this round's windows ----
@@ -226,8 +213,7 @@ int drive(Backend& be, const DriverConfig& cfg, DriverStats& st) {
         st.apply_flops += 2.0 * w.wl * w.wl * (left + right + z) * cfg.p;
       }
     }
-    scan_tickets.push_back(be.scan_async(wins.data(), (int)wins.size(), W));
-    (void)last_progress_round;
+    if (r % std::max(1, cfg.scan_every) == 0) scan_tickets.push_back(be.scan_async(wins.data(), (int)wins.size(), W));
   }
   int nblocks = 0;
   be.finish(nblocks);

@@ -38,27 +38,62 @@ struct ChaseParams {
   Geom g;
   double* H[MS_MAXP];  // internal factor j at H[j-1], column-major, ld = n
   double* U;
-  const double* shifts;
-  const WinDesc* wins;
+  const double* shifts;  // [slots][66][4] pair buffers
+  const int* shift_state;  // [0] newest complete set: (sequence << 8) | slot; [1 + slot] its number of pairs
+  const WinDesc* wins;   // this round's windows in mapped pinned host memory (written by the host)
+  WinDesc* wins_dev;     // device copy made here for the update and scan kernels of the round
+  long long* prof;       // [8] cycle counters of CTA 0 (debug), or nullptr
 };
 
 struct DevExec {
   static constexpr int LANES = 32;
   BState st;
   int b, role, lane;
+  bool prof = false;
+  long long tl = 0, acc[4] = {0, 0, 0, 0};
   template <class F>
   __device__ __forceinline__ void each(F&& f) { f(b, role, lane, st); }
   __device__ __forceinline__ void barrier() { __syncthreads(); }
+  __device__ __forceinline__ void tick(int slot) {
+    if (prof) {
+      const long long t = clock64();
+      acc[slot] += t - tl;
+      tl = t;
+    }
+  }
 };
 
 __global__ void __launch_bounds__(64 * MS_MAXNB, 1) ms_chase_kernel(ChaseParams P) {
   const int tid = threadIdx.x, nt = blockDim.x;
-  const WinDesc d = P.wins[blockIdx.x];
+  const long long P_t0 = clock64();
+  if (P.prof && blockIdx.x == 0 && tid == 0) {
+    // debug: device-side gap between the end of the previous scan kernel and this kernel's start
+    unsigned long long now;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));
+    const unsigned long long last = ((volatile unsigned long long*)P.prof)[15];
+    if (last != 0 && now > last) atomicAdd((unsigned long long*)&P.prof[7], now - last);
+  }
+  __shared__ WinDesc s_desc;
+  if (tid == 0) {
+    s_desc = P.wins[blockIdx.x];
+    if (s_desc.intro) {
+      // newest complete shift set (free-running supply on the side streams)
+      const int st = *(const volatile int*)P.shift_state;
+      const int slot = st & 0xff;
+      const int np = ((const volatile int*)P.shift_state)[1 + slot];
+      s_desc.pair_off = slot * 66;
+      s_desc.npairs = np;
+    }
+    P.wins_dev[blockIdx.x] = s_desc;
+  }
+  __syncthreads();
+  const WinDesc d = s_desc;
   const int W = P.g.W, LD = P.g.LD, p = P.p, n = P.n;
   Ctx c;
   c.p = p; c.W = W; c.LD = LD;
   c.Hw = ms_smem;
   c.Uw = ms_smem + (size_t)p * W * LD;
+  c.mbox = ms_smem + (size_t)2 * p * W * LD;
   c.shifts = P.shifts;
   c.d = d;
   const int wl = d.wl, s = d.s;
@@ -83,9 +118,12 @@ __global__ void __launch_bounds__(64 * MS_MAXNB, 1) ms_chase_kernel(ChaseParams 
   ex.role = (tid >> 5) & 1;
   ex.lane = tid & 31;
   ex.st.active = 0;
-  ex.st.defer_j = 0;
+  ex.prof = (P.prof != nullptr) && blockIdx.x == 0 && tid == 0;
+  const long long tk0 = ex.prof ? clock64() : 0;
+  ex.tl = tk0;
   chase_window(c, ex);
   __syncthreads();
+  const long long tk1 = ex.prof ? clock64() : 0;
   for (int j = 1; j <= p; j++) {
     double* dst = P.H[j - 1] + s + (size_t)s * n;
     const double* src = c.H(j);
@@ -96,6 +134,28 @@ __global__ void __launch_bounds__(64 * MS_MAXNB, 1) ms_chase_kernel(ChaseParams 
       dst[r + (size_t)cc * n] = src[r + (size_t)cc * LD];
       ud[e] = u[r + (size_t)cc * LD];
     }
+  }
+  if (ex.prof) {
+    __syncthreads();
+    const long long tk2 = clock64();
+    atomicAdd((unsigned long long*)&P.prof[0], (unsigned long long)ex.acc[1]);  // chain phases
+    atomicAdd((unsigned long long*)&P.prof[1], (unsigned long long)ex.acc[2]);  // column phases
+    atomicAdd((unsigned long long*)&P.prof[2], (unsigned long long)ex.acc[3]);  // row phases
+    atomicAdd((unsigned long long*)&P.prof[3], (unsigned long long)(tk2 - tk1));  // write-back
+    atomicAdd((unsigned long long*)&P.prof[4], (unsigned long long)(tk2 - P_t0));  // whole CTA
+    atomicAdd((unsigned long long*)&P.prof[5], (unsigned long long)d.T);
+    atomicAdd((unsigned long long*)&P.prof[6], 1ULL);
+  }
+}
+
+// debug: stamps the device clock (launch-gap experiments)
+__global__ void ms_stamp_kernel(long long* prof, int slot) {
+  if (threadIdx.x == 0 && prof) {
+    unsigned long long now;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));
+    const unsigned long long last = ((volatile unsigned long long*)prof)[15];
+    if (last != 0 && now > last) atomicAdd((unsigned long long*)&prof[slot], now - last);
+    ((volatile unsigned long long*)prof)[15] = now;
   }
 }
 
@@ -113,7 +173,7 @@ __global__ void __launch_bounds__(64 * MS_MAXNB, 1) ms_chase_kernel(ChaseParams 
 // ------------------------------------------------------------------------------------------
 constexpr int AP_T = 64;    // tile extent along the long dimension
 constexpr int AP_LD = 68;
-constexpr int AP_SMEM = 2 * 64 * AP_LD * 8;
+constexpr int AP_SMEM = 3 * 64 * AP_LD * 8;  // U_j and two tile buffers
 
 struct ApplyParams {
   int n, p, W, wantT, wantZ, phase, nwin;
@@ -124,9 +184,20 @@ struct ApplyParams {
   const WinDesc* wins;
 };
 
-__global__ void __launch_bounds__(256) ms_apply_kernel(ApplyParams P) {
+// 8-byte asynchronous global -> shared copy (LDGSTS); nbytes = 0 writes zeros without reading.
+__device__ __forceinline__ void ms_cp_async8(double* sdst, const double* gsrc, int nbytes) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(sdst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(sa), "l"(gsrc), "r"(nbytes) : "memory");
+}
+__device__ __forceinline__ void ms_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void ms_cp_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// Software pipeline per CTA: U_j and the tiles are brought in with asynchronous copies; while
+// tile t is multiplied, written back to its buffer and stored, tile t+1 is already in flight into
+// the other buffer.
+__global__ void __launch_bounds__(256, 2) ms_apply_kernel(ApplyParams P) {
   double* Us = ms_smem;               // U(k, c) at Us[c * AP_LD + k]
-  double* Xs = ms_smem + 64 * AP_LD;  // X(r, c) at Xs[c * AP_LD + r]
+  double* Xb[2] = {ms_smem + 64 * AP_LD, ms_smem + 2 * 64 * AP_LD};  // X(r, c) at X[c * AP_LD + r]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n = P.n, p = P.p;
   // item -> (window, factor, kind)
@@ -157,44 +228,52 @@ __global__ void __launch_bounds__(256) ms_apply_kernel(ApplyParams P) {
   const int tfirst = blockIdx.x * P.tpb;
   if (lo + tfirst * AP_T >= hi) return;
   const double* Ug = P.U + (size_t)(j - 1) * n * P.W + (size_t)s * P.W;
-  // ---- stage U (wl x wl, zero padded to 64 x 64) ----
-  for (int e = tid; e < 64 * 64; e += 256) {
-    const int r = e & 63, cc = e >> 6;
-    Us[cc * AP_LD + r] = (r < wl && cc < wl) ? Ug[r + (size_t)cc * wl] : 0.0;
-  }
   // element (r, cc) of the 64 x 64 staging tile <-> global address, by kind:
   //   left:      rows s .. s+wl-1 (r), columns t0 .. t0+tl-1 (cc)
   //   right / Z: rows t0 .. t0+tl-1 (r), columns s .. s+wl-1 (cc)
-  const int wm = warp & 1, wn = warp >> 1;
-  const int gq = lane >> 2, tq = lane & 3;
-  const int kmax = (wl + 3) & ~3;
-  double pre[16];
-  auto fetch = [&](int t0, int tl) {
-#pragma unroll
+  auto fetch = [&](double* dst, int t0, int tl) {
+#pragma unroll 4
     for (int i = 0; i < 16; i++) {
       const int e = tid + 256 * i;
       const int r = e & 63, cc = e >> 6;
-      if (kind == 0)
-        pre[i] = (r < wl && cc < tl) ? X[(s + r) + (size_t)(t0 + cc) * n] : 0.0;
-      else
-        pre[i] = (r < tl && cc < wl) ? X[(t0 + r) + (size_t)(s + cc) * n] : 0.0;
+      bool in;
+      const double* g;
+      if (kind == 0) {
+        in = (r < wl && cc < tl);
+        g = X + (s + r) + (size_t)(t0 + cc) * n;
+      } else {
+        in = (r < tl && cc < wl);
+        g = X + (t0 + r) + (size_t)(s + cc) * n;
+      }
+      ms_cp_async8(dst + cc * AP_LD + r, in ? g : X, in ? 8 : 0);
     }
   };
+  // ---- stage U (wl x wl, zero padded to 64 x 64) and the first tile ----
+#pragma unroll 4
+  for (int i = 0; i < 16; i++) {
+    const int e = tid + 256 * i;
+    const int r = e & 63, cc = e >> 6;
+    const bool in = (r < wl && cc < wl);
+    ms_cp_async8(Us + cc * AP_LD + r, in ? Ug + r + (size_t)cc * wl : Ug, in ? 8 : 0);
+  }
   int t0 = lo + tfirst * AP_T;
   int tl = min(AP_T, hi - t0);
-  fetch(t0, tl);
+  fetch(Xb[0], t0, tl);
+  ms_cp_commit();
+  const int wm = warp & 1, wn = warp >> 1;
+  const int gq = lane >> 2, tq = lane & 3;
+  const int kmax = (wl + 3) & ~3;
   for (int tt = 0; tt < P.tpb; tt++) {
-    __syncthreads();  // Us staged (first pass) / the previous tile has been written out of Xs
-#pragma unroll
-    for (int i = 0; i < 16; i++) {
-      const int e = tid + 256 * i;
-      Xs[(e >> 6) * AP_LD + (e & 63)] = pre[i];
-    }
-    __syncthreads();
+    double* Xs = Xb[tt & 1];
+    ms_cp_wait_all();
+    __syncthreads();  // tile tt (and U) have landed; the other buffer has been stored
     const int t0n = t0 + AP_T;
     const bool more = (tt + 1 < P.tpb) && (t0n < hi);
     const int tln = more ? min(AP_T, hi - t0n) : 0;
-    if (more) fetch(t0n, tln);  // in flight during the multiplication
+    if (more) {
+      fetch(Xb[(tt + 1) & 1], t0n, tln);  // in flight during the multiplication and the store
+      ms_cp_commit();
+    }
     // ---- C = U' X (left)  or  C = X U (right, Z): 64 x 64 x wl ----
     double acc[4][2][2];
 #pragma unroll
@@ -266,51 +345,59 @@ __global__ void __launch_bounds__(256) ms_apply_kernel(ApplyParams P) {
 // ------------------------------------------------------------------------------------------
 // The rows of the bulge chains that sit in the matrix after the round (wins[0..nwin), see
 // chain_after_round) are left alone: subdiagonal entries there are part of the bulges.
+// Dynamic shared memory: 2 n bytes (skip flags, non-zero flags of the subdiagonal).
 constexpr int MS_MAXCHAINS = 160;
 
-__global__ void __launch_bounds__(1024) ms_scan_kernel(double* H1, int n, int nmin, int* ctl, const WinDesc* wins,
-                                                       int nwin, int W, int D) {
+// The result (ctl[0..3]) stays in device memory; a side stream copies it to the host.
+__global__ void __launch_bounds__(1024) ms_scan_kernel(double* H1, int n, int nmin, int* ctl, int seq,
+                                                       const WinDesc* wins, int nwin, int W, int D,
+                                                       long long* prof) {
   __shared__ int s_ihi, s_ilo, s_cnt;
-  __shared__ int s_first[MS_MAXCHAINS], s_last[MS_MAXCHAINS];
+  unsigned char* skip = reinterpret_cast<unsigned char*>(ms_smem);  // skip[z]: entry H1[z+1, z] belongs to a chain
+  unsigned char* nz = skip + n;                                      // nz[k]: H1[k, k-1] != 0 (k >= 1)
   const int tid = threadIdx.x, nt = blockDim.x;
   if (tid == 0) { s_ihi = -1; s_ilo = 0; s_cnt = 0; }
+  for (int k = tid; k < n; k += nt) skip[k] = 0;
+  __syncthreads();
   if (nwin > MS_MAXCHAINS) nwin = MS_MAXCHAINS;  // (the host never plans more)
-  for (int w = tid; w < nwin; w += nt) {
+  for (int e = tid; e < nwin * 32; e += nt) {
+    const int w = e >> 5, o = e & 31;
     int a = 1, b = 0;
-    if (!chain_after_round(wins[w], W, D, a, b)) { a = 1; b = 0; }
-    s_first[w] = a; s_last[w] = b;
+    if (chain_after_round(wins[w], W, D, a, b)) {
+      const int z = a + o;  // a chain covers at most 3 NB + 3 <= 27 entries
+      if (z <= b && z >= 0 && z < n) skip[z] = 1;
+    }
   }
   __syncthreads();
   const double smlnum = DBL_MIN * ((double)n / DBL_EPSILON);
   int cnt = 0;
   for (int k = 1 + tid; k < n; k += nt) {
-    // entry H1[k, k-1]: "z" = k - 1 in the notation of clamp_block_end
-    bool skip = false;
-    for (int w = 0; w < nwin; w++) skip |= (k - 1 >= s_first[w] && k - 1 <= s_last[w]);
-    if (skip) continue;
     double* e = H1 + k + (size_t)(k - 1) * n;
-    const double sub = *e;
-    if (sub != 0.0 && ms_negligible(sub, H1[(k - 1) + (size_t)(k - 1) * n], H1[k + (size_t)k * n], smlnum)) {
+    double sub = *e;
+    if (sub != 0.0 && !skip[k - 1] &&
+        ms_negligible(sub, H1[(k - 1) + (size_t)(k - 1) * n], H1[k + (size_t)k * n], smlnum)) {
       *e = 0.0;
+      sub = 0.0;
       cnt++;
     }
+    nz[k] = (sub != 0.0);
   }
   if (cnt) atomicAdd(&s_cnt, cnt);
   __syncthreads();
   // block ends: k = n-1 or H1[k+1, k] == 0; a block is "large" when no boundary lies within nmin
   for (int k = tid; k < n; k += nt) {
-    const bool end = (k == n - 1) || (H1[(k + 1) + (size_t)k * n] == 0.0);
+    const bool end = (k == n - 1) || !nz[k + 1];
     if (!end) continue;
     int len = 1;
     int r = k;
-    while (r > 0 && len <= nmin && H1[r + (size_t)(r - 1) * n] != 0.0) { r--; len++; }
+    while (r > 0 && len <= nmin && nz[r]) { r--; len++; }
     if (len > nmin) atomicMax(&s_ihi, k);
   }
   __syncthreads();
   const int ihi = s_ihi;
   if (ihi >= 0) {
     for (int k = 1 + tid; k <= ihi; k += nt)
-      if (H1[k + (size_t)(k - 1) * n] == 0.0) atomicMax(&s_ilo, k);
+      if (!nz[k]) atomicMax(&s_ilo, k);
     __syncthreads();
   }
   if (tid == 0) {
@@ -318,6 +405,12 @@ __global__ void __launch_bounds__(1024) ms_scan_kernel(double* H1, int n, int nm
     ctl[1] = ihi;
     ctl[2] = (ihi < 0) ? 1 : 0;
     ctl[3] = s_cnt;
+    ctl[4] = seq;
+    if (prof) {
+      unsigned long long now;
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));
+      ((volatile unsigned long long*)prof)[15] = now;
+    }
   }
 }
 
@@ -331,7 +424,8 @@ struct ShiftParams {
   int p, m;            // the snapshot holds the m x m trailing blocks, [p][m * m] column-major
   const double* snap;
   double* pairs;       // this set's pair buffer
-  int* count;          // number of pairs
+  int* state;          // shift_state of ChaseParams
+  int slot, seq;
   double perturb;
 };
 
@@ -386,7 +480,12 @@ __global__ void __launch_bounds__(256) ms_shifts_kernel(ShiftParams P) {
   int niter = 0;
   const int info = periodic_qr_cta(c, false, false, 30, &niter);
   __syncthreads();
-  if (tid == 0) *P.count = pair_shifts(c.lre + 1, c.lim + 1, info, m, P.perturb, P.pairs);
+  if (tid == 0) {
+    const int np = pair_shifts(c.lre + 1, c.lim + 1, info, m, P.perturb, P.pairs);
+    P.state[1 + P.slot] = np;
+    __threadfence();
+    if (np > 0) atomicMax(P.state, (P.seq << 8) | P.slot);  // publish: newest complete set
+  }
 }
 
 // ------------------------------------------------------------------------------------------

@@ -130,8 +130,8 @@ class Handle:
         o = (C.c_double * 16)()
         check(lib().psd_large_stats(self._h, o))
         names = ["status", "sweeps", "rounds", "windows", "shift_pairs", "exceptional", "final_blocks",
-                 "launches", "apply_flops", "chase_ms", "apply_ms", "shifts_ms", "scan_ms", "final_ms"]
-        return {k: (o[i] if k.endswith(("_ms", "_flops")) else int(o[i])) for i, k in enumerate(names)}
+                 "launches", "apply_flops", "chase_ms", "apply_ms", "shifts_ms", "scan_ms", "final_ms", "rounds_ms", "wall_s"]
+        return {k: (o[i] if k.endswith(("_ms", "_flops", "_s")) else int(o[i])) for i, k in enumerate(names)}
 
     def close(self):
         if self._h:

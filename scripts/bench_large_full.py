@@ -45,7 +45,7 @@ for prof in ([0, 1] if a.profile else [0]):
     kt = h.kernel_times()
     ls = h.large_stats()
     out.update({"profiled_e2e_s": dt, "reduction_panel_ms": kt["large_panel_ms"], "reduction_gemm_ms": kt["large_gemm_ms"],
-                "iteration_ms": kt["iterate_ms"], "ms": ls,
+                "iteration_ms": kt["iterate_ms"], "ms": ls, "rounds_span_ms": ls.get("rounds_ms"),
                 "update_tflops": ls["apply_flops"] / max(1e-9, ls["apply_ms"] * 1e-3) / 1e12,
                 "update_frac_of_cublas": ls["apply_flops"] / max(1e-9, ls["apply_ms"] * 1e-3) / 1e12 / peak,
                 "standard_flops_total": 25 * p * n ** 3,

@@ -40,6 +40,7 @@ struct HostExec {
     }
   }
   void barrier() {}
+  void tick(int) {}
 };
 
 struct EmuBackend {
@@ -56,7 +57,7 @@ struct EmuBackend {
   double& h(int j, int r, int c) { return H[j][r + (size_t)c * n]; }
 
   bool ok() const { return true; }
-  int shift_slots() const { return 4; }
+  int shift_slots() const { return 8; }
   int max_windows() const { return 160; }
   int pair_offset(int slot) const { return slot * 66; }
   std::vector<ScanInfo> scan_ring = std::vector<ScanInfo>(16);
@@ -99,9 +100,9 @@ struct EmuBackend {
   }
   void scan_wait(int slot, ScanInfo& info) { info = scan_ring[slot]; }
 
-  int slot_pairs[4] = {0, 0, 0, 0};
-  int shifts_wait(int slot) { return slot_pairs[slot]; }
-  int shifts_request(int slot, int lo, int m, double perturb) {
+  int slot_pairs[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  int latest_slot = -1;
+  void shifts_request(int slot, int lo, int m, double perturb, bool /*fence*/) {
     std::vector<double> buf((size_t)p * m * m);
     std::vector<psdo::Mat> Hm(p), Zm(p);
     for (int j = 0; j < p; j++) {
@@ -112,10 +113,10 @@ struct EmuBackend {
     }
     std::vector<double> lre(m), lim(m);
     const int inf = psdo::real_periodic_qr(m, p, Hm, Zm, false, false, 30, lre.data(), lim.data());
-    if (pairs.empty()) pairs.assign((size_t)4 * 66 * 4, 0.0);
+    if (pairs.empty()) pairs.assign((size_t)8 * 66 * 4, 0.0);
     if (getenv("MS_EMUL_VERBOSE")) fprintf(stderr, "[emul] shifts slot %d lo %d m %d info %d\n", slot, lo, m, inf);
     slot_pairs[slot] = pair_shifts(lre.data(), lim.data(), inf, m, perturb, pairs.data() + (size_t)pair_offset(slot) * 4);
-    return slot;
+    if (slot_pairs[slot] > 0) latest_slot = slot;  // the emulation completes a request at once
   }
 
 
@@ -179,7 +180,12 @@ struct EmuBackend {
     const int W = g.W, LD = g.LD;
     std::vector<double> Hw((size_t)p * W * LD), Uw((size_t)p * W * LD);
     for (int w = 0; w < cnt; w++) {
-      const WinDesc& d = plan[off + w];
+      WinDesc& dd = plan[off + w];
+      if (dd.intro) {  // newest complete shift set, as the CUDA kernel picks it
+        dd.pair_off = latest_slot >= 0 ? pair_offset(latest_slot) : 0;
+        dd.npairs = latest_slot >= 0 ? slot_pairs[latest_slot] : 0;
+      }
+      const WinDesc& d = dd;
       if (getenv("MS_EMUL_VERBOSE"))
         fprintf(stderr, "[emul] round %lld win s %d wl %d kbase %d nbul %d T %d ilo %d ihi %d pair0 %d/%d intro %d\n", nrounds,
                 d.s, d.wl, d.kbase, d.nbul, d.T, d.ilo, d.ihi, d.pair0, d.npairs, d.intro);
@@ -193,11 +199,13 @@ struct EmuBackend {
           }
       int bihi[MS_MAXNB];
       c.bihi = bihi;
+      std::vector<double> mbox((size_t)MS_MAXNB * MS_MAXP * MB_STRIDE, 0.0);
+      c.mbox = mbox.data();
       for (int b = 0; b < d.nbul; b++) bihi[b] = clamp_block_end(c, b);
       HostExec ex;
       ex.nb = g.NB;
       for (int b = 0; b < g.NB; b++)
-        for (int q = 0; q < 2; q++) { ex.st[b][q].active = 0; ex.st[b][q].defer_j = 0; }
+        for (int q = 0; q < 2; q++) ex.st[b][q].active = 0;
       chase_window(c, ex);
       chase_steps += (long long)d.T * d.nbul;
       if (getenv("MS_EMUL_VERBOSE")) {
@@ -309,6 +317,7 @@ int ms_emul_run(int n, int p, double* Hbuf, double* Zbuf, int wantT, int wantZ, 
     cfg.max_rounds = be.max_rounds + 4;
   }
   if (const char* ev = getenv("MS_EMUL_LAG")) cfg.lag = atoi(ev);
+  if (const char* ev = getenv("MS_EMUL_BLOCKS")) cfg.shift_blocks = atoi(ev);
   if (const char* ev = getenv("MS_EMUL_AHEAD")) cfg.sets_ahead = atoi(ev);
   DriverStats ds;
   const int status = drive(be, cfg, ds);
