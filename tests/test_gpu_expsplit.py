@@ -67,11 +67,13 @@ def test_expsplit_real_eigenvalues_only(psd, oracle, es, left):
     algorithm takes a deflated eigenvalue from the product band without the refinement passes of
     the wantT branch (PeriodicSchurDecompositions.jl:905-912 vs :913-1030): the CPU restatement
     gives 2.4e-10 relative for the -6.5e-12 eigenvalue at p = 5 (1.5e-14 with wantT), so the gate
-    against the 200-digit values is 1e-9 here, and the GPU is additionally held to the oracle's
-    own values to 1e-10 relative per eigenvalue."""
+    against the 200-digit values is 1e-9 here (for the GPU and for the oracle alike), and the two
+    are additionally compared with each other per eigenvalue (2e-9 relative: both sit within 1e-9
+    of the truth, on rounding-level different paths)."""
     A = _storage(es, left, np.float64)
     _, _, lo, io, _ = oracle.rpschur_batched(A, left=left, wantT=False, wantZ=False)
     assert io[0] == 0
+    _gates(es, lo[0], rel=1e-9)
     # a small batch of identical problems: every warp slot of a CTA must give the same answer
     Ab = np.repeat(A, 5, axis=0)
     _, _, lam, info = psd.pschur_batched(Ab, "L" if left else "R", wantT=False, wantZ=False)
@@ -81,7 +83,7 @@ def test_expsplit_real_eigenvalues_only(psd, oracle, es, left):
         for g in lo[0]:
             d = np.abs(lam[b] - g)
             k = int(np.argmin(d))
-            assert d[k] <= 1e-10 * abs(g) or max(abs(g), abs(lam[b][k])) < EPS ** 2, (g, lam[b])
+            assert d[k] <= 2e-9 * abs(g) or max(abs(g), abs(lam[b][k])) < EPS ** 2, (g, lam[b])
     _, _, lam1, info1 = psd.pschur_batched(A, "L" if left else "R", wantT=True, wantZ=False)
     assert info1[0] == 0
     _gates(es, lam1[0])
