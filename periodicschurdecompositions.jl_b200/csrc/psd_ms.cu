@@ -37,6 +37,9 @@ struct Workspace {
   cudaEvent_t evScan[kScanRing] = {nullptr};     // scan kernel done (main stream)
   cudaEvent_t evPub[kScanRing] = {nullptr};      // its result has reached the host (publish stream)
   cudaStream_t pub = nullptr;                    // carries the device -> host copies of the scan results
+  cudaStream_t main = nullptr;                   // the pipeline's own stream: highest priority, so that its
+                                                 // kernels are never queued behind the shift computations
+  cudaEvent_t evIn = nullptr, evOut = nullptr;   // ordering against the caller's stream
   cudaEvent_t evSnap[kShiftSlots] = {nullptr}, evShift[kShiftSlots] = {nullptr};
   cudaStream_t side[kShiftSlots] = {nullptr};
 };
@@ -54,6 +57,9 @@ void ws_destroy(Workspace* ws) {
   for (auto& e : ws->evScan) if (e) cudaEventDestroy(e);
   for (auto& e : ws->evPub) if (e) cudaEventDestroy(e);
   if (ws->pub) cudaStreamDestroy(ws->pub);
+  if (ws->main) cudaStreamDestroy(ws->main);
+  if (ws->evIn) cudaEventDestroy(ws->evIn);
+  if (ws->evOut) cudaEventDestroy(ws->evOut);
   for (int k = 0; k < kShiftSlots; k++) {
     if (ws->evSnap[k]) cudaEventDestroy(ws->evSnap[k]);
     if (ws->evShift[k]) cudaEventDestroy(ws->evShift[k]);
@@ -98,6 +104,13 @@ cudaError_t ws_basic(Workspace* ws) {
   for (auto& e : ws->evScan) if (!e) MS_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   for (auto& e : ws->evPub) if (!e) MS_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   if (!ws->pub) MS_CHECK(cudaStreamCreateWithFlags(&ws->pub, cudaStreamNonBlocking));
+  if (!ws->main) {
+    int lo = 0, hi = 0;  // lo = least, hi = greatest priority (numerically smaller)
+    MS_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    MS_CHECK(cudaStreamCreateWithPriority(&ws->main, cudaStreamNonBlocking, hi));
+  }
+  if (!ws->evIn) MS_CHECK(cudaEventCreateWithFlags(&ws->evIn, cudaEventDisableTiming));
+  if (!ws->evOut) MS_CHECK(cudaEventCreateWithFlags(&ws->evOut, cudaEventDisableTiming));
   for (int k = 0; k < kShiftSlots; k++) {
     if (!ws->evSnap[k]) MS_CHECK(cudaEventCreateWithFlags(&ws->evSnap[k], cudaEventDisableTiming));
     if (!ws->evShift[k]) MS_CHECK(cudaEventCreateWithFlags(&ws->evShift[k], cudaEventDisableTiming));
@@ -187,44 +200,66 @@ struct CudaBackend {
     if (err == cudaSuccess && e != cudaSuccess) err = e;
   }
   int shift_slots() const { return kShiftSlots; }
+  bool trace() const { return dbg_env("PSD_MS_TRACE") != nullptr; }
   int max_windows() const { return kMaxWin; }
   int pair_offset(int slot) const { return slot * 66; }
 
   // Scan of the subdiagonal after a round (wins = that round's windows, already on the device in
   // the plan slot used last); the result lands in a pinned ring slot.
   const WinDesc* last_plan = nullptr;
-  // The scan kernel leaves its result in device memory; a side stream copies it to the host, so
-  // that no operation of the main stream ever waits for a write to host memory (measured: a kernel
-  // that writes its result to mapped host memory delays its successor by ~100 us).
-  int scan_async(const WinDesc* /*host copy, unused here*/, int cnt, int nmin) {
+  // The scan kernel leaves its result and then its sequence number in device memory.  The host
+  // polls for it with small copies on a side stream that has NO dependency on the main stream: an
+  // event (or a write to mapped host memory) after the scan kernel was measured to delay the next
+  // kernel of the main stream by 100 - 140 us (device clock), i.e. a quarter of a round.
+  int fused_slot = -1;  // scan already enqueued as the tail of the round's last update kernel
+  int next_scan_slot() {
     const int slot = (int)(nscan % kScanRing);
     nscan++;
+    scan_seq[slot] = (int)(nscan & 0x3fffffff) + 1;
+    return slot;
+  }
+  int scan_async(const WinDesc* /*host copy, unused here*/, int cnt, int nmin) {
+    if (fused_slot >= 0) {
+      const int slot = fused_slot;
+      fused_slot = -1;
+      if (round_timer >= 0) tm.end(round_timer);
+      round_timer = -1;
+      return slot;
+    }
+    const int slot = next_scan_slot();
     if (!ok()) return slot;
     tm.begin(3);
-    ms_scan_kernel<<<1, 1024, (size_t)2 * n + 16, st>>>(H[0], n, nmin, ws->dCtl + slot * 8, 0, last_plan,
+    ms_scan_kernel<<<1, 1024, (size_t)2 * n + 16, st>>>(H[0], n, nmin, ws->dCtl + slot * 8, scan_seq[slot], last_plan,
                                                           last_plan ? cnt : 0, g.W, g.D, dProf);
     tm.end();
     if (round_timer >= 0) tm.end(round_timer);
     round_timer = -1;
     launches++;
     note(cudaGetLastError());
-    note(cudaEventRecord(ws->evScan[slot], st));
-    note(cudaStreamWaitEvent(ws->pub, ws->evScan[slot], 0));
-    note(cudaMemcpyAsync(ws->hScan + slot * 8, ws->dCtl + slot * 8, 4 * sizeof(int), cudaMemcpyDeviceToHost, ws->pub));
-    note(cudaEventRecord(ws->evPub[slot], ws->pub));
     return slot;
   }
   void scan_wait(int slot, ScanInfo& info) {
     if (!ok()) { info.done = 1; return; }
     {
       Stopwatch sw(wait_scan);
-      for (;;) {
-        const cudaError_t q = cudaEventQuery(ws->evPub[slot]);
-        if (q == cudaSuccess) break;
-        if (q != cudaErrorNotReady) { note(q); break; }
-#if defined(__x86_64__)
-        __builtin_ia32_pause();
-#endif
+      int* h = ws->hScan + slot * 8;
+      bool seen = false;
+      for (long long spins = 0;; spins++) {
+        note(cudaMemcpyAsync(h, ws->dCtl + slot * 8, 8 * sizeof(int), cudaMemcpyDeviceToHost, ws->pub));
+        note(cudaStreamSynchronize(ws->pub));
+        if (!ok()) break;
+        if (seen) break;                 // second copy after the sequence number: every field is final
+        if (h[4] == scan_seq[slot]) { seen = true; continue; }
+        if ((spins & 0xff) == 0xff) {    // a failed launch must not hang the caller
+          const cudaError_t q = cudaStreamQuery(st);
+          if (q == cudaSuccess) {
+            note(cudaMemcpyAsync(h, ws->dCtl + slot * 8, 8 * sizeof(int), cudaMemcpyDeviceToHost, ws->pub));
+            note(cudaStreamSynchronize(ws->pub));
+            if (h[4] != scan_seq[slot]) note(cudaErrorUnknown);
+            break;
+          }
+          if (q != cudaErrorNotReady) { note(q); break; }
+        }
       }
     }
     if (!ok()) { info.done = 1; return; }
@@ -264,9 +299,11 @@ struct CudaBackend {
     if (fence) note(cudaStreamWaitEvent(st, ws->evShift[slot], 0));
   }
 
-  void apply(const WinDesc* wins, int cnt) {
+  void apply(const WinDesc* wins, int cnt, int scan_slot = -1) {
     ApplyParams A;
     A.n = n; A.p = p; A.W = g.W; A.wantT = wantT; A.wantZ = wantZ; A.nwin = cnt;
+    A.do_scan = 0; A.scan_nmin = g.W; A.scan_seq = 0; A.scan_D = g.D; A.scan_ctl = nullptr;
+    A.scan_ticket = (unsigned int*)(ws->dCtl + kCtlMisc + 4); A.prof = dProf;
     for (int j = 0; j < p; j++) { A.H[j] = H[j]; A.Z[j] = Z[j]; }
     A.U = ws->dU; A.wins = wins;
     const int tiles = (n + AP_T - 1) / AP_T;
@@ -279,6 +316,11 @@ struct CudaBackend {
     A.phase = 0;
     ms_apply_kernel<<<dim3(chunks, cnt * p * 2), 256, AP_SMEM, st>>>(A);
     A.phase = 1;
+    if (scan_slot >= 0) {
+      A.do_scan = 1;
+      A.scan_seq = scan_seq[scan_slot];
+      A.scan_ctl = ws->dCtl + scan_slot * 8;
+    }
     ms_apply_kernel<<<dim3(chunks, cnt * p), 256, AP_SMEM, st>>>(A);
     tm.end();
     launches += 2;
@@ -303,8 +345,8 @@ struct CudaBackend {
     C.n = n; C.p = p; C.g = g;
     for (int j = 0; j < p; j++) C.H[j] = H[j];
     C.U = ws->dU; C.shifts = ws->dPairs; C.shift_state = ws->dCtl + kCtlPairs; C.wins = hp_dev; C.wins_dev = dp; C.prof = dProf;
-    if (dProf && getenv("PSD_MS_STAMP")) {
-      const int mode = atoi(getenv("PSD_MS_STAMP"));
+    if (dProf && dbg_env("PSD_MS_STAMP")) {
+      const int mode = atoi(dbg_env("PSD_MS_STAMP"));
       if (mode == 1) ms_stamp_kernel<<<1, 32, 0, st>>>(dProf, 8);
       if (mode == 2) ms_stamp_kernel<<<cnt, 512, chase_smem, st>>>(dProf, 8);
     }
@@ -314,7 +356,8 @@ struct CudaBackend {
     tm.end();
     launches++;
     note(cudaGetLastError());
-    apply(dp, cnt);
+    fused_slot = next_scan_slot();
+    apply(dp, cnt, fused_slot);
     last_plan = dp;
   }
 
@@ -371,10 +414,16 @@ cudaError_t postscale(cudaStream_t st, Workspace* ws, int n, int p, double* cons
   return cudaGetLastError();
 }
 
-cudaError_t iterate(cudaStream_t st, int sm_count, Workspace* ws, int n, int p, double* const* H,
+cudaError_t iterate(cudaStream_t caller, int sm_count, Workspace* ws, int n, int p, double* const* H,
                     double* const* Z, int wantT, int wantZ, int maxitfac, double* dEig, int* dInfo,
                     int profile, Result* res) {
   MS_CHECK(ws_basic(ws));
+  // the pipeline runs on its own high-priority stream, ordered after / before the caller's stream
+  cudaStream_t st = dbg_env("PSD_MS_NO_PRIO") ? caller : ws->main;
+  if (st != caller) {
+    MS_CHECK(cudaEventRecord(ws->evIn, caller));
+    MS_CHECK(cudaStreamWaitEvent(st, ws->evIn, 0));
+  }
   CudaBackend be;
   be.st = st; be.sm_count = sm_count; be.ws = ws;
   be.n = n; be.p = p; be.wantT = wantT; be.wantZ = (wantZ && Z) ? 1 : 0;
@@ -392,14 +441,19 @@ cudaError_t iterate(cudaStream_t st, int sm_count, Workspace* ws, int n, int p, 
   DriverConfig cfg;
   cfg.n = n; cfg.p = p; cfg.wantT = wantT; cfg.wantZ = be.wantZ;
   // shift window: limited by the shared memory of one CTA
-  int nsw = 64;
+  // Shift window: 24 x 24.  Larger windows give better shifts, but the one-CTA computation then
+  // stays resident for ~14 ms (64 x 64), and while such a kernel is resident the first launch of
+  // every round on the main stream was measured to start 100 - 140 us late (24 x 24: 23 us); the
+  // shift sets are stale by dozens of rounds anyway, and the pairs used per eigenvalue do not grow
+  // (profiles/r2_large_n_tuning.md).
+  int nsw = 24;
   while (nsw > 16 && ((size_t)((rp_small_doubles(nsw, p) + 1) & ~1LL) + (size_t)p * (nsw + 1) * nsw) * 8 > 200 * 1024) nsw -= 8;
   cfg.nsw = nsw;
-  if (const char* ev = getenv("PSD_MS_REP")) cfg.rep_max = std::max(1, atoi(ev));
-  if (const char* ev = getenv("PSD_MS_AHEAD")) cfg.sets_ahead = std::max(1, atoi(ev));
-  if (const char* ev = getenv("PSD_MS_SCAN_EVERY")) cfg.scan_every = std::max(1, atoi(ev));
-  if (const char* ev = getenv("PSD_MS_LAG")) cfg.lag = std::max(1, std::min(kPlanRing - 2, atoi(ev)));
-  if (const char* ev = getenv("PSD_MS_NSW")) cfg.nsw = std::max(2, std::min(nsw, atoi(ev)));
+  if (const char* ev = dbg_env("PSD_MS_REP")) cfg.rep_max = std::max(1, atoi(ev));
+  if (const char* ev = dbg_env("PSD_MS_AHEAD")) cfg.sets_ahead = std::max(1, atoi(ev));
+  if (const char* ev = dbg_env("PSD_MS_SCAN_EVERY")) cfg.scan_every = std::max(1, atoi(ev));
+  if (const char* ev = dbg_env("PSD_MS_LAG")) cfg.lag = std::max(1, std::min(kPlanRing - 2, atoi(ev)));
+  if (const char* ev = dbg_env("PSD_MS_NSW")) cfg.nsw = std::max(2, std::min(nsw, atoi(ev)));
   MS_CHECK(grow(ws->dSnap, ws->capSnap, (size_t)kShiftSlots * p * 64 * 64 * sizeof(double)));
   for (int k = 0; k < kShiftSlots; k++) { be.tm_side[k].on = profile != 0; be.tm_side[k].st = ws->side[k]; }
   be.chase_smem = ((size_t)2 * p * g.W * g.LD + (size_t)MS_MAXNB * MS_MAXP * MB_STRIDE) * sizeof(double);
@@ -412,19 +466,20 @@ cudaError_t iterate(cudaStream_t st, int sm_count, Workspace* ws, int n, int p, 
   MS_CHECK(cudaFuncSetAttribute(ms_stamp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)be.chase_smem));
   // every kernel of a round asks for the same (largest) shared-memory carve-out, so that the SMs
   // are not reconfigured between the kernels of the pipeline
-  if (getenv("PSD_MS_SCAN_CARVEOUT")) {
+  if (dbg_env("PSD_MS_SCAN_CARVEOUT")) {
     MS_CHECK(cudaFuncSetAttribute(ms_scan_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
     MS_CHECK(cudaFuncSetAttribute(ms_snapshot_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
   }
-  if (!getenv("PSD_MS_NO_CARVEOUT")) {
+  if (!dbg_env("PSD_MS_NO_CARVEOUT")) {
 
     MS_CHECK(cudaFuncSetAttribute(ms_apply_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
     MS_CHECK(cudaFuncSetAttribute(ms_chase_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
     MS_CHECK(cudaFuncSetAttribute(ms_shifts_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
   }
   MS_CHECK(cudaMemsetAsync(ws->dCtl + kCtlPairs, 0, (kShiftSlots + 1) * sizeof(int), st));
+  MS_CHECK(cudaMemsetAsync(ws->dCtl + kCtlMisc + 4, 0, sizeof(int), st));
   long long* dprof = nullptr;
-  if (getenv("PSD_MS_CHASE_PROF")) {
+  if (dbg_env("PSD_MS_CHASE_PROF")) {
     cudaMalloc((void**)&dprof, 16 * sizeof(long long));
     cudaMemsetAsync(dprof, 0, 16 * sizeof(long long), st);
     be.dProf = dprof;
@@ -437,6 +492,10 @@ cudaError_t iterate(cudaStream_t st, int sm_count, Workspace* ws, int n, int p, 
   for (int k = 0; k < kShiftSlots; k++)
     if (be.slot_used[k]) cudaStreamSynchronize(ws->side[k]);
   cudaStreamSynchronize(ws->pub);
+  if (st != caller) {
+    cudaEventRecord(ws->evOut, st);
+    cudaStreamWaitEvent(caller, ws->evOut, 0);
+  }
   if (!be.ok()) return be.err;
   if (res) {
     res->status = status;
@@ -446,7 +505,7 @@ cudaError_t iterate(cudaStream_t st, int sm_count, Workspace* ws, int n, int p, 
     res->host_seconds = t_drive;
     if (profile) {
       double ms[6] = {0, 0, 0, 0, 0, 0};
-      if (getenv("PSD_MS_VERBOSE")) {
+      if (dbg_env("PSD_MS_VERBOSE")) {
         double gaps[36] = {0};
         cudaStreamSynchronize(st);
         be.tm.collect_gaps(gaps);
@@ -468,7 +527,7 @@ cudaError_t iterate(cudaStream_t st, int sm_count, Workspace* ws, int n, int p, 
     fprintf(stderr, "[psd ms chase, CTA 0 of %lld launches, cycles per launch] chain %.0f | columns %.0f | rows %.0f | write-back %.0f | whole CTA %.0f | steps %.1f | scan end -> chase start %.1f us (globaltimer) | -> stamp kernel %.1f us\n",
             hp[6], hp[0] * k, hp[1] * k, hp[2] * k, hp[3] * k, hp[4] * k, hp[5] * k, hp[7] * k * 1e-3, hp[8] * k * 1e-3);
   }
-  if (getenv("PSD_MS_VERBOSE"))
+  if (dbg_env("PSD_MS_VERBOSE"))
     fprintf(stderr, "[psd ms] n %d p %d W %d NB %d nsw %d: status %d, %d sets, %lld rounds, %lld windows, %lld pairs, %d exceptional, %d final blocks, %.3f TFLOP applied; host %.3f s (blocked: scans %.3f, shifts %.3f, plan ring %.3f)\n",
             n, p, g.W, g.NB, cfg.nsw, status, ds.sweeps, ds.rounds, ds.windows, ds.shift_pairs, ds.exceptional,
             ds.final_blocks, ds.apply_flops * 1e-12, t_drive, be.wait_scan, be.wait_shift, be.wait_plan);

@@ -3,10 +3,22 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <cstdlib>
 #include <string>
 
 namespace psd {
 namespace ms {
+
+// Experiment switches (PSD_MS_* environment variables) exist only in builds made with
+// -DPSD_DEBUG_ENV; the product library never reads the environment.
+inline const char* dbg_env(const char* name) {
+#ifdef PSD_DEBUG_ENV
+  return getenv(name);
+#else
+  (void)name;
+  return nullptr;
+#endif
+}
 
 constexpr int kMaxPeriod = 12;  // = MS_MAXP of psd_ms_core.cuh
 

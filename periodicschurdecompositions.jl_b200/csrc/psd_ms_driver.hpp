@@ -47,7 +47,7 @@ struct DriverStats {
 struct DriverConfig {
   int n = 0, p = 0;
   int wantT = 1, wantZ = 1;
-  int nsw = 64;         // order of the shift window (<= 64, limited by shared memory for large p)
+  int nsw = 24;         // order of the shift window (<= 64, limited by shared memory for large p)
   int rep_max = 2;      // a new shift set is requested after (pairs of a set) x rep_max bulges
   int sets_ahead = 6;   // (unused by the free-running shift supply; kept for the emulation switches)
   int lag = 3;          // rounds between a scan and the plan that uses it
@@ -76,7 +76,7 @@ int drive(Backend& be, const DriverConfig& cfg, DriverStats& st) {
   const int n = cfg.n, W = g.W, D = g.D;
   const long long max_rounds = cfg.max_rounds > 0 ? cfg.max_rounds : 256 + 100LL * n / D;
   const int lag = std::max(1, cfg.lag);
-  const bool trace = getenv("PSD_MS_TRACE") != nullptr;
+  const bool trace = be.trace();
 
   ScanInfo info;
   be.scan_wait(be.scan_async(nullptr, 0, W), info);

@@ -148,6 +148,91 @@ __global__ void __launch_bounds__(64 * MS_MAXNB, 1) ms_chase_kernel(ChaseParams 
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Deflation scan + active block.  ctl (device ints): [0] ilo, [1] ihi, [2] done,
+// [3] number of subdiagonal entries set to zero by this scan.
+// Criterion: |h(k,k-1)| <= max(smlnum, ulp (|h(k-1,k-1)| + |h(k,k)|)) on H_1 (the "Test 1" of the
+// periodic QZ drivers, rgeneralized.jl:1086-1112), which perturbs H_1 by at most 2 ulp ||H_1||.
+// The active block is the lowest unreduced diagonal block of order > nmin.
+// ------------------------------------------------------------------------------------------
+// The rows of the bulge chains that sit in the matrix after the round (wins[0..nwin), see
+// chain_after_round) are left alone: subdiagonal entries there are part of the bulges.
+// Dynamic shared memory: 2 n bytes (skip flags, non-zero flags of the subdiagonal).
+constexpr int MS_MAXCHAINS = 160;
+
+// The result (ctl[0..3]) and then the sequence number ctl[4] stay in device memory; the host polls
+// for them with copies on a side stream.
+__device__ __forceinline__ void ms_scan_body(double* H1, int n, int nmin, int* ctl, int seq, const WinDesc* wins,
+                                             int nwin, int W, int D, long long* prof, unsigned char* smem_bytes) {
+  __shared__ int s_ihi, s_ilo, s_cnt;
+  unsigned char* skip = smem_bytes;  // skip[z]: entry H1[z+1, z] belongs to a chain
+  unsigned char* nz = skip + n;                                      // nz[k]: H1[k, k-1] != 0 (k >= 1)
+  const int tid = threadIdx.x, nt = blockDim.x;
+  if (tid == 0) { s_ihi = -1; s_ilo = 0; s_cnt = 0; }
+  for (int k = tid; k < n; k += nt) skip[k] = 0;
+  __syncthreads();
+  if (nwin > MS_MAXCHAINS) nwin = MS_MAXCHAINS;  // (the host never plans more)
+  for (int e = tid; e < nwin * 32; e += nt) {
+    const int w = e >> 5, o = e & 31;
+    int a = 1, b = 0;
+    if (chain_after_round(wins[w], W, D, a, b)) {
+      const int z = a + o;  // a chain covers at most 3 NB + 3 <= 27 entries
+      if (z <= b && z >= 0 && z < n) skip[z] = 1;
+    }
+  }
+  __syncthreads();
+  const double smlnum = DBL_MIN * ((double)n / DBL_EPSILON);
+  int cnt = 0;
+  for (int k = 1 + tid; k < n; k += nt) {
+    double* e = H1 + k + (size_t)(k - 1) * n;
+    double sub = *e;
+    if (sub != 0.0 && !skip[k - 1] &&
+        ms_negligible(sub, H1[(k - 1) + (size_t)(k - 1) * n], H1[k + (size_t)k * n], smlnum)) {
+      *e = 0.0;
+      sub = 0.0;
+      cnt++;
+    }
+    nz[k] = (sub != 0.0);
+  }
+  if (cnt) atomicAdd(&s_cnt, cnt);
+  __syncthreads();
+  // block ends: k = n-1 or H1[k+1, k] == 0; a block is "large" when no boundary lies within nmin
+  for (int k = tid; k < n; k += nt) {
+    const bool end = (k == n - 1) || !nz[k + 1];
+    if (!end) continue;
+    int len = 1;
+    int r = k;
+    while (r > 0 && len <= nmin && nz[r]) { r--; len++; }
+    if (len > nmin) atomicMax(&s_ihi, k);
+  }
+  __syncthreads();
+  const int ihi = s_ihi;
+  if (ihi >= 0) {
+    for (int k = 1 + tid; k <= ihi; k += nt)
+      if (!nz[k]) atomicMax(&s_ilo, k);
+    __syncthreads();
+  }
+  if (tid == 0) {
+    ctl[0] = (ihi >= 0) ? s_ilo : 0;
+    ctl[1] = ihi;
+    ctl[2] = (ihi < 0) ? 1 : 0;
+    ctl[3] = s_cnt;
+    __threadfence();
+    *(volatile int*)(ctl + 4) = seq;
+    if (prof) {
+      unsigned long long now;
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));
+      ((volatile unsigned long long*)prof)[15] = now;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(1024) ms_scan_kernel(double* H1, int n, int nmin, int* ctl, int seq,
+                                                       const WinDesc* wins, int nwin, int W, int D,
+                                                       long long* prof) {
+  ms_scan_body(H1, n, nmin, ctl, seq, wins, nwin, W, D, prof, reinterpret_cast<unsigned char*>(ms_smem));
+}
+
 // debug: stamps the device clock (launch-gap experiments)
 __global__ void ms_stamp_kernel(long long* prof, int slot) {
   if (threadIdx.x == 0 && prof) {
@@ -178,6 +263,13 @@ constexpr int AP_SMEM = 3 * 64 * AP_LD * 8;  // U_j and two tile buffers
 struct ApplyParams {
   int n, p, W, wantT, wantZ, phase, nwin;
   int tpb;  // tiles per CTA (consecutive tiles of one item: U_j is staged once)
+  // Deflation scan fused into the tail of the last update kernel of a round: the CTA that
+  // finishes last runs it (a stand-alone one-CTA kernel leaves the GPU idle and was measured to
+  // delay the next launch by ~120 us).
+  int do_scan, scan_nmin, scan_seq, scan_D;
+  int* scan_ctl;
+  unsigned int* scan_ticket;  // zero on entry; reset by the scan
+  long long* prof;
   double* H[MS_MAXP];
   double* Z[MS_MAXP];
   const double* U;
@@ -220,13 +312,13 @@ __global__ void __launch_bounds__(256, 2) ms_apply_kernel(ApplyParams P) {
     lo = P.wantT ? 0 : d.ilo;
     hi = s;
   } else {
-    if (!P.wantZ) return;
     X = P.Z[j - 1];
     lo = 0;
-    hi = n;
+    hi = P.wantZ ? n : 0;
   }
   const int tfirst = blockIdx.x * P.tpb;
-  if (lo + tfirst * AP_T >= hi) return;
+  const bool has_work = lo + tfirst * AP_T < hi;
+  if (has_work) {
   const double* Ug = P.U + (size_t)(j - 1) * n * P.W + (size_t)s * P.W;
   // element (r, cc) of the 64 x 64 staging tile <-> global address, by kind:
   //   left:      rows s .. s+wl-1 (r), columns t0 .. t0+tl-1 (cc)
@@ -334,82 +426,19 @@ __global__ void __launch_bounds__(256, 2) ms_apply_kernel(ApplyParams P) {
     t0 = t0n;
     tl = tln;
   }
-}
-
-// ------------------------------------------------------------------------------------------
-// Deflation scan + active block.  ctl (device ints): [0] ilo, [1] ihi, [2] done,
-// [3] number of subdiagonal entries set to zero by this scan.
-// Criterion: |h(k,k-1)| <= max(smlnum, ulp (|h(k-1,k-1)| + |h(k,k)|)) on H_1 (the "Test 1" of the
-// periodic QZ drivers, rgeneralized.jl:1086-1112), which perturbs H_1 by at most 2 ulp ||H_1||.
-// The active block is the lowest unreduced diagonal block of order > nmin.
-// ------------------------------------------------------------------------------------------
-// The rows of the bulge chains that sit in the matrix after the round (wins[0..nwin), see
-// chain_after_round) are left alone: subdiagonal entries there are part of the bulges.
-// Dynamic shared memory: 2 n bytes (skip flags, non-zero flags of the subdiagonal).
-constexpr int MS_MAXCHAINS = 160;
-
-// The result (ctl[0..3]) stays in device memory; a side stream copies it to the host.
-__global__ void __launch_bounds__(1024) ms_scan_kernel(double* H1, int n, int nmin, int* ctl, int seq,
-                                                       const WinDesc* wins, int nwin, int W, int D,
-                                                       long long* prof) {
-  __shared__ int s_ihi, s_ilo, s_cnt;
-  unsigned char* skip = reinterpret_cast<unsigned char*>(ms_smem);  // skip[z]: entry H1[z+1, z] belongs to a chain
-  unsigned char* nz = skip + n;                                      // nz[k]: H1[k, k-1] != 0 (k >= 1)
-  const int tid = threadIdx.x, nt = blockDim.x;
-  if (tid == 0) { s_ihi = -1; s_ilo = 0; s_cnt = 0; }
-  for (int k = tid; k < n; k += nt) skip[k] = 0;
-  __syncthreads();
-  if (nwin > MS_MAXCHAINS) nwin = MS_MAXCHAINS;  // (the host never plans more)
-  for (int e = tid; e < nwin * 32; e += nt) {
-    const int w = e >> 5, o = e & 31;
-    int a = 1, b = 0;
-    if (chain_after_round(wins[w], W, D, a, b)) {
-      const int z = a + o;  // a chain covers at most 3 NB + 3 <= 27 entries
-      if (z <= b && z >= 0 && z < n) skip[z] = 1;
-    }
-  }
-  __syncthreads();
-  const double smlnum = DBL_MIN * ((double)n / DBL_EPSILON);
-  int cnt = 0;
-  for (int k = 1 + tid; k < n; k += nt) {
-    double* e = H1 + k + (size_t)(k - 1) * n;
-    double sub = *e;
-    if (sub != 0.0 && !skip[k - 1] &&
-        ms_negligible(sub, H1[(k - 1) + (size_t)(k - 1) * n], H1[k + (size_t)k * n], smlnum)) {
-      *e = 0.0;
-      sub = 0.0;
-      cnt++;
-    }
-    nz[k] = (sub != 0.0);
-  }
-  if (cnt) atomicAdd(&s_cnt, cnt);
-  __syncthreads();
-  // block ends: k = n-1 or H1[k+1, k] == 0; a block is "large" when no boundary lies within nmin
-  for (int k = tid; k < n; k += nt) {
-    const bool end = (k == n - 1) || !nz[k + 1];
-    if (!end) continue;
-    int len = 1;
-    int r = k;
-    while (r > 0 && len <= nmin && nz[r]) { r--; len++; }
-    if (len > nmin) atomicMax(&s_ihi, k);
-  }
-  __syncthreads();
-  const int ihi = s_ihi;
-  if (ihi >= 0) {
-    for (int k = 1 + tid; k <= ihi; k += nt)
-      if (!nz[k]) atomicMax(&s_ilo, k);
+  }  // has_work
+  if (P.do_scan) {
+    // last CTA of the grid: every update of the round is complete and visible
+    __shared__ unsigned int s_last;
+    __threadfence();
     __syncthreads();
-  }
-  if (tid == 0) {
-    ctl[0] = (ihi >= 0) ? s_ilo : 0;
-    ctl[1] = ihi;
-    ctl[2] = (ihi < 0) ? 1 : 0;
-    ctl[3] = s_cnt;
-    ctl[4] = seq;
-    if (prof) {
-      unsigned long long now;
-      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));
-      ((volatile unsigned long long*)prof)[15] = now;
+    if (tid == 0) s_last = (atomicAdd(P.scan_ticket, 1u) == gridDim.x * gridDim.y - 1) ? 1u : 0u;
+    __syncthreads();
+    if (s_last) {
+      __threadfence();
+      ms_scan_body(P.H[0], n, P.scan_nmin, P.scan_ctl, P.scan_seq, P.wins, P.nwin, P.W, P.scan_D, P.prof,
+                   reinterpret_cast<unsigned char*>(ms_smem));
+      if (tid == 0) *P.scan_ticket = 0;
     }
   }
 }

@@ -58,6 +58,7 @@ struct EmuBackend {
 
   bool ok() const { return true; }
   int shift_slots() const { return 8; }
+  bool trace() const { return getenv("PSD_MS_TRACE") != nullptr; }
   int max_windows() const { return 160; }
   int pair_offset(int slot) const { return slot * 66; }
   std::vector<ScanInfo> scan_ring = std::vector<ScanInfo>(16);
