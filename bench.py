@@ -98,6 +98,15 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def bench_config(batch_per_gpu: int, world: int) -> dict:
+    """The workload description, identical for both arms (the CPU arm times a bounded sample of it,
+    stated in its cpu_baseline.sample)."""
+    return {"workload": "real pschur! p=8 N=32 eigenvalues only (BASELINE configs[1])",
+            "batch_per_gpu": batch_per_gpu, "inputs": "uniform[0,1) seed 1234",
+            "l2": "input 6.55 GB per GPU >> 126 MB L2 (no flush needed)",
+            "parallelism": f"batch shards x{world}, no collective"}
+
+
 def host_cores() -> int:
     """Host threads this process may use (torchrun exports OMP_NUM_THREADS=1, so the OpenMP
     default cannot be trusted: the thread count is always passed explicitly)."""
@@ -140,8 +149,7 @@ def run_reference(args):
         "unit": "problems/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "real pschur! p=8 N=32 eigenvalues only (BASELINE configs[1])",
-                   "batch_per_step": sample, "inputs": "uniform[0,1) seed 1234"},
+        "config": bench_config(args.batch, args.gpus),
         "cpu_baseline": {"value": rate, "unit": "problems/s", "cores": cores, "kind": "port",
                          "sample": f"{sample} problems per step, C++ restatement of the reference "
                                    f"(Julia unavailable), OpenMP over the batch"},
@@ -253,6 +261,69 @@ def cpu_large_baseline(n_small=384, p=LARGE_P):
                       f"Julia unavailable); N=4096 figure = measured x (4096/{n_small})^3, an extrapolation"}
 
 
+def config1_block(psd_b200, h, reps=20):
+    """BASELINE configs[0]: one real p=3 N=50 problem with Schur vectors - latency through the host
+    call, with the CPU restatement of the reference (one core) timed beside it."""
+    import numpy as np
+    from oracle import oracle as O
+    A = O.gen_real(SEED, 50, 3, 1)
+    psd_b200.pschur_batched(A, "R", handle=h)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        T, Z, lam, info = psd_b200.pschur_batched(A, "R", handle=h)
+    gpu_ms = (time.perf_counter() - t0) / reps * 1e3
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        To, Zo, lo, io, _ = O.rpschur_batched(A, nthreads=1)
+    cpu_ms = (time.perf_counter() - t0) / reps * 1e3
+    # a small batch of the same shape (what the GPU is for)
+    Ab = O.gen_real(SEED, 50, 3, 4096)
+    psd_b200.pschur_batched(Ab[:64], "R", handle=h)
+    t0 = time.perf_counter()
+    psd_b200.pschur_batched(Ab, "R", handle=h)
+    gpu_batch = 4096 / (time.perf_counter() - t0)
+    nb = 64 * host_cores()
+    t0 = time.perf_counter()
+    O.rpschur_batched(Ab[:nb], nthreads=host_cores())
+    cpu_batch = nb / (time.perf_counter() - t0)
+    return {"workload": "real pschur! p=3 N=50 :R with T and Z (BASELINE configs[0])",
+            "single_problem_ms": gpu_ms, "info": int(info[0]),
+            "cpu_single_problem_ms": cpu_ms, "cpu_cores_single": 1,
+            "batch_4096_problems_per_s": gpu_batch, "cpu_batch_problems_per_s": cpu_batch,
+            "cpu_cores_batch": host_cores(),
+            "note": "host call with pageable numpy buffers, copies included; CPU = C++ restatement of the reference"}
+
+
+def multi_device_handle_leg(psd_b200, L, torch, world, B, n, p):
+    """The library's own multi-GPU path: ONE psd_rpschur_batched call on a handle that owns all
+    `world` devices (one host thread + streams per device inside the library, contiguous batch
+    shards, host-side gather; no collective), pinned host buffers, H2D/D2H inside the timed region."""
+    import psutil
+    need = world * B * (p * n * n * 8 + n * 16 + 4)
+    if psutil.virtual_memory().available < 2.5 * need:
+        return {"skipped": f"needs {need / 2**30:.1f} GiB of pinned host memory"}
+    hA = torch.empty((world * B, p, n, n), dtype=torch.float64, pin_memory=True)
+    psd_b200.capi.check(L.psd_fill_uniform_host(SEED, n, p, world * B, 0, 0, C.c_void_p(hA.data_ptr())))
+    hE = torch.empty((world * B, n, 2), dtype=torch.float64, pin_memory=True)
+    hI = torch.empty(world * B, dtype=torch.int32, pin_memory=True)
+    hh = psd_b200.Handle(list(range(world)))
+
+    def step():
+        psd_b200.capi.check(L.psd_rpschur_batched(hh.ptr, n, p, world * B, 0, 0, 0, 30, C.c_void_p(hA.data_ptr()),
+                                                  None, C.c_void_p(hE.data_ptr()), C.c_void_p(hI.data_ptr())))
+    step()
+    t0 = time.perf_counter()
+    step(); step()
+    dt = (time.perf_counter() - t0) / 2
+    st = hh.stats()
+    out = {"value": world * B / dt, "unit": "problems/s", "devices": world, "seconds_per_call": dt,
+           "h2d_bytes_per_call": st["h2d_bytes"], "d2h_bytes_per_call": st["d2h_bytes"],
+           "unconverged": int((hI != 0).sum().item()),
+           "what": "one psd_rpschur_batched call on Handle(range(N)), rank 0 only, other ranks idle"}
+    hh.close()
+    return out
+
+
 def run_ours(args):
     import numpy as np
     import torch
@@ -352,6 +423,22 @@ def run_ours(args):
     # e2e result check: same eigenvalues as the device-resident path
     same = bool(torch.equal(hE, dE.cpu()))
 
+    # the library's in-process multi-device path, measured by rank 0 while the other ranks wait
+    handle_leg = None
+    if world > 1:
+        del dA
+        torch.cuda.empty_cache()
+        barrier()
+        # the waiting ranks must not touch their GPUs: a NCCL barrier spins a kernel on every device
+        # (measured: 218 k instead of 430 k problems/s on 2 GPUs), so they wait in a gloo barrier
+        cpu_pg = dist.new_group(backend="gloo")
+        if rank == 0:
+            try:
+                handle_leg = multi_device_handle_leg(psd_b200, L, torch, world, B, n, p)
+            except Exception as ex:
+                handle_leg = {"error": repr(ex)}
+        dist.barrier(group=cpu_pg)
+
     if rank != 0:
         return 0
 
@@ -377,10 +464,7 @@ def run_ours(args):
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": "real pschur! p=8 N=32 eigenvalues only (BASELINE configs[1])",
-                   "batch_per_gpu": B, "inputs": "uniform[0,1) seed 1234",
-                   "l2": "input 6.55 GB per GPU >> 126 MB L2 (no flush needed)",
-                   "parallelism": f"batch shards x{world}, no collective"},
+        "config": bench_config(B, world),
         "e2e": {"value": e2e_value, "unit": "problems/s", "h2d_bytes_per_step": st["h2d_bytes"],
                 "d2h_bytes_per_step": st["d2h_bytes"], "steps": e2e_steps,
                 "matches_device_path": same},
@@ -401,6 +485,13 @@ def run_ours(args):
         "clocks": clocks,
         "unconverged": fails,
     }
+    if handle_leg is not None:
+        line["e2e_single_call_all_devices"] = handle_leg
+    if world == 1:
+        try:
+            line["config1"] = config1_block(psd_b200, h)
+        except Exception as ex:
+            line["config1"] = {"error": repr(ex)}
     if world == 1 and not args.no_large:
         try:
             del dA, dE, dI
