@@ -81,6 +81,10 @@ int psd_handle_device_count(psd_handle_t handle);
  *                                    part first (rschur2x2.jl:89-91)
  *   info out     [batch]
  * maxitfac <= 0 selects the reference default 30.
+ * n >= 192: blocked reduction + small-bulge multishift iteration with FP64 tensor-core updates,
+ * one problem at a time on the whole GPU; results of this path are not
+ * bit-for-bit reproducible from run to run (floating-point atomics in the blocked reduction,
+ * timing-dependent choice between equally valid shift sets), all acceptance predicates hold.
  * ------------------------------------------------------------------------------------- */
 int psd_rpschur_batched(psd_handle_t handle, int n, int p, int64_t batch, int orientation,
                         int wantT, int wantZ, int maxitfac, double* A, double* Z, double* eig,
@@ -89,6 +93,10 @@ int psd_rpschur_batched(psd_handle_t handle, int n, int p, int64_t batch, int or
 /* Same computation on buffers already resident on device `dev_index` (index into the
  * handle's device list), enqueued on `stream` (a cudaStream_t passed as void*; NULL = the
  * handle's own stream for that device).  Asynchronous: the caller synchronises the stream.
+ * All *_dev calls on one device of a handle share one set of scratch buffers; the library orders
+ * them with an event (a call waits for the previous one, whatever stream that was enqueued on), so
+ * calls on different streams are safe but do not overlap.  For n >= 192 (large-N path) the call
+ * synchronises the stream internally (the iteration is driven from the host).
  * Used by bench.py for the HBM-resident throughput figure and by host code that keeps
  * matrices on the GPU. */
 int psd_rpschur_batched_dev(psd_handle_t handle, int dev_index, void* stream, int n, int p,
