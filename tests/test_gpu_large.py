@@ -133,3 +133,60 @@ def test_large_badly_scaled(psd, oracle, scale):
     H, Q = psd.phessenberg_batched(As)
     assert np.isfinite(H).all()
     _check_hess(As[0], H[0], Q[0])
+
+
+@pytest.mark.parametrize("n,p,left", [(300, 1, False), (260, 2, True), (280, 6, False), (200, 9, True), (230, 12, False)])
+def test_large_multishift_shapes(psd, oracle, n, p, left):
+    """the multishift iteration at every window geometry (W = 64 for p <= 3, 56, 48, 40, 32 for
+    larger periods), :R and :L, held to the reference's predicates and to the oracle's eigenvalues"""
+    A = oracle.gen_real(4000 + 10 * p + n, n, p, 1)
+    lr = "L" if left else "R"
+    T, Z, lam, info = psd.pschur_batched(A, lr)
+    assert info[0] == 0
+    st = psd.default_handle().large_stats()
+    assert st["status"] == 0 and st["rounds"] > 0 and st["final_blocks"] > 0, st
+    To, Zo, lo, io, _ = oracle.rpschur_batched(A, left=left)
+    ro = K.pschur_check(A[0], To[0], Zo[0], lo[0], left=left, tol=1e9, check_lambda=False)["residual_eps_a1"]
+    K.pschur_check(A[0], T[0], Z[0], lam[0], left=left, tol=max(40.0, 1.25 * ro), check_lambda=False)
+    scale = np.max(np.abs(lo[0]))
+    assert K.match_eigs(lo[0], lam[0]) <= 100 * n * EPS * scale
+    assert np.count_nonzero(lo[0].imag > 0) == np.count_nonzero(lam[0].imag > 0)
+    # complex pairs adjacent, positive imaginary part first, standardised 2 x 2 blocks (a = d, bc < 0)
+    js = p - 1 if left else 0
+    T1 = K.M(T[0, js])
+    k = 0
+    while k < n:
+        if lam[0][k].imag != 0:
+            assert lam[0][k].imag > 0 and lam[0][k + 1] == np.conj(lam[0][k])
+            assert T1[k + 1, k] != 0
+            k += 2
+        else:
+            k += 1
+    # eigenvalues only / T only give the same eigenvalues
+    _, Z0, lam0, info0 = psd.pschur_batched(A, lr, wantT=False, wantZ=False)
+    assert Z0 is None and info0[0] == 0
+    assert K.match_eigs(lam[0], lam0[0]) <= 1000 * n * EPS * scale
+
+
+def test_large_dev_calls_on_two_streams(psd, oracle):
+    """two device-resident calls on different streams share the handle's scratch set: the library
+    orders them with an event, so both give the result of a call made alone"""
+    import ctypes as C
+    import torch
+    n, p, B = 32, 8, 3000
+    L = psd.lib()
+    h = psd.Handle([0])
+    A = torch.from_numpy(oracle.gen_real(77, n, p, 2 * B)).cuda()
+    E = torch.zeros((2 * B, n, 2), dtype=torch.float64, device="cuda")
+    I = torch.full((2 * B,), -1, dtype=torch.int32, device="cuda")
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    torch.cuda.synchronize()
+    for k, st in enumerate((s1, s2)):
+        psd.capi.check(L.psd_rpschur_batched_dev(
+            h.ptr, 0, C.c_void_p(st.cuda_stream), n, p, B, 0, 0, 0, 30,
+            C.c_void_p(A[k * B:].data_ptr()), None, C.c_void_p(E[k * B:].data_ptr()), C.c_void_p(I[k * B:].data_ptr())))
+    torch.cuda.synchronize()
+    assert (I == 0).all()
+    _, _, lam, info = psd.pschur_batched(A.cpu().numpy(), "R", wantT=False, wantZ=False, handle=h)
+    got = E.cpu().numpy()
+    assert np.array_equal(got[..., 0] + 1j * got[..., 1], lam)
