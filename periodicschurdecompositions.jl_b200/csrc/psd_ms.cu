@@ -7,6 +7,7 @@
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
+#include <string>
 #include <vector>
 
 #include "psd_ms_driver.hpp"
@@ -21,7 +22,7 @@ constexpr int kShiftSlots = 8;   // shift sets in flight (one side stream each)
 constexpr int kMaxWin = MS_MAXCHAINS;
 
 struct Workspace {
-  double* dU = nullptr;  size_t capU = 0;        // [p][n * W]
+  double* dU = nullptr;  size_t capU = 0;        // [2][p][n * W]: accumulated window transformations, by round parity
   double* dPairs = nullptr;                      // [kShiftSlots][66][4] shift pairs
   double* dSnap = nullptr; size_t capSnap = 0;   // [kShiftSlots][p * 64 * 64] trailing-block snapshots
   WinDesc* dPlan = nullptr;                      // [kPlanRing][kMaxWin]
@@ -42,6 +43,9 @@ struct Workspace {
   cudaEvent_t evIn = nullptr, evOut = nullptr;   // ordering against the caller's stream
   cudaEvent_t evSnap[kShiftSlots] = {nullptr}, evShift[kShiftSlots] = {nullptr};
   cudaStream_t side[kShiftSlots] = {nullptr};
+  cudaStream_t scan = nullptr;                   // stand-alone deflation scans (split rounds), high priority
+  cudaStream_t far = nullptr;                    // far window updates of a round, concurrent with the next chase
+  cudaEvent_t evNear[2] = {nullptr, nullptr}, evFar[2] = {nullptr, nullptr}, evChase[2] = {nullptr, nullptr};
 };
 constexpr int kCtlInts = kScanRing * 8 + kShiftSlots + 1 + 16;
 constexpr int kCtlPairs = kScanRing * 8;          // shift supply state: newest set, pair counts
@@ -58,6 +62,13 @@ void ws_destroy(Workspace* ws) {
   for (auto& e : ws->evPub) if (e) cudaEventDestroy(e);
   if (ws->pub) cudaStreamDestroy(ws->pub);
   if (ws->main) cudaStreamDestroy(ws->main);
+  if (ws->far) cudaStreamDestroy(ws->far);
+  if (ws->scan) cudaStreamDestroy(ws->scan);
+  for (int k = 0; k < 2; k++) {
+    if (ws->evNear[k]) cudaEventDestroy(ws->evNear[k]);
+    if (ws->evFar[k]) cudaEventDestroy(ws->evFar[k]);
+    if (ws->evChase[k]) cudaEventDestroy(ws->evChase[k]);
+  }
   if (ws->evIn) cudaEventDestroy(ws->evIn);
   if (ws->evOut) cudaEventDestroy(ws->evOut);
   for (int k = 0; k < kShiftSlots; k++) {
@@ -108,6 +119,17 @@ cudaError_t ws_basic(Workspace* ws) {
     int lo = 0, hi = 0;  // lo = least, hi = greatest priority (numerically smaller)
     MS_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
     MS_CHECK(cudaStreamCreateWithPriority(&ws->main, cudaStreamNonBlocking, hi));
+  }
+  if (!ws->scan) {
+    int lo = 0, hi = 0;
+    MS_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    MS_CHECK(cudaStreamCreateWithPriority(&ws->scan, cudaStreamNonBlocking, hi));
+  }
+  if (!ws->far) MS_CHECK(cudaStreamCreateWithFlags(&ws->far, cudaStreamNonBlocking));
+  for (int k = 0; k < 2; k++) {
+    if (!ws->evNear[k]) MS_CHECK(cudaEventCreateWithFlags(&ws->evNear[k], cudaEventDisableTiming));
+    if (!ws->evFar[k]) MS_CHECK(cudaEventCreateWithFlags(&ws->evFar[k], cudaEventDisableTiming));
+    if (!ws->evChase[k]) MS_CHECK(cudaEventCreateWithFlags(&ws->evChase[k], cudaEventDisableTiming));
   }
   if (!ws->evIn) MS_CHECK(cudaEventCreateWithFlags(&ws->evIn, cudaEventDisableTiming));
   if (!ws->evOut) MS_CHECK(cudaEventCreateWithFlags(&ws->evOut, cudaEventDisableTiming));
@@ -186,7 +208,33 @@ struct CudaBackend {
   long long* dProf = nullptr;
   int round_timer = -1;
   bool slot_used[kShiftSlots] = {false};
-  Timer tm, tm_side[kShiftSlots];
+  Timer tm, tm_far, tm_side[kShiftSlots];
+  long long nround = 0;
+  // debug: device timeline of a few rounds (PSD_MS_TIMELINE=<first round>)
+  long long tl_first = -1;
+  std::vector<cudaEvent_t> tl_ev;
+  std::vector<std::string> tl_name;
+  void mark(const char* name, cudaStream_t s) {
+    if (tl_first < 0 || nround < tl_first || nround >= tl_first + 4) return;
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, s);
+    tl_ev.push_back(e);
+    tl_name.push_back(std::string(name) + " r" + std::to_string(nround));
+  }
+  void timeline_print() {
+    for (size_t i = 0; i < tl_ev.size(); i++) {
+      float f = 0.f;
+      cudaEventSynchronize(tl_ev[i]);
+      cudaEventElapsedTime(&f, tl_ev[0], tl_ev[i]);
+      fprintf(stderr, "[psd ms timeline] %8.1f us  %s\n", f * 1e3, tl_name[i].c_str());
+      }
+    for (auto e : tl_ev) cudaEventDestroy(e);
+    tl_ev.clear();
+  }
+  bool split = true;  // far updates on their own stream
+  bool scan_used = false;
+  cudaEvent_t pending_scan_ev = nullptr;
   double wait_scan = 0.0, wait_shift = 0.0, wait_plan = 0.0;  // host seconds blocked on the device
   struct Stopwatch {
     double& acc;
@@ -251,7 +299,8 @@ struct CudaBackend {
         if (seen) break;                 // second copy after the sequence number: every field is final
         if (h[4] == scan_seq[slot]) { seen = true; continue; }
         if ((spins & 0xff) == 0xff) {    // a failed launch must not hang the caller
-          const cudaError_t q = cudaStreamQuery(st);
+          cudaError_t q = cudaStreamQuery(st);
+          if (q == cudaSuccess && scan_used) q = cudaStreamQuery(ws->scan);
           if (q == cudaSuccess) {
             note(cudaMemcpyAsync(h, ws->dCtl + slot * 8, 8 * sizeof(int), cudaMemcpyDeviceToHost, ws->pub));
             note(cudaStreamSynchronize(ws->pub));
@@ -299,31 +348,48 @@ struct CudaBackend {
     if (fence) note(cudaStreamWaitEvent(st, ws->evShift[slot], 0));
   }
 
-  void apply(const WinDesc* wins, int cnt, int scan_slot = -1) {
+  // Window updates of one list of windows.  part 0: everything, on the main stream.  part 1: the
+  // tiles next to the windows (main stream, the scan rides on its last CTA).  part 2: the rest, on
+  // the far stream.
+  // phases: bit 0 = row updates and Z, bit 1 = column updates
+  void apply(const WinDesc* wins, int cnt, const double* U, int part, int scan_slot = -1, int phases = 3) {
+    cudaStream_t s = (part == 2) ? ws->far : st;
+    Timer& t = (part == 2) ? tm_far : tm;
     ApplyParams A;
     A.n = n; A.p = p; A.W = g.W; A.wantT = wantT; A.wantZ = wantZ; A.nwin = cnt;
     A.do_scan = 0; A.scan_nmin = g.W; A.scan_seq = 0; A.scan_D = g.D; A.scan_ctl = nullptr;
     A.scan_ticket = (unsigned int*)(ws->dCtl + kCtlMisc + 4); A.prof = dProf;
     for (int j = 0; j < p; j++) { A.H[j] = H[j]; A.Z[j] = Z[j]; }
-    A.U = ws->dU; A.wins = wins;
+    A.U = U; A.wins = wins; A.part = part;
     const int tiles = (n + AP_T - 1) / AP_T;
     // consecutive tiles per CTA (U_j staged once): as many as still leave a few waves of CTAs
+    // (about half of the tile slots of an item are empty: left of / below the window)
     int tpb = 1;
     while (tpb < 8 && (long long)(tiles / (2 * tpb)) * cnt * p * 2 >= 6LL * sm_count) tpb *= 2;
+    if (const char* e = dbg_env("PSD_MS_TPB")) tpb = atoi(e);
+    if (part == 1) tpb = 1;
     A.tpb = tpb;
-    const int chunks = (tiles + tpb - 1) / tpb;
-    tm.begin(1);
-    A.phase = 0;
-    ms_apply_kernel<<<dim3(chunks, cnt * p * 2), 256, AP_SMEM, st>>>(A);
-    A.phase = 1;
-    if (scan_slot >= 0) {
-      A.do_scan = 1;
-      A.scan_seq = scan_seq[scan_slot];
-      A.scan_ctl = ws->dCtl + scan_slot * 8;
+    // near part: two tiles right of the window, one above it
+    const int chunks0 = (part == 1) ? 2 : (tiles + tpb - 1) / tpb;
+    const int chunks1 = (part == 1) ? 1 : (tiles + tpb - 1) / tpb;
+    t.begin(1);
+    if (phases & 1) {
+      A.phase = 0;
+      ms_apply_kernel<<<dim3(chunks0, cnt * p * 2), 256, AP_SMEM, s>>>(A);
+      launches++;
+      if (part == 1) mark("near0 end", s);
     }
-    ms_apply_kernel<<<dim3(chunks, cnt * p), 256, AP_SMEM, st>>>(A);
-    tm.end();
-    launches += 2;
+    if (phases & 2) {
+      A.phase = 1;
+      if (scan_slot >= 0) {
+        A.do_scan = 1;
+        A.scan_seq = scan_seq[scan_slot];
+        A.scan_ctl = ws->dCtl + scan_slot * 8;
+      }
+      ms_apply_kernel<<<dim3(chunks1, cnt * p), 256, AP_SMEM, s>>>(A);
+      launches++;
+    }
+    t.end();
     note(cudaGetLastError());
   }
 
@@ -344,25 +410,90 @@ struct CudaBackend {
     ChaseParams C;
     C.n = n; C.p = p; C.g = g;
     for (int j = 0; j < p; j++) C.H[j] = H[j];
-    C.U = ws->dU; C.shifts = ws->dPairs; C.shift_state = ws->dCtl + kCtlPairs; C.wins = hp_dev; C.wins_dev = dp; C.prof = dProf;
+    double* Ucur = ws->dU + (size_t)(nround & 1) * p * n * g.W;
+    C.U = Ucur; C.shifts = ws->dPairs; C.shift_state = ws->dCtl + kCtlPairs; C.wins = hp_dev; C.wins_dev = dp; C.prof = dProf;
     if (dProf && dbg_env("PSD_MS_STAMP")) {
       const int mode = atoi(dbg_env("PSD_MS_STAMP"));
       if (mode == 1) ms_stamp_kernel<<<1, 32, 0, st>>>(dProf, 8);
       if (mode == 2) ms_stamp_kernel<<<cnt, 512, chase_smem, st>>>(dProf, 8);
     }
+    if (pending_scan_ev) {
+      note(cudaStreamWaitEvent(st, pending_scan_ev, 0));
+      pending_scan_ev = nullptr;
+    }
     round_timer = tm.begin(5);
+    mark("chase begin", st);
     tm.begin(0);
     ms_chase_kernel<<<cnt, 64 * g.NB, chase_smem, st>>>(C);
     tm.end();
     launches++;
     note(cudaGetLastError());
     fused_slot = next_scan_slot();
-    apply(dp, cnt, fused_slot);
+    // Round r, main stream: chase(r), near0(r), near1(r); far stream: far0(r), far1(r).  near = the
+    // two tiles (128 columns) right of a window for its row update (near0) and the tile (64 rows)
+    // above it for its column update (near1); far0 / far1 = the other tiles, and all of Z in far0.
+    //   far0(r) waits for chase(r) (and, by stream order, far(r-1));  far1(r) also for near(r);
+    //   near0(r) waits for far(r-1);  chase(r+1) follows near1(r) and runs beside far(r).
+    //  * chase(r+1) cannot touch what far(r) works on: a far entry (i, k) of the row update of a
+    //    window [s, s+wl) has k >= s + wl + 128 > i + 128, a far entry of its column update has
+    //    i < s - 64 <= k - 64, and a diagonal block of order <= 64 holds no entry with k - i >= 64,
+    //    wherever it lies.  The same holds for the shift snapshot (order nsw <= W) and the scan.
+    //  * near1(b) and far0(a) never share an entry: rows of a lie in [s_b - 64, s_b) only if
+    //    s_b < s_a + wl_a + 64, and then the columns of b end before s_a + wl_a + 128.
+    //  * a block rows(a) x cols(b) of two windows a above b gets U_a' from the left and U_b from the
+    //    right; piecewise application is correct as long as a left update of a column finds all
+    //    rows of a in one state with respect to U_b, and vice versa.  By the previous point the
+    //    columns of b are all inside near0(a) when near1(b) reaches rows of a (near0 precedes near1),
+    //    and no row of a has seen U_b when far0(a) reaches columns of b.  far1 runs after every left
+    //    update of the round.
+    //  * near0(r+1) overlaps far(r) (the windows have moved): hence its wait.
+    //  * U is double-buffered by round parity: chase(r+2) runs after near(r+1), i.e. after far(r).
+    const int par = (int)(nround & 1);
+    mark("chase end", st);
+    if (split) {
+      note(cudaEventRecord(ws->evChase[par], st));
+      // the scan reads three diagonals of H_1, which only the chase writes
+      note(cudaStreamWaitEvent(ws->scan, ws->evChase[par], 0));
+      ms_scan_kernel<<<1, 1024, (size_t)2 * n + 16, ws->scan>>>(H[0], n, g.W, ws->dCtl + fused_slot * 8, scan_seq[fused_slot], dp,
+                                                                 cnt, g.W, g.D, dProf);
+      launches++;
+      note(cudaGetLastError());
+      // it also writes the zeros of the deflations: the next chase must see them
+      note(cudaEventRecord(ws->evScan[fused_slot], ws->scan));
+      pending_scan_ev = ws->evScan[fused_slot];
+      scan_used = true;
+      note(cudaStreamWaitEvent(ws->far, ws->evChase[par], 0));
+      mark("far0 begin", ws->far);
+      apply(dp, cnt, Ucur, 2, -1, 1);
+      mark("far0 end", ws->far);
+      if (nround > 0) note(cudaStreamWaitEvent(st, ws->evFar[par ^ 1], 0));
+      mark("near begin", st);
+      apply(dp, cnt, Ucur, 1);
+      mark("near end", st);
+      note(cudaEventRecord(ws->evNear[par], st));
+      note(cudaStreamWaitEvent(ws->far, ws->evNear[par], 0));
+      apply(dp, cnt, Ucur, 2, -1, 2);
+      mark("far1 end", ws->far);
+      note(cudaEventRecord(ws->evFar[par], ws->far));
+    } else {
+      apply(dp, cnt, Ucur, 0, fused_slot);
+    }
+    nround++;
     last_plan = dp;
+  }
+
+  // the far stream joins the main stream
+  void join() {
+    if (pending_scan_ev) {
+      note(cudaStreamWaitEvent(st, pending_scan_ev, 0));
+      pending_scan_ev = nullptr;
+    }
+    if (nround > 0 && split) note(cudaStreamWaitEvent(st, ws->evFar[(nround - 1) & 1], 0));
   }
 
   void finish(int& nblocks) {
     nblocks = 0;
+    join();
     if (!ok()) return;
     note(grow(ws->dList, ws->capList, (size_t)(n / 2 + 1) * sizeof(WinDesc)));
     if (!ok()) return;
@@ -387,7 +518,7 @@ struct CudaBackend {
     if (nblocks > 0 && (wantT || wantZ)) {
       // grid.y is limited to 65535: apply in slices of blocks
       const int per = std::max(1, 60000 / (2 * p));
-      for (int o = 0; o < nblocks; o += per) apply(ws->dList + o, std::min(per, nblocks - o));
+      for (int o = 0; o < nblocks; o += per) apply(ws->dList + o, std::min(per, nblocks - o), ws->dU, 0);
     }
   }
 };
@@ -436,8 +567,12 @@ cudaError_t iterate(cudaStream_t caller, int sm_count, Workspace* ws, int n, int
   be.dEig = dEig; be.dInfo = dInfo;
   be.tm.on = profile != 0;
   be.tm.st = st;
+  be.tm_far.on = profile != 0;
+  be.tm_far.st = ws->far;
+  if (dbg_env("PSD_MS_NO_SPLIT")) be.split = false;
+  if (const char* ev = dbg_env("PSD_MS_TIMELINE")) be.tl_first = atoll(ev);
   const Geom g = be.g;
-  MS_CHECK(grow(ws->dU, ws->capU, (size_t)p * n * g.W * sizeof(double)));
+  MS_CHECK(grow(ws->dU, ws->capU, (size_t)2 * p * n * g.W * sizeof(double)));
   DriverConfig cfg;
   cfg.n = n; cfg.p = p; cfg.wantT = wantT; cfg.wantZ = be.wantZ;
   // shift window: limited by the shared memory of one CTA
@@ -487,11 +622,14 @@ cudaError_t iterate(cudaStream_t caller, int sm_count, Workspace* ws, int n, int
   DriverStats ds;
   const auto t_drive0 = std::chrono::steady_clock::now();
   const int status = drive(be, cfg, ds);
+  be.join();  // (finish() has joined already unless the drive stopped early)
+  if (be.tl_first >= 0) be.timeline_print();
   const double t_drive = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_drive0).count();
   // side streams: nothing of this call may still be running when the caller reuses the buffers
   for (int k = 0; k < kShiftSlots; k++)
     if (be.slot_used[k]) cudaStreamSynchronize(ws->side[k]);
   cudaStreamSynchronize(ws->pub);
+  if (be.scan_used) cudaStreamSynchronize(ws->scan);
   if (st != caller) {
     cudaEventRecord(ws->evOut, st);
     cudaStreamWaitEvent(caller, ws->evOut, 0);
@@ -514,6 +652,7 @@ cudaError_t iterate(cudaStream_t caller, int sm_count, Workspace* ws, int n, int
                 gaps[4 * 6 + 1] + gaps[1 * 6 + 4] + gaps[3 * 6 + 4] + gaps[3 * 6 + 1] + gaps[1 * 6 + 1]);
       }
       be.tm.collect(ms);
+      be.tm_far.collect(ms);
       for (int k = 0; k < kShiftSlots; k++) be.tm_side[k].collect(ms);
       res->ms_chase = ms[0]; res->ms_apply = ms[1]; res->ms_shifts = ms[2]; res->ms_scan = ms[3]; res->ms_final = ms[4];
       res->ms_rounds = ms[5];

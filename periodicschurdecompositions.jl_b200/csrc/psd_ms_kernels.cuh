@@ -263,6 +263,7 @@ constexpr int AP_SMEM = 3 * 64 * AP_LD * 8;  // U_j and two tile buffers
 struct ApplyParams {
   int n, p, W, wantT, wantZ, phase, nwin;
   int tpb;  // tiles per CTA (consecutive tiles of one item: U_j is staged once)
+  int part;  // 0 all tiles, 1 the tiles next to the windows, 2 the others (see the kernel)
   // Deflation scan fused into the tail of the last update kernel of a round: the CTA that
   // finishes last runs it (a stand-alone one-CTA kernel leaves the GPU idle and was measured to
   // delay the next launch by ~120 us).
@@ -284,12 +285,44 @@ __device__ __forceinline__ void ms_cp_async8(double* sdst, const double* gsrc, i
 __device__ __forceinline__ void ms_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void ms_cp_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
-// Software pipeline per CTA: U_j and the tiles are brought in with asynchronous copies; while
-// tile t is multiplied, written back to its buffer and stored, tile t+1 is already in flight into
-// the other buffer.
+// Bulk asynchronous copies (the TMA engine, no LSU instructions per element) completing on an
+// mbarrier.  One copy = one contiguous run of a column; addresses and sizes are multiples of 16.
+__device__ __forceinline__ unsigned ms_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void ms_mbar_init(unsigned long long* b, int cnt) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(ms_smem_u32(b)), "r"(cnt) : "memory");
+}
+__device__ __forceinline__ void ms_mbar_expect_tx(unsigned long long* b, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(ms_smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void ms_mbar_wait(unsigned long long* b, unsigned parity) {
+  asm volatile(
+      "{\n.reg .pred p;\nMS_WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra MS_WAIT_DONE;\nbra MS_WAIT_LOOP;\nMS_WAIT_DONE:\n}\n" ::"r"(ms_smem_u32(b)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void ms_bulk_g2s(double* sdst, const double* gsrc, unsigned bytes, unsigned long long* b) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   ms_smem_u32(sdst)),
+               "l"(gsrc), "r"(bytes), "r"(ms_smem_u32(b))
+               : "memory");
+}
+
+// Software pipeline per CTA: U_j and the tiles are brought in asynchronously; while tile t is
+// multiplied and stored, tile t+1 is already in flight into the other buffer (one CTA barrier per
+// tile).  Tiles whose columns are 16-byte aligned runs (the normal case: even n, window start and
+// length) come in as bulk copies, one per column, signalled on an mbarrier; anything else falls
+// back to 8-byte cp.async.  Results go from the accumulators straight to global memory.
+//
+// part: 0 = every tile; 1 = only the tiles near the window (the 128 columns right of it for the
+// row update, the 64 rows above it for the column update); 2 = the others.  The driver runs part 2
+// of round r on a second stream concurrently with the chase of round r+1 (psd_ms.cu,
+// CudaBackend::round, explains why that is safe and why the near part has this shape).
 __global__ void __launch_bounds__(256, 2) ms_apply_kernel(ApplyParams P) {
   double* Us = ms_smem;               // U(k, c) at Us[c * AP_LD + k]
   double* Xb[2] = {ms_smem + 64 * AP_LD, ms_smem + 2 * 64 * AP_LD};  // X(r, c) at X[c * AP_LD + r]
+  __shared__ unsigned long long bar[2], bar_u;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n = P.n, p = P.p;
   // item -> (window, factor, kind)
@@ -316,14 +349,51 @@ __global__ void __launch_bounds__(256, 2) ms_apply_kernel(ApplyParams P) {
     lo = 0;
     hi = P.wantZ ? n : 0;
   }
-  const int tfirst = blockIdx.x * P.tpb;
-  const bool has_work = lo + tfirst * AP_T < hi;
+  // Tiles of 64 along the long dimension: counted from lo upwards, for the column update from the
+  // window (hi = s) upwards, so that tile 0 is always the one next to the window.
+  const int nt = (hi > lo) ? (hi - lo + AP_T - 1) / AP_T : 0;
+  int ka = 0, kb = nt;  // this launch's tiles of the item
+  if (P.part != 0) {
+    const int nnear = (kind == 0) ? min(2, nt) : (kind == 1) ? min(1, nt) : 0;
+    if (P.part == 1) kb = nnear;
+    else ka = nnear;
+  }
+  auto tile_at = [&](int k, int& t0, int& tl) {
+    if (kind == 1) {
+      t0 = max(lo, hi - AP_T * (k + 1));
+      tl = hi - AP_T * k - t0;
+    } else {
+      t0 = lo + AP_T * k;
+      tl = min(AP_T, hi - t0);
+    }
+  };
+  const int kfirst = ka + blockIdx.x * P.tpb;
+  const bool has_work = kfirst < kb;
   if (has_work) {
   const double* Ug = P.U + (size_t)(j - 1) * n * P.W + (size_t)s * P.W;
+  // bulk copies need 16-byte aligned runs
+  const bool al = ((n | s | wl) & 1) == 0 && ((reinterpret_cast<size_t>(X) | reinterpret_cast<size_t>(P.U)) & 15) == 0;
+  if (al) {
+    if (tid == 0) { ms_mbar_init(&bar[0], 1); ms_mbar_init(&bar[1], 1); ms_mbar_init(&bar_u, 1); }
+    // the padding (rows / columns wl .. 63) is never written by the bulk copies: zero it once
+    for (int e = tid; e < 3 * 64 * AP_LD; e += 256) ms_smem[e] = 0.0;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+  }
   // element (r, cc) of the 64 x 64 staging tile <-> global address, by kind:
   //   left:      rows s .. s+wl-1 (r), columns t0 .. t0+tl-1 (cc)
   //   right / Z: rows t0 .. t0+tl-1 (r), columns s .. s+wl-1 (cc)
-  auto fetch = [&](double* dst, int t0, int tl) {
+  // returns whether the tile went through the bulk path
+  auto fetch = [&](double* dst, int t0, int tl, int buf) -> bool {
+    if (al && ((t0 | tl) & 1) == 0) {
+      const int ncol = (kind == 0) ? tl : wl, len = (kind == 0) ? wl : tl;
+      if (tid == 0) ms_mbar_expect_tx(&bar[buf], (unsigned)(ncol * len * 8));
+      if (tid < ncol) {
+        const double* g = (kind == 0) ? X + s + (size_t)(t0 + tid) * n : X + t0 + (size_t)(s + tid) * n;
+        ms_bulk_g2s(dst + tid * AP_LD, g, (unsigned)(len * 8), &bar[buf]);
+      }
+      return true;
+    }
 #pragma unroll 4
     for (int i = 0; i < 16; i++) {
       const int e = tid + 256 * i;
@@ -339,32 +409,52 @@ __global__ void __launch_bounds__(256, 2) ms_apply_kernel(ApplyParams P) {
       }
       ms_cp_async8(dst + cc * AP_LD + r, in ? g : X, in ? 8 : 0);
     }
+    ms_cp_commit();
+    return false;
   };
   // ---- stage U (wl x wl, zero padded to 64 x 64) and the first tile ----
+  unsigned long long* ubar = nullptr;
+  if (al) {
+    if (tid == 0) ms_mbar_expect_tx(&bar_u, (unsigned)(wl * wl * 8));
+    if (tid >= 64 && tid < 64 + wl) ms_bulk_g2s(Us + (tid - 64) * AP_LD, Ug + (size_t)(tid - 64) * wl, (unsigned)(wl * 8), &bar_u);
+    ubar = &bar_u;
+  } else {
 #pragma unroll 4
-  for (int i = 0; i < 16; i++) {
-    const int e = tid + 256 * i;
-    const int r = e & 63, cc = e >> 6;
-    const bool in = (r < wl && cc < wl);
-    ms_cp_async8(Us + cc * AP_LD + r, in ? Ug + r + (size_t)cc * wl : Ug, in ? 8 : 0);
+    for (int i = 0; i < 16; i++) {
+      const int e = tid + 256 * i;
+      const int r = e & 63, cc = e >> 6;
+      const bool in = (r < wl && cc < wl);
+      ms_cp_async8(Us + cc * AP_LD + r, in ? Ug + r + (size_t)cc * wl : Ug, in ? 8 : 0);
+    }
   }
-  int t0 = lo + tfirst * AP_T;
-  int tl = min(AP_T, hi - t0);
-  fetch(Xb[0], t0, tl);
-  ms_cp_commit();
+  int t0, tl;
+  tile_at(kfirst, t0, tl);
+  unsigned par = 0;       // phase parity of the two tile barriers
+  unsigned in_bulk = 0;   // bit b: the tile in buffer b came through the bulk path
+  if (fetch(Xb[0], t0, tl, 0)) in_bulk |= 1u;
   const int wm = warp & 1, wn = warp >> 1;
   const int gq = lane >> 2, tq = lane & 3;
   const int kmax = (wl + 3) & ~3;
   for (int tt = 0; tt < P.tpb; tt++) {
-    double* Xs = Xb[tt & 1];
+    const int cur = tt & 1;
+    double* Xs = Xb[cur];
     ms_cp_wait_all();
-    __syncthreads();  // tile tt (and U) have landed; the other buffer has been stored
-    const int t0n = t0 + AP_T;
-    const bool more = (tt + 1 < P.tpb) && (t0n < hi);
-    const int tln = more ? min(AP_T, hi - t0n) : 0;
+    if ((in_bulk >> cur) & 1u) {
+      ms_mbar_wait(&bar[cur], (par >> cur) & 1u);
+      par ^= 1u << cur;
+      in_bulk &= ~(1u << cur);
+    }
+    if (ubar) {
+      ms_mbar_wait(ubar, 0);
+      ubar = nullptr;
+    }
+    __syncthreads();  // tile tt (and U) have landed; every warp is done with the other buffer
+    const bool more = (tt + 1 < P.tpb) && (kfirst + tt + 1 < kb);
+    int t0n = 0, tln = 0;
     if (more) {
-      fetch(Xb[(tt + 1) & 1], t0n, tln);  // in flight during the multiplication and the store
-      ms_cp_commit();
+      tile_at(kfirst + tt + 1, t0n, tln);
+      // in flight during the multiplication and the store
+      if (fetch(Xb[cur ^ 1], t0n, tln, cur ^ 1)) in_bulk |= 1u << (cur ^ 1);
     }
     // ---- C = U' X (left)  or  C = X U (right, Z): 64 x 64 x wl ----
     double acc[4][2][2];
@@ -399,7 +489,9 @@ __global__ void __launch_bounds__(256, 2) ms_apply_kernel(ApplyParams P) {
           for (int q = 0; q < 2; q++) ms_dmma(acc[i][q][0], acc[i][q][1], a[i], b[q]);
       }
     }
-    __syncthreads();  // every warp has finished reading Xs
+    // ---- results straight from the accumulators to the tile's place in global memory (every
+    // element of the tile was read into shared memory before; a lane holds C(row gq, columns
+    // 2 tq, 2 tq + 1) of each 8 x 8 fragment, so 8 lanes write 64 contiguous bytes) ----
 #pragma unroll
     for (int i = 0; i < 4; i++)
 #pragma unroll
@@ -408,20 +500,12 @@ __global__ void __launch_bounds__(256, 2) ms_apply_kernel(ApplyParams P) {
         for (int e = 0; e < 2; e++) {
           const int m = wm * 32 + i * 8 + gq;
           const int nn = wn * 16 + q * 8 + 2 * tq + e;
-          Xs[nn * AP_LD + m] = acc[i][q][e];
+          if (kind == 0) {
+            if (m < wl && nn < tl) X[(s + m) + (size_t)(t0 + nn) * n] = acc[i][q][e];
+          } else {
+            if (m < tl && nn < wl) X[(t0 + m) + (size_t)(s + nn) * n] = acc[i][q][e];
+          }
         }
-    __syncthreads();
-    if (kind == 0) {
-      for (int e = tid; e < 64 * 64; e += 256) {
-        const int r = e & 63, cc = e >> 6;
-        if (r < wl && cc < tl) X[(s + r) + (size_t)(t0 + cc) * n] = Xs[cc * AP_LD + r];
-      }
-    } else {
-      for (int e = tid; e < 64 * 64; e += 256) {
-        const int r = e & 63, cc = e >> 6;
-        if (r < tl && cc < wl) X[(t0 + r) + (size_t)(s + cc) * n] = Xs[cc * AP_LD + r];
-      }
-    }
     if (!more) break;
     t0 = t0n;
     tl = tln;
