@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(64 * MS_MAXNB, 1) ms_chase_kernel(ChaseParams 
     for (int e = tid; e < wl * wl; e += nt) {
       const int r = e % wl, cc = e / wl;
       dst[r + (size_t)cc * n] = src[r + (size_t)cc * LD];
-      ud[e] = u[r + (size_t)cc * LD];
+      ud[r + (size_t)cc * W] = u[r + (size_t)cc * LD];
     }
   }
   if (ex.prof) {
@@ -273,7 +273,7 @@ struct ApplyParams {
   long long* prof;
   double* H[MS_MAXP];
   double* Z[MS_MAXP];
-  const double* U;
+  const double* U;  // U_j of the window at s: wl x wl, leading dimension W, at U + ((j-1) n + s) W
   const WinDesc* wins;
 };
 
@@ -416,7 +416,7 @@ __global__ void __launch_bounds__(256, 2) ms_apply_kernel(ApplyParams P) {
   unsigned long long* ubar = nullptr;
   if (al) {
     if (tid == 0) ms_mbar_expect_tx(&bar_u, (unsigned)(wl * wl * 8));
-    if (tid >= 64 && tid < 64 + wl) ms_bulk_g2s(Us + (tid - 64) * AP_LD, Ug + (size_t)(tid - 64) * wl, (unsigned)(wl * 8), &bar_u);
+    if (tid >= 64 && tid < 64 + wl) ms_bulk_g2s(Us + (tid - 64) * AP_LD, Ug + (size_t)(tid - 64) * P.W, (unsigned)(wl * 8), &bar_u);
     ubar = &bar_u;
   } else {
 #pragma unroll 4
@@ -424,7 +424,7 @@ __global__ void __launch_bounds__(256, 2) ms_apply_kernel(ApplyParams P) {
       const int e = tid + 256 * i;
       const int r = e & 63, cc = e >> 6;
       const bool in = (r < wl && cc < wl);
-      ms_cp_async8(Us + cc * AP_LD + r, in ? Ug + r + (size_t)cc * wl : Ug, in ? 8 : 0);
+      ms_cp_async8(Us + cc * AP_LD + r, in ? Ug + r + (size_t)cc * P.W : Ug, in ? 8 : 0);
     }
   }
   int t0, tl;
@@ -462,8 +462,10 @@ __global__ void __launch_bounds__(256, 2) ms_apply_kernel(ApplyParams P) {
     for (int i = 0; i < 4; i++)
 #pragma unroll
       for (int q = 0; q < 2; q++) acc[i][q][0] = acc[i][q][1] = 0.0;
+    // (8 x 8 fragments that lie entirely outside the window order wl are skipped)
     if (kind == 0) {
       // A(m, k) = U(k, m) = Us[m * LD + k];  B(k, nn) = X(k, nn) = Xs[nn * LD + k]
+      const int mi = min(4, (wl - wm * 32 + 7) >> 3);
       for (int k0 = 0; k0 < kmax; k0 += 4) {
         double a[4], b[2];
 #pragma unroll
@@ -472,11 +474,14 @@ __global__ void __launch_bounds__(256, 2) ms_apply_kernel(ApplyParams P) {
         for (int q = 0; q < 2; q++) b[q] = Xs[(wn * 16 + q * 8 + gq) * AP_LD + k0 + tq];
 #pragma unroll
         for (int i = 0; i < 4; i++)
+          if (i < mi) {
 #pragma unroll
-          for (int q = 0; q < 2; q++) ms_dmma(acc[i][q][0], acc[i][q][1], a[i], b[q]);
+            for (int q = 0; q < 2; q++) ms_dmma(acc[i][q][0], acc[i][q][1], a[i], b[q]);
+          }
       }
     } else {
       // A(m, k) = X(m, k) = Xs[k * LD + m];  B(k, nn) = U(k, nn) = Us[nn * LD + k]
+      const int qi = min(2, max(0, (wl - wn * 16 + 7) >> 3));
       for (int k0 = 0; k0 < kmax; k0 += 4) {
         double a[4], b[2];
 #pragma unroll
@@ -484,9 +489,11 @@ __global__ void __launch_bounds__(256, 2) ms_apply_kernel(ApplyParams P) {
 #pragma unroll
         for (int q = 0; q < 2; q++) b[q] = Us[(wn * 16 + q * 8 + gq) * AP_LD + k0 + tq];
 #pragma unroll
-        for (int i = 0; i < 4; i++)
+        for (int q = 0; q < 2; q++)
+          if (q < qi) {
 #pragma unroll
-          for (int q = 0; q < 2; q++) ms_dmma(acc[i][q][0], acc[i][q][1], a[i], b[q]);
+            for (int i = 0; i < 4; i++) ms_dmma(acc[i][q][0], acc[i][q][1], a[i], b[q]);
+          }
       }
     }
     // ---- results straight from the accumulators to the tile's place in global memory (every
@@ -702,7 +709,7 @@ __global__ void __launch_bounds__(256) ms_blocks_kernel(BlockParams P, int nbloc
         for (int e = tid; e < m * m; e += nt) {
           const int r = e % m, cc = e / m;
           dst[r + (size_t)cc * n] = src[r + (size_t)cc * ld];
-          ud[e] = z[r + (size_t)cc * ld];
+          ud[r + (size_t)cc * P.W] = z[r + (size_t)cc * ld];
         }
       }
     }
