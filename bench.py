@@ -237,13 +237,40 @@ def large_n_block(torch, psd_b200, L, h, dev, n=LARGE_N, p=LARGE_P):
         "iteration": {k: ls[k] for k in ("status", "sweeps", "rounds", "windows", "shift_pairs", "final_blocks",
                                          "chase_ms", "apply_ms", "scan_ms", "final_ms")},
         "dmma_window_updates": {"flops": ls["apply_flops"], "ms": ls["apply_ms"], "tflops": upd_tf,
-                                "frac_of_dgemm": upd_tf / peak, "kernel": "psd::ms::ms_apply_kernel"},
+                                "frac_of_dgemm": upd_tf / peak, "kernel": "psd::ms::ms_apply_kernel",
+                                "note": "sum of the launch durations inside the pipeline, where the far updates share "
+                                        "the GPU with the chase of the next round (two streams); 'isolated' = the same "
+                                        "kernel alone on one synthetic N=4096 round (scripts/ubench/apply_bench)",
+                                "isolated": isolated_update_rate(peak)},
         "dmma_reduction_updates": {"flops": kt["large_gemm_flops"], "ms": kt["large_gemm_ms"], "tflops": red_tf,
                                    "frac_of_dgemm": red_tf / peak, "kernel": "psd::dgemm_dmma_kernel"},
         "residual_over_n_eps": res / (n * eps), "orthogonality_over_n_eps": orth / (n * eps),
         "largest_entry_below_structure": low,
         "gates": "BASELINE: residual <= 10 N eps, ||Z'Z - I|| <= 10 N eps, exact quasi-triangular structure",
     }
+
+
+def isolated_update_rate(peak):
+    """Window-update kernel alone: one synthetic round of the N = 4096, p = 4 pipeline (13 windows of
+    order 56), CUDA events, 20 repetitions (scripts/ubench/apply_bench.cu, built by build())."""
+    exe = os.path.join(os.path.dirname(os.path.abspath(__file__)), "scripts", "ubench", "apply_bench")
+    if not os.path.exists(exe):
+        return None
+    try:
+        out = subprocess.run([exe, "4096", "13"], capture_output=True, text=True, timeout=120).stdout
+        best = None
+        for ln in out.splitlines():
+            if ln.startswith("unsplit,"):
+                f = ln.split()
+                us, tf = float(f[f.index("us") - 1]), float(f[f.index("TFLOP/s") - 1])
+                if best is None or tf > best[1]:
+                    best = (us, tf, " ".join(f[:6]))
+        if best is None:
+            return None
+        return {"us_per_round": best[0], "tflops": best[1], "frac_of_dgemm": best[1] / peak, "variant": best[2],
+                "split_matches_unsplit_bitwise": "max |diff| 0.000e+00" in out}
+    except Exception as ex:  # measurement tool only
+        return {"error": repr(ex)}
 
 
 def cpu_large_baseline(n_small=384, p=LARGE_P):

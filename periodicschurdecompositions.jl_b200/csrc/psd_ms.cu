@@ -47,9 +47,11 @@ struct Workspace {
   cudaStream_t far = nullptr;                    // far window updates of a round, concurrent with the next chase
   cudaEvent_t evNear[2] = {nullptr, nullptr}, evFar[2] = {nullptr, nullptr}, evChase[2] = {nullptr, nullptr};
 };
-constexpr int kCtlInts = kScanRing * 8 + kShiftSlots + 1 + 16;
-constexpr int kCtlPairs = kScanRing * 8;          // shift supply state: newest set, pair counts
-constexpr int kCtlMisc = kScanRing * 8 + kShiftSlots + 1;  // [0] expo of the scaling, [1] number of final blocks
+constexpr int kScanInts = MS_SCAN_INTS;            // ints per scan result
+static_assert(kShiftSlots == MS_SHIFT_SLOTS, "shift slot count");
+constexpr int kCtlInts = kScanRing * kScanInts + MS_SS_INTS + 16;
+constexpr int kCtlPairs = kScanRing * kScanInts;   // shift supply state (MS_SS_* offsets)
+constexpr int kCtlMisc = kScanRing * kScanInts + MS_SS_INTS;  // [0] expo of the scaling, [1] number of final blocks
 
 Workspace* ws_create() { return new Workspace(); }
 
@@ -111,7 +113,7 @@ cudaError_t ws_basic(Workspace* ws) {
   if (!ws->dPlan) MS_CHECK(cudaMalloc((void**)&ws->dPlan, (size_t)kPlanRing * kMaxWin * sizeof(WinDesc)));
   if (!ws->hPlan)
     MS_CHECK(cudaHostAlloc((void**)&ws->hPlan, (size_t)kPlanRing * kMaxWin * sizeof(WinDesc), cudaHostAllocMapped | cudaHostAllocPortable));
-  if (!ws->hScan) MS_CHECK(cudaHostAlloc((void**)&ws->hScan, (size_t)kScanRing * 8 * sizeof(int), cudaHostAllocDefault));
+  if (!ws->hScan) MS_CHECK(cudaHostAlloc((void**)&ws->hScan, (size_t)kScanRing * kScanInts * sizeof(int), cudaHostAllocDefault));
   for (auto& e : ws->evScan) if (!e) MS_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   for (auto& e : ws->evPub) if (!e) MS_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   if (!ws->pub) MS_CHECK(cudaStreamCreateWithFlags(&ws->pub, cudaStreamNonBlocking));
@@ -212,15 +214,18 @@ struct CudaBackend {
   long long nround = 0;
   // debug: device timeline of a few rounds (PSD_MS_TIMELINE=<first round>)
   long long tl_first = -1;
+  int tl_cnt = 0;
   std::vector<cudaEvent_t> tl_ev;
   std::vector<std::string> tl_name;
   void mark(const char* name, cudaStream_t s) {
-    if (tl_first < 0 || nround < tl_first || nround >= tl_first + 4) return;
+    if (tl_first == -1) return;
+    if (tl_first >= 0 && (nround < tl_first || nround >= tl_first + 4)) return;
+    if (tl_first < -1 && (nround % 64) >= 2) return;  // sampling mode: two consecutive rounds out of 64
     cudaEvent_t e;
     cudaEventCreate(&e);
     cudaEventRecord(e, s);
     tl_ev.push_back(e);
-    tl_name.push_back(std::string(name) + " r" + std::to_string(nround));
+    tl_name.push_back(std::string(name) + " r" + std::to_string(nround) + " w" + std::to_string(tl_cnt));
   }
   void timeline_print() {
     for (size_t i = 0; i < tl_ev.size(); i++) {
@@ -277,7 +282,7 @@ struct CudaBackend {
     const int slot = next_scan_slot();
     if (!ok()) return slot;
     tm.begin(3);
-    ms_scan_kernel<<<1, 1024, (size_t)2 * n + 16, st>>>(H[0], n, nmin, ws->dCtl + slot * 8, scan_seq[slot], last_plan,
+    ms_scan_kernel<<<1, 1024, (size_t)2 * n + 16, st>>>(H[0], n, nmin, ws->dCtl + slot * kScanInts, scan_seq[slot], last_plan,
                                                           last_plan ? cnt : 0, g.W, g.D, dProf);
     tm.end();
     if (round_timer >= 0) tm.end(round_timer);
@@ -290,10 +295,10 @@ struct CudaBackend {
     if (!ok()) { info.done = 1; return; }
     {
       Stopwatch sw(wait_scan);
-      int* h = ws->hScan + slot * 8;
+      int* h = ws->hScan + slot * kScanInts;
       bool seen = false;
       for (long long spins = 0;; spins++) {
-        note(cudaMemcpyAsync(h, ws->dCtl + slot * 8, 8 * sizeof(int), cudaMemcpyDeviceToHost, ws->pub));
+        note(cudaMemcpyAsync(h, ws->dCtl + slot * kScanInts, kScanInts * sizeof(int), cudaMemcpyDeviceToHost, ws->pub));
         note(cudaStreamSynchronize(ws->pub));
         if (!ok()) break;
         if (seen) break;                 // second copy after the sequence number: every field is final
@@ -302,7 +307,7 @@ struct CudaBackend {
           cudaError_t q = cudaStreamQuery(st);
           if (q == cudaSuccess && scan_used) q = cudaStreamQuery(ws->scan);
           if (q == cudaSuccess) {
-            note(cudaMemcpyAsync(h, ws->dCtl + slot * 8, 8 * sizeof(int), cudaMemcpyDeviceToHost, ws->pub));
+            note(cudaMemcpyAsync(h, ws->dCtl + slot * kScanInts, kScanInts * sizeof(int), cudaMemcpyDeviceToHost, ws->pub));
             note(cudaStreamSynchronize(ws->pub));
             if (h[4] != scan_seq[slot]) note(cudaErrorUnknown);
             break;
@@ -312,8 +317,10 @@ struct CudaBackend {
       }
     }
     if (!ok()) { info.done = 1; return; }
-    const int* c = ws->hScan + slot * 8;
+    const int* c = ws->hScan + slot * kScanInts;
     info.ilo = c[0]; info.ihi = c[1]; info.done = c[2]; info.nzero = c[3];
+    info.nb = std::min(c[5], (int)MS_MAXBLK);
+    for (int b = 0; b < info.nb; b++) { info.blo[b] = c[6 + 2 * b]; info.bhi[b] = c[7 + 2 * b]; }
   }
 
   // Shift set: snapshot of the trailing block on the main stream, eigenvalues on a side stream;
@@ -327,6 +334,7 @@ struct CudaBackend {
     double* snap = ws->dSnap + (size_t)slot * p * 64 * 64;
     SnapParams S;
     S.n = n; S.p = p; S.lo = lo; S.m = m; S.snap = snap;
+    S.seq_word = ws->dCtl + kCtlPairs + MS_SS_SEQ + slot;
     for (int j = 0; j < p; j++) S.H[j] = H[j];
     ms_snapshot_kernel<<<std::min(64, (p * m * m + 255) / 256), 256, 0, st>>>(S);
     note(cudaGetLastError());
@@ -337,7 +345,7 @@ struct CudaBackend {
     P.p = p; P.m = m; P.snap = snap;
     P.pairs = ws->dPairs + (size_t)pair_offset(slot) * 4;
     P.state = ws->dCtl + kCtlPairs;
-    P.slot = slot; P.seq = ++shift_seq;
+    P.slot = slot; P.seq = ++shift_seq; P.lo = lo;
     P.perturb = perturb;
     tm_side[slot].begin(2);
     ms_shifts_kernel<<<1, 256, shift_smem, ss>>>(P);
@@ -384,7 +392,7 @@ struct CudaBackend {
       if (scan_slot >= 0) {
         A.do_scan = 1;
         A.scan_seq = scan_seq[scan_slot];
-        A.scan_ctl = ws->dCtl + scan_slot * 8;
+        A.scan_ctl = ws->dCtl + scan_slot * kScanInts;
       }
       ms_apply_kernel<<<dim3(chunks1, cnt * p), 256, AP_SMEM, s>>>(A);
       launches++;
@@ -422,6 +430,7 @@ struct CudaBackend {
       pending_scan_ev = nullptr;
     }
     round_timer = tm.begin(5);
+    tl_cnt = cnt;
     mark("chase begin", st);
     tm.begin(0);
     ms_chase_kernel<<<cnt, 64 * g.NB, chase_smem, st>>>(C);
@@ -454,7 +463,7 @@ struct CudaBackend {
       note(cudaEventRecord(ws->evChase[par], st));
       // the scan reads three diagonals of H_1, which only the chase writes
       note(cudaStreamWaitEvent(ws->scan, ws->evChase[par], 0));
-      ms_scan_kernel<<<1, 1024, (size_t)2 * n + 16, ws->scan>>>(H[0], n, g.W, ws->dCtl + fused_slot * 8, scan_seq[fused_slot], dp,
+      ms_scan_kernel<<<1, 1024, (size_t)2 * n + 16, ws->scan>>>(H[0], n, g.W, ws->dCtl + fused_slot * kScanInts, scan_seq[fused_slot], dp,
                                                                  cnt, g.W, g.D, dProf);
       launches++;
       note(cudaGetLastError());
@@ -587,6 +596,8 @@ cudaError_t iterate(cudaStream_t caller, int sm_count, Workspace* ws, int n, int
   if (const char* ev = dbg_env("PSD_MS_REP")) cfg.rep_max = std::max(1, atoi(ev));
   if (const char* ev = dbg_env("PSD_MS_AHEAD")) cfg.sets_ahead = std::max(1, atoi(ev));
   if (const char* ev = dbg_env("PSD_MS_SCAN_EVERY")) cfg.scan_every = std::max(1, atoi(ev));
+  if (const char* ev = dbg_env("PSD_MS_MAXBLOCKS")) cfg.max_blocks = std::max(1, atoi(ev));
+  if (const char* ev = dbg_env("PSD_MS_NEWDELAY")) cfg.new_block_delay = std::max(0, atoi(ev));
   if (const char* ev = dbg_env("PSD_MS_LAG")) cfg.lag = std::max(1, std::min(kPlanRing - 2, atoi(ev)));
   if (const char* ev = dbg_env("PSD_MS_NSW")) cfg.nsw = std::max(2, std::min(nsw, atoi(ev)));
   MS_CHECK(grow(ws->dSnap, ws->capSnap, (size_t)kShiftSlots * p * 64 * 64 * sizeof(double)));
@@ -611,7 +622,7 @@ cudaError_t iterate(cudaStream_t caller, int sm_count, Workspace* ws, int n, int
     MS_CHECK(cudaFuncSetAttribute(ms_chase_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
     MS_CHECK(cudaFuncSetAttribute(ms_shifts_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
   }
-  MS_CHECK(cudaMemsetAsync(ws->dCtl + kCtlPairs, 0, (kShiftSlots + 1) * sizeof(int), st));
+  MS_CHECK(cudaMemsetAsync(ws->dCtl + kCtlPairs, 0, MS_SS_INTS * sizeof(int), st));
   MS_CHECK(cudaMemsetAsync(ws->dCtl + kCtlMisc + 4, 0, sizeof(int), st));
   long long* dprof = nullptr;
   if (dbg_env("PSD_MS_CHASE_PROF")) {
@@ -623,7 +634,7 @@ cudaError_t iterate(cudaStream_t caller, int sm_count, Workspace* ws, int n, int
   const auto t_drive0 = std::chrono::steady_clock::now();
   const int status = drive(be, cfg, ds);
   be.join();  // (finish() has joined already unless the drive stopped early)
-  if (be.tl_first >= 0) be.timeline_print();
+  if (be.tl_first != -1) be.timeline_print();
   const double t_drive = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_drive0).count();
   // side streams: nothing of this call may still be running when the caller reuses the buffers
   for (int k = 0; k < kShiftSlots; k++)

@@ -51,6 +51,7 @@ namespace ms {
 
 constexpr int MS_MAXP = 12;   // largest period the windowed path handles
 constexpr int MS_MAXNB = 8;   // most bulges per packet (two warps each: 512 threads per window)
+constexpr int MS_MAXBLK = 8;   // active diagonal blocks reported by a scan
 
 // Window geometry chosen from the period (shared memory holds 2 p windows of order W).
 struct Geom {

@@ -8,10 +8,14 @@
 //   round      every packet in flight moves down by D rows inside its own diagonal window (chase
 //              kernel, one CTA per window), then the off-window parts of H_j and Z_j are updated
 //              on the tensor cores, then the subdiagonal of H_1 is scanned for negligible entries
-//   injection  every second round (as soon as the top window of the active block is free) a new
-//              packet of NB bulges is introduced at the top of the active block, so up to
-//              N / W packets are in flight and the pipeline never drains between "sweeps"
-//   shifts     eigenvalues of the trailing ns x ns block of the active block, computed by the
+//   blocks     every unreduced diagonal block of order > W the scan reports (the lowest
+//              max_blocks of them) is worked on at the same time: the reference finishes the lowest
+//              block before it touches the next one, which on the GPU leaves a handful of windows
+//              per round for two thirds of the rounds
+//   injection  every second round (as soon as the top window of a block is free) a new packet
+//              of NB bulges is introduced at the top of that block, so up to N / W packets are
+//              in flight and the pipeline never drains between "sweeps"
+//   shifts     eigenvalues of the trailing ns x ns block of a block, computed by the
 //              reference algorithm on one CTA on a side stream from a snapshot of that block;
 //              the supply is free running: a new set is requested every few packets, and a packet
 //              takes the newest complete set when it is introduced (chosen on the device), so
@@ -27,6 +31,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <deque>
+#include <utility>
 #include <vector>
 
 #include "psd_ms_core.cuh"
@@ -54,10 +59,15 @@ struct DriverConfig {
   int shift_blocks = 1; // consecutive shift sets come from this many different trailing diagonal blocks
   int scan_every = 1;   // the subdiagonal is scanned after every scan_every-th round
   long long max_rounds = 0;  // 0: 64 + 40 n / D
+  int max_blocks = 4;   // active diagonal blocks worked on concurrently (1: only the lowest, like the reference)
+  int new_block_delay = 6;  // rounds between the first shift request of a new block and its first packet
+                            // (its own shift set is then normally complete; measured in profiles/r2_large_n_tuning.md)
 };
 
 struct ScanInfo {
-  int ilo = 0, ihi = -1, done = 0, nzero = 0;
+  int ilo = 0, ihi = -1, done = 0, nzero = 0;  // lowest active block
+  int nb = 0;                                   // active blocks reported (lowest first)
+  int blo[MS_MAXBLK] = {0}, bhi[MS_MAXBLK] = {0};
 };
 
 struct Packet {
@@ -66,6 +76,17 @@ struct Packet {
   int nbul, pair0, npairs, pair_off;
   int ilo, ihi;  // active block when the packet was introduced
   int fin_s;     // position at which the packet was first seen in finished territory (-1: not yet)
+};
+
+// Shift supply and stagnation counters of one active block.
+struct BlockCtl {
+  int ilo = 0, ihi = -1;
+  int req_lo = -1;        // first source row of the newest shift set requested for it (-1: none)
+  int since_request = 0;  // bulges introduced since then
+  int quota = 0;          // ... after which the next set is requested
+  int idle_sets = 0;      // shift sets requested since the block last changed
+  long long ready_round = 0;  // no packet before this round (first shift set still being computed)
+  bool seen = false;
 };
 
 // status: 0 = reduced to blocks of order <= W and finished; 1 = no convergence (the factors are
@@ -77,68 +98,98 @@ int drive(Backend& be, const DriverConfig& cfg, DriverStats& st) {
   const long long max_rounds = cfg.max_rounds > 0 ? cfg.max_rounds : 256 + 100LL * n / D;
   const int lag = std::max(1, cfg.lag);
   const bool trace = be.trace();
+  const int max_blocks = std::max(1, std::min(cfg.max_blocks, (int)MS_MAXBLK));
 
   ScanInfo info;
   be.scan_wait(be.scan_async(nullptr, 0, W), info);
   std::deque<int> scan_tickets;   // scans made after the rounds enqueued so far
   std::vector<Packet> pk;
   std::vector<WinDesc> wins;
+  std::vector<BlockCtl> blocks;   // active blocks being worked on (at most max_blocks, lowest first)
   int next_slot = 0;
-  int idle_sets = 0;              // shift sets requested since the last deflation
-  int last_ihi = info.ihi, last_ilo = info.ilo;
-  int req_ilo = -1, req_ihi = -1; // block the newest shift set was requested for
-  int since_request = 0;          // bulges introduced since then
-  int quota = 2 * g.NB;           // ... after which the next set is requested
   long long pair_counter = 0;     // running index of the next shift pair (taken modulo the set size on the device)
+  bool any_set = false;
 
-  // Shift supply: free running.  A request snapshots the trailing block of the active block on
-  // the main stream and computes its eigenvalues on a side stream; a packet that is introduced
-  // takes the newest set that is complete at that moment (decided on the device), so the host never
-  // waits for a shift computation.  `fence` makes the main stream wait for this request (first
-  // set; first set of a new active block).
-  auto request_set = [&](double perturb, bool fence) {
-    const int m = info.ihi - info.ilo + 1;
+  // Shift supply: free running.  A request snapshots the trailing part of a block on the main
+  // stream and computes its eigenvalues on a side stream; a packet that is introduced takes the
+  // newest complete set that was computed from rows of its block (decided on the device; failing
+  // that, the newest set of any block), so the host never waits for a shift computation.  `fence`
+  // makes the main stream wait for this request (very first set only).
+  auto request_set = [&](BlockCtl& b, double perturb, bool fence) {
+    const int m = b.ihi - b.ilo + 1;
     int ns = std::min(cfg.nsw, 2 * (m / 3));
     ns = std::max(2, ns & ~1);
     // Many packets are in flight at once; shifts that all approximate the same few eigenvalues
-    // would be wasted, so consecutive sets are the Ritz values of consecutive diagonal blocks of
-    // the trailing part of the active block (block 0 = the trailing block itself).
+    // would be wasted, so consecutive sets can be the Ritz values of consecutive diagonal blocks
+    // of the trailing part of the block (block 0 = the trailing block itself).
     int blk = 0;
     if (cfg.shift_blocks > 1 && !fence) blk = (int)(st.sweeps % cfg.shift_blocks);
-    while (blk > 0 && info.ihi - (blk + 1) * ns + 1 < info.ilo) blk--;
-    be.shifts_request(next_slot, info.ihi - (blk + 1) * ns + 1, ns, perturb, fence);
+    while (blk > 0 && b.ihi - (blk + 1) * ns + 1 < b.ilo) blk--;
+    const int lo = b.ihi - (blk + 1) * ns + 1;
+    be.shifts_request(next_slot, lo, ns, perturb, fence);
     next_slot = (next_slot + 1) % be.shift_slots();
-    req_ilo = info.ilo; req_ihi = info.ihi;
-    since_request = 0;
-    quota = std::max(g.NB, (ns / 2) * std::max(1, cfg.rep_max));
+    b.req_lo = lo;
+    b.since_request = 0;
+    b.quota = std::max(g.NB, (ns / 2) * std::max(1, cfg.rep_max));
+    b.idle_sets++;
     st.sweeps++;
-    idle_sets++;
+    any_set = true;
     if (trace)
-      fprintf(stderr, "[psd ms] shift set %d for block [%d, %d] (%d x %d)%s, %zu packets in flight\n", st.sweeps, info.ilo,
-              info.ihi, ns, ns, fence ? " fenced" : "", pk.size());
+      fprintf(stderr, "[psd ms] shift set %d for block [%d, %d] (%d x %d)%s, %zu packets in flight\n", st.sweeps, b.ilo,
+              b.ihi, ns, ns, fence ? " fenced" : "", pk.size());
   };
 
   for (long long r = 0;; r++) {
     // ---- block information: the scan made `lag` rounds ago ----
+    bool fresh = (r == 0);
     while ((int)scan_tickets.size() > lag - 1) {
       be.scan_wait(scan_tickets.front(), info);
       scan_tickets.pop_front();
-      if (info.nzero > 0 || info.ihi != last_ihi || info.ilo != last_ilo) idle_sets = 0;
-      last_ihi = info.ihi; last_ilo = info.ilo;
+      fresh = true;
     }
     if (!be.ok()) return 1;
+    if (fresh) {
+      // match the reported blocks with the ones being worked on: blocks only shrink or split, so a
+      // reported block continues the entry that contains it - the part that holds the source rows
+      // of the entry's newest shift set inherits the shift supply, other parts start afresh
+      std::vector<BlockCtl> next;
+      const int nb = info.done ? 0 : std::min(info.nb, max_blocks);
+      for (int k = 0; k < nb; k++) {
+        BlockCtl e;
+        e.ilo = info.blo[k]; e.ihi = info.bhi[k];
+        for (const BlockCtl& o : blocks)
+          if (e.ilo >= o.ilo && e.ihi <= o.ihi) {
+            const bool same = (e.ilo == o.ilo && e.ihi == o.ihi);
+            if (o.req_lo >= e.ilo && o.req_lo <= e.ihi) {
+              e.req_lo = o.req_lo; e.since_request = o.since_request; e.quota = o.quota;
+              e.ready_round = o.ready_round;
+            }
+            e.idle_sets = (same && info.nzero == 0) ? o.idle_sets : 0;
+            break;
+          }
+        next.push_back(e);
+      }
+      blocks.swap(next);
+    }
     // ---- retire packets that have left the matrix or travel through finished territory ----
     {
+      // rows that may still belong to an active block: the reported ones and, when the list may
+      // be truncated, everything above the highest reported block
+      auto maybe_active = [&](int row) {
+        if (info.done) return false;
+        for (int k = 0; k < info.nb; k++)
+          if (row >= info.blo[k] && row <= info.bhi[k]) return true;
+        return info.nb == (int)MS_MAXBLK && row < info.blo[info.nb - 1];
+      };
       size_t k = 0;
       for (size_t i = 0; i < pk.size(); i++) {
         // (a) the previous window reached the bottom of the block the packet was planned for
         // (every bulge chased off), or (b) the packet has travelled 2 W rows through finished
-        // territory (blocks of order <= W below the active block) since it was first seen there:
-        // each of its bulges has met an exact zero of the subdiagonal within W + 3 NB rows and has
-        // been chased off at it (clamp_block_end)
+        // territory (blocks of order <= W) since it was first seen there: each of its bulges has
+        // met an exact zero of the subdiagonal within W + 3 NB rows and has been chased off at it
+        // (clamp_block_end)
         Packet& q = pk[i];
-        const int limit = info.done ? -1 : info.ihi;
-        if (q.fin_s < 0 && q.s > limit) q.fin_s = q.s;
+        if (q.fin_s < 0 && !maybe_active(q.s)) q.fin_s = q.s;
         const bool gone = (q.hops > 0 && q.s - D + W >= q.ihi + 1) || (q.fin_s >= 0 && q.s >= q.fin_s + 2 * W);
         if (!gone) pk[k++] = q;
       }
@@ -150,34 +201,33 @@ int drive(Backend& be, const DriverConfig& cfg, DriverStats& st) {
       while (!scan_tickets.empty()) { be.scan_wait(scan_tickets.front(), tmp); scan_tickets.pop_front(); }
       break;
     }
-    const int pass_sets = std::max(1, (info.done ? 1 : (info.ihi - info.ilo + 1) / W) / std::max(1, cfg.nsw / (2 * g.NB)));
-    if (r > max_rounds || idle_sets > 60 + 40 * pass_sets) return 1;
-    // ---- shift sets ----
-    if (!info.done) {
+    if (r > max_rounds) return 1;
+    for (BlockCtl& b : blocks) {
+      const int pass_sets = std::max(1, ((b.ihi - b.ilo + 1) / W) / std::max(1, cfg.nsw / (2 * g.NB)));
+      if (b.idle_sets > 60 + 40 * pass_sets) return 1;
+      // ---- shift sets ----
       const int ex_every = 6 + 4 * pass_sets;  // sets without any deflation before the shifts are spread
       double perturb = 0.0;
-      if (idle_sets >= ex_every && idle_sets % ex_every == 0) perturb = 0.5;  // exceptional shifts
-      const bool other_block = (req_ihi < 0) || (info.ihi < req_ilo);
-      if (other_block || since_request >= quota) {
-        request_set(perturb, other_block);
+      if (b.idle_sets >= ex_every && b.idle_sets % ex_every == 0) perturb = 0.5;  // exceptional shifts
+      if (b.req_lo < 0 || b.since_request >= b.quota) {
+        if (b.req_lo < 0 && any_set) b.ready_round = r + cfg.new_block_delay;
+        request_set(b, perturb, !any_set);
         if (perturb != 0.0) st.exceptional++;
       }
-    }
-    // ---- introduce a packet when the top window of the active block is free ----
-    if (!info.done) {
+      // ---- introduce a packet when the top window of the block is free ----
       bool top_free = true;
       for (const Packet& q : pk)
-        if (q.s < info.ilo + W && q.s + W > info.ilo) top_free = false;
-      if (top_free && (int)pk.size() < be.max_windows()) {
+        if (q.s < b.ilo + W && q.s + W > b.ilo) top_free = false;
+      if (top_free && r >= b.ready_round && (int)pk.size() < be.max_windows()) {
         Packet q;
         q.nbul = g.NB;
         q.pair0 = (int)(pair_counter % 1000000);
         q.npairs = 0;   // the set (and its size) is chosen on the device when the window runs
         q.pair_off = 0;
-        q.ilo = info.ilo; q.ihi = info.ihi;
-        q.s = info.ilo; q.hops = 0; q.fin_s = -1;
+        q.ilo = b.ilo; q.ihi = b.ihi;
+        q.s = b.ilo; q.hops = 0; q.fin_s = -1;
         pair_counter += q.nbul;
-        since_request += q.nbul;
+        b.since_request += q.nbul;
         st.shift_pairs += q.nbul;
         pk.push_back(q);
       }
@@ -203,6 +253,15 @@ int drive(Backend& be, const DriverConfig& cfg, DriverStats& st) {
       q.hops++;
     }
     if (!wins.empty()) {
+      // windows of one round must be disjoint (packets of one block keep their distance by
+      // construction; this also covers packets that outlive a split of their block)
+      {
+        std::vector<std::pair<int, int>> span;
+        for (const WinDesc& w : wins) span.emplace_back(w.s, w.s + w.wl);
+        std::sort(span.begin(), span.end());
+        for (size_t i = 1; i < span.size(); i++)
+          if (span[i].first < span[i - 1].second) return 1;
+      }
       be.round(wins);
       st.rounds++;
       st.windows += (long long)wins.size();

@@ -33,13 +33,16 @@ __device__ __forceinline__ void ms_dmma(double& d0, double& d1, double a, double
 //   U + (j-1) * n * W + s * W,  column-major with leading dimension = order of the window.
 // Windows that exist at the same time are disjoint in index space, so these never overlap.
 // ------------------------------------------------------------------------------------------
+constexpr int MS_SHIFT_SLOTS = 8;
+constexpr int MS_SS_NP = 0, MS_SS_SEQ = MS_SHIFT_SLOTS, MS_SS_LO = 2 * MS_SHIFT_SLOTS;  // offsets into shift_state
+constexpr int MS_SS_INTS = 3 * MS_SHIFT_SLOTS;
 struct ChaseParams {
   int n, p;
   Geom g;
   double* H[MS_MAXP];  // internal factor j at H[j-1], column-major, ld = n
   double* U;
   const double* shifts;  // [slots][66][4] pair buffers
-  const int* shift_state;  // [0] newest complete set: (sequence << 8) | slot; [1 + slot] its number of pairs
+  const int* shift_state;  // per shift slot: number of pairs, sequence number (0: being computed), first source row
   const WinDesc* wins;   // this round's windows in mapped pinned host memory (written by the host)
   WinDesc* wins_dev;     // device copy made here for the update and scan kernels of the round
   long long* prof;       // [8] cycle counters of CTA 0 (debug), or nullptr
@@ -77,12 +80,21 @@ __global__ void __launch_bounds__(64 * MS_MAXNB, 1) ms_chase_kernel(ChaseParams 
   if (tid == 0) {
     s_desc = P.wins[blockIdx.x];
     if (s_desc.intro) {
-      // newest complete shift set (free-running supply on the side streams)
-      const int st = *(const volatile int*)P.shift_state;
-      const int slot = st & 0xff;
-      const int np = ((const volatile int*)P.shift_state)[1 + slot];
-      s_desc.pair_off = slot * 66;
-      s_desc.npairs = np;
+      // newest complete shift set computed from rows of this window's block (free-running supply
+      // on the side streams); failing that the newest complete set of any block; failing that
+      // none (npairs = 0: unshifted start vector)
+      const volatile int* ss = (const volatile int*)P.shift_state;
+      int best = -1, bseq = 0, any = -1, aseq = 0;
+      for (int k = 0; k < MS_SHIFT_SLOTS; k++) {
+        const int sq = ss[MS_SS_SEQ + k];
+        if (sq <= 0) continue;
+        const int lo = ss[MS_SS_LO + k];
+        if (lo >= s_desc.ilo && lo <= s_desc.ihi && sq > bseq) { best = k; bseq = sq; }
+        if (sq > aseq) { any = k; aseq = sq; }
+      }
+      const int slot = best >= 0 ? best : any;
+      s_desc.pair_off = slot >= 0 ? slot * 66 : 0;
+      s_desc.npairs = slot >= 0 ? ss[MS_SS_NP + slot] : 0;
     }
     P.wins_dev[blockIdx.x] = s_desc;
   }
@@ -149,26 +161,30 @@ __global__ void __launch_bounds__(64 * MS_MAXNB, 1) ms_chase_kernel(ChaseParams 
 }
 
 // ------------------------------------------------------------------------------------------
-// Deflation scan + active block.  ctl (device ints): [0] ilo, [1] ihi, [2] done,
-// [3] number of subdiagonal entries set to zero by this scan.
+// Deflation scan + active blocks.  ctl (device ints): [0] ilo, [1] ihi of the lowest active block,
+// [2] done, [3] number of subdiagonal entries set to zero by this scan, [4] sequence number
+// (written last), [5] number of active blocks reported (<= MS_MAXBLK, lowest first), [6 + 2 b],
+// [7 + 2 b] first and last row of block b.
 // Criterion: |h(k,k-1)| <= max(smlnum, ulp (|h(k-1,k-1)| + |h(k,k)|)) on H_1 (the "Test 1" of the
 // periodic QZ drivers, rgeneralized.jl:1086-1112), which perturbs H_1 by at most 2 ulp ||H_1||.
-// The active block is the lowest unreduced diagonal block of order > nmin.
+// Active blocks: the unreduced diagonal blocks of order > nmin.
 // ------------------------------------------------------------------------------------------
 // The rows of the bulge chains that sit in the matrix after the round (wins[0..nwin), see
 // chain_after_round) are left alone: subdiagonal entries there are part of the bulges.
 // Dynamic shared memory: 2 n bytes (skip flags, non-zero flags of the subdiagonal).
 constexpr int MS_MAXCHAINS = 160;
+constexpr int MS_SCAN_CAND = 256;  // candidate blocks kept by the scan before the lowest MS_MAXBLK are reported
+constexpr int MS_SCAN_INTS = 6 + 2 * MS_MAXBLK + 2;  // ints per scan result (see ms_scan_body)
 
 // The result (ctl[0..3]) and then the sequence number ctl[4] stay in device memory; the host polls
 // for them with copies on a side stream.
 __device__ __forceinline__ void ms_scan_body(double* H1, int n, int nmin, int* ctl, int seq, const WinDesc* wins,
                                              int nwin, int W, int D, long long* prof, unsigned char* smem_bytes) {
-  __shared__ int s_ihi, s_ilo, s_cnt;
+  __shared__ int s_cnt;
   unsigned char* skip = smem_bytes;  // skip[z]: entry H1[z+1, z] belongs to a chain
   unsigned char* nz = skip + n;                                      // nz[k]: H1[k, k-1] != 0 (k >= 1)
   const int tid = threadIdx.x, nt = blockDim.x;
-  if (tid == 0) { s_ihi = -1; s_ilo = 0; s_cnt = 0; }
+  if (tid == 0) s_cnt = 0;
   for (int k = tid; k < n; k += nt) skip[k] = 0;
   __syncthreads();
   if (nwin > MS_MAXCHAINS) nwin = MS_MAXCHAINS;  // (the host never plans more)
@@ -196,27 +212,53 @@ __device__ __forceinline__ void ms_scan_body(double* H1, int n, int nmin, int* c
   }
   if (cnt) atomicAdd(&s_cnt, cnt);
   __syncthreads();
-  // block ends: k = n-1 or H1[k+1, k] == 0; a block is "large" when no boundary lies within nmin
-  for (int k = tid; k < n; k += nt) {
-    const bool end = (k == n - 1) || !nz[k + 1];
-    if (!end) continue;
-    int len = 1;
-    int r = k;
-    while (r > 0 && len <= nmin && nz[r]) { r--; len++; }
-    if (len > nmin) atomicMax(&s_ihi, k);
-  }
+  // ---- unreduced diagonal blocks of order > nmin: (start, end) pairs, lowest first ----
+  // start[k] = last position j <= k with H1[j, j-1] == 0 (or 0): every thread takes a contiguous
+  // chunk, a scan over the threads carries the last zero across the chunks
+  __shared__ int s_carry[1024];
+  __shared__ int s_nb, s_blo[MS_SCAN_CAND], s_bhi[MS_SCAN_CAND];
+  if (tid == 0) s_nb = 0;
+  const int chunk = (n + nt - 1) / nt;
+  const int k0 = min(n, tid * chunk), k1 = min(n, k0 + chunk);
+  int lastz = -1;
+  for (int k = k0; k < k1; k++)
+    if (k == 0 || !nz[k]) lastz = k;
+  s_carry[tid] = lastz;
   __syncthreads();
-  const int ihi = s_ihi;
-  if (ihi >= 0) {
-    for (int k = 1 + tid; k <= ihi; k += nt)
-      if (!nz[k]) atomicMax(&s_ilo, k);
+  for (int o = 1; o < nt; o <<= 1) {
+    const int v = (tid >= o) ? s_carry[tid - o] : -1;
+    __syncthreads();
+    if (v > s_carry[tid]) s_carry[tid] = v;
     __syncthreads();
   }
+  {
+    int start = (tid > 0) ? s_carry[tid - 1] : 0;
+    for (int k = k0; k < k1; k++) {
+      if (k == 0 || !nz[k]) start = k;
+      const bool end = (k == n - 1) || !nz[k + 1];
+      if (end && k - start + 1 > nmin) {
+        const int idx = atomicAdd(&s_nb, 1);
+        if (idx < MS_SCAN_CAND) { s_blo[idx] = start; s_bhi[idx] = k; }
+      }
+    }
+  }
+  __syncthreads();
   if (tid == 0) {
-    ctl[0] = (ihi >= 0) ? s_ilo : 0;
-    ctl[1] = ihi;
-    ctl[2] = (ihi < 0) ? 1 : 0;
+    // lowest blocks first (candidates beyond MS_SCAN_CAND are dropped; later scans find them)
+    const int nbk = min(s_nb, MS_SCAN_CAND);
+    for (int a = 1; a < nbk; a++) {
+      const int lo = s_blo[a], hi = s_bhi[a];
+      int b = a - 1;
+      while (b >= 0 && s_bhi[b] < hi) { s_blo[b + 1] = s_blo[b]; s_bhi[b + 1] = s_bhi[b]; b--; }
+      s_blo[b + 1] = lo; s_bhi[b + 1] = hi;
+    }
+    const int nout = min(nbk, MS_MAXBLK);
+    ctl[0] = (nbk > 0) ? s_blo[0] : 0;
+    ctl[1] = (nbk > 0) ? s_bhi[0] : -1;
+    ctl[2] = (nbk == 0) ? 1 : 0;
     ctl[3] = s_cnt;
+    ctl[5] = nout;
+    for (int a = 0; a < nout; a++) { ctl[6 + 2 * a] = s_blo[a]; ctl[7 + 2 * a] = s_bhi[a]; }
     __threadfence();
     *(volatile int*)(ctl + 4) = seq;
     if (prof) {
@@ -432,9 +474,13 @@ __global__ void __launch_bounds__(256, 2) ms_apply_kernel(ApplyParams P) {
   unsigned par = 0;       // phase parity of the two tile barriers
   unsigned in_bulk = 0;   // bit b: the tile in buffer b came through the bulk path
   if (fetch(Xb[0], t0, tl, 0)) in_bulk |= 1u;
-  const int wm = warp & 1, wn = warp >> 1;
   const int gq = lane >> 2, tq = lane & 3;
   const int kmax = (wl + 3) & ~3;
+  // Warp tiles: the 8 x 8 fragments that lie entirely outside the window order wl are skipped, and
+  // the split over the warps is chosen so that the two warps of an SM sub-partition (w and w + 4)
+  // share that saving: left: 32 window rows x 16 columns, the row half from bit 2 of the warp;
+  // right / Z: 16 rows x 32 window columns, the column half from bit 2.
+  const int wh = warp >> 2, wq = warp & 3;
   for (int tt = 0; tt < P.tpb; tt++) {
     const int cur = tt & 1;
     double* Xs = Xb[cur];
@@ -456,22 +502,26 @@ __global__ void __launch_bounds__(256, 2) ms_apply_kernel(ApplyParams P) {
       // in flight during the multiplication and the store
       if (fetch(Xb[cur ^ 1], t0n, tln, cur ^ 1)) in_bulk |= 1u << (cur ^ 1);
     }
-    // ---- C = U' X (left)  or  C = X U (right, Z): 64 x 64 x wl ----
-    double acc[4][2][2];
-#pragma unroll
-    for (int i = 0; i < 4; i++)
-#pragma unroll
-      for (int q = 0; q < 2; q++) acc[i][q][0] = acc[i][q][1] = 0.0;
-    // (8 x 8 fragments that lie entirely outside the window order wl are skipped)
+    // ---- C = U' X (left)  or  C = X U (right, Z): 64 x 64 x wl; results go straight from the
+    // accumulators to the tile's place in global memory (every element of the tile was read into
+    // shared memory before; a lane holds C(row gq, columns 2 tq, 2 tq + 1) of each 8 x 8
+    // fragment, so 8 lanes write 64 contiguous bytes) ----
     if (kind == 0) {
       // A(m, k) = U(k, m) = Us[m * LD + k];  B(k, nn) = X(k, nn) = Xs[nn * LD + k]
-      const int mi = min(4, (wl - wm * 32 + 7) >> 3);
+      double acc[4][2][2];
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int q = 0; q < 2; q++) acc[i][q][0] = acc[i][q][1] = 0.0;
+      const int mi = min(4, (wl - wh * 32 + 7) >> 3);
+      const double* ap = Us + (wh * 32 + gq) * AP_LD + tq;
+      const double* bp = Xs + (wq * 16 + gq) * AP_LD + tq;
       for (int k0 = 0; k0 < kmax; k0 += 4) {
         double a[4], b[2];
 #pragma unroll
-        for (int i = 0; i < 4; i++) a[i] = Us[(wm * 32 + i * 8 + gq) * AP_LD + k0 + tq];
+        for (int i = 0; i < 4; i++) a[i] = ap[i * 8 * AP_LD + k0];
 #pragma unroll
-        for (int q = 0; q < 2; q++) b[q] = Xs[(wn * 16 + q * 8 + gq) * AP_LD + k0 + tq];
+        for (int q = 0; q < 2; q++) b[q] = bp[q * 8 * AP_LD + k0];
 #pragma unroll
         for (int i = 0; i < 4; i++)
           if (i < mi) {
@@ -479,40 +529,50 @@ __global__ void __launch_bounds__(256, 2) ms_apply_kernel(ApplyParams P) {
             for (int q = 0; q < 2; q++) ms_dmma(acc[i][q][0], acc[i][q][1], a[i], b[q]);
           }
       }
-    } else {
-      // A(m, k) = X(m, k) = Xs[k * LD + m];  B(k, nn) = U(k, nn) = Us[nn * LD + k]
-      const int qi = min(2, max(0, (wl - wn * 16 + 7) >> 3));
-      for (int k0 = 0; k0 < kmax; k0 += 4) {
-        double a[4], b[2];
 #pragma unroll
-        for (int i = 0; i < 4; i++) a[i] = Xs[(k0 + tq) * AP_LD + wm * 32 + i * 8 + gq];
-#pragma unroll
-        for (int q = 0; q < 2; q++) b[q] = Us[(wn * 16 + q * 8 + gq) * AP_LD + k0 + tq];
+      for (int i = 0; i < 4; i++)
 #pragma unroll
         for (int q = 0; q < 2; q++)
+#pragma unroll
+          for (int e = 0; e < 2; e++) {
+            const int m = wh * 32 + i * 8 + gq;
+            const int nn = wq * 16 + q * 8 + 2 * tq + e;
+            if (m < wl && nn < tl) X[(s + m) + (size_t)(t0 + nn) * n] = acc[i][q][e];
+          }
+    } else {
+      // A(m, k) = X(m, k) = Xs[k * LD + m];  B(k, nn) = U(k, nn) = Us[nn * LD + k]
+      double acc[2][4][2];
+#pragma unroll
+      for (int i = 0; i < 2; i++)
+#pragma unroll
+        for (int q = 0; q < 4; q++) acc[i][q][0] = acc[i][q][1] = 0.0;
+      const int qi = min(4, (wl - wh * 32 + 7) >> 3);
+      const double* ap = Xs + tq * AP_LD + wq * 16 + gq;
+      const double* bp = Us + (wh * 32 + gq) * AP_LD + tq;
+      for (int k0 = 0; k0 < kmax; k0 += 4) {
+        double a[2], b[4];
+#pragma unroll
+        for (int i = 0; i < 2; i++) a[i] = ap[k0 * AP_LD + i * 8];
+#pragma unroll
+        for (int q = 0; q < 4; q++) b[q] = bp[q * 8 * AP_LD + k0];
+#pragma unroll
+        for (int q = 0; q < 4; q++)
           if (q < qi) {
 #pragma unroll
-            for (int i = 0; i < 4; i++) ms_dmma(acc[i][q][0], acc[i][q][1], a[i], b[q]);
+            for (int i = 0; i < 2; i++) ms_dmma(acc[i][q][0], acc[i][q][1], a[i], b[q]);
           }
       }
-    }
-    // ---- results straight from the accumulators to the tile's place in global memory (every
-    // element of the tile was read into shared memory before; a lane holds C(row gq, columns
-    // 2 tq, 2 tq + 1) of each 8 x 8 fragment, so 8 lanes write 64 contiguous bytes) ----
 #pragma unroll
-    for (int i = 0; i < 4; i++)
+      for (int i = 0; i < 2; i++)
 #pragma unroll
-      for (int q = 0; q < 2; q++)
+        for (int q = 0; q < 4; q++)
 #pragma unroll
-        for (int e = 0; e < 2; e++) {
-          const int m = wm * 32 + i * 8 + gq;
-          const int nn = wn * 16 + q * 8 + 2 * tq + e;
-          if (kind == 0) {
-            if (m < wl && nn < tl) X[(s + m) + (size_t)(t0 + nn) * n] = acc[i][q][e];
-          } else {
+          for (int e = 0; e < 2; e++) {
+            const int m = wq * 16 + i * 8 + gq;
+            const int nn = wh * 32 + q * 8 + 2 * tq + e;
             if (m < tl && nn < wl) X[(t0 + m) + (size_t)(s + nn) * n] = acc[i][q][e];
           }
-        }
+    }
     if (!more) break;
     t0 = t0n;
     tl = tln;
@@ -546,6 +606,7 @@ struct ShiftParams {
   double* pairs;       // this set's pair buffer
   int* state;          // shift_state of ChaseParams
   int slot, seq;
+  int lo;              // first row of the block the set is computed from
   double perturb;
 };
 
@@ -555,9 +616,12 @@ struct SnapParams {
   int n, p, lo, m;
   const double* H[MS_MAXP];
   double* snap;
+  int* seq_word;  // the slot's sequence number: cleared here (main stream), so that no window picks
+                  // the slot while its pairs are being rewritten
 };
 
 __global__ void ms_snapshot_kernel(SnapParams P) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) *(volatile int*)P.seq_word = 0;
   const int m = P.m, total = P.p * m * m;
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
     const int j = e / (m * m), rem = e - j * m * m;
@@ -602,9 +666,10 @@ __global__ void __launch_bounds__(256) ms_shifts_kernel(ShiftParams P) {
   __syncthreads();
   if (tid == 0) {
     const int np = pair_shifts(c.lre + 1, c.lim + 1, info, m, P.perturb, P.pairs);
-    P.state[1 + P.slot] = np;
+    P.state[MS_SS_NP + P.slot] = np;
+    P.state[MS_SS_LO + P.slot] = P.lo;
     __threadfence();
-    if (np > 0) atomicMax(P.state, (P.seq << 8) | P.slot);  // publish: newest complete set
+    if (np > 0) *(volatile int*)(P.state + MS_SS_SEQ + P.slot) = P.seq;  // publish: this slot holds a complete set
   }
 }
 

@@ -84,25 +84,27 @@ struct EmuBackend {
         out.nzero++;
       }
     }
-    int ihi = -1;
-    for (int k = n - 1; k >= 0; k--) {
-      const bool end = (k == n - 1) || h(0, k + 1, k) == 0.0;
-      if (!end) continue;
-      int len = 1, r = k;
-      while (r > 0 && len <= nmin && h(0, r, r - 1) != 0.0) { r--; len++; }
-      if (len > nmin) { ihi = k; break; }
+    // unreduced diagonal blocks of order > nmin, lowest first (as ms_scan_body reports them)
+    out.nb = 0;
+    for (int k = n - 1; k >= 0;) {
+      int r = k;
+      while (r > 0 && h(0, r, r - 1) != 0.0) r--;
+      if (k - r + 1 > nmin && out.nb < (int)MS_MAXBLK) {
+        out.blo[out.nb] = r; out.bhi[out.nb] = k;
+        out.nb++;
+      }
+      k = r - 1;
     }
-    int ilo = 0;
-    if (ihi >= 0)
-      for (int k = 1; k <= ihi; k++)
-        if (h(0, k, k - 1) == 0.0) ilo = k;
-    out.ilo = ilo; out.ihi = ihi; out.done = ihi < 0;
+    out.ilo = out.nb ? out.blo[0] : 0;
+    out.ihi = out.nb ? out.bhi[0] : -1;
+    out.done = out.nb == 0;
     return slot;
   }
   void scan_wait(int slot, ScanInfo& info) { info = scan_ring[slot]; }
 
   int slot_pairs[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  int latest_slot = -1;
+  int slot_seq[8] = {0, 0, 0, 0, 0, 0, 0, 0}, slot_lo[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  int shift_seq = 0;
   void shifts_request(int slot, int lo, int m, double perturb, bool /*fence*/) {
     std::vector<double> buf((size_t)p * m * m);
     std::vector<psdo::Mat> Hm(p), Zm(p);
@@ -117,7 +119,9 @@ struct EmuBackend {
     if (pairs.empty()) pairs.assign((size_t)8 * 66 * 4, 0.0);
     if (getenv("MS_EMUL_VERBOSE")) fprintf(stderr, "[emul] shifts slot %d lo %d m %d info %d\n", slot, lo, m, inf);
     slot_pairs[slot] = pair_shifts(lre.data(), lim.data(), inf, m, perturb, pairs.data() + (size_t)pair_offset(slot) * 4);
-    if (slot_pairs[slot] > 0) latest_slot = slot;  // the emulation completes a request at once
+    // the emulation completes a request at once
+    slot_lo[slot] = lo;
+    slot_seq[slot] = (slot_pairs[slot] > 0) ? ++shift_seq : 0;
   }
 
 
@@ -182,9 +186,16 @@ struct EmuBackend {
     std::vector<double> Hw((size_t)p * W * LD), Uw((size_t)p * W * LD);
     for (int w = 0; w < cnt; w++) {
       WinDesc& dd = plan[off + w];
-      if (dd.intro) {  // newest complete shift set, as the CUDA kernel picks it
-        dd.pair_off = latest_slot >= 0 ? pair_offset(latest_slot) : 0;
-        dd.npairs = latest_slot >= 0 ? slot_pairs[latest_slot] : 0;
+      if (dd.intro) {  // newest complete shift set of this block, as the CUDA kernel picks it
+        int best = -1, bseq = 0, any = -1, aseq = 0;
+        for (int k = 0; k < 8; k++) {
+          if (slot_seq[k] <= 0) continue;
+          if (slot_lo[k] >= dd.ilo && slot_lo[k] <= dd.ihi && slot_seq[k] > bseq) { best = k; bseq = slot_seq[k]; }
+          if (slot_seq[k] > aseq) { any = k; aseq = slot_seq[k]; }
+        }
+        const int sl = best >= 0 ? best : any;
+        dd.pair_off = sl >= 0 ? pair_offset(sl) : 0;
+        dd.npairs = sl >= 0 ? slot_pairs[sl] : 0;
       }
       const WinDesc& d = dd;
       if (getenv("MS_EMUL_VERBOSE"))
@@ -318,6 +329,7 @@ int ms_emul_run(int n, int p, double* Hbuf, double* Zbuf, int wantT, int wantZ, 
     cfg.max_rounds = be.max_rounds + 4;
   }
   if (const char* ev = getenv("MS_EMUL_LAG")) cfg.lag = atoi(ev);
+  if (const char* ev = getenv("MS_EMUL_MAXBLOCKS")) cfg.max_blocks = atoi(ev);
   if (const char* ev = getenv("MS_EMUL_BLOCKS")) cfg.shift_blocks = atoi(ev);
   if (const char* ev = getenv("MS_EMUL_AHEAD")) cfg.sets_ahead = atoi(ev);
   DriverStats ds;
