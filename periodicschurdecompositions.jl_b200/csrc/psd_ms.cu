@@ -373,8 +373,8 @@ struct CudaBackend {
     // consecutive tiles per CTA (U_j staged once): as many as still leave a few waves of CTAs
     // (about half of the tile slots of an item are empty: left of / below the window)
     int tpb = 1;
-    while (tpb < 8 && (long long)(tiles / (2 * tpb)) * cnt * p * 2 >= 6LL * sm_count) tpb *= 2;
-    if (const char* e = dbg_env("PSD_MS_TPB")) tpb = atoi(e);
+    while (tpb < 4 && (long long)(tiles / (2 * tpb)) * cnt * p * 2 >= 6LL * sm_count) tpb *= 2;  // (8: measured slower)
+    if (const char* e = dbg_env("PSD_MS_TPB")) { if (atoi(e) > 0) tpb = atoi(e); }
     if (part == 1) tpb = 1;
     A.tpb = tpb;
     // near part: two tiles right of the window, one above it
