@@ -420,6 +420,7 @@ struct CudaBackend {
     for (int j = 0; j < p; j++) C.H[j] = H[j];
     double* Ucur = ws->dU + (size_t)(nround & 1) * p * n * g.W;
     C.U = Ucur; C.shifts = ws->dPairs; C.shift_state = ws->dCtl + kCtlPairs; C.wins = hp_dev; C.wins_dev = dp; C.prof = dProf;
+    C.idle_count = ws->dCtl + kCtlMisc + 6;
     if (dProf && dbg_env("PSD_MS_STAMP")) {
       const int mode = atoi(dbg_env("PSD_MS_STAMP"));
       if (mode == 1) ms_stamp_kernel<<<1, 32, 0, st>>>(dProf, 8);
@@ -623,7 +624,7 @@ cudaError_t iterate(cudaStream_t caller, int sm_count, Workspace* ws, int n, int
     MS_CHECK(cudaFuncSetAttribute(ms_shifts_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
   }
   MS_CHECK(cudaMemsetAsync(ws->dCtl + kCtlPairs, 0, MS_SS_INTS * sizeof(int), st));
-  MS_CHECK(cudaMemsetAsync(ws->dCtl + kCtlMisc + 4, 0, sizeof(int), st));
+  MS_CHECK(cudaMemsetAsync(ws->dCtl + kCtlMisc + 4, 0, 3 * sizeof(int), st));  // scan ticket, -, idle windows
   long long* dprof = nullptr;
   if (dbg_env("PSD_MS_CHASE_PROF")) {
     cudaMalloc((void**)&dprof, 16 * sizeof(long long));
@@ -646,6 +647,11 @@ cudaError_t iterate(cudaStream_t caller, int sm_count, Workspace* ws, int n, int
     cudaStreamWaitEvent(caller, ws->evOut, 0);
   }
   if (!be.ok()) return be.err;
+  // windows whose packet had no bulge left (identity U_j): their updates were skipped
+  int idle_windows = 0;
+  cudaMemcpyAsync(&idle_windows, ws->dCtl + kCtlMisc + 6, sizeof(int), cudaMemcpyDeviceToHost, st);
+  cudaStreamSynchronize(st);
+  if (ds.windows > 0) ds.apply_flops *= 1.0 - (double)idle_windows / (double)ds.windows;
   if (res) {
     res->status = status;
     res->sweeps = ds.sweeps; res->rounds = ds.rounds; res->windows = ds.windows;
@@ -678,9 +684,9 @@ cudaError_t iterate(cudaStream_t caller, int sm_count, Workspace* ws, int n, int
             hp[6], hp[0] * k, hp[1] * k, hp[2] * k, hp[3] * k, hp[4] * k, hp[5] * k, hp[7] * k * 1e-3, hp[8] * k * 1e-3);
   }
   if (dbg_env("PSD_MS_VERBOSE"))
-    fprintf(stderr, "[psd ms] n %d p %d W %d NB %d nsw %d: status %d, %d sets, %lld rounds, %lld windows, %lld pairs, %d exceptional, %d final blocks, %.3f TFLOP applied; host %.3f s (blocked: scans %.3f, shifts %.3f, plan ring %.3f)\n",
+    fprintf(stderr, "[psd ms] n %d p %d W %d NB %d nsw %d: status %d, %d sets, %lld rounds, %lld windows, %lld pairs, %d exceptional, %d final blocks, %d idle windows, %.3f TFLOP applied; host %.3f s (blocked: scans %.3f, shifts %.3f, plan ring %.3f)\n",
             n, p, g.W, g.NB, cfg.nsw, status, ds.sweeps, ds.rounds, ds.windows, ds.shift_pairs, ds.exceptional,
-            ds.final_blocks, ds.apply_flops * 1e-12, t_drive, be.wait_scan, be.wait_shift, be.wait_plan);
+            ds.final_blocks, idle_windows, ds.apply_flops * 1e-12, t_drive, be.wait_scan, be.wait_shift, be.wait_plan);
   return cudaSuccess;
 }
 

@@ -86,6 +86,8 @@ struct WinDesc {
   int npairs;  // distinct shift pairs of the set
   int pair_off;  // first pair of the set in the pair buffer
   int intro;   // 1: bulges are introduced in this window (positions start at ilo - 1)
+  int idle;    // set by the chase kernel in the device copy: every U_j of the window is the identity
+               // (all bulges of the packet had been chased off), its updates are skipped
 };
 
 struct Ctx {

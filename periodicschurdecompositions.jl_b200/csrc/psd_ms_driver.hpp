@@ -236,6 +236,7 @@ int drive(Backend& be, const DriverConfig& cfg, DriverStats& st) {
     wins.clear();
     for (Packet& q : pk) {
       WinDesc w;
+      w.idle = 0;
       w.ilo = q.ilo; w.ihi = q.ihi; w.nbul = q.nbul; w.pair0 = q.pair0; w.npairs = q.npairs; w.pair_off = q.pair_off;
       if (q.hops == 0) {
         w.intro = 1; w.s = q.ilo; w.kbase = q.ilo - 1; w.T = D + 1 + 3 * (q.nbul - 1);

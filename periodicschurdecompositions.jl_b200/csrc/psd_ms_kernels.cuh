@@ -45,6 +45,7 @@ struct ChaseParams {
   const int* shift_state;  // per shift slot: number of pairs, sequence number (0: being computed), first source row
   const WinDesc* wins;   // this round's windows in mapped pinned host memory (written by the host)
   WinDesc* wins_dev;     // device copy made here for the update and scan kernels of the round
+  int* idle_count;       // number of windows found idle (statistics), or nullptr
   long long* prof;       // [8] cycle counters of CTA 0 (debug), or nullptr
 };
 
@@ -136,6 +137,7 @@ __global__ void __launch_bounds__(64 * MS_MAXNB, 1) ms_chase_kernel(ChaseParams 
   chase_window(c, ex);
   __syncthreads();
   const long long tk1 = ex.prof ? clock64() : 0;
+  int moved = 0;  // some U_j differs from the identity
   for (int j = 1; j <= p; j++) {
     double* dst = P.H[j - 1] + s + (size_t)s * n;
     const double* src = c.H(j);
@@ -144,8 +146,16 @@ __global__ void __launch_bounds__(64 * MS_MAXNB, 1) ms_chase_kernel(ChaseParams 
     for (int e = tid; e < wl * wl; e += nt) {
       const int r = e % wl, cc = e / wl;
       dst[r + (size_t)cc * n] = src[r + (size_t)cc * LD];
-      ud[r + (size_t)cc * W] = u[r + (size_t)cc * LD];
+      const double uv = u[r + (size_t)cc * LD];
+      ud[r + (size_t)cc * W] = uv;
+      moved |= (uv != ((r == cc) ? 1.0 : 0.0));
     }
+  }
+  // a packet whose bulges have all been chased off leaves identities: tell the update kernels
+  moved = __syncthreads_or(moved);
+  if (tid == 0 && !moved) {
+    P.wins_dev[blockIdx.x].idle = 1;
+    if (P.idle_count) atomicAdd(P.idle_count, 1);
   }
   if (ex.prof) {
     __syncthreads();
@@ -410,7 +420,7 @@ __global__ void __launch_bounds__(256, 2) ms_apply_kernel(ApplyParams P) {
     }
   };
   const int kfirst = ka + blockIdx.x * P.tpb;
-  const bool has_work = kfirst < kb;
+  const bool has_work = kfirst < kb && !d.idle;
   if (has_work) {
   const double* Ug = P.U + (size_t)(j - 1) * n * P.W + (size_t)s * P.W;
   // bulk copies need 16-byte aligned runs
@@ -710,6 +720,7 @@ __global__ void __launch_bounds__(1024) ms_blocklist_kernel(BlockParams P) {
       const int slot = atomicAdd(&s_cnt, 1);
       WinDesc d;
       d.s = k; d.wl = m; d.kbase = 0; d.nbul = 0; d.T = 0; d.ilo = k; d.ihi = e; d.pair0 = 0; d.npairs = 1; d.intro = 0;
+      d.idle = 0;
       P.list[slot] = d;
     }
   }

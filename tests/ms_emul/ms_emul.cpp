@@ -229,6 +229,32 @@ struct EmuBackend {
               if (!std::isfinite(c.U(j + 1)[r + (size_t)cc * LD])) { if (!bad) fprintf(stderr, "[emul] non-finite U_%d(%d,%d) win s %d\n", j + 1, r, cc, d.s); bad++; }
             }
       }
+      if (getenv("MS_EMUL_COUNTID")) {
+        bool ident = true;
+        for (int j = 0; j < p && ident; j++)
+          for (int cc = 0; cc < d.wl && ident; cc++)
+            for (int r = 0; r < d.wl; r++)
+              if (c.U(j + 1)[r + (size_t)cc * LD] != ((r == cc) ? 1.0 : 0.0)) { ident = false; break; }
+        static long long nid = 0, nall = 0;
+        nall++;
+        nid += ident;
+        if (nall % 500 == 0) fprintf(stderr, "[emul] identity windows %lld of %lld\n", nid, nall);
+      }
+      if (getenv("MS_EMUL_DUMPU") && nrounds == atoi(getenv("MS_EMUL_DUMPU"))) {
+        // zero pattern of the accumulated window transformations in 4 x 8 blocks (k-step x fragment)
+        for (int j = 0; j < p; j++) {
+          fprintf(stderr, "[emul] U_%d of window s %d wl %d intro %d T %d (rows = k in steps of 4, columns in steps of 8; . = all zero)\n", j + 1, d.s, d.wl, d.intro, d.T);
+          for (int k0 = 0; k0 < d.wl; k0 += 4) {
+            for (int m0 = 0; m0 < d.wl; m0 += 8) {
+              bool nzb = false;
+              for (int k = k0; k < std::min(d.wl, k0 + 4); k++)
+                for (int m = m0; m < std::min(d.wl, m0 + 8); m++) nzb |= (c.U(j + 1)[k + (size_t)m * LD] != 0.0);
+              fputc(nzb ? '#' : '.', stderr);
+            }
+            fputc('\n', stderr);
+          }
+        }
+      }
       for (int j = 0; j < p; j++) {
         double* ud = Uptr(j, d.s);
         for (int cc = 0; cc < d.wl; cc++)
