@@ -585,14 +585,14 @@ cudaError_t iterate(cudaStream_t caller, int sm_count, Workspace* ws, int n, int
   MS_CHECK(grow(ws->dU, ws->capU, (size_t)2 * p * n * g.W * sizeof(double)));
   DriverConfig cfg;
   cfg.n = n; cfg.p = p; cfg.wantT = wantT; cfg.wantZ = be.wantZ;
-  // shift window: limited by the shared memory of one CTA
-  // Shift window: 24 x 24.  Larger windows give better shifts, but the one-CTA computation then
-  // stays resident for ~14 ms (64 x 64), and while such a kernel is resident the first launch of
-  // every round on the main stream was measured to start 100 - 140 us late (24 x 24: 23 us); the
-  // shift sets are stale by dozens of rounds anyway, and the pairs used per eigenvalue do not grow
-  // (profiles/r2_large_n_tuning.md).
-  int nsw = 24;
-  while (nsw > 16 && ((size_t)((rp_small_doubles(nsw, p) + 1) & ~1LL) + (size_t)p * (nsw + 1) * nsw) * 8 > 200 * 1024) nsw -= 8;
+  // Shift window: 12 x 12 (six shift pairs per set).  Larger windows give better Ritz values, but
+  // the one-CTA computation takes longer (64 x 64: 14 ms, during which the first launch of every
+  // round on the main stream was measured to start 100 - 140 us late), and with dozens of packets
+  // in flight every set is stale by many rounds when it is used: measured on three shapes, the
+  // shift pairs per eigenvalue and the run time FALL from 48 over 24 to 12 (N = 4096, p = 4:
+  // iteration 0.86 / 0.65 / 0.59 s; profiles/r2_large_n_tuning.md).
+  int nsw = 12;
+  while (nsw > 8 && ((size_t)((rp_small_doubles(nsw, p) + 1) & ~1LL) + (size_t)p * (nsw + 1) * nsw) * 8 > 200 * 1024) nsw -= 4;
   cfg.nsw = nsw;
   if (const char* ev = dbg_env("PSD_MS_REP")) cfg.rep_max = std::max(1, atoi(ev));
   if (const char* ev = dbg_env("PSD_MS_AHEAD")) cfg.sets_ahead = std::max(1, atoi(ev));
@@ -600,7 +600,12 @@ cudaError_t iterate(cudaStream_t caller, int sm_count, Workspace* ws, int n, int
   if (const char* ev = dbg_env("PSD_MS_MAXBLOCKS")) cfg.max_blocks = std::max(1, atoi(ev));
   if (const char* ev = dbg_env("PSD_MS_NEWDELAY")) cfg.new_block_delay = std::max(0, atoi(ev));
   if (const char* ev = dbg_env("PSD_MS_LAG")) cfg.lag = std::max(1, std::min(kPlanRing - 2, atoi(ev)));
-  if (const char* ev = dbg_env("PSD_MS_NSW")) cfg.nsw = std::max(2, std::min(nsw, atoi(ev)));
+  if (const char* ev = dbg_env("PSD_MS_NSW")) {
+    // (the snapshot buffers hold 64 x 64; the far-stream argument needs nsw <= W)
+    int want = std::max(2, std::min(std::min(64, g.W), atoi(ev)));
+    while (want > 16 && ((size_t)((rp_small_doubles(want, p) + 1) & ~1LL) + (size_t)p * (want + 1) * want) * 8 > 200 * 1024) want -= 8;
+    cfg.nsw = want;
+  }
   MS_CHECK(grow(ws->dSnap, ws->capSnap, (size_t)kShiftSlots * p * 64 * 64 * sizeof(double)));
   for (int k = 0; k < kShiftSlots; k++) { be.tm_side[k].on = profile != 0; be.tm_side[k].st = ws->side[k]; }
   be.chase_smem = ((size_t)2 * p * g.W * g.LD + (size_t)MS_MAXNB * MS_MAXP * MB_STRIDE) * sizeof(double);

@@ -52,7 +52,7 @@ struct DriverStats {
 struct DriverConfig {
   int n = 0, p = 0;
   int wantT = 1, wantZ = 1;
-  int nsw = 24;         // order of the shift window (<= 64, limited by shared memory for large p)
+  int nsw = 12;         // order of the shift window (<= 64, limited by shared memory for large p)
   int rep_max = 2;      // a new shift set is requested after (pairs of a set) x rep_max bulges
   int sets_ahead = 6;   // (unused by the free-running shift supply; kept for the emulation switches)
   int lag = 3;          // rounds between a scan and the plan that uses it
@@ -60,7 +60,7 @@ struct DriverConfig {
   int scan_every = 1;   // the subdiagonal is scanned after every scan_every-th round
   long long max_rounds = 0;  // 0: 64 + 40 n / D
   int max_blocks = 4;   // active diagonal blocks worked on concurrently (1: only the lowest, like the reference)
-  int new_block_delay = 6;  // rounds between the first shift request of a new block and its first packet
+  int new_block_delay = 4;  // rounds between the first shift request of a new block and its first packet
                             // (its own shift set is then normally complete; measured in profiles/r2_large_n_tuning.md)
 };
 
