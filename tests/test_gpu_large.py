@@ -135,10 +135,13 @@ def test_large_badly_scaled(psd, oracle, scale):
     _check_hess(As[0], H[0], Q[0])
 
 
-@pytest.mark.parametrize("n,p,left", [(300, 1, False), (260, 2, True), (280, 6, False), (200, 9, True), (230, 12, False)])
+@pytest.mark.parametrize("n,p,left", [(300, 1, False), (260, 2, True), (280, 6, False), (200, 9, True), (230, 12, False),
+                                      (251, 4, False), (197, 3, True)])
 def test_large_multishift_shapes(psd, oracle, n, p, left):
     """the multishift iteration at every window geometry (W = 64 for p <= 3, 56, 48, 40, 32 for
-    larger periods), :R and :L, held to the reference's predicates and to the oracle's eigenvalues"""
+    larger periods), :R and :L, held to the reference's predicates and to the oracle's eigenvalues;
+    the odd orders take the update kernel's unaligned staging path (8-byte cp.async instead of bulk
+    copies)"""
     A = oracle.gen_real(4000 + 10 * p + n, n, p, 1)
     lr = "L" if left else "R"
     T, Z, lam, info = psd.pschur_batched(A, lr)
