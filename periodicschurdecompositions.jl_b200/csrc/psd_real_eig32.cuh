@@ -137,10 +137,38 @@ PSD_DEV double refl_u(double x0, double x1, double x2, double& u0, double& g, bo
   } else {
     bad = bad || (!ok && ssq != 0.0);
   }
+#ifndef PSD_REFL_SERIAL
+  // u'u / 2 = nn + |x0| nrm (with nrm^2 = nn), so g = -1 / (nn + |x0| nrm) needs no w0, and the
+  // reciprocal seed can be taken from the 20-bit rsqrt seed while the rsqrt is still being
+  // refined; its own Newton steps then use the exact denominator.  Shortens the dependent chain
+  // of a reflector from ~175 to ~125 cycles.
+  double r, y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(nn));
+  const double ax = fabs(x0);
+  {
+    const double d0 = fma(nn * r, ax, nn);
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d0));
+  }
+  const double hx = 0.5 * nn;
+  double e = fma(-hx * r, r, 0.5);
+  r = fma(r, e, r);
+  e = fma(-hx * r, r, 0.5);
+  r = fma(r, e, r);
+  const double nrm = nn * r;
+  const double dd = fma(nrm, ax, nn);
+  double f = fma(-dd, y, 1.0);
+  y = fma(y, f, y);
+  f = fma(-dd, y, 1.0);
+  y = fma(y, f, y);
+  const double gg = -y;
+  const double beta = -copysign(nrm, x0);
+  const double w0 = x0 - beta;
+#else
   const double nrm = nn * fast_rsqrt(nn);
   const double beta = -copysign(nrm, x0);
   const double w0 = x0 - beta;
   const double gg = -2.0 * fast_rcp(fma(w0, w0, ssq));
+#endif
   if (SAFE) {
     u0 = w0;
     g = gg;
