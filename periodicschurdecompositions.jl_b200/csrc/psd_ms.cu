@@ -43,6 +43,7 @@ struct Workspace {
   cudaEvent_t evIn = nullptr, evOut = nullptr;   // ordering against the caller's stream
   cudaEvent_t evSnap[kShiftSlots] = {nullptr}, evShift[kShiftSlots] = {nullptr};
   cudaStream_t side[kShiftSlots] = {nullptr};
+  long long scan_counter = 0;                    // scans issued so far (all calls)
   cudaStream_t scan = nullptr;                   // stand-alone deflation scans (split rounds), high priority
   cudaStream_t far = nullptr;                    // far window updates of a round, concurrent with the next chase
   cudaEvent_t evNear[2] = {nullptr, nullptr}, evFar[2] = {nullptr, nullptr}, evChase[2] = {nullptr, nullptr};
@@ -268,7 +269,9 @@ struct CudaBackend {
   int next_scan_slot() {
     const int slot = (int)(nscan % kScanRing);
     nscan++;
-    scan_seq[slot] = (int)(nscan & 0x3fffffff) + 1;
+    // sequence numbers are unique over the life of the workspace: the result slots keep the values
+    // of earlier calls, and a repeated number would make the host take a stale result for the new one
+    scan_seq[slot] = (int)(++ws->scan_counter & 0x3fffffff) + 1;
     return slot;
   }
   int scan_async(const WinDesc* /*host copy, unused here*/, int cnt, int nmin) {

@@ -193,3 +193,18 @@ def test_large_dev_calls_on_two_streams(psd, oracle):
     _, _, lam, info = psd.pschur_batched(A.cpu().numpy(), "R", wantT=False, wantZ=False, handle=h)
     got = E.cpu().numpy()
     assert np.array_equal(got[..., 0] + 1j * got[..., 1], lam)
+
+
+def test_large_back_to_back_calls(psd):
+    """calls of different shapes on one handle: the scan-result slots of the workspace keep the
+    values of earlier calls, so their sequence numbers must never repeat (a second call with 17 - 31
+    scans used to leave numbers that the third call took for its own results: residual 1e14 eps)"""
+    rng = np.random.default_rng(7)
+    for n, p, graded in [(192, 4, False), (192, 4, True), (333, 3, False), (333, 3, True), (260, 2, False)]:
+        A = rng.uniform(-1.0, 1.0, size=(1, p, n, n))
+        if graded:
+            A *= np.logspace(-3, 3, n)[None, None, :, None]
+        T, Z, lam, info = psd.pschur_batched(A, "R")
+        st = psd.default_handle().large_stats()
+        assert info[0] == 0 and st["status"] == 0, (n, p, graded, st)
+        K.pschur_check(A[0], T[0], Z[0], lam[0], tol=max(40.0, 0.3 * n), check_lambda=False)  # (BASELINE gate: 10 n)
