@@ -114,6 +114,14 @@ int psd_rpschur_hessut_batched(psd_handle_t handle, int n, int p, int64_t batch,
                                int wantZ, int maxitfac, double* A, double* Z, double* eig,
                                int32_t* info);
 
+/* Same, with the Schur vectors accumulated onto orthogonal matrices of the caller: on entry Q
+ * holds Q_1..Q_p of an earlier reduction (storage layout of A), on exit Q_j Z_j.
+ * Replaces pschur!(H1, Hs; Q = Q, wantZ = true, ...) (the `Q` keyword of the inner method,
+ * PeriodicSchurDecompositions.jl:326, 432-437, as used by the Krylov-Schur driver,
+ * krylov.jl:583-591). */
+int psd_rpschur_hessut_q_batched(psd_handle_t handle, int n, int p, int64_t batch, int wantT,
+                                 int maxitfac, double* A, double* Q, double* eig, int32_t* info);
+
 /* Periodic Hessenberg-triangular reduction only, batched (device or host buffers).
  * Replaces phessenberg!(A) (PeriodicSchurDecompositions.jl:213-259) followed by the explicit
  * Q materialisation of the driver (:136-140): on return A holds H_1 (upper Hessenberg) and

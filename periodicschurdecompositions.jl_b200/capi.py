@@ -20,6 +20,7 @@ EXPORTED_SYMBOLS = [
     "psd_rpschur_batched",
     "psd_rpschur_batched_dev",
     "psd_rpschur_hessut_batched",
+    "psd_rpschur_hessut_q_batched",
     "psd_rphess_batched",
     "psd_cpschur_batched",
     "psd_cpschur_hessut_batched",
@@ -75,6 +76,8 @@ def lib():
                                               C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp]
         L.psd_rpschur_hessut_batched.argtypes = [vp, C.c_int, C.c_int, C.c_int64, C.c_int,
                                                  C.c_int, C.c_int, vp, vp, vp, vp]
+        L.psd_rpschur_hessut_q_batched.argtypes = [vp, C.c_int, C.c_int, C.c_int64, C.c_int,
+                                                   C.c_int, vp, vp, vp, vp]
         L.psd_rphess_batched.argtypes = [vp, C.c_int, C.c_int, C.c_int64, C.c_int, vp, vp]
         L.psd_cpschur_batched.argtypes = [vp, C.c_int, C.c_int, C.c_int64, C.c_int, vp, C.c_int,
                                           C.c_int, C.c_int, vp, vp, vp, vp, vp, vp]

@@ -696,6 +696,18 @@ int run_real_shard(psd_handle_s* h, Device& dev, const RealCall& rc, long long f
       PSD_SHARD_CUDA(cudaMemcpyAsync(s.dA, s.hA, bytesA, cudaMemcpyHostToDevice, s.stream));
     }
     *bytes_h2d += (int64_t)bytesA;
+    if (wantZ && rc.z_preset) {
+      // Z enters as the caller's Q_j (accumulated onto)
+      double* srcZ = Z + (size_t)(first + off) * per;
+      if (pinned) {
+        PSD_SHARD_CUDA(cudaMemcpyAsync(s.dZ, srcZ, bytesA, cudaMemcpyHostToDevice, s.stream));
+      } else {
+        if ((e = ensure_pinned(s.hZ, s.hcapZ, bytesA))) return drain_slots(dev, e);
+        std::memcpy(s.hZ, srcZ, bytesA);
+        PSD_SHARD_CUDA(cudaMemcpyAsync(s.dZ, s.hZ, bytesA, cudaMemcpyHostToDevice, s.stream));
+      }
+      *bytes_h2d += (int64_t)bytesA;
+    }
     e = launch_real(h, dev, s, s.stream, rc, nb, s.dA, wantZ ? s.dZ : nullptr, s.dEig, s.dInfo);
     if (e) return drain_slots(dev, e);
     // results
@@ -1110,6 +1122,14 @@ int psd_rpschur_hessut_batched(psd_handle_t h, int n, int p, int64_t batch, int 
                                int maxitfac, double* A, double* Z, double* eig, int32_t* info) {
   RealCall rc{n, p, 0, wantT != 0, wantZ != 0, maxitfac, 0, 1};
   return run_real_host(h, rc, batch, A, Z, eig, info);
+}
+
+int psd_rpschur_hessut_q_batched(psd_handle_t h, int n, int p, int64_t batch, int wantT, int maxitfac, double* A,
+                                 double* Q, double* eig, int32_t* info) {
+  if (!Q) return fail(PSD_ERR_BAD_ARG, "Q must not be NULL");
+  RealCall rc{n, p, 0, wantT != 0, 1, maxitfac, 0, 1};
+  rc.z_preset = 1;
+  return run_real_host(h, rc, batch, A, Q, eig, info);
 }
 
 int psd_rphess_batched(psd_handle_t h, int n, int p, int64_t batch, int wantQ, double* A, double* Q) {

@@ -220,6 +220,16 @@ __global__ void rpschur_kernel(RpschurParams P) {
             Zj[r + (size_t)cc * c.ldz] = (r == cc) ? 1.0 : 0.0;
           }
         }
+      } else if (wantZ && P.use_smem) {
+        // preset Q_j of the caller (rightwards order only): stage them next to the factors
+        for (int j = 1; j <= p; j++) {
+          const double* src = Zb + (size_t)(j - 1) * nn;
+          double* Zj = c.Zp(j);
+          for (int e = tid; e < (int)nn; e += nt) {
+            int r = e % n, cc = e / n;
+            Zj[r + (size_t)cc * c.ldz] = src[e];
+          }
+        }
       }
       // enforce structure: :380-387, :406
       for (int j = 1; j <= p; j++) {

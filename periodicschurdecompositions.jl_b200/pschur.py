@@ -182,15 +182,23 @@ def pschur_batched(A: np.ndarray, lr="R", wantZ: bool = True, wantT: bool = True
 
 
 def pschur_hessut_batched(H: np.ndarray, wantZ: bool = True, wantT: bool = True, maxitfac: int = 30,
-                          handle: Optional[Handle] = None):
+                          handle: Optional[Handle] = None, Q: Optional[np.ndarray] = None):
     """Inner method pschur!(H1, Hs; ...) (PeriodicSchurDecompositions.jl:322) on Hessenberg /
-    triangular input, rightwards order, Z starting from the identity."""
+    triangular input, rightwards order, Z starting from the identity - or, with Q given (storage
+    layout of H), accumulated onto it (the `Q` keyword of the reference, :326): Z = Q_j Z_j."""
     h = handle or default_handle()
     batch, p, n, _ = H.shape
     T = np.ascontiguousarray(H).copy()
-    Z = np.empty_like(T) if wantZ else None
     vals = np.empty((batch, n), dtype=np.complex128)
     info = np.empty(batch, dtype=np.int32)
+    if Q is not None:
+        if Q.shape != H.shape:
+            raise ValueError("Q must have the shape of H")
+        Z = np.ascontiguousarray(Q, dtype=np.float64).copy()
+        check(lib().psd_rpschur_hessut_q_batched(h.ptr, n, p, batch, int(wantT), int(maxitfac),
+                                                 _vp(T), _vp(Z), _vp(vals), _vp(info)))
+        return T, Z, vals, info
+    Z = np.empty_like(T) if wantZ else None
     check(lib().psd_rpschur_hessut_batched(h.ptr, n, p, batch, int(wantT), int(wantZ),
                                            int(maxitfac), _vp(T), _vp(Z), _vp(vals), _vp(info)))
     return T, Z, vals, info

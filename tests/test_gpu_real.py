@@ -115,6 +115,33 @@ def test_hessut_entry(psd, oracle):
             _eig_gate(lo, lam[b], n)
 
 
+def test_hessut_entry_q_preset(psd, oracle):
+    """the `Q` keyword of the inner method (PeriodicSchurDecompositions.jl:326; krylov.jl:583-591):
+    Schur vectors accumulated onto the caller's orthogonal Q_j.  Check: the decomposition holds for
+    B_j = Q_j H_j Q_{j+1}' with the returned vectors, and they equal Q_j Z_j of the plain call."""
+    rng = np.random.default_rng(5)
+    for (n, p) in [(5, 1), (7, 3), (33, 2), (50, 3)]:
+        A = oracle.gen_real(21, n, p, 3)
+        for b in range(3):
+            for j in range(p):
+                A[b, j] = np.triu(K.M(A[b, j]), -1 if j == 0 else 0).T
+        Q = np.empty_like(A)
+        for b in range(3):
+            for j in range(p):
+                Q[b, j] = np.linalg.qr(rng.standard_normal((n, n)))[0].T  # storage = transpose of the matrix
+        T0, Z0, lam0, info0 = psd.pschur_hessut_batched(A)
+        T, Z, lam, info = psd.pschur_hessut_batched(A, Q=Q)
+        assert (info == 0).all() and (info0 == 0).all()
+        for b in range(3):
+            B = np.empty_like(A[b])
+            for j in range(p):
+                B[j] = (K.M(Q[b, j]) @ K.M(A[b, j]) @ K.M(Q[b, (j + 1) % p]).T).T
+            K.pschur_check(B, T[b], Z[b], lam[b], left=False, check_lambda=False)
+            for j in range(p):
+                assert np.allclose(K.M(Z[b, j]), K.M(Q[b, j]) @ K.M(Z0[b, j]), atol=200 * n * EPS)
+            assert np.array_equal(T[b], T0[b]) and np.array_equal(lam[b], lam0[b])
+
+
 def test_reduction_only(psd, oracle):
     # test/runtests.jl:14-50 "Periodic Hessenberg"
     for (n, p) in [(5, 1), (5, 2), (5, 5), (32, 8)]:
