@@ -185,4 +185,53 @@ function gpschur_batched!(A::Array{T, 4}, S::AbstractVector{Bool}, lr::Symbol = 
     return Z, α, β, αscale, info
 end
 
+"""
+    pschur_hessut_batched!(H::Array{Float64,4}; Q = nothing, wantT = true, maxitfac = 30)
+        -> (Z, values, info)
+
+Inner method of the reference on Hessenberg-triangular input (`pschur!(H1, Hs; Q, wantZ, wantT)`,
+PeriodicSchurDecompositions.jl:322), batched, rightwards order.  With `Q` (same shape as `H`) the
+Schur vectors are accumulated onto it, as the `Q` keyword of the reference does (:326, 432-437;
+used by the Krylov-Schur driver, krylov.jl:583-591); `Q` is overwritten and returned.
+"""
+function pschur_hessut_batched!(H::Array{Float64, 4}; Q::Union{Nothing, Array{Float64, 4}} = nothing,
+                                wantT::Bool = true, maxitfac = 30, handle::Handle = default_handle())
+    n, n2, p, B = size(H)
+    n == n2 || throw(DimensionMismatch())
+    vals = Matrix{ComplexF64}(undef, n, B)
+    info = Vector{Int32}(undef, B)
+    if Q === nothing
+        Z = similar(H)
+        rc = ccall((:psd_rpschur_hessut_batched, libpsd), Cint,
+                   (Ptr{Cvoid}, Cint, Cint, Int64, Cint, Cint, Cint, Ptr{Float64}, Ptr{Float64},
+                    Ptr{ComplexF64}, Ptr{Int32}),
+                   handle.ptr, n, p, B, wantT, true, maxitfac, H, Z, vals, info)
+    else
+        size(Q) == size(H) || throw(DimensionMismatch("Q must have the shape of H"))
+        Z = Q
+        rc = ccall((:psd_rpschur_hessut_q_batched, libpsd), Cint,
+                   (Ptr{Cvoid}, Cint, Cint, Int64, Cint, Cint, Ptr{Float64}, Ptr{Float64},
+                    Ptr{ComplexF64}, Ptr{Int32}),
+                   handle.ptr, n, p, B, wantT, maxitfac, H, Z, vals, info)
+    end
+    rc == 0 || error(lasterror(rc))
+    return Z, vals, info
+end
+
+"""
+    large_stats(handle) -> NamedTuple
+
+Report of the last large-N (N >= 192) real decomposition on `handle`: status (0 = the multishift
+iteration finished), shift sets, rounds, window-rounds, shift pairs, exceptional sets, final blocks,
+kernel launches - the counterpart of the `niter` report of the reference (:458-459, 1077).
+"""
+function large_stats(handle::Handle = default_handle())
+    out = Vector{Float64}(undef, 16)
+    rc = ccall((:psd_large_stats, libpsd), Cint, (Ptr{Cvoid}, Ptr{Float64}), handle.ptr, out)
+    rc == 0 || error(lasterror(rc))
+    return (status = Int(out[1]), sets = Int(out[2]), rounds = Int(out[3]), windows = Int(out[4]),
+            shift_pairs = Int(out[5]), exceptional = Int(out[6]), final_blocks = Int(out[7]),
+            launches = Int(out[8]), update_flops = out[9])
+end
+
 end # module
