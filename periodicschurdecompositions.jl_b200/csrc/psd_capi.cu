@@ -671,9 +671,30 @@ int run_real_shard(psd_handle_s* h, Device& dev, const RealCall& rc, long long f
   long long chunk = std::max<long long>(1, (2048LL << 20) / (long long)(per * sizeof(double)));
   if (!pinned) chunk = std::max<long long>(1, std::min<long long>(chunk, (512LL << 20) / (long long)(per * sizeof(double))));
   chunk = std::min(chunk, count);
+  // pageable buffers are staged through pinned ones by the host: at least four chunks, so that the
+  // host copies of one chunk overlap the device work of the others
+  if (!pinned && (size_t)count * per * sizeof(double) >= (64u << 20) && count >= 8)
+    chunk = std::min(chunk, (count + 3) / 4);
   int si = 0;
   int rcode = PSD_OK;
-  long long nb = 0, next = (count > chunk) ? std::max<long long>(1, chunk / 16) : chunk;
+  // results of a pageable call that still sit in a slot's pinned buffers
+  struct Pending {
+    bool any = false;
+    double *dstA = nullptr, *dstZ = nullptr, *dstEig = nullptr;
+    int32_t* dstInfo = nullptr;
+    size_t bytesA = 0, bytesEig = 0, bytesInfo = 0;
+  } pend[kSlotsPerDevice];
+  auto flush = [&](int k) {
+    Pending& q = pend[k];
+    if (!q.any) return;
+    Slot& s = dev.slots[k];
+    if (q.dstA) std::memcpy(q.dstA, s.hA, q.bytesA);
+    if (q.dstZ) std::memcpy(q.dstZ, s.hZ, q.bytesA);
+    if (q.dstEig) std::memcpy(q.dstEig, s.hEig, q.bytesEig);
+    if (q.dstInfo) std::memcpy(q.dstInfo, s.hInfo, q.bytesInfo);
+    q = Pending();
+  };
+  long long nb = 0, next = (count > chunk) ? std::max<long long>(1, chunk / (pinned ? 16 : 2)) : chunk;
   for (long long off = 0; off < count && rcode == PSD_OK; off += nb, si = (si + 1) % kSlotsPerDevice) {
     nb = std::min(next, count - off);
     next = std::min(chunk, next * 4);
@@ -681,6 +702,7 @@ int run_real_shard(psd_handle_s* h, Device& dev, const RealCall& rc, long long f
     if (!s.stream) PSD_SHARD_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
     // the slot's previous chunk must have fully drained before its buffers are reused
     PSD_SHARD_CUDA(cudaStreamSynchronize(s.stream));
+    flush(si);
     int e;
     if ((e = ensure_dev(s.dA, s.capA, nb * per * sizeof(double)))) return drain_slots(dev, e);
     if (wantZ && (e = ensure_dev(s.dZ, s.capZ, nb * per * sizeof(double)))) return drain_slots(dev, e);
@@ -729,18 +751,23 @@ int run_real_shard(psd_handle_s* h, Device& dev, const RealCall& rc, long long f
       if (wantZ) PSD_SHARD_CUDA(cudaMemcpyAsync(s.hZ, s.dZ, bytesA, cudaMemcpyDeviceToHost, s.stream));
       PSD_SHARD_CUDA(cudaMemcpyAsync(s.hEig, s.dEig, bytesEig, cudaMemcpyDeviceToHost, s.stream));
       PSD_SHARD_CUDA(cudaMemcpyAsync(s.hInfo, s.dInfo, bytesInfo, cudaMemcpyDeviceToHost, s.stream));
-      // pageable destination: drain this slot now and copy out (the other slot keeps the
-      // GPU busy meanwhile)
-      PSD_SHARD_CUDA(cudaStreamSynchronize(s.stream));
-      if (outT) std::memcpy(srcA, s.hA, bytesA);
-      if (wantZ) std::memcpy(dstZ, s.hZ, bytesA);
-      if (dstEig) std::memcpy(dstEig, s.hEig, bytesEig);
-      if (dstInfo) std::memcpy(dstInfo, s.hInfo, bytesInfo);
+      // pageable destination: copied out of the pinned buffers when the slot is drained (before its
+      // next use, or at the end), so that the host copies overlap the device work of the other slots
+      Pending& q = pend[si];
+      q.any = true;
+      q.dstA = outT ? srcA : nullptr;
+      q.dstZ = wantZ ? dstZ : nullptr;
+      q.dstEig = dstEig;
+      q.dstInfo = dstInfo;
+      q.bytesA = bytesA; q.bytesEig = bytesEig; q.bytesInfo = bytesInfo;
     }
     *bytes_d2h += (int64_t)((outT ? bytesA : 0) + (wantZ ? bytesA : 0) + bytesEig + bytesInfo);
   }
   for (int k = 0; k < kSlotsPerDevice; k++)
-    if (dev.slots[k].stream) PSD_SHARD_CUDA(cudaStreamSynchronize(dev.slots[k].stream));
+    if (dev.slots[k].stream) {
+      PSD_SHARD_CUDA(cudaStreamSynchronize(dev.slots[k].stream));
+      flush(k);
+    }
   return rcode;
 }
 
@@ -919,11 +946,31 @@ int run_gen_shard(psd_handle_s* h, Device& dev, const GenCall& gc, long long fir
   // chunks above this size are copied straight from / to pageable memory (no pinned staging copy)
   const size_t kStageLimit = 1ULL << 30;
   int si = 0;
+  // results of a staged (pageable) chunk that still sit in a slot's pinned buffers: copied out when
+  // the slot is drained, so that the host copies overlap the device work of the other slots
+  struct Pending {
+    bool any = false;
+    char *dstA = nullptr, *dstZ = nullptr, *dstX[3] = {nullptr, nullptr, nullptr};
+    int32_t* dstInfo = nullptr;
+    size_t bytesA = 0, bytesX[3] = {0, 0, 0}, bytesInfo = 0;
+  } pend[kSlotsPerDevice];
+  auto flush = [&](int k) {
+    Pending& q = pend[k];
+    if (!q.any) return;
+    Slot& s = dev.slots[k];
+    if (q.dstA) std::memcpy(q.dstA, s.hA, q.bytesA);
+    if (q.dstZ) std::memcpy(q.dstZ, s.hZ, q.bytesA);
+    for (int t = 0; t < 3; t++)
+      if (q.dstX[t]) std::memcpy(q.dstX[t], s.hX[t], q.bytesX[t]);
+    if (q.dstInfo) std::memcpy(q.dstInfo, s.hInfo, q.bytesInfo);
+    q = Pending();
+  };
   for (long long off = 0; off < count; off += chunk, si = (si + 1) % kSlotsPerDevice) {
     const long long nb = std::min(chunk, count - off);
     Slot& s = dev.slots[si];
     if (!s.stream) PSD_SHARD_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
     PSD_SHARD_CUDA(cudaStreamSynchronize(s.stream));
+    flush(si);
     int e;
     const size_t bytesA = nb * perB;
     if ((e = ensure_dev(s.dA, s.capA, bytesA))) return drain_slots(dev, e);
@@ -966,16 +1013,21 @@ int run_gen_shard(psd_handle_s* h, Device& dev, const GenCall& gc, long long fir
       for (int k = 0; k < 3; k++)
         PSD_SHARD_CUDA(cudaMemcpyAsync(s.hX[k], s.dX[k], nb * xB[k], cudaMemcpyDeviceToHost, s.stream));
       PSD_SHARD_CUDA(cudaMemcpyAsync(s.hInfo, s.dInfo, bytesInfo, cudaMemcpyDeviceToHost, s.stream));
-      PSD_SHARD_CUDA(cudaStreamSynchronize(s.stream));
-      if (gc.wantT) std::memcpy(srcA, s.hA, bytesA);
-      if (wantZ) std::memcpy(dstZ, s.hZ, bytesA);
-      for (int k = 0; k < 3 && ev; k++) std::memcpy(dstX[k], s.hX[k], nb * xB[k]);
-      if (ev) std::memcpy(dstInfo, s.hInfo, bytesInfo);
+      Pending& q = pend[si];
+      q.any = true;
+      q.dstA = gc.wantT ? srcA : nullptr;
+      q.dstZ = wantZ ? dstZ : nullptr;
+      for (int k = 0; k < 3; k++) { q.dstX[k] = ev ? dstX[k] : nullptr; q.bytesX[k] = nb * xB[k]; }
+      q.dstInfo = ev ? dstInfo : nullptr;
+      q.bytesA = bytesA; q.bytesInfo = bytesInfo;
     }
     *bytes_d2h += (int64_t)((gc.wantT ? bytesA : 0) + (wantZ ? bytesA : 0) + nb * (xB[0] + xB[1] + xB[2]) + bytesInfo);
   }
   for (int k = 0; k < kSlotsPerDevice; k++)
-    if (dev.slots[k].stream) PSD_SHARD_CUDA(cudaStreamSynchronize(dev.slots[k].stream));
+    if (dev.slots[k].stream) {
+      PSD_SHARD_CUDA(cudaStreamSynchronize(dev.slots[k].stream));
+      flush(k);
+    }
   return PSD_OK;
 }
 
