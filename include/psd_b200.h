@@ -264,6 +264,14 @@ int psd_kernel_times(psd_handle_t handle, double ms[8]);
  * updates, out[11] = shift computation, out[12] = deflation scans, out[13] = final blocks. */
 int psd_large_stats(psd_handle_t handle, double out[16]);
 
+/* Iteration counts of the real standard paths.  After this call every psd_rpschur_batched /
+ * psd_rpschur_hessut(_q)_batched call on `handle` stores in iters[b] the number of periodic QR
+ * iterations problem b took (the `niter` the reference reports with @debug,
+ * PeriodicSchurDecompositions.jl:458-459, 1077); iters is host memory with room for the batch of
+ * those calls, NULL switches the report off.  Problems that take the large-N path (N >= 192)
+ * report 0 here and their counters through psd_large_stats. */
+int psd_set_iters_output(psd_handle_t handle, int32_t* iters);
+
 #ifdef __cplusplus
 }
 #endif

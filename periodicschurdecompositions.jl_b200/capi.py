@@ -33,6 +33,7 @@ EXPORTED_SYMBOLS = [
     "psd_set_profiling",
     "psd_kernel_times",
     "psd_large_stats",
+    "psd_set_iters_output",
     "psd_fill_uniform_host",
     "psd_fill_uniform_dev",
 ]
@@ -78,6 +79,7 @@ def lib():
                                                  C.c_int, C.c_int, vp, vp, vp, vp]
         L.psd_rpschur_hessut_q_batched.argtypes = [vp, C.c_int, C.c_int, C.c_int64, C.c_int,
                                                    C.c_int, vp, vp, vp, vp]
+        L.psd_set_iters_output.argtypes = [vp, vp]
         L.psd_rphess_batched.argtypes = [vp, C.c_int, C.c_int, C.c_int64, C.c_int, vp, vp]
         L.psd_cpschur_batched.argtypes = [vp, C.c_int, C.c_int, C.c_int64, C.c_int, vp, C.c_int,
                                           C.c_int, C.c_int, vp, vp, vp, vp, vp, vp]

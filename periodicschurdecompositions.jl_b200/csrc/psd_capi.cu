@@ -84,6 +84,12 @@ struct Slot {
   unsigned char* dS = nullptr;
   size_t capS = 0;
   psd::ms::Workspace* ms = nullptr;  // large-N multishift iteration (psd_ms.cu)
+  // iteration counts (psd_set_iters_output): device buffer, pinned staging, and the pointer the
+  // launch functions read for the chunk being enqueued (nullptr: not wanted)
+  int32_t* dIters = nullptr;
+  int32_t* hIters = nullptr;
+  size_t capIters = 0, hcapIters = 0;
+  int32_t* curIters = nullptr;
   long long* dProf = nullptr;        // PSD_PANEL_PROF cycle counters (debug builds)
 };
 
@@ -112,6 +118,7 @@ struct psd_handle_s {
   double gemm_flops = 0.0;          // FP64 GEMM flops issued by the large-N reduction since then
   double extra_launches = 0.0;      // kernel launches covered by a timer that brackets several
   psd::ms::Result ms_last;          // counters of the most recent large-N iteration
+  int32_t* iters_host = nullptr;    // psd_set_iters_output
   std::mutex tmu;
 };
 
@@ -393,7 +400,7 @@ int launch_real_eig32(psd_handle_s* h, Device& dev, Slot& aux, cudaStream_t stre
         Q.n_full = n; Q.stop = ph.stop; Q.first_phase = (k == 0) ? 1 : 0;
         Q.eig = dEig + (size_t)off * 2 * n;
         Q.info = dInfo + off;
-        Q.iters = nullptr;
+        Q.iters = aux.curIters ? aux.curIters + off : nullptr;
         Q.counter = aux.dPhaseCtr + k;
         Q.force_safe = dbg_env("PSD_EIG32_SAFE") ? 1 : 0;
         const long long ctas = (nb + ph.wpb - 1) / ph.wpb;
@@ -437,7 +444,7 @@ int launch_real(psd_handle_s* h, Device& dev, Slot& aux, cudaStream_t stream, co
   P.n = rc.n; P.p = rc.p; P.batch = batch;
   P.left = rc.left; P.wantT = rc.wantT; P.wantZ = wantZ ? 1 : 0;
   P.maxitfac = rc.maxitfac > 0 ? rc.maxitfac : 30;
-  P.A = dA; P.Z = wantZ ? dZ : nullptr; P.eig = dEig; P.info = dInfo; P.iters = nullptr;
+  P.A = dA; P.Z = wantZ ? dZ : nullptr; P.eig = dEig; P.info = dInfo; P.iters = aux.curIters;
   P.use_smem = pl.use_smem; P.ldh = pl.ldh;
   P.reduce_only = rc.reduce_only; P.skip_reduce = rc.skip_reduce; P.z_preset = rc.z_preset;
   P.counter = aux.dCounter;
@@ -681,8 +688,8 @@ int run_real_shard(psd_handle_s* h, Device& dev, const RealCall& rc, long long f
   struct Pending {
     bool any = false;
     double *dstA = nullptr, *dstZ = nullptr, *dstEig = nullptr;
-    int32_t* dstInfo = nullptr;
-    size_t bytesA = 0, bytesEig = 0, bytesInfo = 0;
+    int32_t *dstInfo = nullptr, *dstIters = nullptr;
+    size_t bytesA = 0, bytesEig = 0, bytesInfo = 0, bytesIters = 0;
   } pend[kSlotsPerDevice];
   auto flush = [&](int k) {
     Pending& q = pend[k];
@@ -692,6 +699,7 @@ int run_real_shard(psd_handle_s* h, Device& dev, const RealCall& rc, long long f
     if (q.dstZ) std::memcpy(q.dstZ, s.hZ, q.bytesA);
     if (q.dstEig) std::memcpy(q.dstEig, s.hEig, q.bytesEig);
     if (q.dstInfo) std::memcpy(q.dstInfo, s.hInfo, q.bytesInfo);
+    if (q.dstIters) std::memcpy(q.dstIters, s.hIters, q.bytesIters);
     q = Pending();
   };
   long long nb = 0, next = (count > chunk) ? std::max<long long>(1, chunk / (pinned ? 16 : 2)) : chunk;
@@ -718,6 +726,15 @@ int run_real_shard(psd_handle_s* h, Device& dev, const RealCall& rc, long long f
       PSD_SHARD_CUDA(cudaMemcpyAsync(s.dA, s.hA, bytesA, cudaMemcpyHostToDevice, s.stream));
     }
     *bytes_h2d += (int64_t)bytesA;
+    const bool wantIters = h->iters_host && !rc.reduce_only;
+    const size_t bytesIters = nb * sizeof(int32_t);
+    s.curIters = nullptr;
+    if (wantIters) {
+      if ((e = ensure_dev(s.dIters, s.capIters, bytesIters))) return drain_slots(dev, e);
+      if ((e = ensure_pinned(s.hIters, s.hcapIters, bytesIters))) return drain_slots(dev, e);
+      PSD_SHARD_CUDA(cudaMemsetAsync(s.dIters, 0, bytesIters, s.stream));
+      s.curIters = s.dIters;
+    }
     if (wantZ && rc.z_preset) {
       // Z enters as the caller's Q_j (accumulated onto)
       double* srcZ = Z + (size_t)(first + off) * per;
@@ -731,7 +748,15 @@ int run_real_shard(psd_handle_s* h, Device& dev, const RealCall& rc, long long f
       *bytes_h2d += (int64_t)bytesA;
     }
     e = launch_real(h, dev, s, s.stream, rc, nb, s.dA, wantZ ? s.dZ : nullptr, s.dEig, s.dInfo);
+    s.curIters = nullptr;
     if (e) return drain_slots(dev, e);
+    if (wantIters) {
+      // always through the slot's pinned buffer; copied out when the slot is drained
+      PSD_SHARD_CUDA(cudaMemcpyAsync(s.hIters, s.dIters, bytesIters, cudaMemcpyDeviceToHost, s.stream));
+      pend[si].any = true;
+      pend[si].dstIters = h->iters_host + (first + off);
+      pend[si].bytesIters = bytesIters;
+    }
     // results
     double* dstEig = eig ? eig + (size_t)(first + off) * 2 * rc.n : nullptr;
     int32_t* dstInfo = info ? info + (first + off) : nullptr;
@@ -753,7 +778,7 @@ int run_real_shard(psd_handle_s* h, Device& dev, const RealCall& rc, long long f
       PSD_SHARD_CUDA(cudaMemcpyAsync(s.hInfo, s.dInfo, bytesInfo, cudaMemcpyDeviceToHost, s.stream));
       // pageable destination: copied out of the pinned buffers when the slot is drained (before its
       // next use, or at the end), so that the host copies overlap the device work of the other slots
-      Pending& q = pend[si];
+      Pending& q = pend[si];  // (dstIters may already be set)
       q.any = true;
       q.dstA = outT ? srcA : nullptr;
       q.dstZ = wantZ ? dstZ : nullptr;
@@ -1182,6 +1207,13 @@ int psd_rpschur_hessut_q_batched(psd_handle_t h, int n, int p, int64_t batch, in
   RealCall rc{n, p, 0, wantT != 0, 1, maxitfac, 0, 1};
   rc.z_preset = 1;
   return run_real_host(h, rc, batch, A, Q, eig, info);
+}
+
+int psd_set_iters_output(psd_handle_t h, int32_t* iters) {
+  if (!h) return fail(PSD_ERR_BAD_ARG, "null handle");
+  std::lock_guard<std::mutex> lock(h->mu);
+  h->iters_host = iters;
+  return PSD_OK;
 }
 
 int psd_rphess_batched(psd_handle_t h, int n, int p, int64_t batch, int wantQ, double* A, double* Q) {

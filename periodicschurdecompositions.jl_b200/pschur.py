@@ -160,12 +160,14 @@ def _vp(a):
 
 
 def pschur_batched(A: np.ndarray, lr="R", wantZ: bool = True, wantT: bool = True,
-                   maxitfac: int = 30, handle: Optional[Handle] = None, overwrite: bool = False):
+                   maxitfac: int = 30, handle: Optional[Handle] = None, overwrite: bool = False,
+                   return_iters: bool = False):
     """Batched real periodic Schur decomposition through psd_rpschur_batched.
 
     A: float64 [batch][p][n][n], each factor column-major (storage layout), user factor order.
     Returns (T, Z, values, info): T is A overwritten (a copy unless overwrite=True), Z is None
-    when wantZ is False, values complex128 [batch][n], info int32 [batch]."""
+    when wantZ is False, values complex128 [batch][n], info int32 [batch].  return_iters=True
+    appends the QR iterations per problem (psd_set_iters_output; int32 [batch])."""
     orient = char_lr(lr)
     if A.dtype != np.float64 or A.ndim != 4 or A.shape[2] != A.shape[3]:
         raise ValueError("A must be float64 with shape [batch][p][n][n]")  # DimensionMismatch, :220
@@ -175,9 +177,18 @@ def pschur_batched(A: np.ndarray, lr="R", wantZ: bool = True, wantT: bool = True
     Z = np.empty_like(T) if wantZ else None
     vals = np.empty((batch, n), dtype=np.complex128)
     info = np.empty(batch, dtype=np.int32)
-    check(lib().psd_rpschur_batched(h.ptr, n, p, batch, 1 if orient == "L" else 0, int(wantT),
-                                    int(wantZ), int(maxitfac), _vp(T), _vp(Z), _vp(vals),
-                                    _vp(info)))
+    iters = np.zeros(batch, dtype=np.int32) if return_iters else None
+    if return_iters:
+        check(lib().psd_set_iters_output(h.ptr, _vp(iters)))
+    try:
+        check(lib().psd_rpschur_batched(h.ptr, n, p, batch, 1 if orient == "L" else 0, int(wantT),
+                                        int(wantZ), int(maxitfac), _vp(T), _vp(Z), _vp(vals),
+                                        _vp(info)))
+    finally:
+        if return_iters:
+            lib().psd_set_iters_output(h.ptr, None)
+    if return_iters:
+        return T, Z, vals, info, iters
     return T, Z, vals, info
 
 

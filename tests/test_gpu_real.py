@@ -142,6 +142,28 @@ def test_hessut_entry_q_preset(psd, oracle):
             assert np.array_equal(T[b], T0[b]) and np.array_equal(lam[b], lam0[b])
 
 
+def test_iteration_counts(psd, oracle):
+    """psd_set_iters_output: QR iterations per problem (the reference's niter, :458-459, 1077),
+    from the one-CTA kernel (with T / Z) and from the warp-per-problem eigenvalue kernel with its
+    occupancy phases; both run the same iteration, so the counts agree problem by problem with the
+    CPU restatement wherever that converges the same way (a sanity band is asserted, not equality:
+    the eigenvalue kernel's reflectors round differently)."""
+    for (n, p, batch) in [(5, 3, 8), (32, 8, 40), (20, 4, 16)]:
+        A = oracle.gen_real(77, n, p, batch)
+        T, Z, lam, info, it_full = psd.pschur_batched(A, "R", return_iters=True)
+        _, _, lam2, info2, it_eig = psd.pschur_batched(A, "R", wantT=False, wantZ=False, return_iters=True)
+        assert (info == 0).all() and (info2 == 0).all()
+        assert (it_full > 0).all() and (it_eig > 0).all()
+        # at least one iteration per two eigenvalues, at most the reference's budget maxitfac * n
+        assert (it_full >= n // 2).all() and (it_full <= 30 * n).all()
+        assert (it_eig >= n // 2).all() and (it_eig <= 30 * n).all()
+        assert np.abs(it_full.astype(float) - it_eig).max() <= 0.5 * it_full.max()
+        # switched off again: a later call must not touch the old buffer
+        keep = it_full.copy()
+        psd.pschur_batched(A, "R")
+        assert np.array_equal(keep, it_full)
+
+
 def test_reduction_only(psd, oracle):
     # test/runtests.jl:14-50 "Periodic Hessenberg"
     for (n, p) in [(5, 1), (5, 2), (5, 5), (32, 8)]:
