@@ -272,6 +272,20 @@ int psd_large_stats(psd_handle_t handle, double out[16]);
  * report 0 here and their counters through psd_large_stats. */
 int psd_set_iters_output(psd_handle_t handle, int32_t* iters);
 
+/* Integrity check of real periodic Schur decompositions on the device, batched.
+ * Replaces checkpsd(P, Hs) (diagnostics.jl:190-263) for PeriodicSchur results (S all true): for
+ * problem b and factor l (user order, host arrays in the storage layout of psd_rpschur_batched)
+ *   err[b*p + l]  = || Z_l T_l Z_l1' - A_l ||_F / (eps ||A_l||_1)   (:R; Z_l1 T_l Z_l' for :L),
+ *                   the "normalized factorization error" the reference returns (O(1) expected,
+ *                   its threshold is 100),
+ *   tri[b*p + l]  = Frobenius norm of T_l below its (quasi-)triangle (tril(T, -2) for the Schur
+ *                   factor, tril(T, -1) for the others; the strict check wants exactly 0),
+ *   orth[b*p + l] = || Z_l Z_l' - I ||_F (the reference's limit is 10 eps n).
+ * tri and orth may be NULL.  The comparison with the thresholds stays with the caller. */
+int psd_rcheckpsd_batched(psd_handle_t handle, int n, int p, int64_t batch, int orientation,
+                          const double* A, const double* T, const double* Z, double* err,
+                          double* tri, double* orth);
+
 #ifdef __cplusplus
 }
 #endif

@@ -34,6 +34,7 @@ EXPORTED_SYMBOLS = [
     "psd_kernel_times",
     "psd_large_stats",
     "psd_set_iters_output",
+    "psd_rcheckpsd_batched",
     "psd_fill_uniform_host",
     "psd_fill_uniform_dev",
 ]
@@ -80,6 +81,7 @@ def lib():
         L.psd_rpschur_hessut_q_batched.argtypes = [vp, C.c_int, C.c_int, C.c_int64, C.c_int,
                                                    C.c_int, vp, vp, vp, vp]
         L.psd_set_iters_output.argtypes = [vp, vp]
+        L.psd_rcheckpsd_batched.argtypes = [vp, C.c_int, C.c_int, C.c_int64, C.c_int, vp, vp, vp, vp, vp, vp]
         L.psd_rphess_batched.argtypes = [vp, C.c_int, C.c_int, C.c_int64, C.c_int, vp, vp]
         L.psd_cpschur_batched.argtypes = [vp, C.c_int, C.c_int, C.c_int64, C.c_int, vp, C.c_int,
                                           C.c_int, C.c_int, vp, vp, vp, vp, vp, vp]

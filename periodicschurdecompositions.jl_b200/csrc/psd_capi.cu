@@ -18,6 +18,7 @@
 
 #include "../../include/psd_b200.h"
 #include "psd_real_kernel.cuh"
+#include "psd_checkpsd.cuh"
 #include "psd_real_hess32.cuh"
 #include "psd_cplx_qz.cuh"
 #include "psd_rowhess.cuh"
@@ -1207,6 +1208,82 @@ int psd_rpschur_hessut_q_batched(psd_handle_t h, int n, int p, int64_t batch, in
   RealCall rc{n, p, 0, wantT != 0, 1, maxitfac, 0, 1};
   rc.z_preset = 1;
   return run_real_host(h, rc, batch, A, Q, eig, info);
+}
+
+int psd_rcheckpsd_batched(psd_handle_t h, int n, int p, int64_t batch, int orientation, const double* A,
+                          const double* T, const double* Z, double* err, double* tri, double* orth) {
+  if (!h) return fail(PSD_ERR_BAD_ARG, "null handle");
+  if (n < 1 || p < 1 || batch < 0 || !A || !T || !Z || !err) return fail(PSD_ERR_BAD_ARG, "bad argument");
+  if (orientation != 0 && orientation != 1) return fail(PSD_ERR_BAD_ARG, "bad orientation");
+  if (h->devs.empty()) return fail(PSD_ERR_NO_DEVICE, "handle has no CUDA device");
+  std::lock_guard<std::mutex> lock(h->mu);
+  if (batch == 0) return PSD_OK;
+  Device& dev = h->devs[0];
+  PSD_CUDA(cudaSetDevice(dev.ordinal));
+  Slot& s = dev.slots[0];
+  if (!s.stream) PSD_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+  PSD_CUDA(cudaStreamSynchronize(s.stream));
+  const size_t per = (size_t)n * n * p;
+  // a diagnostic, not a hot path: plain chunks of at most ~1 GiB per array, synchronous copies
+  const long long chunk = std::max<long long>(1, std::min<long long>(batch, (1LL << 30) / (long long)(per * sizeof(double))));
+  double *dA = nullptr, *dT = nullptr, *dZ = nullptr, *dOut = nullptr;
+  std::vector<double> hout((size_t)chunk * p * 4);
+  auto cleanup = [&] { cudaFree(dA); cudaFree(dT); cudaFree(dZ); cudaFree(dOut); };
+#define PSD_CHK(call)                                                    \
+  do {                                                                   \
+    cudaError_t e__ = (call);                                            \
+    if (e__ != cudaSuccess) {                                            \
+      cleanup();                                                         \
+      return fail(PSD_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__)); \
+    }                                                                    \
+  } while (0)
+  PSD_CHK(cudaMalloc((void**)&dA, chunk * per * sizeof(double)));
+  PSD_CHK(cudaMalloc((void**)&dT, chunk * per * sizeof(double)));
+  PSD_CHK(cudaMalloc((void**)&dZ, chunk * per * sizeof(double)));
+  PSD_CHK(cudaMalloc((void**)&dOut, chunk * p * 4 * sizeof(double)));
+  const int CB = (n <= 1024) ? 4 : 1;
+  const size_t smem = (size_t)2 * n * CB * sizeof(double);
+  if (CB == 4)
+    PSD_CHK(cudaFuncSetAttribute(psd::checkpsd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  else
+    PSD_CHK(cudaFuncSetAttribute(psd::checkpsd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const double eps = 2.220446049250313e-16;
+  for (long long off = 0; off < batch; off += chunk) {
+    const long long nb = std::min(chunk, batch - off);
+    PSD_CHK(cudaMemcpyAsync(dA, A + (size_t)off * per, nb * per * sizeof(double), cudaMemcpyHostToDevice, s.stream));
+    PSD_CHK(cudaMemcpyAsync(dT, T + (size_t)off * per, nb * per * sizeof(double), cudaMemcpyHostToDevice, s.stream));
+    PSD_CHK(cudaMemcpyAsync(dZ, Z + (size_t)off * per, nb * per * sizeof(double), cudaMemcpyHostToDevice, s.stream));
+    PSD_CHK(cudaMemsetAsync(dOut, 0, nb * p * 4 * sizeof(double), s.stream));
+    psd::CheckParams P;
+    P.n = n; P.p = p; P.left = orientation; P.batch = nb;
+    P.A = dA; P.T = dT; P.Z = dZ; P.out = dOut;
+    // enough CTAs to fill the device a few times over
+    long long zc = std::max<long long>(1, std::min<long long>((n + CB - 1) / CB, (4LL * dev.sm_count + nb * p - 1) / (nb * p)));
+    P.cols_per_cta = (int)(((n + zc - 1) / zc + CB - 1) / CB * CB);
+    zc = (n + P.cols_per_cta - 1) / P.cols_per_cta;
+    for (long long b0 = 0; b0 < nb; b0 += 32768) {  // grid.y limit
+      const long long by = std::min<long long>(32768, nb - b0);
+      psd::CheckParams Q = P;
+      Q.A = dA + (size_t)b0 * per; Q.T = dT + (size_t)b0 * per; Q.Z = dZ + (size_t)b0 * per;
+      Q.out = dOut + (size_t)b0 * p * 4;
+      if (CB == 4)
+        psd::checkpsd_kernel<4><<<dim3(p, (unsigned)by, (unsigned)zc), 256, smem, s.stream>>>(Q);
+      else
+        psd::checkpsd_kernel<1><<<dim3(p, (unsigned)by, (unsigned)zc), 256, smem, s.stream>>>(Q);
+    }
+    PSD_CHK(cudaGetLastError());
+    PSD_CHK(cudaMemcpyAsync(hout.data(), dOut, nb * p * 4 * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
+    PSD_CHK(cudaStreamSynchronize(s.stream));
+    for (long long k = 0; k < nb * p; k++) {
+      const double e2 = hout[4 * k], a1 = hout[4 * k + 1], t2 = hout[4 * k + 2], o2 = hout[4 * k + 3];
+      err[off * p + k] = (a1 > 0.0) ? std::sqrt(e2) / eps / a1 : (e2 > 0.0 ? HUGE_VAL : 0.0);
+      if (tri) tri[off * p + k] = std::sqrt(t2);
+      if (orth) orth[off * p + k] = std::sqrt(o2);
+    }
+  }
+#undef PSD_CHK
+  cleanup();
+  return PSD_OK;
 }
 
 int psd_set_iters_output(psd_handle_t h, int32_t* iters) {

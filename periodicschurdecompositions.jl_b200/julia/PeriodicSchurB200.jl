@@ -234,4 +234,28 @@ function large_stats(handle::Handle = default_handle())
             launches = Int(out[8]), update_flops = out[9])
 end
 
+"""
+    checkpsd_batched(A, T, Z, lr = :R; thresh = 100, strict = true) -> (ok, err)
+
+`checkpsd` (diagnostics.jl:190-263) for batched real results in the device layout (n, n, p, batch):
+the normalized factorization errors, the triangularity and the orthogonality norms are formed on
+the GPU; `ok[b]` applies the reference's thresholds.
+"""
+function checkpsd_batched(A::Array{Float64, 4}, T::Array{Float64, 4}, Z::Array{Float64, 4},
+                          lr::Symbol = :R; thresh = 100, strict::Bool = true,
+                          handle::Handle = default_handle())
+    n, n2, p, B = size(A)
+    (n == n2 && size(T) == size(A) && size(Z) == size(A)) || throw(DimensionMismatch())
+    err = Matrix{Float64}(undef, p, B); tri = similar(err); orth = similar(err)
+    rc = ccall((:psd_rcheckpsd_batched, libpsd), Cint,
+               (Ptr{Cvoid}, Cint, Cint, Int64, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
+                Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+               handle.ptr, n, p, B, orient_code(lr), A, T, Z, err, tri, orth)
+    rc == 0 || error(lasterror(rc))
+    cmp = strict ? 0.0 : 10 * eps(Float64) * n
+    ok = [all(tri[:, b] .<= cmp) && all(orth[:, b] .<= 10 * eps(Float64) * n) && all(err[:, b] .<= thresh)
+          for b in 1:B]
+    return ok, err
+end
+
 end # module

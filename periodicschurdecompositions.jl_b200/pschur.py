@@ -192,6 +192,25 @@ def pschur_batched(A: np.ndarray, lr="R", wantZ: bool = True, wantT: bool = True
     return T, Z, vals, info
 
 
+def checkpsd_batched(A: np.ndarray, T: np.ndarray, Z: np.ndarray, lr="R", thresh: float = 100.0,
+                     strict: bool = True, handle: Optional[Handle] = None):
+    """checkpsd(P, Hs) (diagnostics.jl:190-263) for batched real results, norms computed on the
+    device (psd_rcheckpsd_batched).  Returns (ok [batch] bool, err [batch][p], tri, orth)."""
+    orient = char_lr(lr)
+    h = handle or default_handle()
+    batch, p, n, _ = A.shape
+    A = np.ascontiguousarray(A, dtype=np.float64)
+    T = np.ascontiguousarray(T, dtype=np.float64)
+    Z = np.ascontiguousarray(Z, dtype=np.float64)
+    err = np.empty((batch, p)); tri = np.empty((batch, p)); orth = np.empty((batch, p))
+    check(lib().psd_rcheckpsd_batched(h.ptr, n, p, batch, 1 if orient == "L" else 0, _vp(A), _vp(T), _vp(Z),
+                                      _vp(err), _vp(tri), _vp(orth)))
+    eps = np.finfo(np.float64).eps
+    cmp = 0.0 if strict else 10 * eps * n          # ttol, :212, 225
+    ok = (tri <= cmp).all(axis=1) & (orth <= 10 * eps * n).all(axis=1) & (err <= thresh).all(axis=1)
+    return ok, err, tri, orth
+
+
 def pschur_hessut_batched(H: np.ndarray, wantZ: bool = True, wantT: bool = True, maxitfac: int = 30,
                           handle: Optional[Handle] = None, Q: Optional[np.ndarray] = None):
     """Inner method pschur!(H1, Hs; ...) (PeriodicSchurDecompositions.jl:322) on Hessenberg /

@@ -164,6 +164,39 @@ def test_iteration_counts(psd, oracle):
         assert np.array_equal(keep, it_full)
 
 
+def test_device_checkpsd(psd, oracle):
+    """psd_rcheckpsd_batched against the same norms formed with numpy (checkpsd,
+    diagnostics.jl:190-263): good decompositions pass with the reference's thresholds, a perturbed T,
+    a perturbed Z and a non-zero entry below the triangle are each reported in the right place."""
+    for (n, p, batch, lr) in [(5, 3, 6, "R"), (33, 2, 3, "L"), (50, 3, 4, "R"), (200, 2, 1, "R")]:
+        A = oracle.gen_real(91, n, p, batch)
+        T, Z, lam, info = psd.pschur_batched(A, lr)
+        ok, err, tri, orth = psd.checkpsd_batched(A, T, Z, lr)
+        assert ok.all(), (err.max(), tri.max(), orth.max())
+        left = lr == "L"
+        for b in range(batch):
+            for j in range(p):
+                Tj, Aj, Zj, Zn = K.M(T[b, j]), K.M(A[b, j]), K.M(Z[b, j]), K.M(Z[b, (j + 1) % p])
+                Ax = (Zn @ Tj @ Zj.T) if left else (Zj @ Tj @ Zn.T)
+                ref = np.linalg.norm(Ax - Aj) / EPS / np.linalg.norm(Aj, 1)
+                assert abs(err[b, j] - ref) <= 0.05 * ref + 0.5, (err[b, j], ref)
+                ro = np.linalg.norm(Zj @ Zj.T - np.eye(n))
+                assert abs(orth[b, j] - ro) <= 0.05 * ro + 2 * EPS
+        assert (tri == 0).all()
+        # faults
+        T2 = T.copy(); T2[0, p - 1, 0, 0] += 1e-6          # entry (0, 0) of the last factor
+        ok2, err2, _, _ = psd.checkpsd_batched(A, T2, Z, lr)
+        assert not ok2[0] and err2[0, p - 1] > 1e6 and ok2[1:].all()
+        Z2 = Z.copy(); Z2[batch - 1, 0, 1, 0] += 1e-8
+        ok3, _, _, orth3 = psd.checkpsd_batched(A, T, Z2, lr)
+        assert not ok3[batch - 1] and orth3[batch - 1, 0] > 1e-9
+        T3 = T.copy(); T3[0, 0, 0, n - 1] = 1e-30           # storage [col][row]: row n-1, column 0
+        ok4, _, tri4, _ = psd.checkpsd_batched(A, T3, Z, lr)
+        assert not ok4[0] and tri4[0, 0] > 0
+        ok5, _, _, _ = psd.checkpsd_batched(A, T3, Z, lr, strict=False)
+        assert ok5[0]
+
+
 def test_reduction_only(psd, oracle):
     # test/runtests.jl:14-50 "Periodic Hessenberg"
     for (n, p) in [(5, 1), (5, 2), (5, 5), (32, 8)]:
