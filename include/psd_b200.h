@@ -130,6 +130,16 @@ int psd_rpschur_hessut_q_batched(psd_handle_t handle, int n, int p, int64_t batc
 int psd_rphess_batched(psd_handle_t handle, int n, int p, int64_t batch, int wantQ, double* A,
                        double* Q);
 
+/* Same reduction with the result in the reference's own packed form: on return A_j holds H_j in
+ * its upper (Hessenberg for j = 1) part and, below it, the Householder vectors (implicit leading
+ * 1, LAPACK convention), and tau[b][j-1][i] their scalars (n per factor; tau[.][0] uses n-1, the
+ * trailing entries are 0) - exactly the (A[j], tau[j]) from which phessenberg! builds
+ * Hessenberg(A[1], tau[1]) and QR(A[j], tau[j]) (PeriodicSchurDecompositions.jl:229-253).
+ * Host buffers; one CTA per problem at every order (the blocked large-N reduction keeps its
+ * reflectors in compact-WY form and is not used here). */
+int psd_rphess_packed_batched(psd_handle_t handle, int n, int p, int64_t batch, double* A,
+                              double* tau);
+
 /* ---------------------------------------------------------------------------------------
  * Complex (generalized) periodic Schur decomposition, batched.
  * Replaces pschur!(A::Vector{Matrix{ComplexF64}}, S, lr; wantZ, wantT)

@@ -22,6 +22,7 @@ EXPORTED_SYMBOLS = [
     "psd_rpschur_hessut_batched",
     "psd_rpschur_hessut_q_batched",
     "psd_rphess_batched",
+    "psd_rphess_packed_batched",
     "psd_cpschur_batched",
     "psd_cpschur_hessut_batched",
     "psd_rgpschur_batched",
@@ -81,6 +82,7 @@ def lib():
         L.psd_rpschur_hessut_q_batched.argtypes = [vp, C.c_int, C.c_int, C.c_int64, C.c_int,
                                                    C.c_int, vp, vp, vp, vp]
         L.psd_set_iters_output.argtypes = [vp, vp]
+        L.psd_rphess_packed_batched.argtypes = [vp, C.c_int, C.c_int, C.c_int64, vp, vp]
         L.psd_rcheckpsd_batched.argtypes = [vp, C.c_int, C.c_int, C.c_int64, C.c_int, vp, vp, vp, vp, vp, vp]
         L.psd_rphess_batched.argtypes = [vp, C.c_int, C.c_int, C.c_int64, C.c_int, vp, vp]
         L.psd_cpschur_batched.argtypes = [vp, C.c_int, C.c_int, C.c_int64, C.c_int, vp, C.c_int,

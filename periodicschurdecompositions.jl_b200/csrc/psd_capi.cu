@@ -91,6 +91,7 @@ struct Slot {
   int32_t* hIters = nullptr;
   size_t capIters = 0, hcapIters = 0;
   int32_t* curIters = nullptr;
+  double* curTau = nullptr;  // psd_rphess_packed_batched: device tau of the chunk being enqueued
   long long* dProf = nullptr;        // PSD_PANEL_PROF cycle counters (debug builds)
 };
 
@@ -352,6 +353,7 @@ int launch_real_eig32(psd_handle_s* h, Device& dev, Slot& aux, cudaStream_t stre
       P.counter = aux.dCounter;
       P.scratch = nullptr; P.scratch_stride = 0;
       P.packed_out = aux.dPacked;
+      P.tau = nullptr;
       ScopedKernelTimer tm(h, dev, stream, 0);
       psd::rpschur_kernel<<<pl.grid, pl.threads, pl.smem_bytes, stream>>>(P);
       PSD_CUDA(cudaGetLastError());
@@ -433,7 +435,7 @@ int launch_real(psd_handle_s* h, Device& dev, Slot& aux, cudaStream_t stream, co
   if (batch == 0) return PSD_OK;
   RealLaunchPlan pl;
   const bool wantZ = rc.wantZ && dZ;
-  if (rc.n >= kLargeN && !rc.skip_reduce && !dbg_env("PSD_DISABLE_LARGE") && large_feasible(dev, rc.n, rc.p))
+  if (rc.n >= kLargeN && !rc.skip_reduce && !aux.curTau && !dbg_env("PSD_DISABLE_LARGE") && large_feasible(dev, rc.n, rc.p))
     return launch_real_large(h, dev, aux, stream, rc, batch, dA, dZ, dEig, dInfo);
   if (!rc.wantT && !wantZ && !rc.reduce_only && rc.n <= 32 && rc.p >= 3 && !dbg_env("PSD_DISABLE_EIG32"))
     return launch_real_eig32(h, dev, aux, stream, rc, batch, dA, dEig, dInfo);
@@ -451,6 +453,7 @@ int launch_real(psd_handle_s* h, Device& dev, Slot& aux, cudaStream_t stream, co
   P.counter = aux.dCounter;
   P.scratch = nullptr; P.scratch_stride = 0;
   P.packed_out = nullptr;
+  P.tau = aux.curTau;
   if (pl.scratch) {
     size_t stride = (size_t)psd::rp_small_doubles(rc.n, rc.p);
     e = ensure_dev(aux.dScratch, aux.capScratch, stride * sizeof(double) * pl.grid);
@@ -1283,6 +1286,38 @@ int psd_rcheckpsd_batched(psd_handle_t h, int n, int p, int64_t batch, int orien
   }
 #undef PSD_CHK
   cleanup();
+  return PSD_OK;
+}
+
+int psd_rphess_packed_batched(psd_handle_t h, int n, int p, int64_t batch, double* A, double* tau) {
+  if (!h) return fail(PSD_ERR_BAD_ARG, "null handle");
+  if (n < 1 || p < 1 || batch < 0 || !A || !tau) return fail(PSD_ERR_BAD_ARG, "bad argument");
+  if (h->devs.empty()) return fail(PSD_ERR_NO_DEVICE, "handle has no CUDA device");
+  std::lock_guard<std::mutex> lock(h->mu);
+  if (batch == 0) return PSD_OK;
+  Device& dev = h->devs[0];
+  PSD_CUDA(cudaSetDevice(dev.ordinal));
+  Slot& s = dev.slots[0];
+  if (!s.stream) PSD_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+  PSD_CUDA(cudaStreamSynchronize(s.stream));
+  const size_t per = (size_t)n * n * p;
+  const long long chunk = std::max<long long>(1, std::min<long long>(batch, (1LL << 30) / (long long)(per * sizeof(double))));
+  int e;
+  if ((e = ensure_dev(s.dA, s.capA, chunk * per * sizeof(double)))) return e;
+  if ((e = ensure_dev(s.dEig, s.capEig, std::max<size_t>((size_t)chunk * p * n, (size_t)chunk * 2 * n) * sizeof(double)))) return e;
+  if ((e = ensure_dev(s.dInfo, s.capInfo, chunk * sizeof(int32_t)))) return e;
+  RealCall rc{n, p, 0, 1, 0, 30, 1, 0};
+  for (long long off = 0; off < batch; off += chunk) {
+    const long long nb = std::min(chunk, batch - off);
+    PSD_CUDA(cudaMemcpyAsync(s.dA, A + (size_t)off * per, nb * per * sizeof(double), cudaMemcpyHostToDevice, s.stream));
+    s.curTau = s.dEig;  // (the eigenvalue buffer is unused by a reduction-only launch)
+    e = launch_real(h, dev, s, s.stream, rc, nb, s.dA, nullptr, nullptr, s.dInfo);
+    s.curTau = nullptr;
+    if (e) return e;
+    PSD_CUDA(cudaMemcpyAsync(A + (size_t)off * per, s.dA, nb * per * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
+    PSD_CUDA(cudaMemcpyAsync(tau + (size_t)off * p * n, s.dEig, nb * p * n * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
+    PSD_CUDA(cudaStreamSynchronize(s.stream));
+  }
   return PSD_OK;
 }
 

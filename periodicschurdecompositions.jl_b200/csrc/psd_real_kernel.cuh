@@ -38,6 +38,9 @@ struct RpschurParams {
   unsigned long long* counter;  // dynamic work queue over problems
   double* scratch;  // per-CTA small arrays when they do not fit in smem (or nullptr)
   long long scratch_stride;
+  double* tau;         // reduce_only, not nullptr: LAPACK-packed output - the reflector vectors stay
+                       // below the (sub)diagonal of A_j and tau[b][j-1][0..n-1] receives their scalars
+                       // (Hessenberg(A[1], tau[1]), QR(A[j], tau[j]) of phessenberg!, :249-253)
   double* packed_out;  // reduce_only: write packed Hessenberg-triangular factors here instead
                        // of A ([batch][pk_problem_size(n,p)], layout of psd_real_eig32.cuh)
 };
@@ -53,8 +56,10 @@ struct RpschurParams {
 // mode 0: left + right + Z, then finalise the column; mode 1: left only (no finalise);
 // mode 2: right + Z only, then finalise.  Modes 1,2 serialise the two sides when the left
 // and right targets are the same matrix (p == 1).
+// tau_slot != nullptr: packed output - the scaled reflector vector (implicit leading 1) is kept
+// below the pivot and tau is stored, instead of the exact zeros.
 PSD_DEV void reduce_step(const RCtx& c, double* Aj, double* Ajm1, double* Zj, int r0, int col,
-                         int mode = 0) {
+                         int mode = 0, double* tau_slot = nullptr) {
   const int n = c.n, ld = c.ldh;
   const int m = n - r0 + 1;  // reflector order
   if (m <= 1) return;
@@ -115,11 +120,16 @@ PSD_DEV void reduce_step(const RCtx& c, double* Aj, double* Ajm1, double* Zj, in
   }
   __syncthreads();
   if (mode == 1) return;
-  // column `col` of Aj below r0 is dead from here on: store beta and exact zeros.
-  for (int k = c.tid; k < m; k += c.nt) PSD_EL(Aj, ld, r0 + k, col) = (k == 0) ? beta / s : 0.0;
+  // column `col` of Aj below r0 is dead from here on: store beta and exact zeros (or the
+  // reflector vector: every element is read and rewritten by the same thread).
+  for (int k = c.tid; k < m; k += c.nt) {
+    double* e = &PSD_EL(Aj, ld, r0 + k, col);
+    *e = (k == 0) ? beta / s : (tau_slot ? *e * tv : 0.0);
+  }
+  if (tau_slot && c.tid == 0) *tau_slot = tau;
 }
 
-PSD_DEV void phessenberg_cta(const RCtx& c, bool wantZ) {
+PSD_DEV void phessenberg_cta(const RCtx& c, bool wantZ, double* tau = nullptr) {
   const int n = c.n, p = c.p;
   if (wantZ) {
     for (int j = 1; j <= p; j++) {
@@ -133,12 +143,13 @@ PSD_DEV void phessenberg_cta(const RCtx& c, bool wantZ) {
   __syncthreads();
   for (int i = 1; i <= n - 1; i++) {
     for (int j = p; j >= 2; j--)
-      reduce_step(c, c.Hp(j), c.Hp(j - 1), wantZ ? c.Zp(j) : nullptr, i, i);
+      reduce_step(c, c.Hp(j), c.Hp(j - 1), wantZ ? c.Zp(j) : nullptr, i, i, 0, tau ? tau + (size_t)(j - 1) * n + (i - 1) : nullptr);
+    double* t1 = tau ? tau + (i - 1) : nullptr;
     if (p > 1) {
-      reduce_step(c, c.Hp(1), c.Hp(p), wantZ ? c.Zp(1) : nullptr, i + 1, i);
+      reduce_step(c, c.Hp(1), c.Hp(p), wantZ ? c.Zp(1) : nullptr, i + 1, i, 0, t1);
     } else {
       reduce_step(c, c.Hp(1), c.Hp(1), wantZ ? c.Zp(1) : nullptr, i + 1, i, 1);
-      reduce_step(c, c.Hp(1), c.Hp(1), wantZ ? c.Zp(1) : nullptr, i + 1, i, 2);
+      reduce_step(c, c.Hp(1), c.Hp(1), wantZ ? c.Zp(1) : nullptr, i + 1, i, 2, t1);
     }
   }
   __syncthreads();
@@ -210,7 +221,12 @@ __global__ void rpschur_kernel(RpschurParams P) {
     __syncthreads();
 
     if (!P.skip_reduce) {
-      phessenberg_cta(c, wantZ);
+      double* taub = P.tau ? P.tau + (size_t)b * p * n : nullptr;
+      if (taub) {
+        for (int e = tid; e < p * n; e += nt) taub[e] = 0.0;  // (tau = 0 where H = I)
+        __syncthreads();
+      }
+      phessenberg_cta(c, wantZ, taub);
     } else {
       if (wantZ && !P.z_preset) {
         for (int j = 1; j <= p; j++) {

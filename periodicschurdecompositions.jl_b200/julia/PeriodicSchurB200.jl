@@ -258,4 +258,24 @@ function checkpsd_batched(A::Array{Float64, 4}, T::Array{Float64, 4}, Z::Array{F
     return ok, err
 end
 
+"""
+    phessenberg!(A::Vector{Matrix{Float64}}) -> (H1::Hessenberg, pH::Vector{<:QR})
+
+Drop-in for the reference's `phessenberg!` (PeriodicSchurDecompositions.jl:213-259): the reduction
+runs on the GPU and comes back in the reference's own packed form (reflector vectors below the
+(sub)diagonal, `tau`), from which the same `Hessenberg` / `QR` objects are built (:249-253).
+"""
+function phessenberg!(A::Vector{Matrix{Float64}}; handle::Handle = default_handle())
+    buf, n, p = _pack(A)
+    tau = Matrix{Float64}(undef, n, p)
+    rc = ccall((:psd_rphess_packed_batched, libpsd), Cint,
+               (Ptr{Cvoid}, Cint, Cint, Int64, Ptr{Float64}, Ptr{Float64}),
+               handle.ptr, n, p, 1, buf, tau)
+    rc == 0 || error(lasterror(rc))
+    _unpack!(A, buf)
+    H1 = LinearAlgebra.Hessenberg(A[1], tau[1:(n - 1), 1])
+    pH = [LinearAlgebra.QR(A[j], tau[:, j]) for j in 2:p]
+    return H1, pH
+end
+
 end # module

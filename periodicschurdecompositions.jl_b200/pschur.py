@@ -192,6 +192,17 @@ def pschur_batched(A: np.ndarray, lr="R", wantZ: bool = True, wantT: bool = True
     return T, Z, vals, info
 
 
+def phessenberg_packed_batched(A: np.ndarray, handle: Optional[Handle] = None):
+    """phessenberg!(A) with the result in the reference's packed form (:229-253): returns (F, tau),
+    F[b][j] = H_j in the upper part and the Householder vectors below it, tau [batch][p][n]."""
+    h = handle or default_handle()
+    batch, p, n, _ = A.shape
+    F = np.ascontiguousarray(A, dtype=np.float64).copy()
+    tau = np.empty((batch, p, n))
+    check(lib().psd_rphess_packed_batched(h.ptr, n, p, batch, _vp(F), _vp(tau)))
+    return F, tau
+
+
 def checkpsd_batched(A: np.ndarray, T: np.ndarray, Z: np.ndarray, lr="R", thresh: float = 100.0,
                      strict: bool = True, handle: Optional[Handle] = None):
     """checkpsd(P, Hs) (diagnostics.jl:190-263) for batched real results, norms computed on the

@@ -197,6 +197,39 @@ def test_device_checkpsd(psd, oracle):
         assert ok5[0]
 
 
+def test_reduction_packed_output(psd, oracle):
+    """psd_rphess_packed_batched: (A[j], tau[j]) as phessenberg! leaves them
+    (PeriodicSchurDecompositions.jl:229-253).  Q_j is rebuilt from the packed reflectors the way
+    LAPACK's orghr / orgqr (and Julia's Hessenberg / QR Q factors) do, and must reproduce the
+    explicit reduction: Q_j' A_j Q_{j+1} = H_j with the same H_j as psd_rphess_batched."""
+    for (n, p, batch) in [(5, 1, 3), (6, 3, 4), (33, 4, 2), (70, 2, 1), (200, 3, 1)]:  # the last one works in global memory
+        A = oracle.gen_real(61, n, p, batch)
+        F, tau = psd.phessenberg_packed_batched(A)
+        H, Q = psd.phessenberg_batched(A)
+        for b in range(batch):
+            Qs = []
+            for j in range(p):
+                Fj = K.M(F[b, j])
+                first = 1 if j == 0 else 0           # H_1: reflector i acts on rows i+1.., others on rows i..
+                Qj = np.eye(n)
+                for i in range(n - 1):
+                    r0 = i + first
+                    if r0 >= n:
+                        continue
+                    v = np.zeros(n)
+                    v[r0] = 1.0
+                    v[r0 + 1:] = Fj[r0 + 1:, i]
+                    Qj = Qj @ (np.eye(n) - tau[b, j, i] * np.outer(v, v))
+                Qs.append(Qj)
+                assert np.linalg.norm(Qj @ Qj.T - np.eye(n)) < 50 * n * EPS
+            for j in range(p):
+                Hj = np.triu(K.M(F[b, j]), -1 if j == 0 else 0)
+                Aj = K.M(A[b, j])
+                res = np.linalg.norm(Qs[j].T @ Aj @ Qs[(j + 1) % p] - Hj)
+                assert res < 50 * n * EPS * max(1.0, np.linalg.norm(Aj)), (n, p, j, res)
+                assert np.allclose(Hj, K.M(H[b, j]), atol=200 * n * EPS * max(1.0, np.abs(Hj).max()))
+
+
 def test_reduction_only(psd, oracle):
     # test/runtests.jl:14-50 "Periodic Hessenberg"
     for (n, p) in [(5, 1), (5, 2), (5, 5), (32, 8)]:
