@@ -19,7 +19,8 @@
 //  * reflectors are kept un-normalised, H = I + g u u^T with g = -2/(u^T u): one rsqrt and
 //    one reciprocal (MUFU seed + Newton steps) instead of dlarfg's sqrt + three divisions
 //    (householder.jl:66-108); orthogonality of H depends only on g, not on the accuracy of
-//    the norm;
+//    the norm; u^T u / 2 = |x|^2 + |x0| |x|, so the reciprocal's seed is taken from the rsqrt
+//    SEED while the rsqrt is still being refined (refl_u);
 //  * the factors live in shared memory in packed form (upper triangle + kl subdiagonals,
 //    column c at offset c(c+1)/2 + kl*c): 36.4 KB per p=8,N=32 problem instead of 64 KB,
 //    i.e. 6 resident problems per SM instead of 3, and both the column-lane and the row-lane
