@@ -135,8 +135,8 @@ int psd_rphess_batched(psd_handle_t handle, int n, int p, int64_t batch, int wan
  * 1, LAPACK convention), and tau[b][j-1][i] their scalars (n per factor; tau[.][0] uses n-1, the
  * trailing entries are 0) - exactly the (A[j], tau[j]) from which phessenberg! builds
  * Hessenberg(A[1], tau[1]) and QR(A[j], tau[j]) (PeriodicSchurDecompositions.jl:229-253).
- * Host buffers; one CTA per problem at every order (the blocked large-N reduction keeps its
- * reflectors in compact-WY form and is not used here). */
+ * Host buffers, first device of the handle; one CTA per problem at every order (the blocked
+ * large-N reduction keeps its reflectors in compact-WY form and is not used here). */
 int psd_rphess_packed_batched(psd_handle_t handle, int n, int p, int64_t batch, double* A,
                               double* tau);
 
@@ -291,7 +291,8 @@ int psd_set_iters_output(psd_handle_t handle, int32_t* iters);
  *   tri[b*p + l]  = Frobenius norm of T_l below its (quasi-)triangle (tril(T, -2) for the Schur
  *                   factor, tril(T, -1) for the others; the strict check wants exactly 0),
  *   orth[b*p + l] = || Z_l Z_l' - I ||_F (the reference's limit is 10 eps n).
- * tri and orth may be NULL.  The comparison with the thresholds stays with the caller. */
+ * tri and orth may be NULL.  The comparison with the thresholds stays with the caller.  Host
+ * buffers; a diagnostic, run on the first device of the handle in plain synchronous chunks. */
 int psd_rcheckpsd_batched(psd_handle_t handle, int n, int p, int64_t batch, int orientation,
                           const double* A, const double* T, const double* Z, double* err,
                           double* tri, double* orth);
