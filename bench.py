@@ -326,6 +326,43 @@ def config1_block(psd_b200, h, reps=20):
             "note": "host call with pageable numpy buffers, copies included (second call of the shape: staging buffers exist); kernels_only sums the durations of chunk launches that overlap on three streams; CPU = C++ restatement of the reference"}
 
 
+def pinned_input(L, psd_b200, torch, local_rank, shape):
+    """Input buffer of the end-to-end leg.  With PSD_BENCH_WC_INPUT=1: page-locked, write-combined
+    (the host only writes it, the GPU reads it over PCIe every step), allocated while the process is
+    bound to the CPUs next to its GPU so that the pages land on that NUMA node (first touch)."""
+    import numpy as np
+    if not os.environ.get("PSD_BENCH_WC_INPUT"):
+        # default: torch's pinned allocator.  The write-combined / affinity variant below was
+        # measured at 8 GPUs: 1.648 M instead of 1.630 M problems/s end to end (noise); the GPU boxes
+        # are VMs with one NUMA node, and 8 x 13.4 GB/s = 107 GB/s is what their host side delivers.
+        return torch.empty(shape, dtype=torch.float64, pin_memory=True)
+    old = None
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        hnd = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        words = pynvml.nvmlDeviceGetCpuAffinity(hnd, (os.cpu_count() + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            old = os.sched_getaffinity(0)
+            os.sched_setaffinity(0, cpus)
+    except Exception:
+        old = None
+    try:
+        count = int(np.prod(shape))
+        ptr = C.c_void_p()
+        psd_b200.capi.check(L.psd_host_alloc(count * 8, 1, C.byref(ptr)))
+        arr = np.ctypeslib.as_array((C.c_double * count).from_address(ptr.value)).reshape(shape)
+        t = torch.from_numpy(arr)  # (lives until the process exits)
+    except Exception:
+        t = torch.empty(shape, dtype=torch.float64, pin_memory=True)
+    finally:
+        if old:
+            os.sched_setaffinity(0, old)
+    return t
+
+
 def multi_device_handle_leg(psd_b200, L, torch, world, B, n, p):
     """The library's own multi-GPU path: ONE psd_rpschur_batched call on a handle that owns all
     `world` devices (one host thread + streams per device inside the library, contiguous batch
@@ -391,7 +428,7 @@ def run_ours(args):
     first_b = rank * B
 
     # ---- inputs: pinned host master copy + device copy (6.55 GB per GPU at B=100k > L2) ----
-    hA = torch.empty((B, p, n, n), dtype=torch.float64, pin_memory=True)
+    hA = pinned_input(L, psd_b200, torch, local_rank, (B, p, n, n))
     psd_b200.capi.check(L.psd_fill_uniform_host(SEED, n, p, B, first_b, 0, C.c_void_p(hA.data_ptr())))
     hE = torch.empty((B, n, 2), dtype=torch.float64, pin_memory=True)
     hI = torch.empty(B, dtype=torch.int32, pin_memory=True)

@@ -282,6 +282,13 @@ int psd_large_stats(psd_handle_t handle, double out[16]);
  * report 0 here and their counters through psd_large_stats. */
 int psd_set_iters_output(psd_handle_t handle, int32_t* iters);
 
+/* Page-locked host memory for the callers of the batched entry points (a Julia Array is pageable;
+ * buffers from here are copied from / to by DMA directly, without the staging copy).
+ * write_combined != 0: for INPUT buffers the host only writes (the device reads them faster over
+ * PCIe; host reads of such memory are very slow). */
+int psd_host_alloc(size_t bytes, int write_combined, void** out);
+int psd_host_free(void* ptr);
+
 /* Integrity check of real periodic Schur decompositions on the device, batched.
  * Replaces checkpsd(P, Hs) (diagnostics.jl:190-263) for PeriodicSchur results (S all true): for
  * problem b and factor l (user order, host arrays in the storage layout of psd_rpschur_batched)

@@ -35,6 +35,8 @@ EXPORTED_SYMBOLS = [
     "psd_kernel_times",
     "psd_large_stats",
     "psd_set_iters_output",
+    "psd_host_alloc",
+    "psd_host_free",
     "psd_rcheckpsd_batched",
     "psd_fill_uniform_host",
     "psd_fill_uniform_dev",
@@ -82,6 +84,8 @@ def lib():
         L.psd_rpschur_hessut_q_batched.argtypes = [vp, C.c_int, C.c_int, C.c_int64, C.c_int,
                                                    C.c_int, vp, vp, vp, vp]
         L.psd_set_iters_output.argtypes = [vp, vp]
+        L.psd_host_alloc.argtypes = [C.c_size_t, C.c_int, C.POINTER(C.c_void_p)]
+        L.psd_host_free.argtypes = [vp]
         L.psd_rphess_packed_batched.argtypes = [vp, C.c_int, C.c_int, C.c_int64, vp, vp]
         L.psd_rcheckpsd_batched.argtypes = [vp, C.c_int, C.c_int, C.c_int64, C.c_int, vp, vp, vp, vp, vp, vp]
         L.psd_rphess_batched.argtypes = [vp, C.c_int, C.c_int, C.c_int64, C.c_int, vp, vp]

@@ -1321,6 +1321,22 @@ int psd_rphess_packed_batched(psd_handle_t h, int n, int p, int64_t batch, doubl
   return PSD_OK;
 }
 
+int psd_host_alloc(size_t bytes, int write_combined, void** out) {
+  if (!out || bytes == 0) return fail(PSD_ERR_BAD_ARG, "bad argument");
+  *out = nullptr;
+  const unsigned flags = cudaHostAllocPortable | (write_combined ? cudaHostAllocWriteCombined : 0u);
+  cudaError_t e = cudaHostAlloc(out, bytes, flags);
+  if (e != cudaSuccess) return fail(PSD_ERR_CUDA, std::string("cudaHostAlloc: ") + cudaGetErrorString(e));
+  return PSD_OK;
+}
+
+int psd_host_free(void* ptr) {
+  if (!ptr) return PSD_OK;
+  cudaError_t e = cudaFreeHost(ptr);
+  if (e != cudaSuccess) return fail(PSD_ERR_CUDA, std::string("cudaFreeHost: ") + cudaGetErrorString(e));
+  return PSD_OK;
+}
+
 int psd_set_iters_output(psd_handle_t h, int32_t* iters) {
   if (!h) return fail(PSD_ERR_BAD_ARG, "null handle");
   std::lock_guard<std::mutex> lock(h->mu);
