@@ -82,3 +82,21 @@ def test_window_geometry():
         g = emul.geom(p)
         assert g["D"] + 3 * g["NB"] <= g["W"] - 1 and g["LD"] == g["W"] + 1
         assert p * g["W"] * g["LD"] * 16 <= 215000 or g["W"] == 24
+
+
+def test_emulated_several_blocks_at_once(oracle, monkeypatch):
+    """the driver works on every unreduced diagonal block at the same time (max_blocks = 4) instead
+    of finishing the lowest block first as the reference does: same decomposition quality, same
+    eigenvalues, fewer rounds, and no bulge is ever left behind by a packet that outlives a split
+    of its block"""
+    n, p = 420, 3
+    A, H, Q = _problem(oracle, 31, n, p)
+    monkeypatch.setenv("MS_EMUL_MAXBLOCKS", "1")
+    T1, Z1, lam1, info1, st1 = emul.run(H, Q)
+    monkeypatch.setenv("MS_EMUL_MAXBLOCKS", "4")
+    T4, Z4, lam4, info4, st4 = emul.run(H, Q)
+    for (T, Z, lam, info, st) in [(T1, Z1, lam1, info1, st1), (T4, Z4, lam4, info4, st4)]:
+        assert info == 0 and st["status"] == 0 and st["bulges_left_behind"] == 0
+        K.pschur_check(A, T, Z, lam, tol=60.0, check_lambda=False)
+    assert K.match_eigs(lam1, lam4) <= 1e-9 * np.max(np.abs(lam1))
+    assert st4["rounds"] <= st1["rounds"]
