@@ -558,10 +558,12 @@ def run_ours(args):
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak,
                      "traffic": (traffic * units_per_launch) if traffic else None,
-                     "traffic_note": "DRAM bytes of the six phase launches that one timed 'launch' stands for "
-                                     "(ncu capture of the final kernels, profiles/traffic.json): 188.8 KB per "
-                                     "problem = 2.9x the path-level 66 048 B, because every phase hands the "
-                                     "packed prefixes to the next one through HBM",
+                     "traffic_note": ("DRAM bytes of the six phase launches that one timed 'launch' stands for "
+                                      "(ncu capture of the final kernels, profiles/traffic.json, written by "
+                                      "scripts/ncu_traffic.py): %.1f KB per problem = %.1fx the path-level "
+                                      "%d B, because every phase hands the packed prefixes to the next one "
+                                      "through HBM" % (traffic / 1e3, traffic / BYTES_PER_PROBLEM, BYTES_PER_PROBLEM))
+                                     if traffic else None,
                      "fp64_issue": fp64_issue,
                      "peak_kind": f"of {peak_kind}",
                      "kernel": "psd::rpqr_eig32_kernel_t (six occupancy phases, orders 32..12, timed together)",
