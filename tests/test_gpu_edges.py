@@ -100,3 +100,19 @@ def test_generalized_sharded(psd):
     for x, y in zip(a, b):
         assert np.array_equal(x, y)
     h2.close()
+
+
+def test_pageable_staging_with_T_and_Z(psd, oracle):
+    """a pageable call large enough to be cut into several staged chunks (the copies out of the
+    pinned staging buffers are deferred until a slot is reused): every problem's T, Z, eigenvalues
+    must land in its own place - checked against separate small calls on slices of the batch"""
+    n, p, B = 20, 3, 8000                      # 77 MB of factors: at least four chunks
+    A = oracle.gen_real(4321, n, p, B)
+    T, Z, lam, info, it = psd.pschur_batched(A, "R", return_iters=True)
+    assert (info == 0).all() and (it > 0).all()
+    for lo in (0, 1999, 3990, 7900):
+        sl = slice(lo, lo + 100)
+        Ts, Zs, ls, infos, its = psd.pschur_batched(A[sl], "R", return_iters=True)
+        assert np.array_equal(T[sl], Ts) and np.array_equal(Z[sl], Zs) and np.array_equal(lam[sl], ls)
+        assert np.array_equal(it[sl], its)
+    K.pschur_check(A[B - 1], T[B - 1], Z[B - 1], lam[B - 1])
