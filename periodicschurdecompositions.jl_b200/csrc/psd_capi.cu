@@ -272,7 +272,6 @@ int launch_real_eig32(psd_handle_s* h, Device& dev, Slot& aux, cudaStream_t stre
     bool special = (n == 32 && p == 8 && !dbg_env("PSD_NO_SPECIAL"));
     if (const char* ev = dbg_env("PSD_PHASES")) {  // experiment: comma-separated decreasing orders after n
       orders.assign(1, n);
-      special = false;
       for (const char* c = ev; *c;) {
         int v = atoi(c);
         if (v > 1 && v < orders.back()) orders.push_back(v);
