@@ -168,7 +168,7 @@ def test_device_checkpsd(psd, oracle):
     """psd_rcheckpsd_batched against the same norms formed with numpy (checkpsd,
     diagnostics.jl:190-263): good decompositions pass with the reference's thresholds, a perturbed T,
     a perturbed Z and a non-zero entry below the triangle are each reported in the right place."""
-    for (n, p, batch, lr) in [(5, 3, 6, "R"), (33, 2, 3, "L"), (50, 3, 4, "R"), (200, 2, 1, "R")]:
+    for (n, p, batch, lr) in [(5, 3, 6, "R"), (33, 2, 3, "L"), (50, 3, 4, "R"), (200, 2, 1, "R"), (1100, 1, 1, "R")]:  # the last one: one right-hand side per pass
         A = oracle.gen_real(91, n, p, batch)
         T, Z, lam, info = psd.pschur_batched(A, lr)
         ok, err, tri, orth = psd.checkpsd_batched(A, T, Z, lr)
